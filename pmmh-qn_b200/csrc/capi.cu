@@ -1,0 +1,431 @@
+// capi.cu -- extern "C" boundary of libpmmh_qn_b200.so (declared in include/pmmh_qn.h).
+// Plain pointers and sizes in, status codes out; no torch types, no CPU fallback.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/pmmh_qn.h"
+#include "aux_kernels.cuh"
+#include "sv_filter.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* what) {
+    g_last_error = what;
+    return code;
+}
+int fail_cuda(cudaError_t err, const char* where) {
+    char buf[512];
+    snprintf(buf, sizeof(buf), "%s: %s", where, cudaGetErrorString(err));
+    g_last_error = buf;
+    return PMMH_ERR_CUDA;
+}
+#define PMMH_CUDA(call)                                       \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) return fail_cuda(e__, #call); \
+    } while (0)
+
+struct DeviceInfo {
+    int sm = 0, major = 0, minor = 0, coop = 0;
+    bool ok = false;
+};
+
+int get_device_info(DeviceInfo* out) {
+    static thread_local DeviceInfo cache[64];
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return fail_cuda(err, "cudaGetDevice");
+    if (dev < 0 || dev >= 64) return fail(PMMH_ERR_NO_DEVICE, "device ordinal out of range");
+    DeviceInfo& d = cache[dev];
+    if (!d.ok) {
+        PMMH_CUDA(cudaDeviceGetAttribute(&d.sm, cudaDevAttrMultiProcessorCount, dev));
+        PMMH_CUDA(cudaDeviceGetAttribute(&d.major, cudaDevAttrComputeCapabilityMajor, dev));
+        PMMH_CUDA(cudaDeviceGetAttribute(&d.minor, cudaDevAttrComputeCapabilityMinor, dev));
+        PMMH_CUDA(cudaDeviceGetAttribute(&d.coop, cudaDevAttrCooperativeLaunch, dev));
+        d.ok = true;
+    }
+    *out = d;
+    return PMMH_OK;
+}
+
+struct SvPlan {
+    int G, n_teams, grid, NB, RING, SQ, SQW;
+    size_t stamp_bytes, sync_bytes, team_stride, total;
+};
+
+int sv_make_plan(int nobs, int n, int lag, int batch, int hess, int mode, int have_hist, int ctas,
+                 SvPlan* p) {
+    if (nobs < 2 || n < 1 || batch < 1) return fail(PMMH_ERR_INVALID, "sizes must be positive");
+    if (mode == pmmh::kSvFlps) {
+        if (lag < 2 || lag >= 64) return fail(PMMH_ERR_INVALID, "lag must be in [2, 63]");
+        if (nobs < lag + 1) return fail(PMMH_ERR_INVALID, "n_obs must be at least lag + 1");
+    } else {
+        lag = 2;
+    }
+    if ((long long)n + nobs >= (1ll << 31)) return fail(PMMH_ERR_INVALID, "n_particles too large");
+    DeviceInfo di;
+    int rc = get_device_info(&di);
+    if (rc != PMMH_OK) return rc;
+    if (di.major < 10) return fail(PMMH_ERR_NO_DEVICE, "an sm_100 (B200) device is required");
+    if (!di.coop) return fail(PMMH_ERR_NO_DEVICE, "device lacks cooperative launch");
+    int G;
+    if (ctas > 0) G = ctas;
+    else if (batch > 1) G = (n + 4095) / 4096;
+    else G = (n + 1023) / 1024;
+    if (G < 1) G = 1;
+    if (G > di.sm) G = di.sm;
+    int n_teams = di.sm / G;
+    if (n_teams > batch) n_teams = batch;
+    if (n_teams < 1) n_teams = 1;
+    p->G = G;
+    p->n_teams = n_teams;
+    p->grid = G * n_teams;
+    p->NB = ((n + 31) / 32) * 32;
+    if (p->NB < 64) p->NB = 64;
+    p->RING = lag + 1;
+    p->SQ = hess ? (nobs + n - 2) / nobs + 1 : 1;
+    p->SQW = (mode != pmmh::kSvFlps) ? (n + nobs - 1) / nobs : 0;
+    p->stamp_bytes = pmmh::sv_align((size_t)p->grid * sizeof(unsigned));
+    p->sync_bytes = p->stamp_bytes +
+                    pmmh::sv_align((size_t)n_teams * 2 * G * pmmh::kMaxAllgatherHost * sizeof(double));
+    p->team_stride = pmmh::sv_ws_layout(n, nobs, lag, p->NB, p->RING, hess, mode, p->SQ, p->SQW,
+                                        have_hist, nullptr, nullptr);
+    p->total = p->sync_bytes + (size_t)n_teams * p->team_stride;
+    return PMMH_OK;
+}
+
+int sv_run(int mode, const double* d_obs, long long obs_stride, const double* d_params,
+           const double* d_rvr, const double* d_u, int nobs, int n, int lag, int batch, int hess,
+           double* d_filt, double* d_smo, double* d_ll, double* d_grad, double* d_traj, double* d_h1,
+           double* d_h2, long long* d_diag, double* d_xh, int* d_ah, void* d_ws, size_t ws_bytes,
+           int ctas, void* stream) {
+    if (!d_obs || !d_params || !d_rvr || !d_u || !d_filt || !d_ll || !d_traj || !d_diag || !d_ws)
+        return fail(PMMH_ERR_INVALID, "null pointer argument");
+    if (mode == pmmh::kSvFlps && (!d_smo || !d_grad || !d_h1 || !d_h2))
+        return fail(PMMH_ERR_INVALID, "null output pointer");
+    if ((d_xh == nullptr) != (d_ah == nullptr))
+        return fail(PMMH_ERR_INVALID, "d_x_hist and d_a_hist must be given together");
+    SvPlan p;
+    int rc = sv_make_plan(nobs, n, lag, batch, hess, mode, d_xh != nullptr, ctas, &p);
+    if (rc != PMMH_OK) return rc;
+    if (ws_bytes < p.total) return fail(PMMH_ERR_WORKSPACE, "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    PMMH_CUDA(cudaMemsetAsync(d_ws, 0, p.stamp_bytes, st));
+    pmmh::SvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.N = n;
+    a.NOBS = nobs;
+    a.LAG = (mode == pmmh::kSvFlps) ? lag : 2;
+    a.B = batch;
+    a.G = p.G;
+    a.n_teams = p.n_teams;
+    a.NB = p.NB;
+    a.RING = p.RING;
+    a.mode = mode;
+    a.hess = hess;
+    a.SQ = p.SQ;
+    a.SQW = p.SQW;
+    a.obs = d_obs;
+    a.obs_stride = obs_stride;
+    a.params = d_params;
+    a.rvr = d_rvr;
+    a.U = d_u;
+    a.filt = d_filt;
+    a.smo = d_smo;
+    a.loglike = d_ll;
+    a.grad = d_grad;
+    a.traj = d_traj;
+    a.hess1 = d_h1;
+    a.hess2 = d_h2;
+    a.diag = d_diag;
+    a.Xhist = d_xh;
+    a.Ahist = d_ah;
+    a.ws = (char*)d_ws;
+    a.ws_sync_bytes = p.sync_bytes;
+    a.ws_team_stride = p.team_stride;
+    PMMH_CUDA(pmmh::sv_launch(a, p.grid, st));
+    return PMMH_OK;
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    template <typename T>
+    T* as() {
+        return (T*)p;
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+int pmmh_version(void) { return 100; }
+
+const char* pmmh_last_error(void) { return g_last_error.c_str(); }
+
+int pmmh_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+    DeviceInfo di;
+    int rc = get_device_info(&di);
+    if (rc != PMMH_OK) return rc;
+    if (sm_count) *sm_count = di.sm;
+    if (cc_major) *cc_major = di.major;
+    if (cc_minor) *cc_minor = di.minor;
+    return PMMH_OK;
+}
+
+int pmmh_sv_workspace_bytes(int n_obs, int n_particles, int lag, int batch, int compute_hessian,
+                            int mode, int have_history, int ctas_per_problem, size_t* bytes) {
+    if (!bytes) return fail(PMMH_ERR_INVALID, "bytes is null");
+    SvPlan p;
+    int rc = sv_make_plan(n_obs, n_particles, lag, batch, compute_hessian,
+                          mode == 0 ? pmmh::kSvFlps : pmmh::kSvBpfParity, have_history,
+                          ctas_per_problem, &p);
+    if (rc != PMMH_OK) return rc;
+    *bytes = p.total;
+    return PMMH_OK;
+}
+
+int pmmh_flps_sv_corr(const double* d_obs, long long obs_stride, const double* d_params,
+                      const double* d_rvr, const double* d_u, int n_obs, int n_particles, int lag,
+                      int batch, int compute_hessian, double* d_filt, double* d_smo,
+                      double* d_log_like, double* d_gradient, double* d_traj, double* d_hess1,
+                      double* d_hess2, long long* d_diag, double* d_x_hist, int* d_a_hist,
+                      void* d_workspace, size_t workspace_bytes, int ctas_per_problem, void* stream) {
+    return sv_run(pmmh::kSvFlps, d_obs, obs_stride, d_params, d_rvr, d_u, n_obs, n_particles, lag, batch,
+                  compute_hessian ? 1 : 0, d_filt, d_smo, d_log_like, d_gradient, d_traj, d_hess1,
+                  d_hess2, d_diag, d_x_hist, d_a_hist, d_workspace, workspace_bytes, ctas_per_problem,
+                  stream);
+}
+
+int pmmh_bpf_sv_corr(const double* d_obs, long long obs_stride, const double* d_params,
+                     const double* d_rvr, const double* d_u, int n_obs, int n_particles, int batch,
+                     int read_mode, double* d_filt, double* d_log_like, double* d_traj,
+                     long long* d_diag, double* d_x_hist, int* d_a_hist, void* d_workspace,
+                     size_t workspace_bytes, int ctas_per_problem, void* stream) {
+    const int mode = (read_mode == PMMH_BPF_INTENDED) ? pmmh::kSvBpfIntended : pmmh::kSvBpfParity;
+    return sv_run(mode, d_obs, obs_stride, d_params, d_rvr, d_u, n_obs, n_particles, 2, batch, 0, d_filt,
+                  nullptr, d_log_like, nullptr, d_traj, nullptr, nullptr, d_diag, d_x_hist, d_a_hist,
+                  d_workspace, workspace_bytes, ctas_per_problem, stream);
+}
+
+int pmmh_split_rvs(const double* d_rvs, int n_obs, int n_particles, int batch, double* d_r_raw,
+                   double* d_u, void* stream) {
+    if (!d_rvs || !d_r_raw || !d_u || n_obs < 1 || n_particles < 1 || batch < 1)
+        return fail(PMMH_ERR_INVALID, "pmmh_split_rvs: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long per = (long long)n_obs * ((long long)n_particles + 1);
+    PMMH_CUDA(pmmh::launch_copy_head(d_rvs, d_r_raw, n_obs, batch, per, n_obs, st));
+    // flat remainder viewed as [n_particles][n_obs] -> [n_obs][n_particles]
+    PMMH_CUDA(pmmh::launch_transpose(d_rvs + n_obs, d_u, n_particles, n_obs, batch, per,
+                                     (long long)n_obs * n_particles, st));
+    return PMMH_OK;
+}
+
+int pmmh_norm_cdf(const double* d_in, double* d_out, long long n, void* stream) {
+    if (!d_in || !d_out || n < 0) return fail(PMMH_ERR_INVALID, "pmmh_norm_cdf: bad arguments");
+    PMMH_CUDA(pmmh::launch_norm_cdf(d_in, d_out, n, (cudaStream_t)stream));
+    return PMMH_OK;
+}
+
+int pmmh_importance_discrete(const double* d_obs, long long obs_stride, const double* d_params,
+                             const double* d_rvr, const double* d_rvp, int n_obs, int n_particles,
+                             int batch, double* d_filt, double* d_log_like, double* d_traj,
+                             double* d_gradient, int* d_traj_idx, void* stream) {
+    if (!d_obs || !d_params || !d_rvr || !d_rvp || !d_filt || !d_log_like || !d_traj || !d_gradient ||
+        !d_traj_idx || n_obs < 1 || n_particles < 1 || batch < 1)
+        return fail(PMMH_ERR_INVALID, "pmmh_importance_discrete: bad arguments");
+    if ((size_t)3 * n_particles * sizeof(double) > 200 * 1024)
+        return fail(PMMH_ERR_INVALID, "pmmh_importance_discrete: n_particles above 8533 unsupported");
+    PMMH_CUDA(pmmh::launch_importance_discrete(d_obs, obs_stride, d_params, d_rvr, d_rvp, n_obs,
+                                               n_particles, batch, d_filt, d_log_like, d_traj,
+                                               d_gradient, d_traj_idx, (cudaStream_t)stream));
+    return PMMH_OK;
+}
+
+int pmmh_crank_nicolson(const double* d_u, const double* d_xi, double* d_out, long long n,
+                        double sigma_u, unsigned long long seed, unsigned long long philox_offset,
+                        void* stream) {
+    if (!d_u || !d_out || n < 0) return fail(PMMH_ERR_INVALID, "pmmh_crank_nicolson: bad arguments");
+    const double a = sqrt(1.0 - sigma_u * sigma_u);
+    PMMH_CUDA(pmmh::launch_crank_nicolson(d_u, d_xi, d_out, n, a, sigma_u, seed, philox_offset,
+                                          (cudaStream_t)stream));
+    return PMMH_OK;
+}
+
+int pmmh_subsample_workspace_bytes(int m, size_t* bytes) {
+    if (!bytes || m < 1) return fail(PMMH_ERR_INVALID, "pmmh_subsample_workspace_bytes: bad arguments");
+    *bytes = pmmh::subsample_ws_bytes(m);
+    return PMMH_OK;
+}
+
+int pmmh_subsample_indices(const double* d_u, int m, int n_data, int apply_cdf, int* d_idx,
+                           double* d_sorted, void* d_workspace, size_t workspace_bytes, void* stream) {
+    if (!d_u || !d_idx || !d_workspace || m < 1 || n_data < 1)
+        return fail(PMMH_ERR_INVALID, "pmmh_subsample_indices: bad arguments");
+    if (workspace_bytes < pmmh::subsample_ws_bytes(m)) return fail(PMMH_ERR_WORKSPACE, "workspace too small");
+    PMMH_CUDA(pmmh::launch_subsample_indices(d_u, m, n_data, apply_cdf, d_idx, d_sorted, d_workspace,
+                                             (cudaStream_t)stream));
+    return PMMH_OK;
+}
+
+int pmmh_logistic_workspace_bytes(int m, int d, int compute_hessian, size_t* bytes) {
+    if (!bytes || m < 1 || d < 1) return fail(PMMH_ERR_INVALID, "pmmh_logistic_workspace_bytes: bad arguments");
+    *bytes = pmmh::logistic_ws_bytes(m, d, compute_hessian);
+    return PMMH_OK;
+}
+
+int pmmh_logistic_loglike(const double* d_x, const double* d_y, const int* d_idx, int m, int d,
+                          long long row_begin, long long row_end, const double* d_beta,
+                          int compute_hessian, double* d_out, void* d_workspace,
+                          size_t workspace_bytes, void* stream) {
+    if (!d_x || !d_y || !d_idx || !d_beta || !d_out || !d_workspace || m < 1 || d < 1)
+        return fail(PMMH_ERR_INVALID, "pmmh_logistic_loglike: bad arguments");
+    if (d > 32) return fail(PMMH_ERR_INVALID, "pmmh_logistic_loglike: d > 32 not supported yet");
+    if (workspace_bytes < pmmh::logistic_ws_bytes(m, d, compute_hessian))
+        return fail(PMMH_ERR_WORKSPACE, "workspace too small");
+    PMMH_CUDA(pmmh::launch_logistic(d_x, d_y, d_idx, m, d, row_begin, row_end, d_beta,
+                                    compute_hessian ? 1 : 0, d_out, d_workspace, (cudaStream_t)stream));
+    return PMMH_OK;
+}
+
+// ------------------------------------------------------------------ host-buffer wrappers
+
+static int sv_host(int mode, const double* obs, const double* params, const double* rvr,
+                   const double* rvp, int n_obs, int n, int lag, int hess, int read_mode, double* filt,
+                   double* smo, double* log_like, double* gradient, double* traj, double* hess1,
+                   double* hess2, long long* diag) {
+    if (!obs || !params || !rvr || !rvp || !filt || !log_like || !traj)
+        return fail(PMMH_ERR_INVALID, "null host pointer");
+    const size_t nt = (size_t)n_obs * n;
+    size_t ws_bytes = 0;
+    int rc = pmmh_sv_workspace_bytes(n_obs, n, lag, 1, hess, mode, 0, 0, &ws_bytes);
+    if (rc != PMMH_OK) return rc;
+    DevBuf b_obs, b_par, b_rvr, b_rvp, b_u, b_out, b_diag, b_ws;
+    const size_t n_out = (size_t)n_obs * 7 + 1 + 32;   // filt smo traj grad[4] ll h1 h2
+    PMMH_CUDA(b_obs.alloc(n_obs * sizeof(double)));
+    PMMH_CUDA(b_par.alloc(4 * sizeof(double)));
+    PMMH_CUDA(b_rvr.alloc(n_obs * sizeof(double)));
+    PMMH_CUDA(b_rvp.alloc(nt * sizeof(double)));
+    PMMH_CUDA(b_u.alloc(nt * sizeof(double)));
+    PMMH_CUDA(b_out.alloc(n_out * sizeof(double)));
+    PMMH_CUDA(b_diag.alloc(PMMH_DIAG_COUNT * sizeof(long long)));
+    PMMH_CUDA(b_ws.alloc(ws_bytes));
+    PMMH_CUDA(cudaMemcpy(b_obs.p, obs, n_obs * sizeof(double), cudaMemcpyHostToDevice));
+    PMMH_CUDA(cudaMemcpy(b_par.p, params, 4 * sizeof(double), cudaMemcpyHostToDevice));
+    PMMH_CUDA(cudaMemcpy(b_rvr.p, rvr, n_obs * sizeof(double), cudaMemcpyHostToDevice));
+    PMMH_CUDA(cudaMemcpy(b_rvp.p, rvp, nt * sizeof(double), cudaMemcpyHostToDevice));
+    PMMH_CUDA(cudaMemset(b_out.p, 0, n_out * sizeof(double)));
+    PMMH_CUDA(cudaMemset(b_diag.p, 0, PMMH_DIAG_COUNT * sizeof(long long)));
+    PMMH_CUDA(pmmh::launch_transpose(b_rvp.as<double>(), b_u.as<double>(), n, n_obs, 1, 0, 0, 0));
+    double* o = b_out.as<double>();
+    double* d_filt = o;
+    double* d_smo = o + n_obs;
+    double* d_traj = o + 2 * (size_t)n_obs;
+    double* d_grad = o + 3 * (size_t)n_obs;
+    double* d_ll = o + 7 * (size_t)n_obs;
+    double* d_h1 = d_ll + 1;
+    double* d_h2 = d_h1 + 16;
+    if (mode == 0)
+        rc = pmmh_flps_sv_corr(b_obs.as<double>(), 0, b_par.as<double>(), b_rvr.as<double>(),
+                               b_u.as<double>(), n_obs, n, lag, 1, hess, d_filt, d_smo, d_ll, d_grad,
+                               d_traj, d_h1, d_h2, b_diag.as<long long>(), nullptr, nullptr, b_ws.p,
+                               ws_bytes, 0, nullptr);
+    else
+        rc = pmmh_bpf_sv_corr(b_obs.as<double>(), 0, b_par.as<double>(), b_rvr.as<double>(),
+                              b_u.as<double>(), n_obs, n, 1, read_mode, d_filt, d_ll, d_traj,
+                              b_diag.as<long long>(), nullptr, nullptr, b_ws.p, ws_bytes, 0, nullptr);
+    if (rc != PMMH_OK) return rc;
+    PMMH_CUDA(cudaDeviceSynchronize());
+    std::vector<double> h(n_out);
+    PMMH_CUDA(cudaMemcpy(h.data(), o, n_out * sizeof(double), cudaMemcpyDeviceToHost));
+    memcpy(filt, h.data(), n_obs * sizeof(double));
+    if (smo) memcpy(smo, h.data() + n_obs, n_obs * sizeof(double));
+    memcpy(traj, h.data() + 2 * (size_t)n_obs, n_obs * sizeof(double));
+    if (gradient) memcpy(gradient, h.data() + 3 * (size_t)n_obs, 4 * (size_t)n_obs * sizeof(double));
+    *log_like = h[7 * (size_t)n_obs];
+    if (hess1) memcpy(hess1, h.data() + 7 * (size_t)n_obs + 1, 16 * sizeof(double));
+    if (hess2) memcpy(hess2, h.data() + 7 * (size_t)n_obs + 17, 16 * sizeof(double));
+    if (diag)
+        PMMH_CUDA(cudaMemcpy(diag, b_diag.p, PMMH_DIAG_COUNT * sizeof(long long), cudaMemcpyDeviceToHost));
+    return PMMH_OK;
+}
+
+int pmmh_flps_sv_corr_host(const double* obs, const double* params, const double* rvr,
+                           const double* rvp, int n_obs, int n_particles, int lag,
+                           int compute_hessian, double* filt, double* smo, double* log_like,
+                           double* gradient, double* traj, double* hess1, double* hess2,
+                           long long* diag) {
+    if (!smo || !gradient || !hess1 || !hess2) return fail(PMMH_ERR_INVALID, "null host pointer");
+    return sv_host(0, obs, params, rvr, rvp, n_obs, n_particles, lag, compute_hessian ? 1 : 0, 0, filt,
+                   smo, log_like, gradient, traj, hess1, hess2, diag);
+}
+
+int pmmh_bpf_sv_corr_host(const double* obs, const double* params, const double* rvr,
+                          const double* rvp, int n_obs, int n_particles, int read_mode,
+                          double* filt, double* log_like, double* traj, long long* diag) {
+    return sv_host(1, obs, params, rvr, rvp, n_obs, n_particles, 2, 0, read_mode, filt, nullptr,
+                   log_like, nullptr, traj, nullptr, nullptr, diag);
+}
+
+int pmmh_importance_discrete_host(const double* obs, const double* params, double rvr,
+                                  const double* rvp, int n_obs, int n_particles, double* filt,
+                                  double* log_like, double* traj, double* gradient) {
+    if (!obs || !params || !rvp || !filt || !log_like || !traj || !gradient)
+        return fail(PMMH_ERR_INVALID, "null host pointer");
+    const size_t nt = (size_t)n_obs * n_particles;
+    DevBuf b_obs, b_par, b_rvr, b_rvp, b_out, b_idx;
+    const size_t n_out = (size_t)2 * n_obs + 3;
+    PMMH_CUDA(b_obs.alloc(n_obs * sizeof(double)));
+    PMMH_CUDA(b_par.alloc(2 * sizeof(double)));
+    PMMH_CUDA(b_rvr.alloc(sizeof(double)));
+    PMMH_CUDA(b_rvp.alloc(nt * sizeof(double)));
+    PMMH_CUDA(b_out.alloc(n_out * sizeof(double)));
+    PMMH_CUDA(b_idx.alloc(sizeof(int)));
+    PMMH_CUDA(cudaMemcpy(b_obs.p, obs, n_obs * sizeof(double), cudaMemcpyHostToDevice));
+    PMMH_CUDA(cudaMemcpy(b_par.p, params, 2 * sizeof(double), cudaMemcpyHostToDevice));
+    PMMH_CUDA(cudaMemcpy(b_rvr.p, &rvr, sizeof(double), cudaMemcpyHostToDevice));
+    PMMH_CUDA(cudaMemcpy(b_rvp.p, rvp, nt * sizeof(double), cudaMemcpyHostToDevice));
+    double* o = b_out.as<double>();
+    int rc = pmmh_importance_discrete(b_obs.as<double>(), 0, b_par.as<double>(), b_rvr.as<double>(),
+                                      b_rvp.as<double>(), n_obs, n_particles, 1, o, o + 2 * (size_t)n_obs,
+                                      o + n_obs, o + 2 * (size_t)n_obs + 1, b_idx.as<int>(), nullptr);
+    if (rc != PMMH_OK) return rc;
+    PMMH_CUDA(cudaDeviceSynchronize());
+    std::vector<double> h(n_out);
+    PMMH_CUDA(cudaMemcpy(h.data(), o, n_out * sizeof(double), cudaMemcpyDeviceToHost));
+    memcpy(filt, h.data(), n_obs * sizeof(double));
+    memcpy(traj, h.data() + n_obs, n_obs * sizeof(double));
+    *log_like = h[2 * (size_t)n_obs];
+    gradient[0] = h[2 * (size_t)n_obs + 1];
+    gradient[1] = h[2 * (size_t)n_obs + 2];
+    return PMMH_OK;
+}
+
+int pmmh_stratified_host(const double* rnd_sorted, int m, int n_data, int* indices) {
+    if (!rnd_sorted || !indices || m < 1 || n_data < 1) return fail(PMMH_ERR_INVALID, "bad arguments");
+    size_t ws_bytes = pmmh::subsample_ws_bytes(m);
+    DevBuf b_u, b_idx, b_ws;
+    PMMH_CUDA(b_u.alloc(m * sizeof(double)));
+    PMMH_CUDA(b_idx.alloc(m * sizeof(int)));
+    PMMH_CUDA(b_ws.alloc(ws_bytes));
+    PMMH_CUDA(cudaMemcpy(b_u.p, rnd_sorted, m * sizeof(double), cudaMemcpyHostToDevice));
+    int rc = pmmh_subsample_indices(b_u.as<double>(), m, n_data, 0, b_idx.as<int>(), nullptr, b_ws.p,
+                                    ws_bytes, nullptr);
+    if (rc != PMMH_OK) return rc;
+    PMMH_CUDA(cudaDeviceSynchronize());
+    PMMH_CUDA(cudaMemcpy(indices, b_idx.p, m * sizeof(int), cudaMemcpyDeviceToHost));
+    return PMMH_OK;
+}
+
+}  // extern "C"

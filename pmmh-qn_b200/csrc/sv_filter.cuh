@@ -1,0 +1,108 @@
+// sv_filter.cuh -- argument block and workspace layout of the persistent SV particle-filter
+// kernel (shared between the kernel and the C-ABI host code).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace pmmh {
+
+constexpr int kSvThreads = 1024;         // threads per CTA (1 CTA per SM)
+constexpr int kStageDoubles = 12288;     // smem staging window for the cumulative weights
+constexpr int kBinCap = 4096;            // max occupancy of one sort bin before we give up
+constexpr int kMaxAllgatherHost = 48;    // must equal kMaxAllgather (common.cuh)
+
+enum SvMode { kSvFlps = 0, kSvBpfParity = 1, kSvBpfIntended = 2 };
+
+// diag[] slots (per problem, int64)
+enum SvDiag {
+    kDiagNearTies = 0,     // ancestor decisions within 64 ulp of a cumulative-weight tie
+    kDiagMaxBin = 1,       // largest sort-bin occupancy seen
+    kDiagStatus = 2,       // 0 ok, 1 degenerate cloud (bin overflow), 2 non-finite range
+    kDiagKeyTies = 3,      // equal adjacent keys after sorting
+    kDiagWavefront = 4,    // bpf parity mode: max dependency-chain depth
+    kDiagTrajIdx = 5,      // bpf: sampled trajectory index (Q10)
+    kDiagCount = 8
+};
+
+struct SvArgs {
+    int N, NOBS, LAG, B;
+    int G, n_teams;
+    int NB;          // sort bins
+    int RING;        // ring depth of the X / A / R histories (LAG + 1), or NOBS with full history
+    int mode, hess;
+    int SQ;          // low slots of X kept for all times (Q7 / Q11)
+    int SQW;         // low slots of W kept for all times (Q10, bpf only)
+    const double* obs;
+    long long obs_stride;     // 0: shared observations
+    const double* params;     // [B][4]
+    const double* rvr;        // [B][NOBS]  (already Phi-transformed)
+    const double* U;          // [B][NOBS][N] time-major
+    double *filt, *smo, *loglike, *grad, *traj, *hess1, *hess2;
+    long long* diag;          // [B][kDiagCount]
+    double* Xhist;            // optional [B][NOBS][N]
+    int* Ahist;               // optional [B][NOBS][N]
+    char* ws;                 // workspace base
+    size_t ws_sync_bytes;     // leading region: stamps + slots for all CTAs
+    size_t ws_team_stride;
+};
+
+struct SvWs {
+    double *cum, *xnew, *tkey, *sh0, *sh1, *shtail, *Xring, *Rring, *Xlow, *Wlow, *X0;
+    int *aun, *rnk, *tpay, *tidx, *hist, *binstart, *Aring, *root0, *root1;
+};
+
+__host__ __device__ inline size_t sv_align(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// Bump-allocates the per-team workspace; returns its size.  `have_hist` = caller supplied
+// Xhist/Ahist (then no rings are carved).
+__host__ __device__ inline size_t sv_ws_layout(int N, int NOBS, int LAG, int NB, int RING, int hess,
+                                               int mode, int SQ, int SQW, int have_hist, char* base,
+                                               SvWs* w) {
+    size_t off = 0;
+    size_t n = (size_t)N;
+#define PMMH_CARVE(field, type, count)                         \
+    do {                                                       \
+        if (w) w->field = (type*)(base + off);                 \
+        off += sv_align((size_t)(count) * sizeof(type));       \
+    } while (0)
+    PMMH_CARVE(hist, int, NB);
+    PMMH_CARVE(binstart, int, NB + 1);
+    PMMH_CARVE(cum, double, n);
+    PMMH_CARVE(xnew, double, n);
+    PMMH_CARVE(tkey, double, n);
+    PMMH_CARVE(sh0, double, n);
+    PMMH_CARVE(sh1, double, n);
+    PMMH_CARVE(shtail, double, (size_t)LAG * n);
+    PMMH_CARVE(aun, int, n);
+    PMMH_CARVE(rnk, int, n);
+    PMMH_CARVE(tpay, int, n);
+    PMMH_CARVE(tidx, int, n);
+    PMMH_CARVE(Xlow, double, (size_t)NOBS * SQ);
+    PMMH_CARVE(Wlow, double, (size_t)NOBS * (SQW > 0 ? SQW : 1));
+    if (!have_hist) {
+        PMMH_CARVE(Xring, double, (size_t)RING * n);
+        PMMH_CARVE(Aring, int, (size_t)RING * n);
+    } else if (w) {
+        w->Xring = nullptr;
+        w->Aring = nullptr;
+    }
+    if (hess) PMMH_CARVE(Rring, double, (size_t)RING * 4 * n);
+    else if (w) w->Rring = nullptr;
+    if (mode != kSvFlps) {
+        PMMH_CARVE(root0, int, n);
+        PMMH_CARVE(root1, int, n);
+        PMMH_CARVE(X0, double, n);
+    } else if (w) {
+        w->root0 = w->root1 = nullptr;
+        w->X0 = nullptr;
+    }
+#undef PMMH_CARVE
+    return off;
+}
+
+// Host-side launcher (sv_filter.cu)
+cudaError_t sv_launch(const SvArgs& a, int grid, cudaStream_t stream);
+int sv_dynamic_smem_bytes(int G);
+
+}  // namespace pmmh
