@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the likelihood-estimation hot path (BASELINE.json).
+
+Workload (config 2 of BASELINE.json, the size its target is quoted on): stochastic-volatility
+fixed-lag particle smoother, T = 1000 returns, N = 2^20 particles, log-likelihood + gradient
+(hess = 0), synthetic returns and u.  One "step" = one evaluation.  With --gpus N every rank
+evaluates its own independent (theta, u) problem (chain-batched sharding, no collective on the
+data path) => weak scaling; `value` is the whole-job particle-timesteps/s.
+
+  python bench.py                      # 1 GPU, defaults
+  torchrun ... bench.py --gpus N ...   # one rank per GPU (the driver launches this)
+  python bench.py --impl reference     # the reference's own CPU implementation (oracle/_ref)
+
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests", "golden")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+T_STEPS = 1000
+NOBS = T_STEPS + 1
+LAG = 10
+PARAMS = (0.2, 0.9, 0.4, -0.5)
+BYTES_PER_PARTICLE_STEP = 96          # 7s + 40 at s = 8 (filter + fixed-lag gradient)
+METRIC = "particle_timesteps_per_sec"
+UNIT = "particle-timesteps/s"
+
+
+def measured_hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler(object):
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, smax, reasons = [], None, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in out.splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8 or parts[0] != str(self.gpu_index):
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax = float(parts[2])
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- reference arm
+def _ref_worker(args):
+    """One evaluation of the reference's compiled flps_sv_corr (N=1024, T=1000) in this process."""
+    seed, reps = args
+    import build_ref
+    import golden_inputs as gi
+    ref = build_ref.load("sv", 1024, NOBS, LAG)
+    obs = gi.sv_obs(NOBS)
+    rvr, rvp = gi.split_particle(gi.sv_rvs(1024, NOBS, seed), NOBS)
+    params = np.array(PARAMS)
+    t0 = time.perf_counter()
+    ll = 0.0
+    for _ in range(reps):
+        ll = ref.flps_sv_corr(obs, params, rvr, rvp, 0)[2]
+    return time.perf_counter() - t0, float(ll)
+
+
+def _port_worker(args):
+    seed, n = args
+    import golden_inputs as gi
+    import oracle
+    obs = gi.sv_obs(NOBS)
+    rvr, rvp = gi.split_particle(gi.sv_rvs(n, NOBS, seed), NOBS)
+    t0 = time.perf_counter()
+    out = oracle.flps_sv_corr(obs, np.array(PARAMS), rvr, rvp, n, LAG, 0)
+    return time.perf_counter() - t0, out["log_like"]
+
+
+def cpu_reference_throughput(steps, warmup):
+    """Times the reference's CPU path on all host cores (one process per core, independent
+    chains, because the reference itself is single-threaded).  Returns (value, info dict)."""
+    import multiprocessing as mp
+    import build_ref
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    have_ref = build_ref.load("sv", 1024, NOBS, LAG) is not None
+    ctx = mp.get_context("fork")
+    if have_ref:
+        n, kind, fn = 1024, "reference", _ref_worker
+        make = lambda k: [(1000 * k + w, 1) for w in range(cores)]   # noqa: E731
+    else:
+        n, kind, fn = 16384, "port", _port_worker
+        make = lambda k: [(1000 * k + w, n) for w in range(cores)]   # noqa: E731
+    times = []
+    with ctx.Pool(cores) as pool:
+        for k in range(warmup + steps):
+            t0 = time.perf_counter()
+            pool.map(fn, make(k))
+            dt = time.perf_counter() - t0
+            if k >= warmup:
+                times.append(dt)
+    per_step = float(np.mean(times))
+    value = cores * n * T_STEPS / per_step
+    info = {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "%s flps_sv_corr (hess=0), T=%d, N=%d, one independent evaluation per core "
+                      "per step (N=2^20 is infeasible on the reference: O(T^2 N) ancestry copies)"
+                      % ("compiled reference (oracle/_ref)" if have_ref else "oracle port", T_STEPS, n)}
+    return value, per_step, info
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    value, per_step, info = cpu_reference_throughput(args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "sv_flps_T1000_N2^20_grad", "reference_sample": info["sample"]},
+        "cpu_baseline": info,
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- our arm
+class BenchSVModel(object):
+    """Minimal model object with the attributes the estimator reads (the reference's
+    StochasticVolatilityModel, models/stochastic_volatility.py, stays ordinary Python)."""
+    short_name = 'sv'
+
+    def __init__(self, obs, params):
+        self.obs = np.asarray(obs, dtype=np.float64).reshape(-1, 1)
+        self.no_obs = self.obs.shape[0] - 1
+        self.params = dict(zip(('mu', 'phi', 'sigma_v', 'rho'), [float(p) for p in params]))
+        self.no_params = 4
+        self.params_to_estimate = ('mu', 'phi', 'sigma_v', 'rho')
+        self.params_to_estimate_idx = np.arange(4)
+        self.using_gradients = True
+        self.using_hessians = False
+
+    def get_all_params(self):
+        return np.array([self.params[k] for k in self.params])
+
+    def log_prior_gradient(self):
+        return {k: 0.0 for k in self.params}
+
+    def log_prior_hessian(self):
+        return {k: 0.0 for k in self.params}
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import golden_inputs as gi
+    from pmmh_qn_b200 import ParticleMethodsCUDA, kernels as K
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = args.particles
+    obs_h = gi.sv_obs(NOBS)
+    obs = torch.from_numpy(obs_h).to(dev)
+    params = torch.tensor([PARAMS], dtype=torch.float64, device=dev)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    # device-resident inputs (8.4 GB of u >> 126 MB of L2: nothing survives between steps)
+    u = torch.randn((1, NOBS, n), dtype=torch.float64, device=dev, generator=g)
+    rvr = torch.rand((1, NOBS), dtype=torch.float64, device=dev, generator=g)
+    ws = K.Workspace()
+
+    def step():
+        return K.flps_sv_corr(obs, params, rvr, u, lag=LAG, compute_hessian=False, workspace=ws)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        out = step()
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    e_all0 = torch.cuda.Event(enable_timing=True)
+    e_all1 = torch.cuda.Event(enable_timing=True)
+    e_all0.record()
+    for k in range(args.steps):
+        ev[k][0].record()
+        out = step()
+        ev[k][1].record()
+    e_all1.record()
+    sync_all()
+    clocks = sampler.stop()
+    total_ms = e_all0.elapsed_time(e_all1)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    if dist is not None:
+        tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+    ms_per_step = total_ms / args.steps
+    value = world * n * T_STEPS / (ms_per_step * 1e-3)
+    ll = float(out["log_like"][0])
+    diag = out["diag"][0].tolist()
+
+    # ---- end to end through the public estimator API with HOST (pinned) buffers
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    model = BenchSVModel(obs_h, PARAMS)
+    est = ParticleMethodsCUDA(model, no_particles=n, fixed_lag=LAG, device=dev)
+    rvs_pinned = torch.empty((NOBS, n + 1), dtype=torch.float64, pin_memory=True)
+    rvs_pinned.copy_(torch.randn((NOBS, n + 1), dtype=torch.float64, device=dev, generator=g))
+    rvs_np = rvs_pinned.numpy()
+    del u
+    torch.cuda.empty_cache()
+    ok = est.smoother(model, rvs={'rvs': rvs_np})      # warm-up
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ok = est.smoother(model, rvs={'rvs': rvs_np}) and ok
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    e2e_value = world * n * T_STEPS * e2e_steps / e2e_s
+    h2d = rvs_np.nbytes + (NOBS + 4 + NOBS) * 8
+    d2h = (NOBS * 3 + 4 * NOBS + 1 + 32 + 8) * 8
+
+    if rank == 0:
+        peak, peak_src = measured_hbm_peak()
+        achieved = n * T_STEPS * BYTES_PER_PARTICLE_STEP / (kern_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "sv_flps_T1000_N2^20_grad" if n == (1 << 20) else
+                       "sv_flps_T1000_N%d_grad" % n,
+                       "T": T_STEPS, "N": n, "lag": LAG, "compute_hessian": 0,
+                       "per_gpu": "one independent evaluation per GPU per step (chain-batched sharding)",
+                       "l2": "inputs larger than L2 (u = %.1f GB streamed once per step)" % (NOBS * n * 8 / 1e9)},
+            "loglik_evals_per_sec": world / (ms_per_step * 1e-3),
+            "log_like": ll, "near_ties": int(diag[0]), "status": int(diag[2]), "e2e_ok": bool(ok),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": args.traffic_bytes,
+                         "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": n * T_STEPS * BYTES_PER_PARTICLE_STEP,
+                         "kernel": "sv_pf_kernel<false>", "kernel_ms": kern_ms},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                    "api": "ParticleMethodsCUDA.smoother(model, rvs={'rvs': pinned ndarray})"},
+            "gpu_launches": args.steps * 1,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            _, _, info = cpu_reference_throughput(1, 0)
+            line["cpu_baseline"] = info
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--particles", type=int, default=1 << 20)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--traffic-bytes", type=float, default=None,
+                    help="dram bytes per launch from the committed ncu capture (profiles/)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    if args.traffic_bytes is None:
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+                args.traffic_bytes = float(json.load(fh)["dram_bytes_per_launch"])
+        except Exception:
+            args.traffic_bytes = None
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -19,8 +19,9 @@
 //     [x_min, x_max] +- 6.5 sd, outliers clamp into the end bins), atomics give each key a
 //     slot inside its bin, a scan gives bin offsets, and a tiny all-pairs rank orders each bin.
 //     Any correct sort reproduces the reference's qsort order for distinct keys.
-//   * resampling = team-wide scan of the normalised weights + per-child binary search in a
-//     shared-memory window of the cumulative weights (Q3: cum[0] not normalised).
+//   * resampling = team-wide scan of the shifted weights in POSITION order (deterministic) +
+//     per-child binary search in a shared-memory window of the cumulative weights, which are
+//     normalised by their total at lookup.
 //   * the genealogy is O(T N): composed one-step ancestors A_t in a ring of depth LAG+1; the
 //     fixed-lag pair (x_{t-L+1}, x_{t-L+2}) of each particle is found by chasing A.
 //   * quirks Q1, Q3-Q8, Q11 of the reference are reproduced (see oracle/pmmh_oracle.c).
@@ -174,18 +175,32 @@ __device__ __forceinline__ double obs_wrap(const double* obs, int k, int nobs) {
     return obs[k < 0 ? k + nobs : k];   // Cython memoryview wraparound (Q8)
 }
 
-// lower_bound of cp in the (Q3-)normalised cumulative weights restricted to [l, h];
+// lower_bound of cp in the normalised cumulative weights cum[m] / sum_w restricted to [l, h];
 // returns h if every entry is below cp (the reference's `cur < N-1` clamp when h = N-1).
 __device__ __forceinline__ int search_cum_global(const double* cum, double sum_w, double cp, int l,
                                                  int h) {
     while (l < h) {
         int m = (l + h) >> 1;
-        double v = cum[m];
-        if (m > 0) v = v / sum_w;
+        const double v = cum[m] / sum_w;
         if (v < cp) l = m + 1;
         else h = m;
     }
     return l;
+}
+
+// Block-wide inclusive scan step used only by the (rare) bpf trajectory draw.
+__device__ __forceinline__ double block_incl_scan(double v, double* s_w /*[32]*/, double* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const double incl = warp_incl_scan(v, lane);
+    __syncthreads();
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    double base = 0.0;
+    for (int k = 0; k < warp; ++k) base = base + s_w[k];
+    double tot = 0.0;
+    for (int k = 0; k < nwarp; ++k) tot = tot + s_w[k];
+    *total = tot;
+    return base + incl;
 }
 
 template <bool HESS>
@@ -206,7 +221,8 @@ __global__ void __launch_bounds__(kSvThreads, 1) sv_pf_kernel(SvArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwarp = blockDim.x >> 5;
     const int N = a.N, NOBS = a.NOBS, LAG = a.LAG, NB = a.NB, G = a.G;
-    const int SQ = a.SQ;
+    const int SQ = a.SQ, SQW = a.SQW;
+    const bool flps = (a.mode == kSvFlps);
 
     Team tm;
     tm.G = G;
@@ -234,14 +250,13 @@ __global__ void __launch_bounds__(kSvThreads, 1) sv_pf_kernel(SvArgs a) {
         const double* rvr = a.rvr + (size_t)prob * NOBS;
         const double* U = a.U + (size_t)prob * NOBS * N;
         double* o_filt = a.filt + (size_t)prob * NOBS;
-        double* o_smo = a.smo + (size_t)prob * NOBS;
-        double* o_grad = a.grad + (size_t)prob * 4 * NOBS;
+        double* o_smo = flps ? a.smo + (size_t)prob * NOBS : nullptr;
+        double* o_grad = flps ? a.grad + (size_t)prob * 4 * NOBS : nullptr;
         double* o_traj = a.traj + (size_t)prob * NOBS;
         long long* o_diag = a.diag + (size_t)prob * kDiagCount;
 
         SvWs w;
-        sv_ws_layout(N, NOBS, LAG, NB, a.RING, a.hess, a.mode, SQ, a.SQW, a.Xhist != nullptr, wsbase,
-                     &w);
+        sv_ws_layout(N, NOBS, LAG, NB, a.RING, a.hess, a.mode, SQ, SQW, a.Xhist != nullptr, wsbase, &w);
         double* Xh;
         int* Ah;
         int RING;
@@ -274,145 +289,170 @@ __global__ void __launch_bounds__(kSvThreads, 1) sv_pf_kernel(SvArgs a) {
         c.sr = c.sigmav * c.rho;
         const double logN = log((double)N);
 
-        // ---------------- time 0 (stochastic_volatility.pyx:306-323, Q1)
+        // ---------------- time 0
+        // flps (stochastic_volatility.pyx:306-323, Q1): every particle equals mu + stDev*0.0
+        // bpf  (:110-122): x0_j = mu + stDev * rvp[0 + j*NOBS], then sorted (handled as step i = 0)
         const double stdev0 = c.sigmav / sqrt(1.0 - (c.phi * c.phi));
         const double x0 = c.mu + stdev0 * 0.0;
         for (int b = tb.p0 + tid; b < tb.p1; b += blockDim.x) w.hist[b] = 0;
-        for (int j = tp.p0 + tid; j < tp.p1; j += blockDim.x) {
-            XT(0)[j] = x0;
-            AT(0)[j] = j;
-            w.sh0[j] = 1.0;
-            if (j < SQ) w.Xlow[j] = x0;
-            if (HESS) {
+        if (flps) {
+            for (int j = tp.p0 + tid; j < tp.p1; j += blockDim.x) {
+                XT(0)[j] = x0;
+                AT(0)[j] = j;
+                w.sh0[j] = 1.0;
+                if (j < SQ) w.Xlow[j] = x0;
+                if (HESS) {
 #pragma unroll
-                for (int cc = 0; cc < 4; ++cc) RT(0, cc)[j] = 0.0;
+                    for (int cc = 0; cc < 4; ++cc) RT(0, cc)[j] = 0.0;
+                }
             }
-        }
-        if (lead) {
-            for (int t = tid; t < NOBS; t += blockDim.x) {
-                o_smo[t] = 0.0;
-                o_grad[t] = 0.0;
-                o_grad[NOBS + t] = 0.0;
-                o_grad[2 * NOBS + t] = 0.0;
-                o_grad[3 * NOBS + t] = 0.0;
+            if (lead) {
+                for (int t = tid; t < NOBS; t += blockDim.x) {
+                    o_smo[t] = 0.0;
+                    o_grad[t] = 0.0;
+                    o_grad[NOBS + t] = 0.0;
+                    o_grad[2 * NOBS + t] = 0.0;
+                    o_grad[3 * NOBS + t] = 0.0;
+                }
+                if (tid == 0) o_traj[0] = x0;
             }
-            if (tid == 0) o_traj[0] = x0;
         }
         if (tid < 20) s_hacc[tid] = 0.0;
-        if (tid == 0) s_S[0] = (double)N;
-        double S_prev = (double)N;
         double loglike = 0.0;
-        long long near_ties = 0;
+        double shift_prev = 0.0;
+        long long near_ties = 0, key_ties2 = 0;   // key_ties2 counts each tie pair twice
         int max_occ_seen = 0;
-        long long key_ties = 0;
+        int wavefront_max = 0;
         int status = 0;
         team_barrier(tm, s_gather);
 
-        for (int i = 1; i <= NOBS; ++i) {
+        for (int i = flps ? 1 : 0; i <= NOBS; ++i) {
+            const bool init_step = (i == 0);
             const int t = i - 1;
             const double* shp = (t & 1) ? w.sh1 : w.sh0;
             double* shn = (i & 1) ? w.sh1 : w.sh0;
-            const double* Xp = XT(t);
+            const double* Xp = init_step ? nullptr : XT(t);
+            double S_t = 1.0;
 
-            // =========== phase A: weights of time t -> filter mean, smoother terms, scan
-            double acc[NACC];
+            if (!init_step) {
+                // =========== phase A: weights of time t (position order => deterministic sums):
+                //   S_t = sum sh, filter mean, fixed-lag smoother terms, then the cumulative sums.
+                //   All sums are accumulated un-normalised and divided by S_t afterwards.
+                double acc[NACC];
 #pragma unroll
-            for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
-            const int sb = tp.seg_begin(warp), se = tp.seg_end(warp);
-            {
-                double carry = 0.0;
-                for (int base = sb; base < se; base += 32) {
-                    const int j = base + lane;
-                    double wj = 0.0;
-                    if (j < se) {
-                        wj = shp[j] / S_prev;
-                        const double wx = wj * Xp[j];
-                        if (isfinite(wx)) acc[0] += wx;
+                for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+                const int sb = tp.seg_begin(warp), se = tp.seg_end(warp);
+                {
+                    double carry = 0.0;
+                    for (int base = sb; base < se; base += 32) {
+                        const int j = base + lane;
+                        double sj = 0.0;
+                        if (j < se) {
+                            sj = shp[j];
+                            if (!isfinite(sj)) sj = 0.0;
+                            const double wx = sj * Xp[j];
+                            if (isfinite(wx)) acc[0] += wx;
+                        }
+                        const double incl = warp_incl_scan(sj, lane);
+                        carry = carry + __shfl_sync(kFullMask, incl, 31);
                     }
-                    const double incl = warp_incl_scan(wj, lane);
-                    carry = carry + __shfl_sync(kFullMask, incl, 31);
+                    if (lane == 0) s_wtot[warp] = carry;
                 }
-                if (lane == 0) s_wtot[warp] = carry;
-            }
-            if (a.mode == kSvFlps && t >= LAG) {
-                // fixed-lag smoother, stochastic_volatility.pyx:445-534 (Q5: obs[t - LAG])
-                const double yl = obs[t - LAG];
-                for (int j = tp.p0 + tid; j < tp.p1; j += blockDim.x) {
-                    const double wj = shp[j] / S_prev;
-                    int b = j;
-                    for (int k = 0; k < LAG - 2; ++k) b = AT(t - k)[b];
-                    const double next = XT(t - LAG + 2)[b];
-                    const int bc = AT(t - LAG + 2)[b];
-                    const double curr = XT(t - LAG + 1)[bc];
-                    double sq, g[4];
-                    sv_score_main(c, curr, next, yl, sq, g);
-                    acc[1] += wj * curr;
-                    acc[2] += g[0] * wj;
-                    acc[3] += g[1] * wj;
-                    acc[4] += g[2] * wj;
-                    acc[5] += g[3] * wj;
-                    if (HESS) {
-                        double al[4];
+                if (flps && t >= LAG) {
+                    // fixed-lag smoother, stochastic_volatility.pyx:445-534 (Q5: obs[t - LAG])
+                    const double yl = obs[t - LAG];
+                    for (int j = tp.p0 + tid; j < tp.p1; j += blockDim.x) {
+                        double sj = shp[j];
+                        if (!isfinite(sj)) sj = 0.0;
+                        int b = j;
+                        for (int k = 0; k < LAG - 2; ++k) b = AT(t - k)[b];
+                        const double next = XT(t - LAG + 2)[b];
+                        const int bc = AT(t - LAG + 2)[b];
+                        const double curr = XT(t - LAG + 1)[bc];
+                        double sq, g[4];
+                        sv_score_main(c, curr, next, yl, sq, g);
+                        acc[1] += sj * curr;
+                        acc[2] += g[0] * sj;
+                        acc[3] += g[1] * sj;
+                        acc[4] += g[2] * sj;
+                        acc[5] += g[3] * sj;
+                        if (HESS) {
+                            double al[4];
 #pragma unroll
-                        for (int cc = 0; cc < 4; ++cc) al[cc] = RT(t - LAG + 2, cc)[b];
-                        sv_hessian_terms(c, curr, sq, yl, g, al, wj, &acc[6]);
+                            for (int cc = 0; cc < 4; ++cc) al[cc] = RT(t - LAG + 2, cc)[b];
+                            sv_hessian_terms(c, curr, sq, yl, g, al, sj, &acc[6]);
+                        }
                     }
                 }
-            }
-            block_sum<NACC>(acc, s_red);
-            if (warp == 0) {
-                const double v = (lane < nwarp) ? s_wtot[lane] : 0.0;
-                const double incl = warp_incl_scan(v, lane);
-                const double excl = __shfl_up_sync(kFullMask, incl, 1);
-                s_wbase[lane] = (lane == 0) ? 0.0 : excl;
-                if (lane == 31) s_vals[0] = incl;
-            }
-            if (tid < NACC) s_vals[1 + tid] = acc[tid];
-            team_allgather(tm, s_vals, 1 + NACC, s_gather);
-            for (int k = warp; k < 1 + NACC; k += nwarp) {
-                const double s = gathered_sum(s_gather, 1 + NACC, k, G, lane);
-                if (lane == 0) s_tot[k] = s;
-            }
-            if (warp == nwarp - 1) {
-                const double s = gathered_sum(s_gather, 1 + NACC, 0, tm.rank, lane);
-                if (lane == 0) s_tot[kMaxAllgather - 1] = s;
-            }
-            __syncthreads();
-            const double sum_w = s_tot[0];
-            const double P = s_tot[kMaxAllgather - 1];
-            if (lead && tid == 0) {
-                o_filt[t] = s_tot[1];
-                if (a.mode == kSvFlps && t >= LAG) {
-                    const int tt = t - LAG + 1;
-                    o_smo[tt] = s_tot[2];
-                    o_grad[tt] = s_tot[3];
-                    o_grad[NOBS + tt] = s_tot[4];
-                    o_grad[2 * NOBS + tt] = s_tot[5];
-                    o_grad[3 * NOBS + tt] = s_tot[6];
+                block_sum<NACC>(acc, s_red);
+                if (warp == 0) {
+                    const double v = (lane < nwarp) ? s_wtot[lane] : 0.0;
+                    const double incl = warp_incl_scan(v, lane);
+                    const double excl = __shfl_up_sync(kFullMask, incl, 1);
+                    s_wbase[lane] = (lane == 0) ? 0.0 : excl;
+                    if (lane == 31) s_vals[0] = incl;
                 }
-            }
-            if (HESS && tid < 20 && a.mode == kSvFlps && t >= LAG) s_hacc[tid] += s_tot[7 + tid];
-            if (i == NOBS) break;
-
-            // pass 2: cumulative weights (un-normalised; Q3 handled at lookup)
-            {
-                const double wb = s_wbase[warp];
-                double carry = 0.0;
-                for (int base = sb; base < se; base += 32) {
-                    const int j = base + lane;
-                    const double wj = (j < se) ? shp[j] / S_prev : 0.0;
-                    const double incl = warp_incl_scan(wj, lane);
-                    if (j < se) w.cum[j] = P + ((wb + carry) + incl);
-                    carry = carry + __shfl_sync(kFullMask, incl, 31);
+                if (tid < NACC) s_vals[1 + tid] = acc[tid];
+                team_allgather(tm, s_vals, 1 + NACC, s_gather);
+                for (int k = warp; k < 1 + NACC; k += nwarp) {
+                    const double s = gathered_sum(s_gather, 1 + NACC, k, G, lane);
+                    if (lane == 0) s_tot[k] = s;
                 }
-            }
-            team_barrier(tm, s_gather);
+                if (warp == nwarp - 1) {
+                    const double s = gathered_sum(s_gather, 1 + NACC, 0, tm.rank, lane);
+                    if (lane == 0) s_tot[kMaxAllgather - 1] = s;
+                }
+                __syncthreads();
+                S_t = s_tot[0];
+                const double P = s_tot[kMaxAllgather - 1];
+                if (t >= 1) loglike += shift_prev + log(S_t) - logN;   // :537 / :186
+                if (lead && tid == 0) {
+                    o_filt[t] = s_tot[1] / S_t;
+                    if (flps && t >= LAG) {
+                        const int tt = t - LAG + 1;
+                        o_smo[tt] = s_tot[2] / S_t;
+                        o_grad[tt] = s_tot[3] / S_t;
+                        o_grad[NOBS + tt] = s_tot[4] / S_t;
+                        o_grad[2 * NOBS + tt] = s_tot[5] / S_t;
+                        o_grad[3 * NOBS + tt] = s_tot[6] / S_t;
+                    }
+                }
+                if (tid == 0) s_S[t % kMaxLag] = S_t;
+                if (HESS && tid < 20 && flps && t >= LAG) s_hacc[tid] += s_tot[7 + tid] / S_t;
+                if (!flps) {
+                    // Q10: keep the normalised weights of the low slots of every time step
+                    for (int j = tp.p0 + tid; j < tp.p1 && j < SQW; j += blockDim.x) {
+                        double sj = shp[j];
+                        if (!isfinite(sj)) sj = 0.0;
+                        w.Wlow[(size_t)t * SQW + j] = sj / S_t;
+                    }
+                }
+                if (i == NOBS) break;
 
-            // =========== phase B: resample (systematic_corr :694-715), propagate (:354-358),
-            //             bin histogram
-            const double y1 = obs[i - 1];
+                // pass 2: cumulative (un-normalised) weights; normalised by S_t at lookup
+                {
+                    const double wb = s_wbase[warp];
+                    double carry = 0.0;
+                    for (int base = sb; base < se; base += 32) {
+                        const int j = base + lane;
+                        double sj = (j < se) ? shp[j] : 0.0;
+                        if (!isfinite(sj)) sj = 0.0;
+                        const double incl = warp_incl_scan(sj, lane);
+                        if (j < se) w.cum[j] = P + ((wb + carry) + incl);
+                        carry = carry + __shfl_sync(kFullMask, incl, 31);
+                    }
+                }
+                team_barrier(tm, s_gather);
+            }
+
+            // =========== phase B: resample (systematic_corr :694-715), propagate (:354-358 /
+            //             :142-146), bin histogram
+            const double y1 = init_step ? 0.0 : obs[i - 1];
             const double yi = obs[i];
-            if (tid == 0) {
+            double tmin = INFINITY, tmax = -INFINITY;
+            if (flps && tid == 0) {
+                // bin range predicted from the sorted parents: exact range of the propagation
+                // mean over [x_min, x_max], widened by 6.5 sd (outliers clamp into end bins)
                 const double xmin = Xp[0], xmax = Xp[N - 1];
                 const double cc = c.sr * y1;
                 auto f = [&](double x) { return (c.mu + c.phi * (x - c.mu)) + cc * exp(-0.5 * x); };
@@ -433,93 +473,173 @@ __global__ void __launch_bounds__(kSvThreads, 1) sv_pf_kernel(SvArgs a) {
                 s_bin[0] = isfinite(lo) ? lo : 0.0;
                 s_bin[1] = scale;
             }
-            const double u = rvr[i];
-            if (tp.p1 > tp.p0) {
-                if (tid == 0)
-                    s_lohi[0] = search_cum_global(w.cum, sum_w, (u + (double)tp.p0) / (double)N, 0, N - 1);
-                if (tid == 32)
-                    s_lohi[1] =
-                        search_cum_global(w.cum, sum_w, (u + (double)(tp.p1 - 1)) / (double)N, 0, N - 1);
-            }
-            __syncthreads();
-            const double bin_lo = s_bin[0], bin_scale = s_bin[1];
-            double tmin = INFINITY;
-            if (tp.p1 > tp.p0) {
-                const int wlo = s_lohi[0], whi = s_lohi[1];
-                const int wlen = whi - wlo + 1;
-                const bool staged = (wlen <= kStageDoubles);
-                if (staged) {
-                    for (int k = tid; k < wlen; k += blockDim.x) {
-                        const int m = wlo + k;
-                        double v = w.cum[m];
-                        if (m > 0) v = v / sum_w;
-                        s_stage[k] = v;
-                    }
-                    __syncthreads();
-                }
-                const double* Ui = U + (size_t)i * N;
+            if (init_step) {
+                // bpf time 0: unsorted initial cloud
                 for (int j = tp.p0 + tid; j < tp.p1; j += blockDim.x) {
-                    const double cp = (u + (double)j) / (double)N;
-                    int aj;
-                    double cv_hi, cv_lo;
-                    if (staged) {
-                        int l = 0, h = wlen - 1;
-                        while (l < h) {
-                            const int m = (l + h) >> 1;
-                            if (s_stage[m] < cp) l = m + 1;
-                            else h = m;
-                        }
-                        aj = wlo + l;
-                        cv_hi = s_stage[l];
-                        cv_lo = (l > 0) ? s_stage[l - 1] : -1.0;
-                    } else {
-                        aj = search_cum_global(w.cum, sum_w, cp, wlo, whi);
-                        cv_hi = w.cum[aj];
-                        if (aj > 0) cv_hi = cv_hi / sum_w;
-                        cv_lo = -1.0;
-                        if (aj > 0) {
-                            cv_lo = w.cum[aj - 1];
-                            if (aj - 1 > 0) cv_lo = cv_lo / sum_w;
-                        }
-                    }
-                    // diagnostics: decisions within 64 ulp of a cumulative-weight tie
-                    {
-                        const double tol = 64.0 * 2.220446049250313e-16 * cp;
-                        if (fabs(cv_hi - cp) <= tol || (cv_lo >= 0.0 && fabs(cp - cv_lo) <= tol))
-                            near_ties++;
-                    }
-                    const double xp = Xp[aj];
-                    double mean = c.mu + c.phi * (xp - c.mu);
-                    mean += c.sr * exp(-0.5 * xp) * y1;
-                    const double xn = mean + c.sd * ld_stream_f64(&Ui[j]);
-                    const int b = sv_bin(xn, bin_lo, bin_scale, NB);
-                    const int r = atomicAdd(&w.hist[b], 1);
+                    const double xn = c.mu + stdev0 * ld_stream_f64(&U[j]);
                     w.xnew[j] = xn;
-                    w.aun[j] = aj;
-                    w.rnk[j] = r;
+                    w.aun[j] = j;
                     tmin = fmin(tmin, xn);
+                    tmax = fmax(tmax, xn);
+                }
+            } else {
+                const double u = rvr[i];
+                if (tp.p1 > tp.p0) {
+                    if (tid == 0)
+                        s_lohi[0] = search_cum_global(w.cum, S_t, (u + (double)tp.p0) / (double)N, 0, N - 1);
+                    if (tid == 32)
+                        s_lohi[1] =
+                            search_cum_global(w.cum, S_t, (u + (double)(tp.p1 - 1)) / (double)N, 0, N - 1);
+                }
+                __syncthreads();
+                if (tp.p1 > tp.p0) {
+                    const int wlo = s_lohi[0], whi = s_lohi[1];
+                    const int wlen = whi - wlo + 1;
+                    const bool staged = (wlen <= kStageDoubles);
+                    if (staged) {
+                        for (int k = tid; k < wlen; k += blockDim.x) s_stage[k] = w.cum[wlo + k] / S_t;
+                        __syncthreads();
+                    }
+                    const double bin_lo = s_bin[0], bin_scale = s_bin[1];
+                    const double* Ui = U + (size_t)i * N;
+                    for (int j = tp.p0 + tid; j < tp.p1; j += blockDim.x) {
+                        const double cp = (u + (double)j) / (double)N;
+                        int aj;
+                        double cv_hi, cv_lo;
+                        if (staged) {
+                            int l = 0, h = wlen - 1;
+                            while (l < h) {
+                                const int m = (l + h) >> 1;
+                                if (s_stage[m] < cp) l = m + 1;
+                                else h = m;
+                            }
+                            aj = wlo + l;
+                            cv_hi = s_stage[l];
+                            cv_lo = (l > 0) ? s_stage[l - 1] : -1.0;
+                        } else {
+                            aj = search_cum_global(w.cum, S_t, cp, wlo, whi);
+                            cv_hi = w.cum[aj] / S_t;
+                            cv_lo = (aj > 0) ? w.cum[aj - 1] / S_t : -1.0;
+                        }
+                        {   // diagnostics: decisions within 64 ulp of a cumulative-weight tie
+                            const double tol = 64.0 * 2.220446049250313e-16 * cp;
+                            if (fabs(cv_hi - cp) <= tol || (cv_lo >= 0.0 && fabs(cp - cv_lo) <= tol))
+                                near_ties++;
+                        }
+                        const double xp = Xp[aj];
+                        double mean = c.mu + c.phi * (xp - c.mu);
+                        w.aun[j] = aj;
+                        if (flps || a.mode == kSvBpfIntended) {
+                            mean += c.sr * exp(-0.5 * xp) * y1;
+                            const double xn = mean + c.sd * ld_stream_f64(&Ui[j]);
+                            w.xnew[j] = xn;
+                            tmin = fmin(tmin, xn);
+                            tmax = fmax(tmax, xn);
+                            if (flps) {
+                                const int b = sv_bin(xn, bin_lo, bin_scale, NB);
+                                w.rnk[j] = atomicAdd(&w.hist[b], 1);
+                            }
+                        } else {
+                            // bpf parity mode (Q2): the leverage term reads x_new[a_j] of THIS step
+                            // if a_j < j (else 0.0).  Resolve the dependency chains in rounds.
+                            w.tkey[j] = mean;              // mean without the leverage term
+                            if (aj >= j) {
+                                mean += c.sr * exp(-0.5 * 0.0) * y1;
+                                const double xn = mean + c.sd * ld_stream_f64(&Ui[j]);
+                                w.xnew[j] = xn;
+                                w.rnk[j] = 0;              // resolved in round 0
+                                tmin = fmin(tmin, xn);
+                                tmax = fmax(tmax, xn);
+                            } else {
+                                w.rnk[j] = 0x7fffffff;     // unresolved
+                            }
+                        }
+                    }
+                }
+                if (a.mode == kSvBpfParity) {
+                    const double* Ui = U + (size_t)i * N;
+                    for (int round = 1;; ++round) {
+                        team_barrier(tm, s_gather);
+                        double rem[1] = {0.0};
+                        for (int j = tp.p0 + tid; j < tp.p1; j += blockDim.x) {
+                            if (w.rnk[j] != 0x7fffffff) continue;
+                            const int aj = w.aun[j];
+                            if (w.rnk[aj] < round) {
+                                double mean = w.tkey[j];
+                                mean += c.sr * exp(-0.5 * w.xnew[aj]) * y1;
+                                const double xn = mean + c.sd * ld_stream_f64(&Ui[j]);
+                                w.xnew[j] = xn;
+                                w.rnk[j] = round;
+                                tmin = fmin(tmin, xn);
+                                tmax = fmax(tmax, xn);
+                            } else {
+                                rem[0] += 1.0;
+                            }
+                        }
+                        block_sum<1>(rem, s_red);
+                        if (tid == 0) s_vals[0] = rem[0];
+                        team_allgather(tm, s_vals, 1, s_gather);
+                        double left = 0.0;
+                        for (int cc = 0; cc < G; ++cc) left += s_gather[cc];
+                        __syncthreads();
+                        wavefront_max = max(wavefront_max, round);
+                        if (left == 0.0) break;
+                    }
                 }
             }
-            {
+            {   // tile min / max of the new keys
                 tmin = warp_min(tmin);
-                if (lane == 0) s_red[warp] = tmin;
+                tmax = warp_max(tmax);
+                if (lane == 0) {
+                    s_red[warp] = tmin;
+                    s_red[32 + warp] = tmax;
+                }
                 __syncthreads();
                 if (warp == 0) {
                     double v = (lane < nwarp) ? s_red[lane] : INFINITY;
+                    double v2 = (lane < nwarp) ? s_red[32 + lane] : -INFINITY;
                     v = warp_min(v);
-                    if (lane == 0) s_vals[0] = v;
+                    v2 = warp_max(v2);
+                    if (lane == 0) {
+                        s_vals[0] = v;
+                        s_vals[1] = v2;
+                    }
                 }
             }
-            team_allgather(tm, s_vals, 1, s_gather);
+            team_allgather(tm, s_vals, 2, s_gather);
             if (warp == 0) {
-                const double v = gathered_min(s_gather, 1, 0, G, lane);
-                if (lane == 0) s_tot[0] = v;
+                const double v = gathered_min(s_gather, 2, 0, G, lane);
+                const double v2 = gathered_max(s_gather, 2, 1, G, lane);
+                if (lane == 0) {
+                    s_tot[0] = v;
+                    s_tot[3] = v2;
+                }
             }
+            __syncthreads();
+            const double kmin = s_tot[0];
+            if (!flps) {
+                // bootstrap filter: data-driven bin range [min, max], then the histogram pass
+                const double kmax = s_tot[3];
+                const double width = kmax - kmin;
+                double scale = (double)NB / width;
+                if (!(width > 0.0) || !isfinite(scale) || !isfinite(kmin)) scale = 0.0;
+                if (tid == 0) {
+                    s_bin[0] = isfinite(kmin) ? kmin : 0.0;
+                    s_bin[1] = scale;
+                }
+                __syncthreads();
+                for (int j = tp.p0 + tid; j < tp.p1; j += blockDim.x) {
+                    const int b = sv_bin(w.xnew[j], s_bin[0], s_bin[1], NB);
+                    w.rnk[j] = atomicAdd(&w.hist[b], 1);
+                }
+                team_barrier(tm, s_gather);
+            }
+            const double bin_lo = s_bin[0], bin_scale = s_bin[1];
 
             // =========== phase C: scan of the bin histogram -> bin offsets
             const int bsb = tb.seg_begin(warp), bse = tb.seg_end(warp);
-            int occ = 0;
             {
+                int occ = 0;
                 int carry = 0;
                 for (int base = bsb; base < bse; base += 32) {
                     const int b = base + lane;
@@ -535,7 +655,6 @@ __global__ void __launch_bounds__(kSvThreads, 1) sv_pf_kernel(SvArgs a) {
                 }
             }
             __syncthreads();
-            const double kmin = s_tot[0];
             if (warp == 0) {
                 const int v = (lane < nwarp) ? s_iwtot[lane] : 0;
                 const int incl = warp_incl_scan(v, lane);
@@ -581,7 +700,7 @@ __global__ void __launch_bounds__(kSvThreads, 1) sv_pf_kernel(SvArgs a) {
             team_barrier(tm, s_gather);
 
             // =========== phase D: scatter into bins; Q4 shift (last log-weight above lw[0])
-            const double lw0 = sv_logw(kmin, yi);
+            const double lw0 = init_step ? 0.0 : sv_logw(kmin, yi);
             double pmax = -INFINITY;
             for (int j = tp.p0 + tid; j < tp.p1; j += blockDim.x) {
                 const double key = w.xnew[j];
@@ -590,9 +709,12 @@ __global__ void __launch_bounds__(kSvThreads, 1) sv_pf_kernel(SvArgs a) {
                 w.tkey[slot] = key;
                 w.tpay[slot] = w.aun[j];
                 if (HESS) w.tidx[slot] = j;
-                const double lw = sv_logw(key, yi);
-                w.cum[slot] = lw;   // cum is free until the next phase A: reuse as log-weight scratch
-                if (lw > lw0 && isfinite(lw)) pmax = fmax(pmax, key);
+                double lw = 0.0;
+                if (!init_step) {
+                    lw = sv_logw(key, yi);
+                    if (lw > lw0 && isfinite(lw)) pmax = fmax(pmax, key);
+                }
+                w.cum[slot] = lw;   // cum is free until the next phase A: log-weight scratch
             }
             {
                 pmax = warp_max(pmax);
@@ -611,11 +733,12 @@ __global__ void __launch_bounds__(kSvThreads, 1) sv_pf_kernel(SvArgs a) {
             }
             __syncthreads();
             const double kq = s_tot[0];
-            const double shift = (kq > -INFINITY) ? sv_logw(kq, yi) : lw0;
+            const double shift = init_step ? 0.0 : ((kq > -INFINITY) ? sv_logw(kq, yi) : lw0);
 
             // =========== phase E: order each bin (all-pairs rank), write the sorted generation,
             //             weights (:427-437), alpha recursion (:361-390)
-            double eacc[2] = {0.0, 0.0};   // sum of shifted weights, key ties
+            const int* rootp = (t & 1) ? w.root1 : w.root0;
+            int* rootn = (i & 1) ? w.root1 : w.root0;
             for (int s = tp.p0 + tid; s < tp.p1; s += blockDim.x) {
                 const double key = w.tkey[s];
                 const int pay = w.tpay[s];
@@ -629,7 +752,7 @@ __global__ void __launch_bounds__(kSvThreads, 1) sv_pf_kernel(SvArgs a) {
                     const double k2 = w.tkey[q];
                     if (k2 < key) rank++;
                     else if (k2 == key) {
-                        eacc[1] += 0.5;
+                        key_ties2++;
                         bool less;
                         if (HESS) less = w.tidx[q] < oj;
                         else {
@@ -643,12 +766,22 @@ __global__ void __launch_bounds__(kSvThreads, 1) sv_pf_kernel(SvArgs a) {
                 XT(i)[p] = key;
                 AT(i)[p] = pay;
                 if (p < SQ) w.Xlow[(size_t)i * SQ + p] = key;
-                if (p == 0 && lead) o_traj[i] = key;   // Q11: traj[i] = X_i[0]
-                const double lw = w.cum[s];
-                const double sh = exp(lw - shift);
-                if (isfinite(sh)) eacc[0] += sh;
+                if (p == 0 && i >= 1) o_traj[i] = key;   // Q11: traj[i] = X_i[0]
+                double sh = 1.0;
+                if (!init_step) {
+                    sh = exp(w.cum[s] - shift);
+                    if (!flps && !isfinite(sh)) sh = 0.0;   // :173-176
+                }
                 shn[p] = sh;
-                if (i >= NOBS - LAG) w.shtail[(size_t)(i - (NOBS - LAG)) * N + p] = sh;
+                if (flps && i >= NOBS - LAG) w.shtail[(size_t)(i - (NOBS - LAG)) * N + p] = sh;
+                if (!flps) {
+                    if (init_step) {
+                        w.X0[p] = key;
+                        rootn[p] = p;
+                    } else {
+                        rootn[p] = rootp[pay];
+                    }
+                }
                 if (HESS) {
                     // Q7: particles[i - 1 + ancestors[j]] read through the flat layout
                     const long long q = (long long)i - 1 + pay;
@@ -675,24 +808,13 @@ __global__ void __launch_bounds__(kSvThreads, 1) sv_pf_kernel(SvArgs a) {
                     RT(i, 3)[p] = a3 + RT(t, 3)[pay];
                 }
             }
-            block_sum<2>(eacc, s_red);
-            if (tid < 2) s_vals[tid] = eacc[tid];
-            team_allgather(tm, s_vals, 2, s_gather);
-            if (warp < 2) {
-                const double s = gathered_sum(s_gather, 2, warp, G, lane);
-                if (lane == 0) s_tot[warp] = s;
-            }
-            __syncthreads();
-            const double S_i = s_tot[0];
-            key_ties += (long long)s_tot[1];
-            loglike += shift + log(S_i) - logN;   // :537
-            S_prev = S_i;
-            if (tid == 0) s_S[i % kMaxLag] = S_i;
-            __syncthreads();
+            shift_prev = shift;
+            team_barrier(tm, s_gather);
         }   // time loop
+        team_barrier(tm, s_gather);
 
         // =========== tail (stochastic_volatility.pyx:540-626, Q6)
-        if (a.mode == kSvFlps && status == 0) {
+        if (flps && status == 0) {
             const int T = NOBS - 1;
             const double* shT = (T & 1) ? w.sh1 : w.sh0;
             const double S_T = s_S[T % kMaxLag];
@@ -709,24 +831,27 @@ __global__ void __launch_bounds__(kSvThreads, 1) sv_pf_kernel(SvArgs a) {
                 for (int j = tp.p0 + tid; j < tp.p1; j += blockDim.x) {
                     int b = j;
                     int bprev = j;     // index at lag k-1
-                    int b_l2 = j;      // index at lag LAG-2 (for alpha)
                     for (int h = 0; h < k; ++h) {
                         bprev = b;
                         b = AT(T - h)[b];
                     }
                     const double curr = XT(ip)[b];
-                    tacc[0] += (shT[j] / S_T) * curr;
+                    double sT = shT[j];
+                    if (!isfinite(sT)) sT = 0.0;
+                    tacc[0] += (sT / S_T) * curr;
                     if (k >= 1) {
                         const double next = XT(ip + 1)[bprev];
                         double sq, g[4];
                         sv_score_tail(c, curr, next, y1, sq, g);
-                        const double wi = sh_ip[j] / S_ip;
+                        double si = sh_ip[j];
+                        if (!isfinite(si)) si = 0.0;
+                        const double wi = si / S_ip;
                         tacc[1] += g[0] * wi;
                         tacc[2] += g[1] * wi;
                         tacc[3] += g[2] * wi;
                         tacc[4] += g[3] * wi;
                         if (HESS) {
-                            b_l2 = j;
+                            int b_l2 = j;   // index at lag LAG-2 (for alpha)
                             for (int h = 0; h < LAG - 2; ++h) b_l2 = AT(T - h)[b_l2];
                             double al[4];
 #pragma unroll
@@ -760,17 +885,58 @@ __global__ void __launch_bounds__(kSvThreads, 1) sv_pf_kernel(SvArgs a) {
             }
         }
 
+        // =========== bpf trajectory (:189-192): Q10 flat weights + Q11
+        int traj_idx = 0;
+        if (!flps && status == 0 && lead) {
+            // cumulative sum over W_flat[k] = w_{k % NOBS}[k / NOBS], k < N (sampleParticle_corr)
+            const double rnd = rvr[0];
+            double total = 0.0;
+            {
+                double part[1] = {0.0};
+                for (int k = tid; k < N; k += blockDim.x)
+                    part[0] += w.Wlow[(size_t)(k % NOBS) * SQW + (k / NOBS)];
+                block_sum<1>(part, s_red);
+                total = part[0];
+            }
+            double carry = 0.0;
+            int found = N;
+            for (int base = 0; base < N; base += blockDim.x) {
+                const int k = base + tid;
+                const double v = (k < N) ? w.Wlow[(size_t)(k % NOBS) * SQW + (k / NOBS)] : 0.0;
+                double chunk_total;
+                const double incl = carry + block_incl_scan(v, s_wtot, &chunk_total);
+                carry = carry + chunk_total;
+                if (k < N) {
+                    const double cn = (k == 0) ? incl : incl / total;   // Q3
+                    if (!(cn < rnd)) found = min(found, k);
+                }
+                __syncthreads();
+            }
+            found = -warp_max(-found);
+            if (lane == 0) s_iwtot[warp] = found;
+            __syncthreads();
+            if (tid == 0) {
+                int f = N;
+                for (int k = 0; k < nwarp; ++k) f = min(f, s_iwtot[k]);
+                if (f >= N) f = N - 1;   // the reference would read out of bounds; out of contract
+                const int* rootT = ((NOBS - 1) & 1) ? w.root1 : w.root0;
+                o_traj[0] = w.X0[rootT[f]];
+                s_iwbase[0] = f;
+            }
+            __syncthreads();
+            traj_idx = s_iwbase[0];
+        }
+
         // =========== outputs
         if (lead) {
             if (tid == 0) {
                 a.loglike[prob] = (status == 0) ? loglike : NAN;
                 o_diag[kDiagMaxBin] = max_occ_seen;
                 o_diag[kDiagStatus] = status;
-                o_diag[kDiagKeyTies] = key_ties;
-                o_diag[kDiagWavefront] = 0;
-                o_diag[kDiagTrajIdx] = 0;
+                o_diag[kDiagWavefront] = wavefront_max;
+                o_diag[kDiagTrajIdx] = traj_idx;
             }
-            if (tid < 16) {
+            if (flps && tid < 16) {
                 // expand the upper triangles into the symmetric 4x4 outputs
                 const int r = tid >> 2, cidx = tid & 3;
                 const int k = min(r, cidx), l = max(r, cidx);
@@ -779,15 +945,15 @@ __global__ void __launch_bounds__(kSvThreads, 1) sv_pf_kernel(SvArgs a) {
                 a.hess2[(size_t)prob * 16 + tid] = HESS ? s_hacc[10 + tri] : 0.0;
             }
         }
-        // near-tie counter: every CTA contributes
-        {
-            double nt[1] = {(double)near_ties};
-            block_sum<1>(nt, s_red);
-            if (tid == 0) s_vals[0] = nt[0];
-            team_allgather(tm, s_vals, 1, s_gather);
-            if (warp == 0) {
-                const double s = gathered_sum(s_gather, 1, 0, G, lane);
-                if (lane == 0 && lead) o_diag[kDiagNearTies] = (long long)s;
+        {   // tie counters: every CTA contributes
+            double nt[2] = {(double)near_ties, (double)key_ties2};
+            block_sum<2>(nt, s_red);
+            if (tid < 2) s_vals[tid] = nt[tid];
+            team_allgather(tm, s_vals, 2, s_gather);
+            if (warp < 2) {
+                const double s = gathered_sum(s_gather, 2, warp, G, lane);
+                if (lane == 0 && lead) o_diag[warp == 0 ? kDiagNearTies : kDiagKeyTies] =
+                    (long long)(warp == 0 ? s : s * 0.5);
             }
             __syncthreads();
         }

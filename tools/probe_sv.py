@@ -49,6 +49,8 @@ def run(n, nobs=1001, batch=1, hess=False, hist=False, ctas=0, reps=3, lag=10):
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which == "one":
+        run(int(sys.argv[2]), hess=bool(int(sys.argv[3])), reps=int(sys.argv[4]))
     if which in ("all", "single"):
         for n in (4096, 65536, 262144, 1048576):
             run(n)
