@@ -146,8 +146,10 @@ def split_rvs(rvs, n_obs, n_particles):
     """rvs [B, n_obs, N+1] (or [n_obs, N+1]) -> (r_raw [B, n_obs], u [B, n_obs, N] time-major)."""
     lib = _lib.load()
     _need_cuda(rvs)
-    batch = 1 if rvs.dim() == 2 else rvs.shape[0]
-    assert rvs.numel() == batch * n_obs * (n_particles + 1) and rvs.dtype == _F64
+    per = n_obs * (n_particles + 1)
+    batch = rvs.numel() // per
+    if batch * per != rvs.numel() or batch < 1 or rvs.dtype != _F64:
+        raise _lib.PmmhError("split_rvs: expected float64 rvs with a multiple of n_obs*(N+1) entries")
     r_raw = torch.empty((batch, n_obs), dtype=_F64, device=rvs.device)
     u = torch.empty((batch, n_obs, n_particles), dtype=_F64, device=rvs.device)
     _lib.check(lib.pmmh_split_rvs(_ptr(rvs), n_obs, n_particles, batch, _ptr(r_raw), _ptr(u),
