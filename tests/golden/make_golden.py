@@ -212,7 +212,7 @@ def gen_estimators():
     model.params = np.array(beta, copy=True)
     model.params_prior = gi.logit_prior(d)
     model.true_params = np.array(beta, copy=True)
-    model.create_inference_model(params_to_estimate=range(d))
+    model.create_inference_model()   # as scripts/helper_higgs.py:50 does
     model.using_gradients = True
     est = DirectComputation(model)
     assert est.dim_rvs == m
