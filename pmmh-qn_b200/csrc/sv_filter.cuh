@@ -11,6 +11,8 @@ constexpr int kSvThreads = 1024;         // threads per CTA (1 CTA per SM)
 constexpr int kStageDoubles = 12288;     // smem staging window for the cumulative weights
 constexpr int kBinCap = 4096;            // max occupancy of one sort bin before we give up
 constexpr int kMaxAllgatherHost = 48;    // must equal kMaxAllgather (common.cuh)
+constexpr int kFastChunk = 3072;         // fast path: bucket capacity == records per smem sort pass
+constexpr int kFastMaxBuckets = 4096;
 
 enum SvMode { kSvFlps = 0, kSvBpfParity = 1, kSvBpfIntended = 2 };
 
@@ -28,7 +30,8 @@ enum SvDiag {
 struct SvArgs {
     int N, NOBS, LAG, B;
     int G, n_teams;
-    int NB;          // sort bins
+    int NB;          // sort bins (general kernel)
+    int NBK;         // coarse buckets (fast kernel)
     int RING;        // ring depth of the X / A / R histories (LAG + 1), or NOBS with full history
     int mode, hess;
     int SQ;          // low slots of X kept for all times (Q7 / Q11)
@@ -104,5 +107,10 @@ __host__ __device__ inline size_t sv_ws_layout(int N, int NOBS, int LAG, int NB,
 // Host-side launcher (sv_filter.cu)
 cudaError_t sv_launch(const SvArgs& a, int grid, cudaStream_t stream);
 int sv_dynamic_smem_bytes(int G);
+
+// fast path (sv_fast.cu)
+size_t sv_fast_ws_bytes(int N, int NBK, int RING);
+int sv_fast_smem_bytes(int G, int NBK);
+cudaError_t sv_fast_launch(const SvArgs& a, int grid, cudaStream_t stream);
 
 }  // namespace pmmh
