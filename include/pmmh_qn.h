@@ -60,6 +60,9 @@ extern "C" {
 #define PMMH_DIAG_KEY_TIES 3    /* equal keys met while sorting */
 #define PMMH_DIAG_WAVEFRONT 4   /* bpf parity mode: deepest dependency chain */
 #define PMMH_DIAG_TRAJ_IDX 5    /* bpf: sampled trajectory index */
+#define PMMH_DIAG_KERNEL 6      /* kernel that produced the outputs: 1 general, 2 exchange */
+#define PMMH_DIAG_FAST_INFO 7   /* exchange kernel: abandon reason (1 run / 2 chunk overflow) |
+                                   step << 8 | longest mailbox run << 32 */
 #define PMMH_DIAG_COUNT 8
 
 int pmmh_version(void);
@@ -68,6 +71,19 @@ const char* pmmh_last_error(void);
 int pmmh_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
 /* ---------------------------------------------------------------- SV particle methods -- */
+
+/* Kernel selection for pmmh_flps_sv_corr (process-wide; default 0).
+ *   0  automatic: the two-barrier "exchange" kernel for log-likelihood + gradient
+ *      (compute_hessian == 0), the general kernel for everything else and as the fallback
+ *      for problems the exchange kernel abandons (degenerate particle clouds)
+ *   1  general kernel only
+ *   2  diagnostics: like 0 but without the fallback pass (abandoned problems keep status 1)
+ * Call before pmmh_sv_workspace_bytes: the workspace size depends on it. */
+int pmmh_sv_set_algorithm(int algorithm);
+
+/* Development hook: d_clocks = device buffer of [n_ctas][16] int64 (or NULL to switch off);
+ * the exchange kernel adds the SM clock cycles each CTA spent per phase. */
+int pmmh_sv_debug_profile(long long* d_clocks);
 
 /* Bytes of device workspace pmmh_flps_sv_corr / pmmh_bpf_sv_corr need for these sizes.
  * mode: 0 = flps, 1 = bpf.  have_history: caller passes d_x_hist / d_a_hist.

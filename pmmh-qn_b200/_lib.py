@@ -17,7 +17,7 @@ c_size = ctypes.c_size_t
 c_vp = ctypes.c_void_p
 c_dbl = ctypes.c_double
 
-DIAG_NEAR_TIES, DIAG_MAX_BIN, DIAG_STATUS, DIAG_KEY_TIES, DIAG_WAVEFRONT, DIAG_TRAJ_IDX = range(6)
+DIAG_NEAR_TIES, DIAG_MAX_BIN, DIAG_STATUS, DIAG_KEY_TIES, DIAG_WAVEFRONT, DIAG_TRAJ_IDX, DIAG_KERNEL = range(7)
 DIAG_COUNT = 8
 BPF_PARITY, BPF_INTENDED = 0, 1
 
@@ -26,6 +26,8 @@ SIGNATURES = {
     "pmmh_version": (c_int, []),
     "pmmh_last_error": (ctypes.c_char_p, []),
     "pmmh_device_info": (c_int, [ctypes.POINTER(c_int)] * 3),
+    "pmmh_sv_set_algorithm": (c_int, [c_int]),
+    "pmmh_sv_debug_profile": (c_int, [c_vp]),
     "pmmh_sv_workspace_bytes": (c_int, [c_int] * 8 + [ctypes.POINTER(c_size)]),
     "pmmh_flps_sv_corr": (c_int, [c_vp, c_ll, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int,
                                   c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,

@@ -58,7 +58,16 @@ int get_device_info(DeviceInfo* out) {
 struct SvPlan {
     int G, n_teams, grid, NB, RING, SQ, SQW;
     size_t stamp_bytes, sync_bytes, team_stride, total;
+    // exchange kernel (sv_fast.cu); use_fast = 0 when the problem is not eligible
+    int use_fast, NSUB;
+    size_t fast_sync_bytes, fast_team_stride, fast_total, general_total;
 };
+
+// 0 = automatic (exchange kernel where eligible, general kernel otherwise and as its fallback),
+// 1 = general kernel only, 2 = exchange kernel where eligible WITHOUT the fallback pass (diagnostics)
+int g_sv_algorithm = 0;
+long long* g_sv_prof = nullptr;   // development: per-CTA phase clocks of the exchange kernel
+constexpr int kMaxDynSmem = 227 * 1024;
 
 int sv_make_plan(int nobs, int n, int lag, int batch, int hess, int mode, int have_hist, int ctas,
                  SvPlan* p) {
@@ -97,7 +106,25 @@ int sv_make_plan(int nobs, int n, int lag, int batch, int hess, int mode, int ha
                     pmmh::sv_align((size_t)n_teams * 2 * G * pmmh::kMaxAllgatherHost * sizeof(double));
     p->team_stride = pmmh::sv_ws_layout(n, nobs, lag, p->NB, p->RING, hess, mode, p->SQ, p->SQW,
                                         have_hist, nullptr, nullptr);
-    p->total = p->sync_bytes + (size_t)n_teams * p->team_stride;
+    p->general_total = p->sync_bytes + (size_t)n_teams * p->team_stride;
+    p->total = p->general_total;
+    p->use_fast = 0;
+    p->NSUB = 0;
+    p->fast_sync_bytes = p->fast_team_stride = p->fast_total = 0;
+    if (mode == pmmh::kSvFlps && !hess && g_sv_algorithm != 1) {
+        const int S = pmmh::sv_fast_nsub(n, G);
+        const long long nv = (long long)S * G * pmmh::kFastCap;
+        if (S <= pmmh::kFastMaxSub && nv < (1ll << 31) &&
+            pmmh::sv_fast_smem_bytes(n, G, S) <= kMaxDynSmem &&
+            2 * S + 10 <= pmmh::kMaxAllgatherHost) {
+            p->use_fast = 1;
+            p->NSUB = S;
+            p->fast_sync_bytes = pmmh::sv_fast_sync_bytes(G, n_teams);
+            p->fast_team_stride = pmmh::sv_fast_ws_bytes(n, G, S, p->RING, lag);
+            p->fast_total = p->fast_sync_bytes + (size_t)n_teams * p->fast_team_stride;
+            if (p->fast_total > p->total) p->total = p->fast_total;
+        }
+    }
     return PMMH_OK;
 }
 
@@ -117,7 +144,6 @@ int sv_run(int mode, const double* d_obs, long long obs_stride, const double* d_
     if (rc != PMMH_OK) return rc;
     if (ws_bytes < p.total) return fail(PMMH_ERR_WORKSPACE, "workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
-    PMMH_CUDA(cudaMemsetAsync(d_ws, 0, p.stamp_bytes, st));
     pmmh::SvArgs a;
     memset(&a, 0, sizeof(a));
     a.N = n;
@@ -147,9 +173,22 @@ int sv_run(int mode, const double* d_obs, long long obs_stride, const double* d_
     a.diag = d_diag;
     a.Xhist = d_xh;
     a.Ahist = d_ah;
+    a.prof = g_sv_prof;
     a.ws = (char*)d_ws;
+    if (p.use_fast) {
+        // exchange kernel first; problems it abandons (diag status 1) are re-run by the general
+        // kernel in the same stream, reusing the workspace
+        a.NSUB = p.NSUB;
+        a.ws_sync_bytes = p.fast_sync_bytes;
+        a.ws_team_stride = p.fast_team_stride;
+        PMMH_CUDA(cudaMemsetAsync(d_ws, 0, p.fast_sync_bytes, st));
+        PMMH_CUDA(pmmh::sv_fast_launch(a, p.grid, st));
+        if (g_sv_algorithm == 2) return PMMH_OK;   // diagnostics: no fallback pass
+        a.only_failed = 1;
+    }
     a.ws_sync_bytes = p.sync_bytes;
     a.ws_team_stride = p.team_stride;
+    PMMH_CUDA(cudaMemsetAsync(d_ws, 0, p.stamp_bytes, st));
     PMMH_CUDA(pmmh::sv_launch(a, p.grid, st));
     return PMMH_OK;
 }
@@ -181,6 +220,17 @@ int pmmh_device_info(int* sm_count, int* cc_major, int* cc_minor) {
     if (sm_count) *sm_count = di.sm;
     if (cc_major) *cc_major = di.major;
     if (cc_minor) *cc_minor = di.minor;
+    return PMMH_OK;
+}
+
+int pmmh_sv_set_algorithm(int algorithm) {
+    if (algorithm < 0 || algorithm > 2) return fail(PMMH_ERR_INVALID, "algorithm must be 0, 1 or 2");
+    g_sv_algorithm = algorithm;
+    return PMMH_OK;
+}
+
+int pmmh_sv_debug_profile(long long* d_clocks) {
+    g_sv_prof = d_clocks;
     return PMMH_OK;
 }
 

@@ -113,6 +113,8 @@ __global__ void __launch_bounds__(kSvThreads, 1) sv_pf_kernel(SvArgs a) {
     constexpr int NACC = HESS ? 26 : 6;   // filt, smo, grad[4], (hess1[10], hess2[10])
 
     for (int prob = team_id; prob < a.B; prob += a.n_teams) {
+        // fallback pass: only the problems the exchange kernel (sv_fast.cu) abandoned
+        if (a.only_failed && a.diag[(size_t)prob * kDiagCount + kDiagStatus] != 1) continue;
         const double* obs = a.obs + (size_t)prob * a.obs_stride;
         const double* par = a.params + (size_t)prob * 4;
         const double* rvr = a.rvr + (size_t)prob * NOBS;
@@ -803,6 +805,7 @@ __global__ void __launch_bounds__(kSvThreads, 1) sv_pf_kernel(SvArgs a) {
                 o_diag[kDiagStatus] = status;
                 o_diag[kDiagWavefront] = wavefront_max;
                 o_diag[kDiagTrajIdx] = traj_idx;
+                o_diag[kDiagKernel] = 1;
             }
             if (flps && tid < 16) {
                 // expand the upper triangles into the symmetric 4x4 outputs

@@ -11,8 +11,11 @@ constexpr int kSvThreads = 1024;         // threads per CTA (1 CTA per SM)
 constexpr int kStageDoubles = 12288;     // smem staging window for the cumulative weights
 constexpr int kBinCap = 4096;            // max occupancy of one sort bin before we give up
 constexpr int kMaxAllgatherHost = 48;    // must equal kMaxAllgather (common.cuh)
-constexpr int kFastChunk = 3072;         // fast path: bucket capacity == records per smem sort pass
-constexpr int kFastMaxBuckets = 4096;
+constexpr int kFastCap = 4096;           // exchange kernel: records per chunk (smem sort capacity)
+constexpr int kFastFill = 2400;          // exchange kernel: target average chunk occupancy
+constexpr int kFastMaxSub = 6;           // exchange kernel: at most this many chunks per CTA
+
+constexpr int kProfSlots = 16;
 
 enum SvMode { kSvFlps = 0, kSvBpfParity = 1, kSvBpfIntended = 2 };
 
@@ -24,6 +27,8 @@ enum SvDiag {
     kDiagKeyTies = 3,      // equal adjacent keys after sorting
     kDiagWavefront = 4,    // bpf parity mode: max dependency-chain depth
     kDiagTrajIdx = 5,      // bpf: sampled trajectory index (Q10)
+    kDiagKernel = 6,       // which kernel produced the outputs: 1 general, 2 exchange
+    kDiagFastInfo = 7,     // exchange kernel: reason (1 run, 2 chunk overflow) | step << 8 | longest run << 32
     kDiagCount = 8
 };
 
@@ -31,7 +36,8 @@ struct SvArgs {
     int N, NOBS, LAG, B;
     int G, n_teams;
     int NB;          // sort bins (general kernel)
-    int NBK;         // coarse buckets (fast kernel)
+    int NSUB;        // exchange kernel: chunks per CTA
+    int only_failed; // general kernel: only run problems whose diag status is 1 (fallback pass)
     int RING;        // ring depth of the X / A / R histories (LAG + 1), or NOBS with full history
     int mode, hess;
     int SQ;          // low slots of X kept for all times (Q7 / Q11)
@@ -45,6 +51,7 @@ struct SvArgs {
     long long* diag;          // [B][kDiagCount]
     double* Xhist;            // optional [B][NOBS][N]
     int* Ahist;               // optional [B][NOBS][N]
+    long long* prof;          // optional [grid][kProfSlots] per-CTA phase clocks (development)
     char* ws;                 // workspace base
     size_t ws_sync_bytes;     // leading region: stamps + slots for all CTAs
     size_t ws_team_stride;
@@ -108,9 +115,11 @@ __host__ __device__ inline size_t sv_ws_layout(int N, int NOBS, int LAG, int NB,
 cudaError_t sv_launch(const SvArgs& a, int grid, cudaStream_t stream);
 int sv_dynamic_smem_bytes(int G);
 
-// fast path (sv_fast.cu)
-size_t sv_fast_ws_bytes(int N, int NBK, int RING);
-int sv_fast_smem_bytes(int G, int NBK);
+// exchange kernel (sv_fast.cu)
+int sv_fast_nsub(int N, int G);
+size_t sv_fast_ws_bytes(int N, int G, int S, int RING, int LAG);
+size_t sv_fast_sync_bytes(int G, int n_teams);
+int sv_fast_smem_bytes(int N, int G, int S);
 cudaError_t sv_fast_launch(const SvArgs& a, int grid, cudaStream_t stream);
 
 }  // namespace pmmh

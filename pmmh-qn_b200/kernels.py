@@ -51,6 +51,12 @@ def device_info():
     return sm.value, major.value, minor.value
 
 
+def set_sv_algorithm(algorithm):
+    """0 = automatic (exchange kernel where eligible), 1 = general kernel only (pmmh_sv_set_algorithm)."""
+    lib = _lib.load()
+    _lib.check(lib.pmmh_sv_set_algorithm(int(algorithm)), "pmmh_sv_set_algorithm")
+
+
 def sv_workspace_bytes(n_obs, n_particles, lag, batch, compute_hessian, mode=0, have_history=False,
                        ctas_per_problem=0):
     lib = _lib.load()
