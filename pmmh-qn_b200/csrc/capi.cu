@@ -59,7 +59,7 @@ struct SvPlan {
     int G, n_teams, grid, NB, RING, SQ, SQW;
     size_t stamp_bytes, sync_bytes, team_stride, total;
     // exchange kernel (sv_fast.cu); use_fast = 0 when the problem is not eligible
-    int use_fast, NSUB;
+    int use_fast, NSUB, CP;
     size_t fast_sync_bytes, fast_team_stride, fast_total, general_total;
 };
 
@@ -111,16 +111,18 @@ int sv_make_plan(int nobs, int n, int lag, int batch, int hess, int mode, int ha
     p->use_fast = 0;
     p->NSUB = 0;
     p->fast_sync_bytes = p->fast_team_stride = p->fast_total = 0;
-    if (mode == pmmh::kSvFlps && !hess && g_sv_algorithm != 1) {
+    p->CP = 0;
+    if (mode == pmmh::kSvFlps && !hess && g_sv_algorithm != 1 && pmmh::sv_fast_eligible(n, G)) {
         const int S = pmmh::sv_fast_nsub(n, G);
-        const long long nv = (long long)S * G * pmmh::kFastCap;
-        if (S <= pmmh::kFastMaxSub && nv < (1ll << 31) &&
-            pmmh::sv_fast_smem_bytes(n, G, S) <= kMaxDynSmem &&
+        const int CP = pmmh::sv_fast_pair_cap(n, G);
+        const long long nv = (long long)G * G * CP;
+        if (nv < (1ll << 31) && pmmh::sv_fast_smem_bytes(n, G, S) <= kMaxDynSmem &&
             2 * S + 10 <= pmmh::kMaxAllgatherHost) {
             p->use_fast = 1;
             p->NSUB = S;
+            p->CP = CP;
             p->fast_sync_bytes = pmmh::sv_fast_sync_bytes(G, n_teams);
-            p->fast_team_stride = pmmh::sv_fast_ws_bytes(n, G, S, p->RING, lag);
+            p->fast_team_stride = pmmh::sv_fast_ws_bytes(n, G, S, CP, p->RING, lag, have_hist);
             p->fast_total = p->fast_sync_bytes + (size_t)n_teams * p->fast_team_stride;
             if (p->fast_total > p->total) p->total = p->fast_total;
         }
@@ -179,6 +181,7 @@ int sv_run(int mode, const double* d_obs, long long obs_stride, const double* d_
         // exchange kernel first; problems it abandons (diag status 1) are re-run by the general
         // kernel in the same stream, reusing the workspace
         a.NSUB = p.NSUB;
+        a.CP = p.CP;
         a.ws_sync_bytes = p.fast_sync_bytes;
         a.ws_team_stride = p.fast_team_stride;
         PMMH_CUDA(cudaMemsetAsync(d_ws, 0, p.fast_sync_bytes, st));

@@ -2,47 +2,42 @@
 // fixed-lag gradient (flps_sv_corr with compute_hessian = 0, stochastic_volatility.pyx:205-655;
 // the call the quasi-Newton sampler makes twice per iteration, mh_quasi_newton.py:333,378).
 //
-// Why a second kernel: the ncu capture of the general kernel (profiles/r1_v0_*) and the B200
-// micro-benchmarks (tools/microbench.cu, profiles/r1_microbench.txt) showed that a time step is
-// bound by (1) grid-wide barriers (~1.3 us each, 7 per step), (2) global atomics on hot
-// addresses (~100 ns per same-address op) and (3) un-coalesced global accesses, which cost one
-// LSU wavefront per lane whether they hit L2 (4 us per 2^20) or HBM (25 us per 2^20).  This
-// kernel is organised so that a step has TWO barriers, no global atomics and (apart from the
-// fixed-lag look-ups) only coalesced global traffic:
+// One persistent cooperative launch runs all T time steps.  A team of G CTAs (one per SM) owns
+// one problem.  A time step has TWO team-wide exchanges and no global atomics:
 //
-//   phase A  (children, birth order; CTA c owns children [c N/G, (c+1) N/G))
-//     * correlated systematic resampling (:694-715): the CTA stages the cumulative weights of
-//       the parents it can need, every parent computes the index of its first child in closed
-//       form (exact predicate re-checked), and a block-wide max-scan turns the marks into the
-//       ancestor of every child
-//     * propagation (:354-358), then the child is routed by value: the chip-wide sort is a
-//       one-pass sample sort whose splitters are quantiles of the predicted child distribution
-//       (all-gathered first and second moment of the propagation mean, normal shape).  The
-//       child record is written to the mailbox of its destination chunk; slots come from
-//       shared-memory atomics, the per-(chunk, source) run has a fixed base address
-//   barrier 1
-//   phase B  (chunks; CTA c owns chunks c, c+G, c+2G, ... so that shape errors of the splitters
-//             average out)
-//     * reads the runs addressed to the chunk (coalesced), sorts them entirely in shared
-//       memory (fine counting sort + all-pairs inside a fine bin), evaluates the log-weights
-//       (:427-437), writes the sorted generation as 32-byte records with 256-bit stores, the
-//       chunk-local cumulative weights, and accumulates the filter mean, the moments for the
-//       next splitters and the fixed-lag smoother terms (:445-470)
-//   barrier 2 = all-gather of the chunk totals (weights, counts) and partial sums
-//
-// A particle's position is "virtual": chunk * kCap + rank inside the chunk.  Dense positions
-// (the reference's 0..N-1) are only needed for the tail (:540-562) and for the optional
-// history outputs, and follow from the all-gathered chunk counts.
-// Every record carries the virtual positions of its ancestors 1..4 steps back, so the
-// ancestor LAG-2 steps back is reached with ceil((LAG-2)/4) look-ups instead of LAG-2.
+//   phase A  (parents -> children; every CTA works on the parents it already holds)
+//     The sorted generation is cut into ND = S * G value-range chunks; CTA c owns S of them,
+//     interleaved over the range (mirrored on odd rounds so that linear trends of the weight
+//     function cancel) -- its share of the children is then close to 1/G whatever the weights.
+//     After the exchange every CTA knows the weight total of every chunk, hence the global
+//     cumulative weight in front of its own chunks.  Correlated systematic resampling
+//     (:694-715) is evaluated parent-side in closed form: parent p owns the children
+//     [ub(p-1), ub(p)), ub(p) = number of thresholds (u + j) / N at or below its cumulative
+//     weight (exact predicate re-checked).  Children are generated in birth order from
+//     coalesced reads of u, propagated (:354-358) and routed by value to the CTA that will
+//     sort them: the chip-wide sort is a one-pass sample sort whose splitters follow the
+//     empirical cdf of the previous generation.  The child record (32 bytes = one sector: value,
+//     parent value, ids of the ancestors 1..4 steps back) is written straight into the
+//     destination's region of the generation table; its slot is deterministic
+//     (source CTA, stable rank among that source's children for that destination).
+//   exchange 1 (barrier; the per-(destination, source) counts travel through global memory)
+//   phase B  (arrivals -> sorted generation; CTA c works on what was routed to it)
+//     Records never move again: a particle's id is its arrival slot.  The CTA reads the
+//     arrivals (coalesced runs), evaluates log-weights (:427-437), the fixed-lag score terms
+//     (:445-470; the ancestor LAG-2 steps back is reached through the carried ids in
+//     ceil((LAG-2)/4) look-ups) and all weighted sums in arrival order, and sorts (key, arrival
+//     index) pairs in shared memory: counting sort on the chunk-relative position followed by
+//     an all-pairs pass inside a bin.  A block scan in sorted order gives the cumulative
+//     weights.
+//   exchange 2 = all-gather of the chunk totals (weights, counts) and partial sums
 //
 // Differences to the reference that stay inside the stated tolerances: sums over particles are
 // fixed-order tree sums (deterministic); the weight shift is the maximum of the log-weight
 // over the predicted range (the reference's my_max, Q4, picks another element; the shift
 // cancels analytically); log N(y; 0, e^{x/2}) is evaluated as -0.9189.. - x/2 - y^2 e^{-x}/2.
-// If a chunk or a run overflows its capacity (a degenerate cloud, or a child distribution far
-// from normal) the evaluation is abandoned with status 1 and the host code re-runs the general
-// kernel (sv_filter.cu) for that problem.
+// If the arrivals of a CTA exceed its shared-memory capacity or a (destination, source) run
+// overflows (a degenerate cloud), the evaluation is abandoned with status 1 and the host code
+// re-runs the general kernel (sv_filter.cu) for that problem.
 #include <math.h>
 
 #include "common.cuh"
@@ -53,30 +48,39 @@ namespace pmmh {
 
 namespace {
 
-constexpr int kThreads = kSvThreads;
-constexpr int kCap = kFastCap;           // records per chunk (shared-memory sort capacity)
-constexpr int kFineBins = 4096;
-constexpr int kWinCap = 8192;            // staged window entries per piece (phase A)
-constexpr int kChildBlock = 2 * kThreads;   // children routed per shared-memory staging pass
+constexpr int kT = kFastThreads;
+constexpr int kNW = kT / 32;
+constexpr int kCap = kFastCap;           // arrivals per CTA and generation (shared-memory capacity)
+constexpr int kBinBits = 12;
+constexpr int kBins = 1 << kBinBits;     // counting-sort bins per CTA (all its chunks together)
+constexpr int kSubBits = 18;             // key bits below the bin index
+constexpr int kKeyBits = kBinBits + kSubBits;   // 30
 constexpr int kLutCells = 2048;
 constexpr int kMaxLagF = 64;
 constexpr int kSlotW = kMaxAllgather;    // doubles per CTA in the exchange buffers
 constexpr int kNumSums = 10;             // fx, m1, m2, minx, lag[5], flag
+constexpr int kRounds = 4;               // children per thread and tile
+constexpr int kTile = kT * kRounds;
+constexpr int kBinOccMax = 1024;         // a fuller bin means a degenerate cloud: abandon
+constexpr int kMaxSub = kFastMaxSub;
+
+static_assert(kCap <= 16384, "arrival indices are packed into 14 bits");
+static_assert(kBins % kT == 0, "bin scan layout");
 
 struct __align__(32) Rec {   // one particle of one generation
     double x;      // value
     double xpar;   // value of its parent (time - 1)
-    int b[4];      // virtual positions of its ancestors 1, 2, 3, 4 steps back
+    int b[4];      // ids of its ancestors 1, 2, 3, 4 steps back
 };
 static_assert(sizeof(Rec) == 32, "a record is one 32-byte sector");
 
 // 256-bit global accesses (sm_100: LDG.E.ENL2.256 / STG.E.ENL2.256).  Loads are .cg: the data
 // was written by other CTAs of this launch, L1 must not serve it.
-__device__ __forceinline__ void st_rec(Rec* p, const Rec& r) {
-    const unsigned long long w2 = ((unsigned long long)(unsigned)r.b[1] << 32) | (unsigned)r.b[0];
-    const unsigned long long w3 = ((unsigned long long)(unsigned)r.b[3] << 32) | (unsigned)r.b[2];
-    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(__double_as_longlong(r.x)),
-                 "l"(__double_as_longlong(r.xpar)), "l"(w2), "l"(w3)
+__device__ __forceinline__ void st_rec(Rec* p, double x, double xpar, int b0, int b1, int b2, int b3) {
+    const unsigned long long w2 = ((unsigned long long)(unsigned)b1 << 32) | (unsigned)b0;
+    const unsigned long long w3 = ((unsigned long long)(unsigned)b3 << 32) | (unsigned)b2;
+    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(__double_as_longlong(x)),
+                 "l"(__double_as_longlong(xpar)), "l"(w2), "l"(w3)
                  : "memory");
 }
 __device__ __forceinline__ Rec ld_rec(const Rec* p) {
@@ -91,32 +95,33 @@ __device__ __forceinline__ Rec ld_rec(const Rec* p) {
     r.b[3] = (int)(d >> 32);
     return r;
 }
+__device__ __forceinline__ double ld_rec_x(const Rec* p) { return __ldcg(&p->x); }
+__device__ __forceinline__ int ld_rec_b(const Rec* p, int k) { return __ldcg(&p->b[k]); }
 
 struct FastWs {
-    Rec* gen;        // [RING][NV]      sorted generations (virtual positions)
-    double* cumloc;  // [NV]            chunk-local inclusive cumulative shifted weights
-    double* shtail;  // [LAG][NV]       shifted weights of the last LAG generations (tail)
-    Rec* mail;       // [G][NBLK * kChildBlock]  children of every source CTA, per block of
-                     //                 kChildBlock children grouped by destination chunk
-    int* tab;        // [G][NBLK][ND + 1]  start of every destination's run inside a block
-    int* offs;       // [RING][ND + 1]  dense offset of every chunk, per generation
+    Rec* rec;      // [RING][G * G * CP]  generation tables; id = (dest * G + source) * CP + rank
+    int* cnt;      // [2][G][G]           arrivals per (destination, source), by generation parity
+    int* did;      // [LAG][N]            id of the particle at every dense position (last LAG gens)
+    double* dsh;   // [LAG][N]            its shifted weight
+    int* dpos;     // [2][G * G * CP]     dense position of every id (history output only)
+    double* lev;   // [ND + 2]            target cumulative mass at every chunk boundary
 };
 
-__host__ __device__ inline size_t fast_ws_carve(int ND, int G, int RING, int LAG, int NBLK, char* base,
-                                                FastWs* w) {
-    const size_t NV = (size_t)ND * kCap;
+__host__ __device__ inline size_t fast_ws_carve(int N, int G, int S, int CP, int RING, int LAG, int hist,
+                                                char* base, FastWs* w) {
+    const size_t NV = (size_t)G * G * CP;
     size_t off = 0;
 #define PMMH_CARVE(field, type, count)                   \
     do {                                                 \
         if (w) w->field = (type*)(base + off);           \
         off += sv_align((size_t)(count) * sizeof(type)); \
     } while (0)
-    PMMH_CARVE(gen, Rec, (size_t)RING * NV);
-    PMMH_CARVE(cumloc, double, NV);
-    PMMH_CARVE(shtail, double, (size_t)LAG * NV);
-    PMMH_CARVE(mail, Rec, (size_t)G * NBLK * kChildBlock);
-    PMMH_CARVE(tab, int, (size_t)G * NBLK * (ND + 1));
-    PMMH_CARVE(offs, int, (size_t)RING * (ND + 1));
+    PMMH_CARVE(rec, Rec, (size_t)RING * NV);
+    PMMH_CARVE(cnt, int, (size_t)2 * G * G);
+    PMMH_CARVE(did, int, (size_t)LAG * N);
+    PMMH_CARVE(dsh, double, (size_t)LAG * N);
+    PMMH_CARVE(dpos, int, hist ? 2 * NV : 1);
+    PMMH_CARVE(lev, double, (size_t)S * G + 2);
 #undef PMMH_CARVE
     return off;
 }
@@ -159,91 +164,100 @@ __device__ __forceinline__ void team_exchange(TeamF& t, const double* vals, int 
     __syncthreads();
 }
 
-// ---- block-wide scans -------------------------------------------------------------------
-// In-place exclusive scan of data[0..n), n <= 4 * blockDim.x; returns the total.
-// s_w: shared int[33].
-__device__ __forceinline__ int block_excl_scan4(int* data, int n, int* s_w) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int v[4], tsum = 0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int k = tid * 4 + q;
-        v[q] = (k < n) ? data[k] : 0;
-        tsum += v[q];
-    }
-    const int incl = warp_incl_scan(tsum, lane);
+// ---- block-wide scans (kT threads; fixed order => deterministic) ---------------------------
+// exclusive prefix of one value per thread; *total = sum over the block.  s_w: shared [kNW + 1].
+__device__ __forceinline__ double block_excl_scan_d(double v, double* s_w, double* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double incl = warp_incl_scan(v, lane);
     __syncthreads();
     if (lane == 31) s_w[warp] = incl;
     __syncthreads();
     if (warp == 0) {
-        const int tv = s_w[lane];
+        const double tv = (lane < kNW) ? s_w[lane] : 0.0;
+        const double ti = warp_incl_scan(tv, lane);
+        __syncwarp();
+        if (lane < kNW) s_w[lane] = ti - tv;
+        if (lane == kNW - 1) s_w[kNW] = ti;
+    }
+    __syncthreads();
+    const double r = s_w[warp] + (incl - v);
+    *total = s_w[kNW];
+    return r;
+}
+__device__ __forceinline__ int block_excl_scan_i(int v, int* s_w, int* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int incl = warp_incl_scan(v, lane);
+    __syncthreads();
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const int tv = (lane < kNW) ? s_w[lane] : 0;
         const int ti = warp_incl_scan(tv, lane);
         __syncwarp();
-        s_w[lane] = ti - tv;
-        if (lane == 31) s_w[32] = ti;
+        if (lane < kNW) s_w[lane] = ti - tv;
+        if (lane == kNW - 1) s_w[kNW] = ti;
     }
     __syncthreads();
-    int run = s_w[warp] + (incl - tsum);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int k = tid * 4 + q;
-        if (k < n) data[k] = run;
-        run += v[q];
-    }
-    const int total = s_w[32];
-    __syncthreads();
-    return total;
+    const int r = s_w[warp] + (incl - v);
+    *total = s_w[kNW];
+    return r;
 }
-
-// In-place inclusive max-scan of data[0..n) (any n).  s_w: shared int[33].
-__device__ __forceinline__ void block_incl_maxscan(int* data, int n, int* s_w) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int carry = INT_MIN;
-    for (int base = 0; base < n; base += 4 * kThreads) {
-        int v[4];
-        int m = INT_MIN;
+// exclusive running maximum (identity = lowest)
+__device__ __forceinline__ int block_excl_maxscan_i(int v, int* s_w, int lowest) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = v;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int k = base + tid * 4 + q;
-            v[q] = (k < n) ? data[k] : INT_MIN;
-            m = max(m, v[q]);
-            v[q] = m;
-        }
-        int incl = m;
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(kFullMask, incl, d);
+        if (lane >= d) incl = max(incl, o);
+    }
+    int excl = __shfl_up_sync(kFullMask, incl, 1);
+    if (lane == 0) excl = lowest;
+    __syncthreads();
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int ti = (lane < kNW) ? s_w[lane] : lowest;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const int o = __shfl_up_sync(kFullMask, incl, d);
-            if (lane >= d) incl = max(incl, o);
+            const int o = __shfl_up_sync(kFullMask, ti, d);
+            if (lane >= d) ti = max(ti, o);
         }
-        int excl = __shfl_up_sync(kFullMask, incl, 1);
-        if (lane == 0) excl = INT_MIN;
-        __syncthreads();
-        if (lane == 31) s_w[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            const int tv = s_w[lane];
-            int ti = tv;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int o = __shfl_up_sync(kFullMask, ti, d);
-                if (lane >= d) ti = max(ti, o);
-            }
-            int te = __shfl_up_sync(kFullMask, ti, 1);
-            if (lane == 0) te = INT_MIN;
-            __syncwarp();
-            s_w[lane] = te;
-            if (lane == 31) s_w[32] = ti;
-        }
-        __syncthreads();
-        const int pre = max(carry, max(s_w[warp], excl));
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int k = base + tid * 4 + q;
-            if (k < n) data[k] = max(pre, v[q]);
-        }
-        carry = max(carry, s_w[32]);
-        __syncthreads();
+        int te = __shfl_up_sync(kFullMask, ti, 1);
+        if (lane == 0) te = lowest;
+        __syncwarp();
+        if (lane < kNW) s_w[lane] = te;
     }
+    __syncthreads();
+    return max(s_w[warp], excl);
+}
+__device__ __forceinline__ double block_excl_maxscan_d(double v, double* s_w) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double o = __shfl_up_sync(kFullMask, incl, d);
+        if (lane >= d) incl = fmax(incl, o);
+    }
+    double excl = __shfl_up_sync(kFullMask, incl, 1);
+    if (lane == 0) excl = 0.0;
+    __syncthreads();
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        double ti = (lane < kNW) ? s_w[lane] : 0.0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double o = __shfl_up_sync(kFullMask, ti, d);
+            if (lane >= d) ti = fmax(ti, o);
+        }
+        double te = __shfl_up_sync(kFullMask, ti, 1);
+        if (lane == 0) te = 0.0;
+        __syncwarp();
+        if (lane < kNW) s_w[lane] = te;
+    }
+    __syncthreads();
+    return fmax(s_w[warp], excl);
 }
 
 // Inverse standard normal cdf (Acklam's rational approximation, |rel err| < 1.2e-9).  Only
@@ -273,28 +287,47 @@ __device__ double inv_norm_cdf(double p) {
            ((((d0 * q + d1) * q + d2) * q + d3) * q + 1.0);
 }
 
-// strict weak order of the chunk sort: value first, then the rest of the record (records that
-// compare equal on everything are bit-identical, so their relative order cannot matter)
-__device__ __forceinline__ bool rec_less(double xa, double pa, const int4& ba, double xb, double pb,
-                                         const int4& bb) {
-    if (xa != xb) return xa < xb;
-    if (ba.x != bb.x) return ba.x < bb.x;
-    if (ba.y != bb.y) return ba.y < bb.y;
-    if (ba.z != bb.z) return ba.z < bb.z;
-    if (ba.w != bb.w) return ba.w < bb.w;
-    return pa < pb;
-}
-
 // norm_logpdf(y, 0, exp(x/2)) (:428,659-664) with e = exp(-x/2): -0.5 log(2 pi) - x/2 - y^2 e^2 / 2
 __device__ __forceinline__ double logw_e(double x, double e, double half_y2) {
     return (-0.91893853320467267 - 0.5 * x) - half_y2 * (e * e);
 }
 
-__device__ __forceinline__ int fine_bin(double x, double lo, double scale) {
-    const double t = (x - lo) * scale;
-    if (!(t >= 0.0)) return 0;
-    if (t >= (double)kFineBins) return kFineBins - 1;
-    return (int)t;
+// chunk k of the sorted generation -> (owning CTA, local chunk index); mirrored on odd rounds
+__device__ __forceinline__ int chunk_owner(int k, int G) {
+    const int l = k / G, r = k - l * G;
+    return (l & 1) ? (G - 1 - r) : r;
+}
+__device__ __forceinline__ int chunk_of(int l, int rank, int G) {
+    return l * G + ((l & 1) ? (G - 1 - rank) : rank);
+}
+
+// threshold of child j (:711): (u + j) / N
+__device__ __forceinline__ double child_cp(double u, int j, int N, bool pow2, double invN) {
+    return pow2 ? (u + (double)j) * invN : (u + (double)j) / (double)N;
+}
+// number of thresholds at or below c = smallest j in [0, N] whose threshold exceeds c
+__device__ __forceinline__ int first_child_above(double c, double u, int N, bool pow2, double invN) {
+    if (!(c == c)) return N;
+    double guess = c * (double)N - u;
+    if (!(guess > -1.0)) guess = -1.0;
+    if (guess > (double)N) guess = (double)N;
+    int fc = (int)floor(guess) + 1;
+    if (fc < 0) fc = 0;
+    if (fc > N) fc = N;
+    while (fc > 0 && child_cp(u, fc - 1, N, pow2, invN) > c) --fc;
+    while (fc < N && !(child_cp(u, fc, N, pow2, invN) > c)) ++fc;
+    return fc;
+}
+
+// arrival index -> slot inside the destination region (runs of the G sources, CP apart)
+__device__ __forceinline__ int arrival_slot(const int* s_off, int G, int CP, int e) {
+    int lo = 0, hi = G - 1;   // largest s with s_off[s] <= e
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_off[mid] <= e) lo = mid;
+        else hi = mid - 1;
+    }
+    return lo * CP + (e - s_off[lo]);
 }
 
 // development instrumentation: cycles per phase, accumulated by thread 0 of every CTA
@@ -307,57 +340,59 @@ __device__ __forceinline__ int fine_bin(double x, double lo, double scale) {
         }                                        \
     } while (0)
 
-__global__ void __launch_bounds__(kThreads, 1) sv_fast_kernel(SvArgs a) {
+__global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
     long long prof_acc[kProfSlots];
     long long prof_t = clock64();
 #pragma unroll
     for (int q = 0; q < kProfSlots; ++q) prof_acc[q] = 0;
     extern __shared__ __align__(32) unsigned char dsm_raw[];
     const int N = a.N, NOBS = a.NOBS, LAG = a.LAG, G = a.G, RING = a.RING;
-    const int S = a.NSUB, ND = S * G;
+    const int S = a.NSUB, ND = S * G, CP = a.CP;
     const int KW = 2 * S + kNumSums;    // doubles per CTA per exchange
-    const size_t NV = (size_t)ND * kCap;
+    const size_t NV = (size_t)G * G * CP;
     const int per_tile = (N + G - 1) / G;
-    const int NBLK = (per_tile + kChildBlock - 1) / kChildBlock;
+    int lbits = 0;
+    while ((1 << lbits) < S) ++lbits;
+    const int kb = kKeyBits - lbits;           // key bits inside a chunk
+    const double key_span = (double)(1u << kb);
 
     // ---- dynamic shared memory
-    double* s_cw = (double*)dsm_raw;                 // [ND]     chunk weight totals
-    double* s_cP = s_cw + ND;                        // [ND + 1] exclusive prefix of s_cw
-    double* s_z = s_cP + (ND + 1);                   // [ND + 1] splitters in z space ([0] unused)
-    int* s_cc = (int*)(s_z + (ND + 1));              // [ND]     chunk counts
-    int* s_coff = s_cc + ND;                         // [ND + 1] dense offsets (this generation)
-    int* s_coffp = s_coff + (ND + 1);                // [ND + 1] dense offsets (previous generation)
-    int* s_cnt = s_coffp + (ND + 1);                 // [ND]     per-destination counters (phase A)
-    int* s_lut = s_cnt + ND;                         // [kLutCells]
-    unsigned char* s_union = (unsigned char*)(((size_t)(s_lut + kLutCells) + 31) & ~(size_t)31);
-    //   view G: exchange output
-    double* s_gather = (double*)s_union;                               // [G * KW]
-    //   view A (phase A)
-    double* s_cn = (double*)s_union;                                   // [kWinCap + 1]
-    Rec* s_stage = (Rec*)(s_cn + kWinCap + 4);                         // [kChildBlock]
-    int* s_off = (int*)(s_stage + kChildBlock);                        // [ND + 1]
-    int* s_par = s_off + (ND + 2);                                     // [per_tile]
-    //   view B (phase B)
-    double* s_x = (double*)s_union;                                    // [kCap]
-    double* s_xp = s_x + kCap;                                         // [kCap]
-    int4* s_b = (int4*)(s_xp + kCap);                                  // [kCap]
-    int* s_fh = (int*)(s_b + kCap);                                    // [kFineBins + 8]
-    unsigned short* s_slot = (unsigned short*)(s_fh + kFineBins + 8);  // [kCap]
-    unsigned short* s_inv = s_slot + kCap;                             // [kCap]
-    int* s_roff = (int*)(s_inv + kCap);                                // [G * NBLK + 8] run starts
-    int* s_rbase = s_roff + (G * NBLK + 8);                            // [G * NBLK] run base in mail
+    double* s_sh = (double*)dsm_raw;                                  // [kCap]  arrival order: shifted weight
+    double* s_z = s_sh + kCap;                                        // [ND + 2] splitters in z space
+    unsigned* s_karr = (unsigned*)(s_z + ((ND + 3) & ~1));            // [kCap]  arrival order: key
+    unsigned* s_k32 = s_karr + kCap;                                  // [kCap]  bin order: (sub key, arrival)
+    int* s_hist = (int*)(s_k32 + kCap);                               // [kBins + 8]
+    unsigned short* s_e = (unsigned short*)(s_hist + kBins + 8);      // [kCap]  sorted position -> arrival
+    unsigned short* s_lut = s_e + kCap;                               // [kLutCells]
+    int* s_off = (int*)(s_lut + kLutCells);                           // [G + 1] arrival runs
+    //   views of the s_karr region (dead between pass 2 of phase B and the next pass 1)
+    double* s_gather = (double*)s_karr;                               // [G * KW] exchange output
+    int* s_fc = (int*)s_karr;                                         // [kCap]  sorted position -> end of its children
+    //   views of the s_k32 region (dead between pass 3 of phase B and the next pass 2)
+    double* s_P = (double*)s_k32;                                     // [ND + 2] cumulative weight in front of every chunk
+    double* s_zn = s_P + (ND + 2);                                    // [ND + 2]
+    int* s_coff = (int*)(s_zn + (ND + 2));                            // [ND + 2] dense offset of every chunk
+    double* s_H = (double*)(s_coff + ((ND + 3) & ~1));                // [ND + 2] blended cdf at the splitters
+    double* s_g1 = (double*)s_k32;                                    // [G * 8]  small exchanges
+    //   views of the s_hist region (phase A)
+    unsigned short* s_wh = (unsigned short*)s_hist;                   // [kNW][G] per-warp destination counts
+    int* s_dbase = (int*)(s_wh + ((kNW * G + 1) & ~1));               // [G]
 
     __shared__ double s_vals[kSlotW];
     __shared__ double s_tot[16];
     __shared__ double s_red[12 * 32];
-    __shared__ double s_w[33], s_wx[33];
-    __shared__ int s_iw[33];
+    __shared__ double s_w[kNW + 1];
+    __shared__ int s_iw[kNW + 1];
     __shared__ int s_misc[8];
-    __shared__ double s_dmisc[4];
     __shared__ double s_S[kMaxLagF];
+    // per local chunk
+    __shared__ int s_lstart[kMaxSub + 1];    // first sorted position
+    __shared__ double s_Cb[kMaxSub + 1];     // CTA-wide cumulative weight in front of it
+    __shared__ double s_lP0[kMaxSub];        // global cumulative weight in front of it
+    __shared__ int s_lLB[kMaxSub], s_lUB[kMaxSub], s_lco[kMaxSub + 1], s_lcoff[kMaxSub];
+    __shared__ double s_lzlo[kMaxSub], s_lzsc[kMaxSub];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int nwarp = kThreads / 32;
 
     TeamF tm;
     tm.G = G;
@@ -368,17 +403,13 @@ __global__ void __launch_bounds__(kThreads, 1) sv_fast_kernel(SvArgs a) {
     tm.slots = (double*)(a.ws + sv_align((size_t)a.n_teams * 128)) + (size_t)team_id * 2 * G * kSlotW;
     char* wsbase = a.ws + a.ws_sync_bytes + (size_t)team_id * a.ws_team_stride;
     const bool lead = (tm.rank == 0);
-    const int p0 = min(N, tm.rank * per_tile), p1 = min(N, p0 + per_tile);
+    const int me = tm.rank;
+    const int p0 = min(N, me * per_tile), p1 = min(N, p0 + per_tile);
 
     FastWs w;
-    fast_ws_carve(ND, G, RING, LAG, NBLK, wsbase, &w);
-#define GEN(t) (w.gen + (size_t)((t) % RING) * NV)
-#define OFFS(t) (w.offs + (size_t)((t) % RING) * (ND + 1))
-
-    // ---- splitters in z space (constant for the whole launch) and their look-up table
-    for (int k = tid; k <= ND; k += kThreads)
-        s_z[k] = (k == 0) ? -INFINITY : ((k == ND) ? INFINITY : inv_norm_cdf((double)k / (double)ND));
-    __syncthreads();
+    fast_ws_carve(N, G, S, CP, RING, LAG, a.Xhist != nullptr, wsbase, &w);
+#define GEN(t) (w.rec + (size_t)((t) % RING) * NV)
+    const size_t my_base = (size_t)me * G * CP;   // first id of my region
 
     for (int prob = team_id; prob < a.B; prob += a.n_teams) {
         const double* obs = a.obs + (size_t)prob * a.obs_stride;
@@ -398,32 +429,75 @@ __global__ void __launch_bounds__(kThreads, 1) sv_fast_kernel(SvArgs a) {
         const double invN_exact = 1.0 / (double)N;
         const bool n_pow2 = (N & (N - 1)) == 0;   // then (u + j) / N == (u + j) * (1 / N) exactly
 
+        // ---- chunk boundaries in standardised space z.  In the bulk the chunks hold equal mass;
+        // towards the tails a chunk is at most wmax wide, wmax = a fraction of the spread of the
+        // children of one parent.  A parent chunk then scatters its children over many chunks
+        // (bounded arrivals per (destination, source) run) and a tail that suddenly carries most
+        // of the weight is shared by many CTAs.  lev[k] = target cumulative mass at boundary k;
+        // the boundaries start at the normal quantiles of the levels.
+        {
+            const double zmax = 5.0, phi0 = 0.3989422804014327;
+            const double varx = (c.sigmav * c.sigmav) / (1.0 - c.phi * c.phi);
+            double sigz = c.sd / sqrt(c.phi * c.phi * varx + c.sd * c.sd);
+            if (!(sigz > 0.0) || !(sigz <= 1.0)) sigz = 1.0;
+            double wmax = 0.3 * sigz;
+            if (ND > 2 && wmax < 8.0 * zmax / (double)ND) wmax = 8.0 * zmax / (double)ND;
+            // bulk density M phi(z), tails 1 / wmax: find M so that ND - 2 chunks cover [-zmax, zmax]
+            double mlo = 0.0, mhi = 2.0 * ND + 8.0, Mc = 0.0, zc = 0.0;
+            for (int it = 0; it < 60; ++it) {
+                Mc = 0.5 * (mlo + mhi);
+                const double q = Mc * wmax * phi0;
+                zc = (q > 1.0) ? sqrt(2.0 * log(q)) : 0.0;
+                if (zc > zmax) zc = zmax;
+                const double cover = Mc * (1.0 - erfc(zc * 0.70710678118654752)) + 2.0 * (zmax - zc) / wmax;
+                if (cover > (double)(ND - 2)) mhi = Mc;
+                else mlo = Mc;
+            }
+            const double Lt = (zmax - zc) / wmax;                                   // chunks per tail
+            const double Lb = Mc * (1.0 - erfc(zc * 0.70710678118654752));          // chunks in the bulk
+            const double Plo = 0.5 * erfc(zc * 0.70710678118654752);                // mass below -zc
+            for (int k = tid; k <= ND; k += kT) {
+                double z;
+                if (k == 0) z = -INFINITY;
+                else if (k == ND) z = INFINITY;
+                else {
+                    const double t = (double)(k - 1);
+                    if (t <= Lt) z = -zmax + t * wmax;
+                    else if (t <= Lt + Lb) z = inv_norm_cdf(Plo + (t - Lt) / Mc);
+                    else z = zc + (t - Lt - Lb) * wmax;
+                    if (z > zmax) z = zmax;
+                    if (z < -zmax) z = -zmax;
+                }
+                s_z[k] = z;
+                w.lev[k] = (k == 0) ? 0.0 : ((k == ND) ? 1.0 : 0.5 * erfc(-z * 0.70710678118654752));
+            }
+        }
+
         // ---------------- time 0 (:306-323, Q1): every particle equals mu + stDev * 0.0
         const double stdev0 = c.sigmav / sqrt(1.0 - (c.phi * c.phi));
         const double x0 = c.mu + stdev0 * 0.0;
-        for (int l = 0; l < S; ++l) {
-            const int k = l * G + tm.rank;
-            const int cntk = N / ND + (k < N % ND ? 1 : 0);
-            const int offk = k * (N / ND) + min(k, N % ND);
-            Rec r;
-            r.x = x0;
-            r.xpar = x0;
-            r.b[0] = r.b[1] = r.b[2] = r.b[3] = 0;
-            for (int q = tid; q < cntk; q += kThreads) {
-                st_rec(&GEN(0)[(size_t)k * kCap + q], r);
-                w.cumloc[(size_t)k * kCap + q] = (double)(q + 1);
-                if (Xh) {
-                    Xh[offk + q] = x0;
-                    Ah[offk + q] = offk + q;
-                }
+        int n_d = 0;
+        if (tid == 0) {
+            int acc0 = 0;
+            for (int l = 0; l < S; ++l) {
+                const int k = chunk_of(l, me, G);
+                s_lstart[l] = acc0;
+                acc0 += N / ND + (k < N % ND ? 1 : 0);
             }
-            if (tid == 0) {
-                s_vals[2 * l] = (double)cntk;       // weight total (all shifted weights are 1)
-                s_vals[2 * l + 1] = (double)cntk;   // count
-            }
+            s_lstart[S] = acc0;
         }
+        for (int s = tid; s <= G; s += kT) s_off[s] = 0;
+        __syncthreads();
+        n_d = s_lstart[S];
+        for (int s = 1 + tid; s <= G; s += kT) s_off[s] = n_d;   // generation 0: one run
+        for (int q = tid; q < n_d; q += kT) {
+            s_sh[q] = 1.0;
+            s_e[q] = (unsigned short)q;
+            st_rec(&GEN(0)[my_base + q], x0, x0, 0, 0, 0, 0);
+        }
+        __syncthreads();
         if (lead) {
-            for (int t = tid; t < NOBS; t += kThreads) {
+            for (int t = tid; t < NOBS; t += kT) {
                 o_smo[t] = 0.0;
                 o_grad[t] = 0.0;
                 o_grad[NOBS + t] = 0.0;
@@ -433,75 +507,135 @@ __global__ void __launch_bounds__(kThreads, 1) sv_fast_kernel(SvArgs a) {
         }
         // moment shift: the propagation mean of the step-1 children is the same for all
         double cshift = (c.mu + c.phi * (x0 - c.mu)) + c.sr * exp(-0.5 * x0) * obs[0];
-        for (int k = tid; k <= ND; k += kThreads) {
-            s_coff[k] = 0;
-            if (prob != team_id)   // a previous problem adapted the splitters: start again from normal quantiles
-                s_z[k] = (k == 0) ? -INFINITY : ((k == ND) ? INFINITY : inv_norm_cdf((double)k / (double)ND));
-        }
-        if (tid == 0) {
-            double cn = 0.0;
-            for (int l = 0; l < S; ++l) cn += s_vals[2 * l + 1];
-            s_vals[2 * S + 0] = cn * x0;   // sum sh * x
-            s_vals[2 * S + 1] = 0.0;       // sum sh * (f - cshift)
-            s_vals[2 * S + 2] = 0.0;       // sum sh * (f - cshift)^2
-            s_vals[2 * S + 3] = x0;        // min x
-            for (int q = 4; q < kNumSums; ++q) s_vals[2 * S + q] = 0.0;
-        }
+        double acc[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) acc[q] = 0.0;
+        double minx = x0;
+        if (tid == 0) acc[0] = (double)n_d * x0;   // sum sh * x
+        int chunk_over = 0;
+        double tpre = 0.0;                          // cumulative weight in front of my sorted positions
         double loglike = 0.0, shift = 0.0;
-        long long near_ties = 0, key_ties2 = 0;
-        int max_chunk = 0, status = 0;
+        long long near_ties = 0, key_ties = 0;
+        int max_occ = 0, status = 0, max_arr = 0;
         long long fail_info = 0;
-        team_exchange(tm, s_vals, KW, s_gather);
 
         for (int i = 0; i < NOBS; ++i) {
-            PROF_MARK(0);   // barrier 2 (wait + gather)
-            // =========== bookkeeping for generation i (just gathered)
-            // chunk tables; chunk k = l * G + cta
-            for (int k = tid; k < ND; k += kThreads) {
-                const int cta = k % G, l = k / G;
-                s_cw[k] = s_gather[cta * KW + 2 * l];
-                s_cc[k] = (int)s_gather[cta * KW + 2 * l + 1];
-                s_coffp[k] = s_coff[k];
+            // =========== cumulative weights of generation i in sorted order (CTA-local), publish
+            const int R = (n_d + kT - 1) / kT;
+            {
+                const int q0 = min(n_d, tid * R), q1 = min(n_d, q0 + R);
+                double tsum = 0.0;
+                for (int q = q0; q < q1; ++q) tsum += s_sh[s_e[q]];
+                double total;
+                tpre = block_excl_scan_d(tsum, s_w, &total);
+                if (tid == 0)
+                    for (int l = 0; l <= S; ++l)
+                        if (s_lstart[l] == 0) s_Cb[l] = 0.0;
+                __syncthreads();
+                int lc = 0;
+                while (lc < S && s_lstart[lc + 1] <= q0) ++lc;   // chunk of my first position
+                double run = tpre;
+                for (int q = q0; q < q1; ++q) {
+                    run += s_sh[s_e[q]];
+                    while (lc < S && s_lstart[lc + 1] == q + 1) {
+                        s_Cb[lc + 1] = run;
+                        ++lc;
+                    }
+                }
+                __syncthreads();
+                double sums[8] = {acc[0], acc[1], acc[2], acc[4], acc[5], acc[6], acc[7], acc[8]};
+                block_sum<8>(sums, s_red);
+                minx = warp_min(minx);
+                if (lane == 0) s_w[warp] = minx;
+                chunk_over = __syncthreads_or(chunk_over);
+                if (warp == 0) {
+                    double v = (lane < kNW) ? s_w[lane] : INFINITY;
+                    v = warp_min(v);
+                    if (lane == 0) s_vals[2 * S + 3] = v;
+                }
+                if (tid < S) {
+                    s_vals[2 * tid] = s_Cb[tid + 1] - s_Cb[tid];
+                    s_vals[2 * tid + 1] = (double)(s_lstart[tid + 1] - s_lstart[tid]);
+                }
+                if (tid == 0) {
+                    s_vals[2 * S + 0] = sums[0];
+                    s_vals[2 * S + 1] = sums[1];
+                    s_vals[2 * S + 2] = sums[2];
+                    s_vals[2 * S + 4] = sums[3];
+                    s_vals[2 * S + 5] = sums[4];
+                    s_vals[2 * S + 6] = sums[5];
+                    s_vals[2 * S + 7] = sums[6];
+                    s_vals[2 * S + 8] = sums[7];
+                    s_vals[2 * S + 9] = (double)chunk_over;
+                }
             }
-            if (tid == 0) s_coffp[ND] = s_coff[ND];
-            for (int q = warp; q < kNumSums; q += nwarp) {
+            PROF_MARK(0);   // cumulative weights + block sums
+            team_exchange(tm, s_vals, KW, s_gather);   // exchange 2
+            PROF_MARK(1);   // exchange 2 (wait + gather)
+
+            // =========== bookkeeping for generation i (just gathered)
+            for (int q = warp; q < kNumSums; q += kNW) {
                 double s;
                 if (q == 3) s = gathered_min(s_gather, KW, 2 * S + q, G, lane);
                 else if (q == 9) s = gathered_max(s_gather, KW, 2 * S + q, G, lane);
                 else s = gathered_sum(s_gather, KW, 2 * S + q, G, lane);
                 if (lane == 0) s_tot[q] = s;
             }
-            __syncthreads();
-            if (warp == 0) {
-                // prefixes over the chunks in chunk order (one warp, sequential chunks of 32:
-                // a fixed order, identical in every CTA)
-                double carry = 0.0;
-                int icarry = 0;
-                for (int base = 0; base < ND; base += 32) {
-                    const int k = base + lane;
-                    const double v = (k < ND) ? s_cw[k] : 0.0;
-                    const int iv = (k < ND) ? s_cc[k] : 0;
-                    const double incl = warp_incl_scan(v, lane);
-                    const int iincl = warp_incl_scan(iv, lane);
-                    if (k < ND) {
-                        s_cP[k] = carry + (incl - v);
-                        s_coff[k] = icarry + (iincl - iv);
-                    }
-                    carry = carry + __shfl_sync(kFullMask, incl, 31);
-                    icarry = icarry + __shfl_sync(kFullMask, iincl, 31);
+            {
+                // prefixes over the chunks in chunk order: thread t owns PERT consecutive chunks
+                const int PERT = (ND + kT - 1) / kT;
+                const int k0 = min(ND, tid * PERT), k1 = min(ND, k0 + PERT);
+                double wsum = 0.0;
+                int csum = 0, cmax = 0;
+                for (int k = k0; k < k1; ++k) {
+                    const int cta = chunk_owner(k, G), l = k / G;
+                    wsum += s_gather[cta * KW + 2 * l];
+                    const int cc = (int)s_gather[cta * KW + 2 * l + 1];
+                    csum += cc;
+                    cmax = max(cmax, cc);
                 }
-                if (lane == 0) {
-                    s_cP[ND] = carry;
-                    s_coff[ND] = icarry;
+                double wtot;
+                int ctot;
+                const double wpre = block_excl_scan_d(wsum, s_w, &wtot);
+                const int cpre = block_excl_scan_i(csum, s_iw, &ctot);
+                // enforce a non-decreasing prefix across threads (tree sums may dip by an ulp)
+                double runw = wpre;
+                int runc = cpre;
+                double last = wpre;
+                for (int k = k0; k < k1; ++k) {
+                    const int cta = chunk_owner(k, G), l = k / G;
+                    last = runw;
+                    runw += s_gather[cta * KW + 2 * l];
+                    runc += (int)s_gather[cta * KW + 2 * l + 1];
                 }
+                const double floorw = block_excl_maxscan_d((k1 > k0) ? last : 0.0, s_w);
+                runw = wpre;
+                runc = cpre;
+                for (int k = k0; k < k1; ++k) {
+                    const int cta = chunk_owner(k, G), l = k / G;
+                    s_P[k] = fmax(runw, floorw);
+                    s_coff[k] = runc;
+                    runw += s_gather[cta * KW + 2 * l];
+                    runc += (int)s_gather[cta * KW + 2 * l + 1];
+                }
+                if (tid == kT - 1) {
+                    s_P[ND] = fmax(wtot, fmax(runw, floorw));
+                    s_coff[ND] = ctot;
+                }
+                max_occ = max(max_occ, cmax);
             }
             __syncthreads();
-            if (s_tot[9] > 0.0) {   // a chunk overflowed in phase B (uniform decision)
+            if (s_tot[9] > 0.0) {   // a CTA overflowed in phase B (uniform decision)
                 status = 1;
                 fail_info = 2 | ((long long)i << 8);
                 break;
             }
-            const double S_i = s_cP[ND];
+            const double S_i = s_P[ND];
+            if (!(S_i > 0.0) || !isfinite(S_i) || s_coff[ND] != N) {
+                status = 1;
+                fail_info = 3 | ((long long)i << 8);
+                break;
+            }
             if (i >= 1) loglike += shift + log(S_i) - logN;   // :537
             if (tid == 0) s_S[i % kMaxLagF] = S_i;
             if (lead && tid == 0) {
@@ -516,23 +650,29 @@ __global__ void __launch_bounds__(kThreads, 1) sv_fast_kernel(SvArgs a) {
                     o_grad[3 * NOBS + tt] = s_tot[8] / S_i;
                 }
             }
-            if (lead)
-                for (int k = tid; k <= ND; k += kThreads) OFFS(i)[k] = s_coff[k];
-            {
-                int mc = 0;
-                for (int k = tid; k < ND; k += kThreads) mc = max(mc, s_cc[k]);
-                max_chunk = max(max_chunk, mc);
-            }
-            if (Xh && i >= 1) {
-                // history outputs: dense layout, ancestors as dense positions of generation i-1
-                for (int l = 0; l < S; ++l) {
-                    const int k = l * G + tm.rank;
-                    const int cntk = s_cc[k], offk = s_coff[k];
-                    for (int q = tid; q < cntk; q += kThreads) {
-                        const Rec r = ld_rec(&GEN(i)[(size_t)k * kCap + q]);
-                        Xh[(size_t)i * N + offk + q] = r.x;
-                        const int pk = r.b[0] / kCap, pr = r.b[0] - pk * kCap;
-                        Ah[(size_t)i * N + offk + q] = s_coffp[pk] + pr;
+            if (tid < S) s_lcoff[tid] = s_coff[chunk_of(tid, me, G)];
+            __syncthreads();
+            // dense-position maps: history outputs, and the last LAG generations for the tail
+            if (Xh != nullptr || i >= NOBS - LAG) {
+                const Rec* Gi = GEN(i);
+                int* dposc = w.dpos + (size_t)(i & 1) * NV;
+                const int* dposp = w.dpos + (size_t)((i + 1) & 1) * NV;
+                for (int q = tid; q < n_d; q += kT) {
+                    int l = 0;
+                    while (l + 1 < S && s_lstart[l + 1] <= q) ++l;
+                    const int dense = s_lcoff[l] + (q - s_lstart[l]);
+                    const int e = s_e[q];
+                    const size_t id = my_base + arrival_slot(s_off, G, CP, e);
+                    if (i >= NOBS - LAG) {
+                        const size_t sl = (size_t)(i - (NOBS - LAG)) * N + dense;
+                        w.did[sl] = (int)id;
+                        w.dsh[sl] = s_sh[e];
+                    }
+                    if (Xh) {
+                        const Rec r = ld_rec(&Gi[id]);
+                        Xh[(size_t)i * N + dense] = r.x;
+                        Ah[(size_t)i * N + dense] = (i == 0) ? dense : __ldcg(&dposp[r.b[0]]);
+                        dposc[id] = dense;
                     }
                 }
             }
@@ -559,26 +699,80 @@ __global__ void __launch_bounds__(kThreads, 1) sv_fast_kernel(SvArgs a) {
                 shift = logw_e(xs, exp(-0.5 * xs), half_y2);
             }
             cshift = m1;
-            __syncthreads();   // s_gather (view G) is dead from here on
 
+            // ----- per local chunk: cumulative weight in front, range of children
+            const double u = rvr[inext];
+            if (tid < S) {
+                const int l = tid, k = chunk_of(l, me, G);
+                const int cntl = s_lstart[l + 1] - s_lstart[l];
+                int lb = 0, ub = 0;
+                s_lP0[l] = s_P[k];
+                if (cntl > 0) {
+                    lb = (s_coff[k] == 0) ? 0 : first_child_above(s_P[k] / S_i, u, N, n_pow2, invN_exact);
+                    int kn = k + 1;   // next chunk that holds particles
+                    while (kn < ND && s_coff[kn + 1] == s_coff[kn]) ++kn;
+                    ub = (kn >= ND) ? N : first_child_above(s_P[kn] / S_i, u, N, n_pow2, invN_exact);
+                    if (ub < lb) ub = lb;
+                }
+                s_lLB[l] = lb;
+                s_lUB[l] = ub;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int accn = 0;
+                for (int l = 0; l < S; ++l) {
+                    s_lco[l] = accn;
+                    accn += s_lUB[l] - s_lLB[l];
+                }
+                s_lco[S] = accn;
+            }
             // ----- splitters of step inext.  In standardised space z = (x - m1) / sdc they start
             // as normal quantiles; afterwards they follow the shape the cloud really has: the
-            // chunk counts of generation i give the empirical cdf at the current splitters, and
-            // the new splitters are its ND-quantiles (piecewise linear inside a chunk, normal
-            // tails in the two unbounded chunks).  Every CTA computes the same values.
-            if (i >= 1 && ND > 1) {
-                double* s_zn = s_cn;
-                for (int k = 1 + tid; k < ND; k += kThreads) {
-                    const long long tgt = (long long)k * N;
-                    int lo2 = 0, hi2 = ND - 1;   // largest m with coff[m] / N <= k / ND
+            // chunk counts of generation i give the empirical cdf F at the current splitters.
+            // A chunk should hold neither much more than its share of the particles (arrivals
+            // per CTA) nor much more than its share of the weight (children per CTA when an
+            // outlying observation puts all the weight into one tail), so the new splitters are
+            // the quantiles, at the levels, of H = (F + W) / 2, W = cdf of the predicted weight
+            // w_{i+1}(x) dF (piecewise linear inside a chunk, normal tails in the two unbounded
+            // chunks).  Every CTA computes the same values.
+            if (ND > 1) {
+                const int PERT = (ND + kT - 1) / kT;
+                const int k0 = min(ND, tid * PERT), k1 = min(ND, k0 + PERT);
+                double wsum = 0.0;
+                for (int k = k0; k < k1; ++k) {
+                    const double Fk = (i == 0) ? __ldcg(&w.lev[k]) : (double)s_coff[k] / (double)N;
+                    const double Fk1 = (i == 0) ? __ldcg(&w.lev[k + 1]) : (double)s_coff[k + 1] / (double)N;
+                    const double zl = (k == 0) ? s_z[1] - 0.5 : s_z[k];
+                    const double zr = (k == ND - 1) ? s_z[ND - 1] + 0.5 : s_z[k + 1];
+                    const double xm = m1 + sdc * (0.5 * (zl + zr));
+                    double wv = exp(logw_e(xm, exp(-0.5 * xm), half_y2) - shift);
+                    if (!isfinite(wv)) wv = 0.0;
+                    const double wm = (Fk1 - Fk) * wv;
+                    s_zn[k] = wm;
+                    wsum += wm;
+                }
+                double wtot;
+                const double wpre = block_excl_scan_d(wsum, s_w, &wtot);
+                const bool use_w = (wtot > 0.0) && isfinite(wtot);
+                double runw = wpre;
+                for (int k = k0; k < k1; ++k) {
+                    const double Fk = (i == 0) ? __ldcg(&w.lev[k]) : (double)s_coff[k] / (double)N;
+                    s_H[k] = use_w ? 0.5 * (Fk + runw / wtot) : Fk;
+                    runw += s_zn[k];
+                }
+                if (tid == 0) s_H[ND] = 1.0;
+                __syncthreads();
+                for (int k = 1 + tid; k < ND; k += kT) {
+                    const double Tk = __ldcg(&w.lev[k]);
+                    int lo2 = 0, hi2 = ND - 1;   // largest m with H[m] <= lev[k]
                     while (lo2 < hi2) {
                         const int mid = (lo2 + hi2 + 1) >> 1;
-                        if ((long long)s_coff[mid] * ND <= tgt) lo2 = mid;
+                        if (s_H[mid] <= Tk) lo2 = mid;
                         else hi2 = mid - 1;
                     }
                     const int m = lo2;
-                    const double Fm = (double)s_coff[m] / (double)N, Fm1 = (double)s_coff[m + 1] / (double)N;
-                    double frac = ((double)k / (double)ND - Fm) / (Fm1 - Fm);
+                    const double Fm = s_H[m], Fm1 = s_H[m + 1];
+                    double frac = (Tk - Fm) / (Fm1 - Fm);
                     if (!(frac >= 0.0)) frac = 0.0;
                     if (frac > 1.0) frac = 1.0;
                     double zn;
@@ -593,19 +787,19 @@ __global__ void __launch_bounds__(kThreads, 1) sv_fast_kernel(SvArgs a) {
                     } else {
                         zn = s_z[m] + frac * (s_z[m + 1] - s_z[m]);
                     }
-                    s_zn[k] = zn;
+                    s_P[k] = zn;   // s_P is free: the per-chunk values were copied out above
                 }
                 __syncthreads();
-                for (int k = 1 + tid; k < ND; k += kThreads) s_z[k] = s_zn[k];
+                for (int k = 1 + tid; k < ND; k += kT) s_z[k] = s_P[k];
                 __syncthreads();
             }
-            double lut_lo = -1.0, lut_scale = 1.0;
+            double lut_lo = -1.0, lut_scale = 0.0;
             if (ND > 1) {
                 const double zlo = s_z[1] - 1e-9, zhi = s_z[ND - 1] + 1e-9;
                 lut_lo = zlo;
                 lut_scale = (double)kLutCells / (zhi - zlo);
                 if (!isfinite(lut_scale) || !(lut_scale > 0.0)) lut_scale = 0.0;
-                for (int cidx = tid; cidx < kLutCells; cidx += kThreads) {
+                for (int cidx = tid; cidx < kLutCells; cidx += kT) {
                     const double edge = (lut_scale > 0.0) ? lut_lo + (double)cidx / lut_scale : -INFINITY;
                     int lo2 = 0, hi2 = ND - 1;   // largest d in [0, ND-1] with s_z[d] <= edge (s_z[0] = -inf)
                     while (lo2 < hi2) {
@@ -613,472 +807,431 @@ __global__ void __launch_bounds__(kThreads, 1) sv_fast_kernel(SvArgs a) {
                         if (s_z[mid] <= edge) lo2 = mid;
                         else hi2 = mid - 1;
                     }
-                    s_lut[cidx] = lo2;
+                    s_lut[cidx] = (unsigned short)lo2;
                 }
+            } else {
+                for (int cidx = tid; cidx < kLutCells; cidx += kT) s_lut[cidx] = 0;
             }
-            __syncthreads();
-
-            PROF_MARK(1);   // bookkeeping, splitters, LUT
-            // =========== phase A: resample (:694-715) + propagate (:354-358) + route, step inext
-            const double u = rvr[inext];
-            const Rec* Gi = GEN(i);
-            for (int k = tid; k < ND; k += kThreads) s_cnt[k] = 0;
-            for (int k = tid; k < p1 - p0; k += kThreads) s_par[k] = -1;
-            int pair_over = 0;
-            if (p1 > p0) {
-                const double cp_first = n_pow2 ? (u + (double)p0) * invN_exact : (u + (double)p0) / (double)N;
-                const double cp_last =
-                    n_pow2 ? (u + (double)(p1 - 1)) * invN_exact : (u + (double)(p1 - 1)) / (double)N;
-                // chunk-level bracket: first chunk whose inclusive cumulative weight reaches cp
-                if (warp == 0) {
-                    int k_lo = ND - 1, k_hi = ND - 1;
-                    for (int k = lane; k < ND; k += 32) {
-                        const double endc = (s_cP[k] + s_cw[k]) / S_i;
-                        if (s_cc[k] > 0 && endc >= cp_first) k_lo = min(k_lo, k);
-                        if (s_cc[k] > 0 && endc >= cp_last) k_hi = min(k_hi, k);
-                    }
-                    k_lo = -warp_max(-k_lo);
-                    k_hi = -warp_max(-k_hi);
-                    if (lane == 0) {
-                        s_misc[0] = k_lo;
-                        s_misc[1] = k_hi;
-                    }
-                }
-                __syncthreads();
-                const int k_lo = s_misc[0], k_hi = s_misc[1];
-                // walk the window chunk by chunk, in pieces of kWinCap entries
-                for (int k = k_lo; k <= k_hi; ++k) {
-                    const int cntk = s_cc[k];
-                    if (cntk == 0) continue;
-                    const double Pk = s_cP[k];
-                    const double* cl = w.cumloc + (size_t)k * kCap;
-                    for (int e0 = 0; e0 < cntk; e0 += kWinCap) {
-                        const int len = min(kWinCap, cntk - e0);
-                        __syncthreads();
-                        // s_cn[0] = normalised cumulative weight just before entry e0
-                        if (tid == 0) s_cn[0] = (e0 == 0) ? (Pk / S_i) : ((Pk + __ldcg(&cl[e0 - 1])) / S_i);
-                        for (int q = tid; q < len; q += kThreads)
-                            s_cn[q + 1] = (Pk + __ldcg(&cl[e0 + q])) / S_i;
-                        __syncthreads();
-                        for (int q = tid; q < len; q += kThreads) {
-                            // entry (k, e0 + q): index of its first possible child
-                            const double cprev = s_cn[q];
-                            // the very first particle of the generation serves every child whose
-                            // cp is below its cumulative weight: its first child is child 0
-                            const bool first_ever = (e0 + q == 0) && (s_coff[k] == 0);
-                            int fc;
-                            if (first_ever) {
-                                fc = 0;
-                            } else if (!(cprev == cprev)) {
-                                fc = N;   // NaN weights: no children (the evaluation fails below)
-                            } else {
-                                // smallest j >= 0 with cp_j > cprev  (i.e. NOT cum >= cp_j)
-                                double guess = cprev * (double)N - u;
-                                if (!(guess > -1.0)) guess = -1.0;
-                                if (guess > (double)N) guess = (double)N;
-                                fc = (int)floor(guess) + 1;
-                                if (fc < 0) fc = 0;
-                                if (fc > N) fc = N;
-                                while (fc > 0) {
-                                    const double cpm = n_pow2 ? (u + (double)(fc - 1)) * invN_exact
-                                                              : (u + (double)(fc - 1)) / (double)N;
-                                    if (cpm > cprev) --fc;
-                                    else break;
-                                }
-                                while (fc < N) {
-                                    const double cpj = n_pow2 ? (u + (double)fc) * invN_exact
-                                                              : (u + (double)fc) / (double)N;
-                                    if (cpj > cprev) break;
-                                    ++fc;
-                                }
-                                // diagnostics: decisions within 64 ulp of a cumulative-weight tie,
-                                // counted by the CTA that owns the child
-                                const double tol = 64.0 * 2.220446049250313e-16 * cprev;
-                                if (fc - 1 >= p0 && fc - 1 < p1) {
-                                    const double cpa = n_pow2 ? (u + (double)(fc - 1)) * invN_exact
-                                                              : (u + (double)(fc - 1)) / (double)N;
-                                    if (fabs(cprev - cpa) <= tol) near_ties++;
-                                }
-                                if (fc >= p0 && fc < p1) {
-                                    const double cpb = n_pow2 ? (u + (double)fc) * invN_exact
-                                                              : (u + (double)fc) / (double)N;
-                                    if (fabs(cpb - cprev) <= tol) near_ties++;
-                                }
-                            }
-                            if (fc < p1) atomicMax(&s_par[max(fc, p0) - p0], k * kCap + e0 + q);
-                        }
-                    }
-                }
-                __syncthreads();
-                PROF_MARK(2);   // window: first-child marks
-                block_incl_maxscan(s_par, p1 - p0, s_iw);
-            }
-            PROF_MARK(3);   // max-scan
-            // children, in blocks of kChildBlock: propagate, pick the destination chunk, group the
-            // block by destination in shared memory, write it out coalesced together with the
-            // table of run starts
+            PROF_MARK(2);   // bookkeeping, splitters, LUT
+            // ----- end of children per sorted position (s_fc aliases the gather buffer: all
+            //       reads of s_gather are behind the barriers above)
             {
+                const int q0 = min(n_d, tid * R), q1 = min(n_d, q0 + R);
+                int lc = 0;
+                while (lc < S && s_lstart[lc + 1] <= q0) ++lc;
+                double run = tpre;
+                int m = 0;
+                for (int q = q0; q < q1; ++q) {
+                    run += s_sh[s_e[q]];
+                    while (lc < S - 1 && s_lstart[lc + 1] <= q) ++lc;
+                    int ub;
+                    if (q + 1 == s_lstart[lc + 1]) {
+                        ub = s_lUB[lc];
+                    } else {
+                        const double cc = (s_lP0[lc] + (run - s_Cb[lc])) / S_i;
+                        ub = first_child_above(cc, u, N, n_pow2, invN_exact);
+                        // diagnostics: decisions within 64 ulp of a cumulative-weight tie
+                        const double tol = 64.0 * 2.220446049250313e-16 * cc;
+                        if (ub > 0 && fabs(cc - child_cp(u, ub - 1, N, n_pow2, invN_exact)) <= tol) near_ties++;
+                        if (ub < N && fabs(child_cp(u, ub, N, n_pow2, invN_exact) - cc) <= tol) near_ties++;
+                    }
+                    m = max(m, ub);
+                    s_fc[q] = m;
+                }
+                const int mt = block_excl_maxscan_i((q1 > q0) ? m : 0, s_iw, 0);
+                lc = 0;
+                while (lc < S && s_lstart[lc + 1] <= q0) ++lc;
+                for (int q = q0; q < q1; ++q) {
+                    while (lc < S - 1 && s_lstart[lc + 1] <= q) ++lc;
+                    int v = max(s_fc[q], mt);
+                    v = max(v, s_lLB[lc]);
+                    v = min(v, s_lUB[lc]);
+                    if (q + 1 == s_lstart[lc + 1]) v = s_lUB[lc];
+                    s_fc[q] = v;
+                }
+            }
+            for (int q = tid; q < kNW * G; q += kT) s_wh[q] = 0;
+            for (int q = tid; q < G; q += kT) s_dbase[q] = 0;
+            __syncthreads();
+            PROF_MARK(3);   // children ranges
+
+            // =========== phase A: children of my parents, in birth order: propagate (:354-358),
+            //             route, write the record into the destination's region
+            int pair_over = 0;
+            {
+                int n_c = s_lco[S];
+                if (n_c > 60000) {   // per-warp run offsets are 16 bit: a degenerate cloud, abandon
+                    pair_over = 1;
+                    n_c = 0;
+                }
                 const double* Ui = U + (size_t)inext * N;
-                Rec* my_mail = w.mail + (size_t)tm.rank * NBLK * kChildBlock;
-                int* my_tab = w.tab + (size_t)tm.rank * NBLK * (ND + 1);
-                for (int blk = 0; blk < NBLK; ++blk) {
-                    const int jb = p0 + blk * kChildBlock;
-                    const int nb = max(0, min(kChildBlock, p1 - jb));
-                    Rec r[2];
-                    int dst[2], slot[2];
+                const Rec* Gi = GEN(i);
+                Rec* Gn = GEN(inext);
+                unsigned short* my_wh = s_wh + warp * G;
+                for (int tile0 = 0; tile0 < n_c; tile0 += kTile) {
+                    double xn[kRounds], xp[kRounds];
+                    int pb0[kRounds], pb1[kRounds], pb2[kRounds], pb3[kRounds];
+                    int dr[kRounds];   // destination << 16 | rank inside this warp's run
 #pragma unroll
-                    for (int m = 0; m < 2; ++m) {
-                        const int j = jb + m * kThreads + tid;
-                        dst[m] = -1;
-                        slot[m] = 0;
-                        if (j < p1) {
-                            int vp = s_par[j - p0];
-                            if (vp < 0) {   // no parent found (non-finite weights): abandon
-                                vp = 0;
-                                pair_over = 1;
-                            }
+                    for (int r = 0; r < kRounds; ++r) {
+                        const int t = tile0 + warp * (32 * kRounds) + r * 32 + lane;
+                        const bool valid = t < n_c;
+                        int d = G;   // inactive lanes never match a destination
+                        dr[r] = -1;
+                        if (valid) {
+                            int l = 0;
+                            while (l + 1 < S && s_lco[l + 1] <= t) ++l;
+                            const int j = s_lLB[l] + (t - s_lco[l]);
                             const double un = ld_stream_f64(&Ui[j]);
-                            const Rec pr = ld_rec(&Gi[vp]);
-                            const double xp = pr.x;
-                            double mean = c.mu + c.phi * (xp - c.mu);
-                            mean += c.sr * exp(-0.5 * xp) * y1;
-                            const double xn = mean + c.sd * un;
-                            int d = 0;
+                            // parent: first sorted position of chunk l whose children end beyond j
+                            int lo2 = s_lstart[l], hi2 = s_lstart[l + 1] - 1;
+                            while (lo2 < hi2) {
+                                const int mid = (lo2 + hi2) >> 1;
+                                if (s_fc[mid] > j) hi2 = mid;
+                                else lo2 = mid + 1;
+                            }
+                            const int pid = (int)(my_base + arrival_slot(s_off, G, CP, s_e[lo2]));
+                            const Rec pr = ld_rec(&Gi[pid]);
+                            double mean = c.mu + c.phi * (pr.x - c.mu);
+                            mean += c.sr * exp(-0.5 * pr.x) * y1;
+                            const double xnew = mean + c.sd * un;
+                            int kc = 0;
                             if (ND > 1) {
-                                const double zx = (xn - m1) * inv_sdc;
+                                const double zx = (xnew - m1) * inv_sdc;
                                 const double tt = (zx - lut_lo) * lut_scale;
                                 const int cell =
                                     (tt >= 0.0) ? ((tt < (double)kLutCells) ? (int)tt : kLutCells - 1) : 0;
-                                d = s_lut[cell];
-                                while (d + 1 < ND && zx >= s_z[d + 1]) ++d;
-                                while (d > 0 && zx < s_z[d]) --d;
+                                kc = s_lut[cell];
+                                while (kc + 1 < ND && zx >= s_z[kc + 1]) ++kc;
+                                while (kc > 0 && zx < s_z[kc]) --kc;
                             }
-                            dst[m] = d;
-                            slot[m] = atomicAdd(&s_cnt[d], 1);
-                            r[m].x = xn;
-                            r[m].xpar = xp;
-                            r[m].b[0] = vp;
-                            r[m].b[1] = pr.b[0];
-                            r[m].b[2] = pr.b[1];
-                            r[m].b[3] = pr.b[2];
+                            d = chunk_owner(kc, G);
+                            xn[r] = xnew;
+                            xp[r] = pr.x;
+                            pb0[r] = pid;
+                            pb1[r] = pr.b[0];
+                            pb2[r] = pr.b[1];
+                            pb3[r] = pr.b[2];
+                        }
+                        // stable rank inside the warp: lanes with the same destination
+                        const unsigned peers = __match_any_sync(kFullMask, d);
+                        if (valid) {
+                            const int before = __popc(peers & ((1u << lane) - 1u));
+                            const int base = my_wh[d];
+                            __syncwarp(peers);
+                            if (before == 0) my_wh[d] = (unsigned short)(base + __popc(peers));
+                            dr[r] = (d << 16) | (base + before);
+                        }
+                        __syncwarp();
+                    }
+                    __syncthreads();
+                    // stable offsets of every warp's run inside the (destination, me) run
+                    for (int d = tid; d < G; d += kT) {
+                        int base = s_dbase[d];
+                        for (int wv = 0; wv < kNW; ++wv) {
+                            const int t = s_wh[wv * G + d];
+                            s_wh[wv * G + d] = (unsigned short)base;
+                            base += t;
+                        }
+                        s_dbase[d] = base;
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int r = 0; r < kRounds; ++r) {
+                        if (dr[r] >= 0) {
+                            const int d = dr[r] >> 16;
+                            const int rank = (int)my_wh[d] + (dr[r] & 0xffff);
+                            if (rank < CP)
+                                st_rec(&Gn[((size_t)d * G + me) * CP + rank], xn[r], xp[r], pb0[r], pb1[r],
+                                       pb2[r], pb3[r]);
+                            else {
+                                if (!pair_over) {   // diagnostics of the first overflowing run
+                                    a.hess1[(size_t)prob * 16 + 0] = (double)me;
+                                    a.hess1[(size_t)prob * 16 + 1] = (double)n_c;
+                                    a.hess1[(size_t)prob * 16 + 2] = (double)d;
+                                    a.hess1[(size_t)prob * 16 + 3] = (double)rank;
+                                    a.hess1[(size_t)prob * 16 + 4] = m1;
+                                    a.hess1[(size_t)prob * 16 + 5] = sdc;
+                                    a.hess1[(size_t)prob * 16 + 6] = S_i;
+                                    a.hess1[(size_t)prob * 16 + 7] = xn[r];
+                                    for (int q = 0; q < 8 && q < S; ++q) {
+                                        a.hess1[(size_t)prob * 16 + 8 + q] = (double)(s_lUB[q] - s_lLB[q]);
+                                        a.hess2[(size_t)prob * 16 + q] = (double)(s_lstart[q + 1] - s_lstart[q]);
+                                        a.hess2[(size_t)prob * 16 + 8 + q] = s_z[chunk_of(q, me, G)];
+                                    }
+                                }
+                                pair_over = 1;
+                            }
                         }
                     }
                     __syncthreads();
-                    // run starts of this block = exclusive scan of the destination counters
-                    for (int k = tid; k < ND; k += kThreads) s_off[k] = s_cnt[k];
-                    __syncthreads();
-                    block_excl_scan4(s_off, ND, s_iw);
-                    if (tid == 0) s_off[ND] = nb;
-                    __syncthreads();
-#pragma unroll
-                    for (int m = 0; m < 2; ++m)
-                        if (dst[m] >= 0) s_stage[s_off[dst[m]] + slot[m]] = r[m];
-                    for (int k = tid; k < ND; k += kThreads) s_cnt[k] = 0;
-                    __syncthreads();
-                    for (int q = tid; q < nb; q += kThreads) st_rec(&my_mail[(size_t)blk * kChildBlock + q], s_stage[q]);
-                    for (int k = tid; k <= ND; k += kThreads) my_tab[(size_t)blk * (ND + 1) + k] = s_off[k];
+                    for (int q = tid; q < kNW * G; q += kT) s_wh[q] = 0;
                     __syncthreads();
                 }
+                int* cn = w.cnt + (size_t)(inext & 1) * G * G;
+                for (int d = tid; d < G; d += kT) cn[(size_t)d * G + me] = min(s_dbase[d], CP);
             }
             pair_over = __syncthreads_or(pair_over);
             PROF_MARK(4);   // children: propagate + route + write
             if (tid == 0) s_vals[0] = (double)pair_over;
-            team_exchange(tm, s_vals, 1, s_gather);   // barrier 1
+            team_exchange(tm, s_vals, 1, s_g1);   // exchange 1
             {
                 double f = 0.0;
-                for (int cc = tid; cc < G; cc += kThreads) f = fmax(f, s_gather[cc]);
+                for (int cc = tid; cc < G; cc += kT) f = fmax(f, s_g1[cc]);
                 const int any = __syncthreads_or(f > 0.0);
                 if (any) {
                     status = 1;   // a run overflowed (uniform decision)
-                    if (lead && tid == 0) {   // diagnostics of the failing step
-                        a.hess1[(size_t)prob * 16 + 0] = m1;
-                        a.hess1[(size_t)prob * 16 + 1] = sdc;
-                        a.hess1[(size_t)prob * 16 + 2] = S_i;
-                        a.hess1[(size_t)prob * 16 + 3] = s_tot[1];
-                        a.hess1[(size_t)prob * 16 + 4] = s_tot[2];
-                        a.hess1[(size_t)prob * 16 + 5] = s_tot[0] / S_i;
-                        a.hess1[(size_t)prob * 16 + 6] = c.sd;
-                        for (int q = 0; q < 9 && q < ND; ++q) a.hess2[(size_t)prob * 16 + q] = (double)s_cnt[q * (ND / 9 > 0 ? ND / 9 : 1)];
-                    }
                     fail_info = 1 | ((long long)inext << 8);
                     break;
                 }
             }
+            PROF_MARK(5);   // exchange 1
 
-            PROF_MARK(5);   // barrier 1
-            // =========== phase B: sort my chunks of generation inext in shared memory
-            Rec* Gn = GEN(inext);
+            // =========== phase B: my arrivals of generation inext
+            {
+                const int* cn = w.cnt + (size_t)(inext & 1) * G * G + (size_t)me * G;
+                int total = 0;
+                // runs of the sources (G <= kT is guaranteed by the launch: G <= SM count)
+                const int cv = (tid < G) ? __ldcg(&cn[tid]) : 0;
+                const int pre = block_excl_scan_i(cv, s_iw, &total);
+                if (tid < G) s_off[tid] = pre;
+                if (tid == 0) s_off[G] = total;
+                for (int q = tid; q < kBins + 8; q += kT) s_hist[q] = 0;
+                n_d = total;
+                chunk_over = 0;
+                if (n_d > kCap) {
+                    chunk_over = 1;
+                    n_d = 0;
+                }
+                max_arr = max(max_arr, total);
+                __syncthreads();
+            }
+            if (tid < S) {
+                const int k = chunk_of(tid, me, G);
+                double zlo = (k == 0) ? ((ND > 1) ? s_z[1] - 2.0 : -8.0) : s_z[k];
+                double zhi = (k == ND - 1) ? ((ND > 1) ? s_z[ND - 1] + 2.0 : 8.0) : s_z[k + 1];
+                double sc = key_span / (zhi - zlo);
+                if (!isfinite(sc) || !(sc > 0.0)) sc = 0.0;
+                s_lzlo[tid] = zlo;
+                s_lzsc[tid] = sc;
+            }
+            __syncthreads();
+            const Rec* Gn = GEN(inext);
             const double yl = (inext >= LAG) ? obs[inext - LAG] : 0.0;   // Q5
             const int K = LAG - 2;
-            double acc[9];
+            const int hop0 = (K > 4) ? 3 : (K - 1);   // which carried id starts the look-ups (K >= 1)
 #pragma unroll
             for (int q = 0; q < 9; ++q) acc[q] = 0.0;
-            double minx = INFINITY;
-            int chunk_over = 0;
-            for (int l = 0; l < S; ++l) {
-                const int k = l * G + tm.rank;
-                // (1) the runs addressed to chunk k: one per (source CTA, child block)
-                __syncthreads();
-                const int NR = G * NBLK;
-                for (int q = tid; q < NR; q += kThreads) {
-                    const int* tb = w.tab + (size_t)q * (ND + 1) + k;
-                    const int st = __ldcg(&tb[0]), en = __ldcg(&tb[1]);
-                    s_roff[q] = en - st;
-                    s_rbase[q] = q * kChildBlock + st;
-                }
-                __syncthreads();
-                int cnt = block_excl_scan4(s_roff, NR, s_iw);
-                if (tid == 0) s_roff[NR] = cnt;
-                if (cnt > kCap) {
-                    chunk_over = 1;
-                    cnt = 0;
-                }
-                __syncthreads();
-                // (2) load the records, key range
-                double kmn = INFINITY, kmx = -INFINITY;
-                for (int q = tid; q < cnt; q += kThreads) {
-                    int lo2 = 0, hi2 = NR - 1;   // largest run with s_roff[run] <= q
-                    while (lo2 < hi2) {
-                        const int mid = (lo2 + hi2 + 1) >> 1;
-                        if (s_roff[mid] <= q) lo2 = mid;
-                        else hi2 = mid - 1;
-                    }
-                    const Rec r = ld_rec(&w.mail[(size_t)s_rbase[lo2] + (q - s_roff[lo2])]);
-                    s_x[q] = r.x;
-                    s_xp[q] = r.xpar;
-                    s_b[q] = make_int4(r.b[0], r.b[1], r.b[2], r.b[3]);
-                    kmn = fmin(kmn, r.x);
-                    kmx = fmax(kmx, r.x);
-                }
-                PROF_MARK(6);   // phase B: run table + record load
-                for (int q = tid; q <= kFineBins; q += kThreads) s_fh[q] = 0;
-                kmn = warp_min(kmn);
-                kmx = warp_max(kmx);
-                if (lane == 0) {
-                    s_w[warp] = kmn;
-                    s_wx[warp] = kmx;
-                }
-                __syncthreads();
-                if (warp == 0) {
-                    double v1 = s_w[lane], v2 = s_wx[lane];
-                    v1 = warp_min(v1);
-                    v2 = warp_max(v2);
-                    if (lane == 0) {
-                        s_dmisc[0] = v1;
-                        s_dmisc[1] = v2;
-                    }
-                }
-                __syncthreads();
-                const double fmin_k = s_dmisc[0];
-                double fscale = (double)kFineBins / (s_dmisc[1] - fmin_k);
-                if (!(s_dmisc[1] > fmin_k) || !isfinite(fscale)) fscale = 0.0;
-                if (cnt > 0) minx = fmin(minx, fmin_k);
-                // (3) fine counting sort
-                int fb[kCap / kThreads], rf[kCap / kThreads];
+            minx = INFINITY;
+            // ---- pass 1 (arrival order): key + histogram, weight, sums, fixed-lag terms
+            for (int e0 = 0; e0 < n_d; e0 += 4 * kT) {
+                double x[4];
+                int hb[4];
+                size_t id[4];
 #pragma unroll
-                for (int m = 0; m < kCap / kThreads; ++m) {
-                    const int q = tid + m * kThreads;
-                    fb[m] = 0;
-                    rf[m] = 0;
-                    if (q < cnt) {
-                        fb[m] = fine_bin(s_x[q], fmin_k, fscale);
-                        rf[m] = atomicAdd(&s_fh[fb[m]], 1);
+                for (int r = 0; r < 4; ++r) {
+                    const int e = e0 + r * kT + tid;
+                    x[r] = 0.0;
+                    hb[r] = 0;
+                    id[r] = 0;
+                    if (e < n_d) {
+                        id[r] = my_base + arrival_slot(s_off, G, CP, e);
+                        x[r] = ld_rec_x(&Gn[id[r]]);
+                        if (inext >= LAG && K >= 1) hb[r] = ld_rec_b(&Gn[id[r]], hop0);
                     }
                 }
-                __syncthreads();
-                block_excl_scan4(s_fh, kFineBins, s_iw);
-                if (tid == 0) s_fh[kFineBins] = cnt;
-                __syncthreads();
+                // fixed-lag look-ups (:445-470): ancestor LAG-2 steps back
+                double pc[4], pn[4];
+                if (inext >= LAG) {
+                    if (K == 0) {
 #pragma unroll
-                for (int m = 0; m < kCap / kThreads; ++m) {
-                    const int q = tid + m * kThreads;
-                    if (q < cnt) s_slot[s_fh[fb[m]] + rf[m]] = (unsigned short)q;
-                }
-                __syncthreads();
-                // (4) order inside each fine bin (all pairs; ~1 record per bin on average)
-                for (int s = tid; s < cnt; s += kThreads) {
-                    const int q = s_slot[s];
-                    const double key = s_x[q];
-                    const int f = fine_bin(key, fmin_k, fscale);
-                    const int st = s_fh[f], en = s_fh[f + 1];
-                    int rank = 0;
-                    if (en - st > 1) {
-                        const double kp = s_xp[q];
-                        const int4 kb = s_b[q];
-                        for (int o = st; o < en; ++o) {
-                            if (o == s) continue;
-                            const int q2 = s_slot[o];
-                            const double x2 = s_x[q2];
-                            bool lt = rec_less(x2, s_xp[q2], s_b[q2], key, kp, kb);
-                            if (x2 == key) {
-                                key_ties2++;
-                                // bit-identical records: any fixed order will do
-                                if (!lt && !rec_less(key, kp, kb, x2, s_xp[q2], s_b[q2])) lt = (o < s);
+                        for (int r = 0; r < 4; ++r) {
+                            const int e = e0 + r * kT + tid;
+                            pc[r] = pn[r] = 0.0;
+                            if (e < n_d) {
+                                pc[r] = __ldcg(&Gn[id[r]].xpar);
+                                pn[r] = x[r];
                             }
-                            if (lt) rank++;
+                        }
+                    } else {
+                        int tcur = inext, rem = K;
+                        while (rem > 4) {   // jump 4 generations through the carried ids
+                            tcur -= 4;
+                            rem -= 4;
+                            const int nb = (rem > 4) ? 3 : (rem - 1);
+                            const Rec* Gt = GEN(tcur);
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) {
+                                const int e = e0 + r * kT + tid;
+                                if (e < n_d) hb[r] = ld_rec_b(&Gt[hb[r]], nb);
+                            }
+                        }
+                        tcur -= rem;
+                        const Rec* Gt = GEN(tcur);
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            const int e = e0 + r * kT + tid;
+                            pc[r] = pn[r] = 0.0;
+                            if (e < n_d) {
+                                const double2 v = __ldcg((const double2*)&Gt[hb[r]]);
+                                pn[r] = v.x;
+                                pc[r] = v.y;
+                            }
                         }
                     }
-                    s_inv[st + rank] = (unsigned short)q;
                 }
-                __syncthreads();
-                PROF_MARK(7);   // phase B: shared-memory sort
-                // (5) sorted order: weights (:427-437), record + cumulative weight writes, sums
-                double carry = 0.0;
-                for (int rowb = 0; rowb < cnt; rowb += kThreads) {
-                    const int r = rowb + tid;
-                    const bool valid = r < cnt;
-                    double shv = 0.0;
-                    if (valid) {
-                        const int q = s_inv[r];
-                        Rec rec;
-                        rec.x = s_x[q];
-                        rec.xpar = s_xp[q];
-                        const int4 bb = s_b[q];
-                        rec.b[0] = bb.x;
-                        rec.b[1] = bb.y;
-                        rec.b[2] = bb.z;
-                        rec.b[3] = bb.w;
-                        const double e = exp(-0.5 * rec.x);
-                        shv = exp(logw_e(rec.x, e, half_y2) - shift);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int e = e0 + r * kT + tid;
+                    if (e < n_d) {
+                        const double xv = x[r];
+                        // chunk and key
+                        int kc = 0;
+                        const double zx = (xv - m1) * inv_sdc;
+                        if (ND > 1) {
+                            const double tt = (zx - lut_lo) * lut_scale;
+                            const int cell = (tt >= 0.0) ? ((tt < (double)kLutCells) ? (int)tt : kLutCells - 1) : 0;
+                            kc = s_lut[cell];
+                            while (kc + 1 < ND && zx >= s_z[kc + 1]) ++kc;
+                            while (kc > 0 && zx < s_z[kc]) --kc;
+                        }
+                        const int l = kc / G;
+                        const double tq = (zx - s_lzlo[l]) * s_lzsc[l];
+                        unsigned kq = 0;
+                        if (tq >= 0.0) kq = (tq < key_span) ? (unsigned)tq : ((1u << kb) - 1u);
+                        const unsigned key = ((unsigned)l << kb) | kq;
+                        s_karr[e] = key;
+                        atomicAdd(&s_hist[key >> kSubBits], 1);
+                        // weight (:427-437)
+                        const double eh = exp(-0.5 * xv);
+                        double shv = exp(logw_e(xv, eh, half_y2) - shift);
                         if (!isfinite(shv)) shv = 0.0;
-                        const size_t vp = (size_t)k * kCap + r;
-                        st_rec(&Gn[vp], rec);
-                        if (inext >= NOBS - LAG) w.shtail[(size_t)(inext - (NOBS - LAG)) * NV + vp] = shv;
-                        const double sx = shv * rec.x;
+                        s_sh[e] = shv;
+                        minx = fmin(minx, xv);
+                        const double sx = shv * xv;
                         if (isfinite(sx)) acc[0] += sx;
                         // propagation mean of the next step (for the splitters)
-                        const double df = ((c.mu + c.phi * (rec.x - c.mu)) + c.sr * e * yi) - cshift;
+                        const double df = ((c.mu + c.phi * (xv - c.mu)) + c.sr * eh * yi) - cshift;
                         const double sdf = shv * df;
                         if (isfinite(sdf)) {
                             acc[1] += sdf;
                             acc[2] += sdf * df;
                         }
                         if (inext >= LAG) {
-                            // fixed-lag smoother terms (:445-470): ancestor LAG-2 steps back
-                            Rec cur = rec;
-                            int tcur = inext, rem = K;
-                            while (rem > 4) {
-                                tcur -= 4;
-                                cur = ld_rec(&GEN(tcur)[cur.b[3]]);
-                                rem -= 4;
-                            }
-                            if (rem > 0) {
-                                tcur -= rem;
-                                cur = ld_rec(&GEN(tcur)[cur.b[rem - 1]]);
-                            }
                             double sq, g[4];
-                            sv_score_main(c, cur.xpar, cur.x, yl, sq, g);
-                            acc[4] += shv * cur.xpar;
+                            sv_score_main(c, pc[r], pn[r], yl, sq, g);
+                            acc[4] += shv * pc[r];
                             acc[5] += g[0] * shv;
                             acc[6] += g[1] * shv;
                             acc[7] += g[2] * shv;
                             acc[8] += g[3] * shv;
                         }
                     }
-                    // block-wide inclusive scan of this row of weights (fixed order)
-                    const double incl = warp_incl_scan(shv, lane);
-                    if (lane == 31) s_w[warp] = incl;
-                    __syncthreads();
-                    if (warp == 0) {
-                        const double tv = s_w[lane];
-                        const double ti = warp_incl_scan(tv, lane);
-                        const double te = __shfl_up_sync(kFullMask, ti, 1);
-                        s_wx[lane] = (lane == 0) ? 0.0 : te;
-                        if (lane == 31) s_dmisc[2] = ti;
-                    }
-                    __syncthreads();
-                    if (valid) w.cumloc[(size_t)k * kCap + r] = carry + (s_wx[warp] + incl);
-                    // the chunk total must equal the last cumulative value bit for bit
-                    const int last = min(cnt - 1 - rowb, kThreads - 1);
-                    if (tid == last) s_dmisc[3] = carry + (s_wx[warp] + incl);
-                    __syncthreads();
-                    carry = s_dmisc[3];
-                    __syncthreads();
                 }
-                if (tid == 0) {
-                    s_vals[2 * l] = carry;
-                    s_vals[2 * l + 1] = (double)cnt;
-                }
-                PROF_MARK(8);   // phase B: weights, record writes, fixed-lag look-ups
             }
+            __syncthreads();
+            PROF_MARK(6);   // phase B pass 1
+            // ---- bin offsets (exclusive scan of the histogram)
             {
-                double sums[8] = {acc[0], acc[1], acc[2], acc[4], acc[5], acc[6], acc[7], acc[8]};
-                block_sum<8>(sums, s_red);
-                minx = warp_min(minx);
-                if (lane == 0) s_w[warp] = minx;
-                chunk_over = __syncthreads_or(chunk_over);
-                if (warp == 0) {
-                    double v = s_w[lane];
-                    v = warp_min(v);
-                    if (lane == 0) s_vals[2 * S + 3] = v;
+                constexpr int PB = kBins / kT;
+                int v[PB], tsum = 0, occ = 0;
+#pragma unroll
+                for (int q = 0; q < PB; ++q) {
+                    v[q] = s_hist[tid * PB + q];
+                    tsum += v[q];
+                    occ = max(occ, v[q]);
                 }
-                if (tid == 0) {
-                    s_vals[2 * S + 0] = sums[0];
-                    s_vals[2 * S + 1] = sums[1];
-                    s_vals[2 * S + 2] = sums[2];
-                    s_vals[2 * S + 4] = sums[3];
-                    s_vals[2 * S + 5] = sums[4];
-                    s_vals[2 * S + 6] = sums[5];
-                    s_vals[2 * S + 7] = sums[6];
-                    s_vals[2 * S + 8] = sums[7];
-                    s_vals[2 * S + 9] = (double)chunk_over;
+                int total;
+                int run = block_excl_scan_i(tsum, s_iw, &total);
+#pragma unroll
+                for (int q = 0; q < PB; ++q) {
+                    s_hist[tid * PB + q] = run;
+                    run += v[q];
+                }
+                if (occ > kBinOccMax) chunk_over = 1;
+                __syncthreads();
+                if (tid <= S) {
+                    // first sorted position of every local chunk = start of its first bin
+                    const int b = tid << (kBinBits - lbits);
+                    s_lstart[tid] = (tid == S || b >= kBins) ? n_d : s_hist[b];
+                }
+                __syncthreads();
+                if (__syncthreads_or(chunk_over)) {
+                    chunk_over = 1;
+                    n_d = 0;   // abandon: skip the sort, the flag travels with the next exchange
+                    if (tid <= S) s_lstart[tid] = 0;
                 }
             }
-            PROF_MARK(9);   // phase B: block sums
-            team_exchange(tm, s_vals, KW, s_gather);   // barrier 2
+            // ---- pass 2: scatter (sub key, arrival) into bin order
+            for (int e = tid; e < n_d; e += kT) {
+                const unsigned key = s_karr[e];
+                const int slot = atomicAdd(&s_hist[key >> kSubBits], 1);
+                s_k32[slot] = ((key & ((1u << kSubBits) - 1u)) << 14) | (unsigned)e;
+            }
+            __syncthreads();
+            // ---- pass 3: order inside each bin (all pairs; ~2 records per bin on average)
+            for (int e = tid; e < n_d; e += kT) {
+                const unsigned key = s_karr[e];
+                const int bin = (int)(key >> kSubBits);
+                const unsigned sub = key & ((1u << kSubBits) - 1u);
+                const int st = (bin > 0) ? s_hist[bin - 1] : 0, en = s_hist[bin];
+                int rank = 0;
+                for (int o = st; o < en; ++o) {
+                    const unsigned v = s_k32[o];
+                    const unsigned sub2 = v >> 14;
+                    const int e2 = (int)(v & 0x3fffu);
+                    if (e2 == e) continue;
+                    bool lt = sub2 < sub;
+                    if (sub2 == sub) {
+                        // same 30-bit key: decide on the exact values, then on the arrival index
+                        const double xa = ld_rec_x(&Gn[my_base + arrival_slot(s_off, G, CP, e)]);
+                        const double xb = ld_rec_x(&Gn[my_base + arrival_slot(s_off, G, CP, e2)]);
+                        if (xb == xa) {
+                            key_ties++;
+                            lt = e2 < e;
+                        } else {
+                            lt = xb < xa;
+                        }
+                    }
+                    if (lt) rank++;
+                }
+                s_e[st + rank] = (unsigned short)e;
+            }
+            __syncthreads();
+            PROF_MARK(7);   // phase B sort
         }   // time loop
-        PROF_MARK(10);
+        PROF_MARK(8);
 
         // ---------------- tail (:540-562, Q6), dense positions
         if (status == 0) {
             const int T = NOBS - 1;
             const double S_T = s_S[T % kMaxLagF];
-            int* s_offT = (int*)s_union;   // [ND + 2] dense chunk offsets of generation T
-            int* s_offI = s_offT + (ND + 2);
+            __syncthreads();
+            if (tid == 0) s_vals[0] = 0.0;
+            team_exchange(tm, s_vals, 1, s_g1);   // the dense maps of generation T are complete
+            const int* didT = w.did + (size_t)(LAG - 1) * N;
+            const double* shT = w.dsh + (size_t)(LAG - 1) * N;
             for (int k = 0; k < LAG; ++k) {
                 const int ip = T - k;
-                __syncthreads();
-                for (int q = tid; q <= ND; q += kThreads) {
-                    s_offT[q] = __ldcg(&OFFS(T)[q]);
-                    s_offI[q] = __ldcg(&OFFS(ip)[q]);
-                }
-                __syncthreads();
                 double tacc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
                 const double S_ip = s_S[ip % kMaxLagF];
                 const double y1 = obs_wrap(obs, ip - 1, NOBS);
-                const double* shT = w.shtail + (size_t)(T - (NOBS - LAG)) * NV;
-                const double* shI = w.shtail + (size_t)(ip - (NOBS - LAG)) * NV;
-                for (int j = p0 + tid; j < p1; j += kThreads) {
-                    // dense -> virtual at time T and at time ip
-                    int lo2 = 0, hi2 = ND - 1;
-                    while (lo2 < hi2) {
-                        const int mid = (lo2 + hi2 + 1) >> 1;
-                        if (s_offT[mid] <= j) lo2 = mid;
-                        else hi2 = mid - 1;
-                    }
-                    const int vpT = lo2 * kCap + (j - s_offT[lo2]);
-                    lo2 = 0;
-                    hi2 = ND - 1;
-                    while (lo2 < hi2) {
-                        const int mid = (lo2 + hi2 + 1) >> 1;
-                        if (s_offI[mid] <= j) lo2 = mid;
-                        else hi2 = mid - 1;
-                    }
-                    const int vpI = lo2 * kCap + (j - s_offI[lo2]);
-                    int b = vpT, bprev = vpT;
+                const double* shI = w.dsh + (size_t)(ip - (NOBS - LAG)) * N;
+                for (int j = p0 + tid; j < p1; j += kT) {
+                    int b = __ldcg(&didT[j]), bprev = b;
                     for (int h = 0; h < k; ++h) {
                         bprev = b;
-                        b = ld_rec(&GEN(T - h)[b]).b[0];
+                        b = ld_rec_b(&GEN(T - h)[b], 0);
                     }
-                    const double curr = ld_rec(&GEN(ip)[b]).x;
-                    double sT = __ldcg(&shT[vpT]);
+                    const double curr = ld_rec_x(&GEN(ip)[b]);
+                    double sT = __ldcg(&shT[j]);
                     if (!isfinite(sT)) sT = 0.0;
                     tacc[0] += (sT / S_T) * curr;
                     if (k >= 1) {
-                        const double next = ld_rec(&GEN(ip + 1)[bprev]).x;
+                        const double next = ld_rec_x(&GEN(ip + 1)[bprev]);
                         double sq, g[4];
                         sv_score_tail(c, curr, next, y1, sq, g);
-                        double si = __ldcg(&shI[vpI]);
+                        double si = __ldcg(&shI[j]);
                         if (!isfinite(si)) si = 0.0;
                         const double wi = si / S_ip;
                         tacc[1] += g[0] * wi;
@@ -1089,11 +1242,9 @@ __global__ void __launch_bounds__(kThreads, 1) sv_fast_kernel(SvArgs a) {
                 }
                 block_sum<5>(tacc, s_red);
                 if (tid < 5) s_vals[tid] = tacc[tid];
-                double* s_g2 = (double*)(s_offI + (ND + 2));
-                s_g2 = (double*)(((size_t)s_g2 + 15) & ~(size_t)15);
-                team_exchange(tm, s_vals, 5, s_g2);
+                team_exchange(tm, s_vals, 5, s_g1);
                 if (warp < 5) {
-                    const double s = gathered_sum(s_g2, 5, warp, G, lane);
+                    const double s = gathered_sum(s_g1, 5, warp, G, lane);
                     if (lane == 0) s_tot[warp] = s;
                 }
                 __syncthreads();
@@ -1121,7 +1272,6 @@ __global__ void __launch_bounds__(kThreads, 1) sv_fast_kernel(SvArgs a) {
                 o_diag[kDiagWavefront] = 0;
                 o_diag[kDiagTrajIdx] = 0;
                 o_diag[kDiagKernel] = 2;
-                o_diag[kDiagFastInfo] = fail_info;
             }
             if (tid < 16 && status == 0) {
                 a.hess1[(size_t)prob * 16 + tid] = 0.0;
@@ -1129,59 +1279,71 @@ __global__ void __launch_bounds__(kThreads, 1) sv_fast_kernel(SvArgs a) {
             }
         }
         {
-            double nt[3] = {(double)near_ties, (double)key_ties2, 0.0};
+            double nt[3] = {(double)near_ties, (double)key_ties, 0.0};
             block_sum<3>(nt, s_red);
-            int mc = max_chunk;
-            mc = warp_max(mc);
-            __syncthreads();
-            if (lane == 0) s_iw[warp] = mc;
+            int mo = warp_max(max_occ);
+            if (lane == 0) s_iw[warp] = mo;
             __syncthreads();
             if (tid == 0) {
-                int m2 = 0;
-                for (int q = 0; q < nwarp; ++q) m2 = max(m2, s_iw[q]);
+                for (int q = 0; q < kNW; ++q) mo = max(mo, s_iw[q]);
                 s_vals[0] = nt[0];
                 s_vals[1] = nt[1];
-                s_vals[2] = (double)m2;
-                s_vals[3] = 0.0;
+                s_vals[2] = (double)mo;
+                s_vals[3] = (double)max_arr;
             }
-            double* s_g2 = (double*)s_union;
-            team_exchange(tm, s_vals, 4, s_g2);
+            team_exchange(tm, s_vals, 4, s_g1);
             if (warp < 2) {
-                const double s = gathered_sum(s_g2, 4, warp, G, lane);
+                const double s = gathered_sum(s_g1, 4, warp, G, lane);
                 if (lane == 0 && lead)
                     o_diag[warp == 0 ? kDiagNearTies : kDiagKeyTies] = (long long)(warp == 0 ? s : s * 0.5);
             } else if (warp == 2) {
-                const double s = gathered_max(s_g2, 4, 2, G, lane);
+                const double s = gathered_max(s_g1, 4, 2, G, lane);
                 if (lane == 0 && lead) o_diag[kDiagMaxBin] = (long long)s;
             } else if (warp == 3) {
-                const double s = gathered_max(s_g2, 4, 3, G, lane);
+                const double s = gathered_max(s_g1, 4, 3, G, lane);
                 if (lane == 0 && lead) o_diag[kDiagFastInfo] = fail_info | ((long long)s << 32);
             }
             __syncthreads();
         }
     }   // problem loop
-    PROF_MARK(11);   // tail + outputs
+    PROF_MARK(9);   // tail + outputs
     if (a.prof && threadIdx.x == 0)
         for (int q = 0; q < kProfSlots; ++q) a.prof[(size_t)blockIdx.x * kProfSlots + q] += prof_acc[q];
 #undef GEN
-#undef OFFS
 }
 
 }  // namespace
 
+// chunks per CTA: as many as possible (interleaving them over the value range is what balances
+// the children per CTA and the arrivals per (destination, source) run), at least 32 particles each
 int sv_fast_nsub(int N, int G) {
     const int per = (N + G - 1) / G;
-    int s = (per + kFastFill - 1) / kFastFill;
-    return s < 1 ? 1 : s;
+    int s = per / 32;
+    if (s < 1) s = 1;
+    if (s > kFastMaxSub) s = kFastMaxSub;
+    return s;
 }
 
-static int fast_nblk(int N, int G) {
-    const int per_tile = (N + G - 1) / G;
-    return (per_tile + kChildBlock - 1) / kChildBlock;
+// capacity of one (destination, source) run: twice the mean plus eight standard deviations
+int sv_fast_pair_cap(int N, int G) {
+    const int per = (N + G - 1) / G;
+    if (G == 1) return (N + 8) & ~7;
+    const double mean = (double)N / ((double)G * (double)G);
+    long long cp = (long long)(4.0 * mean + 12.0 * sqrt(mean) + 64.0);
+    if (G <= 8 && cp < 2ll * per + 64) cp = 2ll * per + 64;   // few CTAs: runs follow the parents' range
+    if (cp > N) cp = N;
+    if (cp * G < per + 1) cp = (per + G) / G + 1;   // generation 0 lives in one region
+    return (int)((cp + 7) & ~7ll);
 }
 
-size_t sv_fast_ws_bytes(int N, int G, int S, int RING, int LAG) {
-    return fast_ws_carve(S * G, G, RING, LAG, fast_nblk(N, G), nullptr, nullptr);
+// is the problem eligible (shared-memory capacity with 30 % head room)?
+int sv_fast_eligible(int N, int G) {
+    const int per = (N + G - 1) / G;
+    return (long long)per * 13 <= (long long)kCap * 10 && G <= kT;
+}
+
+size_t sv_fast_ws_bytes(int N, int G, int S, int CP, int RING, int LAG, int hist) {
+    return fast_ws_carve(N, G, S, CP, RING, LAG, hist, nullptr, nullptr);
 }
 
 size_t sv_fast_sync_bytes(int G, int n_teams) {
@@ -1190,22 +1352,10 @@ size_t sv_fast_sync_bytes(int G, int n_teams) {
 
 int sv_fast_smem_bytes(int N, int G, int S) {
     const int ND = S * G;
-    const int KW = 2 * S + kNumSums;
-    const int per_tile = (N + G - 1) / G;
-    size_t head = (size_t)(ND + (ND + 1) + (ND + 1)) * sizeof(double) +
-                  (size_t)(ND + (ND + 1) + (ND + 1) + ND + kLutCells) * sizeof(int) + 32;
-    const size_t viewG = (size_t)G * KW * sizeof(double);
-    const int NR = G * fast_nblk(N, G);
-    const size_t viewA = (size_t)(kWinCap + 4) * sizeof(double) + (size_t)kChildBlock * sizeof(Rec) +
-                         (size_t)(ND + 2 + per_tile) * sizeof(int);
-    const size_t viewB = (size_t)kCap * (8 + 8 + 16) + (size_t)(kFineBins + 8) * sizeof(int) +
-                         (size_t)2 * kCap * sizeof(unsigned short) + (size_t)(2 * NR + 8) * sizeof(int);
-    const size_t viewT = (size_t)2 * (ND + 2) * sizeof(int) + 16 + (size_t)G * 5 * sizeof(double);
-    size_t v = viewG;
-    if (viewA > v) v = viewA;
-    if (viewB > v) v = viewB;
-    if (viewT > v) v = viewT;
-    return (int)(head + v + 64);
+    size_t b = (size_t)kCap * 8 + (size_t)((ND + 3) & ~1) * 8 + (size_t)kCap * 4 * 2 +
+               (size_t)(kBins + 8) * 4 + (size_t)kCap * 2 + (size_t)kLutCells * 2 + (size_t)(G + 1) * 4;
+    (void)N;
+    return (int)(b + 64);
 }
 
 cudaError_t sv_fast_launch(const SvArgs& a, int grid, cudaStream_t stream) {
@@ -1213,7 +1363,7 @@ cudaError_t sv_fast_launch(const SvArgs& a, int grid, cudaStream_t stream) {
     cudaError_t err = cudaFuncSetAttribute(sv_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (err != cudaSuccess) return err;
     void* kargs[] = {(void*)&a};
-    return cudaLaunchCooperativeKernel((void*)sv_fast_kernel, dim3(grid), dim3(kThreads), kargs, smem, stream);
+    return cudaLaunchCooperativeKernel((void*)sv_fast_kernel, dim3(grid), dim3(kT), kargs, smem, stream);
 }
 
 }  // namespace pmmh

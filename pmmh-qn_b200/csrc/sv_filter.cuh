@@ -11,9 +11,9 @@ constexpr int kSvThreads = 1024;         // threads per CTA (1 CTA per SM)
 constexpr int kStageDoubles = 12288;     // smem staging window for the cumulative weights
 constexpr int kBinCap = 4096;            // max occupancy of one sort bin before we give up
 constexpr int kMaxAllgatherHost = 48;    // must equal kMaxAllgather (common.cuh)
-constexpr int kFastCap = 4096;           // exchange kernel: records per chunk (smem sort capacity)
-constexpr int kFastFill = 2400;          // exchange kernel: target average chunk occupancy
-constexpr int kFastMaxSub = 6;           // exchange kernel: at most this many chunks per CTA
+constexpr int kFastThreads = 512;        // exchange kernel: threads per CTA (128 registers each)
+constexpr int kFastCap = 10240;          // exchange kernel: arrivals per CTA and generation (smem capacity)
+constexpr int kFastMaxSub = 8;           // exchange kernel: at most this many chunks per CTA
 
 constexpr int kProfSlots = 16;
 
@@ -28,7 +28,7 @@ enum SvDiag {
     kDiagWavefront = 4,    // bpf parity mode: max dependency-chain depth
     kDiagTrajIdx = 5,      // bpf: sampled trajectory index (Q10)
     kDiagKernel = 6,       // which kernel produced the outputs: 1 general, 2 exchange
-    kDiagFastInfo = 7,     // exchange kernel: reason (1 run, 2 chunk overflow) | step << 8 | longest run << 32
+    kDiagFastInfo = 7,     // exchange kernel: reason (1 run, 2 CTA overflow, 3 weights) | step << 8 | most arrivals << 32
     kDiagCount = 8
 };
 
@@ -37,6 +37,7 @@ struct SvArgs {
     int G, n_teams;
     int NB;          // sort bins (general kernel)
     int NSUB;        // exchange kernel: chunks per CTA
+    int CP;          // exchange kernel: capacity of one (destination, source) run
     int only_failed; // general kernel: only run problems whose diag status is 1 (fallback pass)
     int RING;        // ring depth of the X / A / R histories (LAG + 1), or NOBS with full history
     int mode, hess;
@@ -117,7 +118,9 @@ int sv_dynamic_smem_bytes(int G);
 
 // exchange kernel (sv_fast.cu)
 int sv_fast_nsub(int N, int G);
-size_t sv_fast_ws_bytes(int N, int G, int S, int RING, int LAG);
+int sv_fast_pair_cap(int N, int G);
+int sv_fast_eligible(int N, int G);
+size_t sv_fast_ws_bytes(int N, int G, int S, int CP, int RING, int LAG, int hist);
 size_t sv_fast_sync_bytes(int G, int n_teams);
 int sv_fast_smem_bytes(int N, int G, int S);
 cudaError_t sv_fast_launch(const SvArgs& a, int grid, cudaStream_t stream);
