@@ -115,14 +115,14 @@ int sv_make_plan(int nobs, int n, int lag, int batch, int hess, int mode, int ha
     if (mode == pmmh::kSvFlps && !hess && g_sv_algorithm != 1 && pmmh::sv_fast_eligible(n, G)) {
         const int S = pmmh::sv_fast_nsub(n, G);
         const int CP = pmmh::sv_fast_pair_cap(n, G);
-        const long long nv = (long long)G * G * CP;
+        const long long nv = (long long)G * G * (pmmh::kFastThreads / 32) * CP;
         if (nv < (1ll << 31) && pmmh::sv_fast_smem_bytes(n, G, S) <= kMaxDynSmem &&
             2 * S + 10 <= pmmh::kMaxAllgatherHost) {
             p->use_fast = 1;
             p->NSUB = S;
             p->CP = CP;
             p->fast_sync_bytes = pmmh::sv_fast_sync_bytes(G, n_teams);
-            p->fast_team_stride = pmmh::sv_fast_ws_bytes(n, G, S, CP, p->RING, lag, have_hist);
+            p->fast_team_stride = pmmh::sv_fast_ws_bytes(n, G, S, CP, lag, have_hist);
             p->fast_total = p->fast_sync_bytes + (size_t)n_teams * p->fast_team_stride;
             if (p->fast_total > p->total) p->total = p->fast_total;
         }

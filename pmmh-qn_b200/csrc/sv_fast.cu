@@ -59,10 +59,13 @@ constexpr int kLutCells = 2048;
 constexpr int kMaxLagF = 64;
 constexpr int kSlotW = kMaxAllgather;    // doubles per CTA in the exchange buffers
 constexpr int kNumSums = 10;             // fx, m1, m2, minx, lag[5], flag
-constexpr int kRounds = 4;               // children per thread and tile
+constexpr int kRounds = (kT >= 1024) ? 2 : 4;   // children per thread in flight (phase A)
+constexpr int kB1 = (kT >= 1024) ? 2 : 4;       // arrivals per thread in flight (phase B pass 1)
+constexpr int kB2 = (kT >= 1024) ? 4 : 8;       // look-ups per thread in flight (fixed-lag terms)
 constexpr int kTile = kT * kRounds;
 constexpr int kBinOccMax = 1024;         // a fuller bin means a degenerate cloud: abandon
 constexpr int kMaxSub = kFastMaxSub;
+constexpr int kPHint = 2 * kCap / 32;   // parent hints cover this many blocks of 32 children
 
 static_assert(kCap <= 16384, "arrival indices are packed into 14 bits");
 static_assert(kBins % kT == 0, "bin scan layout");
@@ -99,28 +102,41 @@ __device__ __forceinline__ double ld_rec_x(const Rec* p) { return __ldcg(&p->x);
 __device__ __forceinline__ int ld_rec_b(const Rec* p, int k) { return __ldcg(&p->b[k]); }
 
 struct FastWs {
-    Rec* rec;      // [RING][G * G * CP]  generation tables; id = (dest * G + source) * CP + rank
-    int* cnt;      // [2][G][G]           arrivals per (destination, source), by generation parity
-    int* did;      // [LAG][N]            id of the particle at every dense position (last LAG gens)
-    double* dsh;   // [LAG][N]            its shifted weight
-    int* dpos;     // [2][G * G * CP]     dense position of every id (history output only)
-    double* lev;   // [ND + 2]            target cumulative mass at every chunk boundary
+    Rec* mail;       // [2][G * NR * CW]   child records by generation parity; NR = G * kNW runs per
+                     //                    destination: slot = ((dest * G + source) * kNW + warp) * CW + rank
+    int* cnt;        // [2][G][NR]         arrivals per (destination, source, warp)
+    int* b4tab;      // [RB4][G * kCap]    compact tables written by the destination in arrival order
+    double2* xptab;  // [RXP][G * kCap]    (index = compact id = dest * kCap + arrival): id 4 steps back,
+    int* b1tab;      // [LAG][G * kCap]    (value, parent value), parent id (last LAG generations)
+    int* did;        // [LAG][N]           compact id of the particle at every dense position (last LAG gens)
+    double* dsh;     // [LAG][N]           its shifted weight
+    int* dpos;       // [2][G * kCap]      dense position of every compact id (history output only)
+    double* lev;     // [ND + 2]           target cumulative mass at every chunk boundary
 };
 
-__host__ __device__ inline size_t fast_ws_carve(int N, int G, int S, int CP, int RING, int LAG, int hist,
-                                                char* base, FastWs* w) {
-    const size_t NV = (size_t)G * G * CP;
+__host__ __device__ inline int fast_rb4(int LAG) {
+    const int K = LAG - 2;
+    return (K > 4 ? K - 4 : 0) + 2;
+}
+
+__host__ __device__ inline size_t fast_ws_carve(int N, int G, int S, int CW, int LAG, int hist, char* base,
+                                                FastWs* w) {
+    const size_t NVM = (size_t)G * G * kNW * CW;
+    const size_t NC = (size_t)G * kCap;
     size_t off = 0;
 #define PMMH_CARVE(field, type, count)                   \
     do {                                                 \
         if (w) w->field = (type*)(base + off);           \
         off += sv_align((size_t)(count) * sizeof(type)); \
     } while (0)
-    PMMH_CARVE(rec, Rec, (size_t)RING * NV);
-    PMMH_CARVE(cnt, int, (size_t)2 * G * G);
+    PMMH_CARVE(mail, Rec, 2 * NVM);
+    PMMH_CARVE(cnt, int, (size_t)2 * G * G * kNW);
+    PMMH_CARVE(b4tab, int, (size_t)fast_rb4(LAG) * NC);
+    PMMH_CARVE(xptab, double2, (size_t)(LAG + 1) * NC);
+    PMMH_CARVE(b1tab, int, (size_t)LAG * NC);
     PMMH_CARVE(did, int, (size_t)LAG * N);
     PMMH_CARVE(dsh, double, (size_t)LAG * N);
-    PMMH_CARVE(dpos, int, hist ? 2 * NV : 1);
+    PMMH_CARVE(dpos, int, hist ? 2 * NC : 1);
     PMMH_CARVE(lev, double, (size_t)S * G + 2);
 #undef PMMH_CARVE
     return off;
@@ -293,8 +309,10 @@ __device__ __forceinline__ double logw_e(double x, double e, double half_y2) {
 }
 
 // chunk k of the sorted generation -> (owning CTA, local chunk index); mirrored on odd rounds
-__device__ __forceinline__ int chunk_owner(int k, int G) {
-    const int l = k / G, r = k - l * G;
+// k / G for 0 <= k < 65536 with gm = ceil(2^32 / G)
+__device__ __forceinline__ int div_g(int k, unsigned gm) { return (int)__umulhi((unsigned)k, gm); }
+__device__ __forceinline__ int chunk_owner(int k, int G, unsigned gm) {
+    const int l = div_g(k, gm), r = k - l * G;
     return (l & 1) ? (G - 1 - r) : r;
 }
 __device__ __forceinline__ int chunk_of(int l, int rank, int G) {
@@ -319,38 +337,50 @@ __device__ __forceinline__ int first_child_above(double c, double u, int N, bool
     return fc;
 }
 
-// arrival index -> slot inside the destination region (runs of the G sources, CP apart)
-__device__ __forceinline__ int arrival_slot(const int* s_off, int G, int CP, int e) {
-    int lo = 0, hi = G - 1;   // largest s with s_off[s] <= e
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (s_off[mid] <= e) lo = mid;
-        else hi = mid - 1;
+// arrival index -> slot inside the destination region (NR runs, CW apart).  s_hint[e >> 3] is
+// the run that holds arrival (e & ~7), so the walk below is a step or two.
+__device__ __forceinline__ int arrival_slot(const unsigned short* s_off, const unsigned short* s_hint, int CW,
+                                            int e) {
+    int r = s_hint[e >> 3];
+    while ((int)s_off[r + 1] <= e) ++r;
+    return r * CW + (e - (int)s_off[r]);
+}
+// builds s_hint for arrivals [0, n_d) (all threads; the caller synchronises)
+__device__ __forceinline__ void build_hints(const unsigned short* s_off, unsigned short* s_hint, int NR, int n_d) {
+    for (int h = threadIdx.x; h <= (n_d >> 3); h += blockDim.x) {
+        const int e = h << 3;
+        int lo = 0, hi = NR - 1;   // largest r with s_off[r] <= e
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if ((int)s_off[mid] <= e) lo = mid;
+            else hi = mid - 1;
+        }
+        s_hint[h] = (unsigned short)lo;
     }
-    return lo * CP + (e - s_off[lo]);
 }
 
 // development instrumentation: cycles per phase, accumulated by thread 0 of every CTA
-#define PROF_MARK(slot)                          \
-    do {                                         \
-        if (a.prof && threadIdx.x == 0) {        \
-            const long long now__ = clock64();   \
-            prof_acc[slot] += now__ - prof_t;    \
-            prof_t = now__;                      \
-        }                                        \
+#define PROF_MARK(slot)                                                          \
+    do {                                                                         \
+        if (a.prof && threadIdx.x == 0) {                                        \
+            const long long now__ = clock64();                                   \
+            a.prof[(size_t)blockIdx.x * kProfSlots + (slot)] += now__ - prof_t;  \
+            prof_t = now__;                                                      \
+        }                                                                        \
     } while (0)
 
 __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
-    long long prof_acc[kProfSlots];
     long long prof_t = clock64();
-#pragma unroll
-    for (int q = 0; q < kProfSlots; ++q) prof_acc[q] = 0;
     extern __shared__ __align__(32) unsigned char dsm_raw[];
-    const int N = a.N, NOBS = a.NOBS, LAG = a.LAG, G = a.G, RING = a.RING;
-    const int S = a.NSUB, ND = S * G, CP = a.CP;
+    const int N = a.N, NOBS = a.NOBS, LAG = a.LAG, G = a.G;
+    const int S = a.NSUB, ND = S * G, CW = a.CP, NR = G * kNW;
     const int KW = 2 * S + kNumSums;    // doubles per CTA per exchange
-    const size_t NV = (size_t)G * G * CP;
+    const size_t NVM = (size_t)G * NR * CW;   // mailbox records per generation
+    const size_t NC = (size_t)G * kCap;       // compact ids per generation
+    const int K = LAG - 2;                    // the fixed-lag terms need the ancestor K steps back
+    const int RB4 = fast_rb4(LAG), RXP = LAG + 1;
     const int per_tile = (N + G - 1) / G;
+    const unsigned gmagic = (unsigned)((0x100000000ull + (unsigned)G - 1u) / (unsigned)G);
     int lbits = 0;
     while ((1 << lbits) < S) ++lbits;
     const int kb = kKeyBits - lbits;           // key bits inside a chunk
@@ -358,13 +388,15 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
 
     // ---- dynamic shared memory
     double* s_sh = (double*)dsm_raw;                                  // [kCap]  arrival order: shifted weight
-    double* s_z = s_sh + kCap;                                        // [ND + 2] splitters in z space
-    unsigned* s_karr = (unsigned*)(s_z + ((ND + 3) & ~1));            // [kCap]  arrival order: key
+    unsigned* s_karr = (unsigned*)(s_sh + kCap);                      // [kCap]  arrival order: key
     unsigned* s_k32 = s_karr + kCap;                                  // [kCap]  bin order: (sub key, arrival)
     int* s_hist = (int*)(s_k32 + kCap);                               // [kBins + 8]
     unsigned short* s_e = (unsigned short*)(s_hist + kBins + 8);      // [kCap]  sorted position -> arrival
     unsigned short* s_lut = s_e + kCap;                               // [kLutCells]
-    int* s_off = (int*)(s_lut + kLutCells);                           // [G + 1] arrival runs
+    unsigned short* s_hint = s_lut + kLutCells;                       // [kCap / 8 + 8] arrival -> run hints
+    unsigned short* s_phint = s_hint + (kCap / 8 + 8);                // [kPHint + 8] child block -> parent hints
+    double* s_z = (double*)(s_phint + (kPHint + 8));                  // [ND + 2] splitters in z space
+    unsigned short* s_off = (unsigned short*)(s_z + (ND + 2));        // [NR + 2] arrival runs
     //   views of the s_karr region (dead between pass 2 of phase B and the next pass 1)
     double* s_gather = (double*)s_karr;                               // [G * KW] exchange output
     int* s_fc = (int*)s_karr;                                         // [kCap]  sorted position -> end of its children
@@ -376,7 +408,8 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
     double* s_g1 = (double*)s_k32;                                    // [G * 8]  small exchanges
     //   views of the s_hist region (phase A)
     unsigned short* s_wh = (unsigned short*)s_hist;                   // [kNW][G] per-warp destination counts
-    int* s_dbase = (int*)(s_wh + ((kNW * G + 1) & ~1));               // [G]
+    //   views of the s_k32 region (phase B pass 1)
+    int* s_hb = (int*)s_k32;                                          // [kCap]  arrival order: first look-up id
 
     __shared__ double s_vals[kSlotW];
     __shared__ double s_tot[16];
@@ -407,9 +440,13 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
     const int p0 = min(N, me * per_tile), p1 = min(N, p0 + per_tile);
 
     FastWs w;
-    fast_ws_carve(N, G, S, CP, RING, LAG, a.Xhist != nullptr, wsbase, &w);
-#define GEN(t) (w.rec + (size_t)((t) % RING) * NV)
-    const size_t my_base = (size_t)me * G * CP;   // first id of my region
+    fast_ws_carve(N, G, S, CW, LAG, a.Xhist != nullptr, wsbase, &w);
+#define MAIL(t) (w.mail + (size_t)((t) & 1) * NVM)
+#define B4T(t) (w.b4tab + (size_t)((t) % RB4) * NC)
+#define XPT(t) (w.xptab + (size_t)((t) % RXP) * NC)
+#define B1T(t) (w.b1tab + (size_t)((t) - (NOBS - LAG)) * NC)
+    const size_t my_base = (size_t)me * NR * CW;   // first mailbox slot of my region
+    const int my_cid = me * kCap;                  // first compact id of my region
 
     for (int prob = team_id; prob < a.B; prob += a.n_teams) {
         const double* obs = a.obs + (size_t)prob * a.obs_stride;
@@ -486,14 +523,16 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
             }
             s_lstart[S] = acc0;
         }
-        for (int s = tid; s <= G; s += kT) s_off[s] = 0;
         __syncthreads();
         n_d = s_lstart[S];
-        for (int s = 1 + tid; s <= G; s += kT) s_off[s] = n_d;   // generation 0: one run
+        for (int r = tid; r <= NR; r += kT) s_off[r] = (r == 0) ? 0 : (unsigned short)n_d;   // generation 0: one run
+        for (int h = tid; h <= (n_d >> 3); h += kT) s_hint[h] = 0;
         for (int q = tid; q < n_d; q += kT) {
             s_sh[q] = 1.0;
             s_e[q] = (unsigned short)q;
-            st_rec(&GEN(0)[my_base + q], x0, x0, 0, 0, 0, 0);
+            st_rec(&MAIL(0)[my_base + q], x0, x0, 0, 0, 0, 0);
+            B4T(0)[my_cid + q] = 0;
+            XPT(0)[my_cid + q] = make_double2(x0, x0);
         }
         __syncthreads();
         if (lead) {
@@ -588,7 +627,7 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
                 double wsum = 0.0;
                 int csum = 0, cmax = 0;
                 for (int k = k0; k < k1; ++k) {
-                    const int cta = chunk_owner(k, G), l = k / G;
+                    const int cta = chunk_owner(k, G, gmagic), l = div_g(k, gmagic);
                     wsum += s_gather[cta * KW + 2 * l];
                     const int cc = (int)s_gather[cta * KW + 2 * l + 1];
                     csum += cc;
@@ -603,7 +642,7 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
                 int runc = cpre;
                 double last = wpre;
                 for (int k = k0; k < k1; ++k) {
-                    const int cta = chunk_owner(k, G), l = k / G;
+                    const int cta = chunk_owner(k, G, gmagic), l = div_g(k, gmagic);
                     last = runw;
                     runw += s_gather[cta * KW + 2 * l];
                     runc += (int)s_gather[cta * KW + 2 * l + 1];
@@ -612,7 +651,7 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
                 runw = wpre;
                 runc = cpre;
                 for (int k = k0; k < k1; ++k) {
-                    const int cta = chunk_owner(k, G), l = k / G;
+                    const int cta = chunk_owner(k, G, gmagic), l = div_g(k, gmagic);
                     s_P[k] = fmax(runw, floorw);
                     s_coff[k] = runc;
                     runw += s_gather[cta * KW + 2 * l];
@@ -654,25 +693,24 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
             __syncthreads();
             // dense-position maps: history outputs, and the last LAG generations for the tail
             if (Xh != nullptr || i >= NOBS - LAG) {
-                const Rec* Gi = GEN(i);
-                int* dposc = w.dpos + (size_t)(i & 1) * NV;
-                const int* dposp = w.dpos + (size_t)((i + 1) & 1) * NV;
+                const Rec* Gi = MAIL(i);
+                int* dposc = w.dpos + (size_t)(i & 1) * NC;
+                const int* dposp = w.dpos + (size_t)((i + 1) & 1) * NC;
                 for (int q = tid; q < n_d; q += kT) {
                     int l = 0;
                     while (l + 1 < S && s_lstart[l + 1] <= q) ++l;
                     const int dense = s_lcoff[l] + (q - s_lstart[l]);
                     const int e = s_e[q];
-                    const size_t id = my_base + arrival_slot(s_off, G, CP, e);
                     if (i >= NOBS - LAG) {
                         const size_t sl = (size_t)(i - (NOBS - LAG)) * N + dense;
-                        w.did[sl] = (int)id;
+                        w.did[sl] = my_cid + e;
                         w.dsh[sl] = s_sh[e];
                     }
                     if (Xh) {
-                        const Rec r = ld_rec(&Gi[id]);
+                        const Rec r = ld_rec(&Gi[my_base + arrival_slot(s_off, s_hint, CW, e)]);
                         Xh[(size_t)i * N + dense] = r.x;
                         Ah[(size_t)i * N + dense] = (i == 0) ? dense : __ldcg(&dposp[r.b[0]]);
-                        dposc[id] = dense;
+                        dposc[my_cid + e] = dense;
                     }
                 }
             }
@@ -851,50 +889,84 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
                 }
             }
             for (int q = tid; q < kNW * G; q += kT) s_wh[q] = 0;
-            for (int q = tid; q < G; q += kT) s_dbase[q] = 0;
+            __syncthreads();
+            // parent hints: s_phint[b] = sorted position of the parent of child 32 b (CTA order)
+            const bool use_ph = s_lco[S] <= 32 * kPHint;
+            if (use_ph) {
+                for (int q = tid; q < n_d; q += kT) {
+                    int l = 0;
+                    while (l + 1 < S && s_lstart[l + 1] <= q) ++l;
+                    const int ca = (q == s_lstart[l]) ? s_lLB[l] : s_fc[q - 1];
+                    const int cb = s_fc[q];
+                    if (cb > ca) {
+                        const int ta = s_lco[l] + (ca - s_lLB[l]), tb = s_lco[l] + (cb - s_lLB[l]);
+                        for (int bb = (ta + 31) >> 5; (bb << 5) < tb; ++bb) s_phint[bb] = (unsigned short)q;
+                    }
+                }
+            }
             __syncthreads();
             PROF_MARK(3);   // children ranges
 
             // =========== phase A: children of my parents, in birth order: propagate (:354-358),
-            //             route, write the record into the destination's region
+            //             route, write the record into the destination's region.  Every warp owns
+            //             a contiguous share of the children and its own run per destination:
+            //             no block-wide synchronisation in this phase.
             int pair_over = 0;
             {
                 int n_c = s_lco[S];
-                if (n_c > 60000) {   // per-warp run offsets are 16 bit: a degenerate cloud, abandon
+                if (n_c > 60000 * kNW) {   // per-warp run counters are 16 bit: a degenerate cloud, abandon
                     pair_over = 1;
                     n_c = 0;
                 }
                 const double* Ui = U + (size_t)inext * N;
-                const Rec* Gi = GEN(i);
-                Rec* Gn = GEN(inext);
+                const Rec* Gi = MAIL(i);
+                Rec* Gn = MAIL(inext);
                 unsigned short* my_wh = s_wh + warp * G;
-                for (int tile0 = 0; tile0 < n_c; tile0 += kTile) {
-                    double xn[kRounds], xp[kRounds];
-                    int pb0[kRounds], pb1[kRounds], pb2[kRounds], pb3[kRounds];
-                    int dr[kRounds];   // destination << 16 | rank inside this warp's run
+                // rounds of 32 consecutive children are dealt to the warps round-robin: the runs a
+                // warp writes then do not follow the value range of one stretch of parents
+                const int tw1 = n_c;
+                for (int t0 = warp * 32; t0 < n_c; t0 += 32 * kNW * kRounds) {
+                    double un[kRounds];
+                    Rec pr[kRounds];
+                    int pcid[kRounds];
 #pragma unroll
                     for (int r = 0; r < kRounds; ++r) {
-                        const int t = tile0 + warp * (32 * kRounds) + r * 32 + lane;
-                        const bool valid = t < n_c;
-                        int d = G;   // inactive lanes never match a destination
-                        dr[r] = -1;
-                        if (valid) {
+                        const int t = t0 + r * 32 * kNW + lane;
+                        pcid[r] = -1;
+                        un[r] = 0.0;
+                        pr[r].x = 0.0;
+                        pr[r].b[0] = pr[r].b[1] = pr[r].b[2] = 0;
+                        if (t < tw1) {
                             int l = 0;
                             while (l + 1 < S && s_lco[l + 1] <= t) ++l;
                             const int j = s_lLB[l] + (t - s_lco[l]);
-                            const double un = ld_stream_f64(&Ui[j]);
+                            un[r] = ld_stream_f64(&Ui[j]);
                             // parent: first sorted position of chunk l whose children end beyond j
                             int lo2 = s_lstart[l], hi2 = s_lstart[l + 1] - 1;
+                            if (use_ph) {
+                                const int bb = t >> 5;
+                                lo2 = max(lo2, (int)s_phint[bb]);
+                                if (((bb + 1) << 5) < n_c) hi2 = min(hi2, (int)s_phint[bb + 1]);
+                            }
                             while (lo2 < hi2) {
                                 const int mid = (lo2 + hi2) >> 1;
                                 if (s_fc[mid] > j) hi2 = mid;
                                 else lo2 = mid + 1;
                             }
-                            const int pid = (int)(my_base + arrival_slot(s_off, G, CP, s_e[lo2]));
-                            const Rec pr = ld_rec(&Gi[pid]);
-                            double mean = c.mu + c.phi * (pr.x - c.mu);
-                            mean += c.sr * exp(-0.5 * pr.x) * y1;
-                            const double xnew = mean + c.sd * un;
+                            const int e = s_e[lo2];
+                            pcid[r] = my_cid + e;
+                            pr[r] = ld_rec(&Gi[my_base + arrival_slot(s_off, s_hint, CW, e)]);
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < kRounds; ++r) {
+                        const bool valid = pcid[r] >= 0;
+                        int d = G;   // inactive lanes never match a destination
+                        double xnew = 0.0;
+                        if (valid) {
+                            double mean = c.mu + c.phi * (pr[r].x - c.mu);
+                            mean += c.sr * exp(-0.5 * pr[r].x) * y1;
+                            xnew = mean + c.sd * un[r];
                             int kc = 0;
                             if (ND > 1) {
                                 const double zx = (xnew - m1) * inv_sdc;
@@ -905,71 +977,31 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
                                 while (kc + 1 < ND && zx >= s_z[kc + 1]) ++kc;
                                 while (kc > 0 && zx < s_z[kc]) --kc;
                             }
-                            d = chunk_owner(kc, G);
-                            xn[r] = xnew;
-                            xp[r] = pr.x;
-                            pb0[r] = pid;
-                            pb1[r] = pr.b[0];
-                            pb2[r] = pr.b[1];
-                            pb3[r] = pr.b[2];
+                            d = chunk_owner(kc, G, gmagic);
                         }
-                        // stable rank inside the warp: lanes with the same destination
+                        // stable rank inside the warp's run: lanes with the same destination
                         const unsigned peers = __match_any_sync(kFullMask, d);
                         if (valid) {
                             const int before = __popc(peers & ((1u << lane) - 1u));
                             const int base = my_wh[d];
                             __syncwarp(peers);
                             if (before == 0) my_wh[d] = (unsigned short)(base + __popc(peers));
-                            dr[r] = (d << 16) | (base + before);
+                            const int rank = base + before;
+                            if (rank < CW)
+                                st_rec(&Gn[(((size_t)d * G + me) * kNW + warp) * CW + rank], xnew, pr[r].x, pcid[r],
+                                       pr[r].b[0], pr[r].b[1], pr[r].b[2]);
+                            else
+                                pair_over = 1;
                         }
                         __syncwarp();
                     }
-                    __syncthreads();
-                    // stable offsets of every warp's run inside the (destination, me) run
-                    for (int d = tid; d < G; d += kT) {
-                        int base = s_dbase[d];
-                        for (int wv = 0; wv < kNW; ++wv) {
-                            const int t = s_wh[wv * G + d];
-                            s_wh[wv * G + d] = (unsigned short)base;
-                            base += t;
-                        }
-                        s_dbase[d] = base;
-                    }
-                    __syncthreads();
-#pragma unroll
-                    for (int r = 0; r < kRounds; ++r) {
-                        if (dr[r] >= 0) {
-                            const int d = dr[r] >> 16;
-                            const int rank = (int)my_wh[d] + (dr[r] & 0xffff);
-                            if (rank < CP)
-                                st_rec(&Gn[((size_t)d * G + me) * CP + rank], xn[r], xp[r], pb0[r], pb1[r],
-                                       pb2[r], pb3[r]);
-                            else {
-                                if (!pair_over) {   // diagnostics of the first overflowing run
-                                    a.hess1[(size_t)prob * 16 + 0] = (double)me;
-                                    a.hess1[(size_t)prob * 16 + 1] = (double)n_c;
-                                    a.hess1[(size_t)prob * 16 + 2] = (double)d;
-                                    a.hess1[(size_t)prob * 16 + 3] = (double)rank;
-                                    a.hess1[(size_t)prob * 16 + 4] = m1;
-                                    a.hess1[(size_t)prob * 16 + 5] = sdc;
-                                    a.hess1[(size_t)prob * 16 + 6] = S_i;
-                                    a.hess1[(size_t)prob * 16 + 7] = xn[r];
-                                    for (int q = 0; q < 8 && q < S; ++q) {
-                                        a.hess1[(size_t)prob * 16 + 8 + q] = (double)(s_lUB[q] - s_lLB[q]);
-                                        a.hess2[(size_t)prob * 16 + q] = (double)(s_lstart[q + 1] - s_lstart[q]);
-                                        a.hess2[(size_t)prob * 16 + 8 + q] = s_z[chunk_of(q, me, G)];
-                                    }
-                                }
-                                pair_over = 1;
-                            }
-                        }
-                    }
-                    __syncthreads();
-                    for (int q = tid; q < kNW * G; q += kT) s_wh[q] = 0;
-                    __syncthreads();
                 }
-                int* cn = w.cnt + (size_t)(inext & 1) * G * G;
-                for (int d = tid; d < G; d += kT) cn[(size_t)d * G + me] = min(s_dbase[d], CP);
+                __syncthreads();
+                int* cn = w.cnt + (size_t)(inext & 1) * G * NR;
+                for (int q = tid; q < kNW * G; q += kT) {
+                    const int wv = div_g(q, gmagic), d = q - wv * G;
+                    cn[(size_t)d * NR + me * kNW + wv] = min((int)s_wh[q], CW);
+                }
             }
             pair_over = __syncthreads_or(pair_over);
             PROF_MARK(4);   // children: propagate + route + write
@@ -989,22 +1021,30 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
 
             // =========== phase B: my arrivals of generation inext
             {
-                const int* cn = w.cnt + (size_t)(inext & 1) * G * G + (size_t)me * G;
+                const int* cn = w.cnt + (size_t)(inext & 1) * G * NR + (size_t)me * NR;
+                // runs of the (source, warp) pairs: thread t owns PR consecutive runs
+                const int PR = (NR + kT - 1) / kT;
+                const int r0 = min(NR, tid * PR), r1 = min(NR, r0 + PR);
+                int csum = 0;
+                for (int r = r0; r < r1; ++r) csum += __ldcg(&cn[r]);
                 int total = 0;
-                // runs of the sources (G <= kT is guaranteed by the launch: G <= SM count)
-                const int cv = (tid < G) ? __ldcg(&cn[tid]) : 0;
-                const int pre = block_excl_scan_i(cv, s_iw, &total);
-                if (tid < G) s_off[tid] = pre;
-                if (tid == 0) s_off[G] = total;
+                int run = block_excl_scan_i(csum, s_iw, &total);
+                const bool fits = total <= kCap;
+                for (int r = r0; r < r1; ++r) {
+                    s_off[r] = (unsigned short)(fits ? run : 0);
+                    run += __ldcg(&cn[r]);
+                }
+                if (tid == 0) s_off[NR] = (unsigned short)(fits ? total : 0);
                 for (int q = tid; q < kBins + 8; q += kT) s_hist[q] = 0;
                 n_d = total;
                 chunk_over = 0;
-                if (n_d > kCap) {
+                if (!fits) {
                     chunk_over = 1;
                     n_d = 0;
                 }
                 max_arr = max(max_arr, total);
                 __syncthreads();
+                build_hints(s_off, s_hint, NR, n_d);
             }
             if (tid < S) {
                 const int k = chunk_of(tid, me, G);
@@ -1016,111 +1056,110 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
                 s_lzsc[tid] = sc;
             }
             __syncthreads();
-            const Rec* Gn = GEN(inext);
+            const Rec* Gn = MAIL(inext);
             const double yl = (inext >= LAG) ? obs[inext - LAG] : 0.0;   // Q5
-            const int K = LAG - 2;
-            const int hop0 = (K > 4) ? 3 : (K - 1);   // which carried id starts the look-ups (K >= 1)
+            const bool lagged = inext >= LAG;
+            const int hop0 = (K >= 1) ? ((K - 1) & 3) : 0;   // carried id that starts the look-ups
 #pragma unroll
             for (int q = 0; q < 9; ++q) acc[q] = 0.0;
             minx = INFINITY;
-            // ---- pass 1 (arrival order): key + histogram, weight, sums, fixed-lag terms
-            for (int e0 = 0; e0 < n_d; e0 += 4 * kT) {
-                double x[4];
-                int hb[4];
-                size_t id[4];
+            // ---- pass 1 (arrival order): compact tables, key + histogram, weight, sums
+            {
+                int* b4n = B4T(inext);
+                double2* xpn = XPT(inext);
+                int* b1n = (inext >= NOBS - LAG) ? B1T(inext) : nullptr;
+                for (int e0 = 0; e0 < n_d; e0 += kB1 * kT) {
+                    Rec rc[kB1];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const int e = e0 + r * kT + tid;
-                    x[r] = 0.0;
-                    hb[r] = 0;
-                    id[r] = 0;
-                    if (e < n_d) {
-                        id[r] = my_base + arrival_slot(s_off, G, CP, e);
-                        x[r] = ld_rec_x(&Gn[id[r]]);
-                        if (inext >= LAG && K >= 1) hb[r] = ld_rec_b(&Gn[id[r]], hop0);
+                    for (int r = 0; r < kB1; ++r) {
+                        const int e = e0 + r * kT + tid;
+                        rc[r].x = 0.0;
+                        if (e < n_d) rc[r] = ld_rec(&Gn[my_base + arrival_slot(s_off, s_hint, CW, e)]);
+                    }
+#pragma unroll
+                    for (int r = 0; r < kB1; ++r) {
+                        const int e = e0 + r * kT + tid;
+                        if (e < n_d) {
+                            const double xv = rc[r].x;
+                            b4n[my_cid + e] = rc[r].b[3];
+                            xpn[my_cid + e] = make_double2(xv, rc[r].xpar);
+                            if (b1n) b1n[my_cid + e] = rc[r].b[0];
+                            s_hb[e] = (hop0 == 3) ? rc[r].b[3] : ((hop0 == 2) ? rc[r].b[2] : ((hop0 == 1) ? rc[r].b[1] : rc[r].b[0]));
+                            // chunk and key
+                            int kc = 0;
+                            const double zx = (xv - m1) * inv_sdc;
+                            if (ND > 1) {
+                                const double tt = (zx - lut_lo) * lut_scale;
+                                const int cell =
+                                    (tt >= 0.0) ? ((tt < (double)kLutCells) ? (int)tt : kLutCells - 1) : 0;
+                                kc = s_lut[cell];
+                                while (kc + 1 < ND && zx >= s_z[kc + 1]) ++kc;
+                                while (kc > 0 && zx < s_z[kc]) --kc;
+                            }
+                            const int l = div_g(kc, gmagic);
+                            const double tq = (zx - s_lzlo[l]) * s_lzsc[l];
+                            unsigned kq = 0;
+                            if (tq >= 0.0) kq = (tq < key_span) ? (unsigned)tq : ((1u << kb) - 1u);
+                            const unsigned key = ((unsigned)l << kb) | kq;
+                            s_karr[e] = key;
+                            atomicAdd(&s_hist[key >> kSubBits], 1);
+                            // weight (:427-437)
+                            const double eh = exp(-0.5 * xv);
+                            double shv = exp(logw_e(xv, eh, half_y2) - shift);
+                            if (!isfinite(shv)) shv = 0.0;
+                            s_sh[e] = shv;
+                            minx = fmin(minx, xv);
+                            const double sx = shv * xv;
+                            if (isfinite(sx)) acc[0] += sx;
+                            // propagation mean of the next step (for the splitters)
+                            const double df = ((c.mu + c.phi * (xv - c.mu)) + c.sr * eh * yi) - cshift;
+                            const double sdf = shv * df;
+                            if (isfinite(sdf)) {
+                                acc[1] += sdf;
+                                acc[2] += sdf * df;
+                            }
+                            if (lagged && K == 0) {   // the pair is the record itself
+                                double sq, g[4];
+                                sv_score_main(c, rc[r].xpar, xv, yl, sq, g);
+                                acc[4] += shv * rc[r].xpar;
+                                acc[5] += g[0] * shv;
+                                acc[6] += g[1] * shv;
+                                acc[7] += g[2] * shv;
+                                acc[8] += g[3] * shv;
+                            }
+                        }
                     }
                 }
-                // fixed-lag look-ups (:445-470): ancestor LAG-2 steps back
-                double pc[4], pn[4];
-                if (inext >= LAG) {
-                    if (K == 0) {
+            }
+            // ---- fixed-lag terms (:445-470): ancestor K = LAG - 2 steps back through the compact
+            //      tables: the carried id reaches generation inext - ((K-1) % 4 + 1), then 4 at a time
+            if (lagged && K >= 1) {
+                const int g1 = inext - (hop0 + 1);
+                const int nh = (K - 1) >> 2;
+                const double2* xpk = XPT(inext - K);
+                for (int e0 = 0; e0 < n_d; e0 += kB2 * kT) {
+                    int hb[kB2];
 #pragma unroll
-                        for (int r = 0; r < 4; ++r) {
-                            const int e = e0 + r * kT + tid;
-                            pc[r] = pn[r] = 0.0;
-                            if (e < n_d) {
-                                pc[r] = __ldcg(&Gn[id[r]].xpar);
-                                pn[r] = x[r];
-                            }
-                        }
-                    } else {
-                        int tcur = inext, rem = K;
-                        while (rem > 4) {   // jump 4 generations through the carried ids
-                            tcur -= 4;
-                            rem -= 4;
-                            const int nb = (rem > 4) ? 3 : (rem - 1);
-                            const Rec* Gt = GEN(tcur);
-#pragma unroll
-                            for (int r = 0; r < 4; ++r) {
-                                const int e = e0 + r * kT + tid;
-                                if (e < n_d) hb[r] = ld_rec_b(&Gt[hb[r]], nb);
-                            }
-                        }
-                        tcur -= rem;
-                        const Rec* Gt = GEN(tcur);
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) {
-                            const int e = e0 + r * kT + tid;
-                            pc[r] = pn[r] = 0.0;
-                            if (e < n_d) {
-                                const double2 v = __ldcg((const double2*)&Gt[hb[r]]);
-                                pn[r] = v.x;
-                                pc[r] = v.y;
-                            }
-                        }
+                    for (int r = 0; r < kB2; ++r) {
+                        const int e = e0 + r * kT + tid;
+                        hb[r] = (e < n_d) ? s_hb[e] : 0;
                     }
-                }
+                    for (int h = 0; h < nh; ++h) {
+                        const int* bt = B4T(g1 - 4 * h);
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const int e = e0 + r * kT + tid;
-                    if (e < n_d) {
-                        const double xv = x[r];
-                        // chunk and key
-                        int kc = 0;
-                        const double zx = (xv - m1) * inv_sdc;
-                        if (ND > 1) {
-                            const double tt = (zx - lut_lo) * lut_scale;
-                            const int cell = (tt >= 0.0) ? ((tt < (double)kLutCells) ? (int)tt : kLutCells - 1) : 0;
-                            kc = s_lut[cell];
-                            while (kc + 1 < ND && zx >= s_z[kc + 1]) ++kc;
-                            while (kc > 0 && zx < s_z[kc]) --kc;
-                        }
-                        const int l = kc / G;
-                        const double tq = (zx - s_lzlo[l]) * s_lzsc[l];
-                        unsigned kq = 0;
-                        if (tq >= 0.0) kq = (tq < key_span) ? (unsigned)tq : ((1u << kb) - 1u);
-                        const unsigned key = ((unsigned)l << kb) | kq;
-                        s_karr[e] = key;
-                        atomicAdd(&s_hist[key >> kSubBits], 1);
-                        // weight (:427-437)
-                        const double eh = exp(-0.5 * xv);
-                        double shv = exp(logw_e(xv, eh, half_y2) - shift);
-                        if (!isfinite(shv)) shv = 0.0;
-                        s_sh[e] = shv;
-                        minx = fmin(minx, xv);
-                        const double sx = shv * xv;
-                        if (isfinite(sx)) acc[0] += sx;
-                        // propagation mean of the next step (for the splitters)
-                        const double df = ((c.mu + c.phi * (xv - c.mu)) + c.sr * eh * yi) - cshift;
-                        const double sdf = shv * df;
-                        if (isfinite(sdf)) {
-                            acc[1] += sdf;
-                            acc[2] += sdf * df;
-                        }
-                        if (inext >= LAG) {
+                        for (int r = 0; r < kB2; ++r) hb[r] = __ldcg(&bt[hb[r]]);
+                    }
+                    double2 pv[kB2];
+#pragma unroll
+                    for (int r = 0; r < kB2; ++r) pv[r] = __ldcg(&xpk[hb[r]]);
+#pragma unroll
+                    for (int r = 0; r < kB2; ++r) {
+                        const int e = e0 + r * kT + tid;
+                        if (e < n_d) {
+                            const double shv = s_sh[e];
                             double sq, g[4];
-                            sv_score_main(c, pc[r], pn[r], yl, sq, g);
-                            acc[4] += shv * pc[r];
+                            sv_score_main(c, pv[r].y, pv[r].x, yl, sq, g);
+                            acc[4] += shv * pv[r].y;
                             acc[5] += g[0] * shv;
                             acc[6] += g[1] * shv;
                             acc[7] += g[2] * shv;
@@ -1184,8 +1223,8 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
                     bool lt = sub2 < sub;
                     if (sub2 == sub) {
                         // same 30-bit key: decide on the exact values, then on the arrival index
-                        const double xa = ld_rec_x(&Gn[my_base + arrival_slot(s_off, G, CP, e)]);
-                        const double xb = ld_rec_x(&Gn[my_base + arrival_slot(s_off, G, CP, e2)]);
+                        const double xa = ld_rec_x(&Gn[my_base + arrival_slot(s_off, s_hint, CW, e)]);
+                        const double xb = ld_rec_x(&Gn[my_base + arrival_slot(s_off, s_hint, CW, e2)]);
                         if (xb == xa) {
                             key_ties++;
                             lt = e2 < e;
@@ -1221,14 +1260,14 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
                     int b = __ldcg(&didT[j]), bprev = b;
                     for (int h = 0; h < k; ++h) {
                         bprev = b;
-                        b = ld_rec_b(&GEN(T - h)[b], 0);
+                        b = __ldcg(&B1T(T - h)[b]);
                     }
-                    const double curr = ld_rec_x(&GEN(ip)[b]);
+                    const double curr = __ldcg(&XPT(ip)[b]).x;
                     double sT = __ldcg(&shT[j]);
                     if (!isfinite(sT)) sT = 0.0;
                     tacc[0] += (sT / S_T) * curr;
                     if (k >= 1) {
-                        const double next = ld_rec_x(&GEN(ip + 1)[bprev]);
+                        const double next = __ldcg(&XPT(ip + 1)[bprev]).x;
                         double sq, g[4];
                         sv_score_tail(c, curr, next, y1, sq, g);
                         double si = __ldcg(&shI[j]);
@@ -1307,9 +1346,10 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
         }
     }   // problem loop
     PROF_MARK(9);   // tail + outputs
-    if (a.prof && threadIdx.x == 0)
-        for (int q = 0; q < kProfSlots; ++q) a.prof[(size_t)blockIdx.x * kProfSlots + q] += prof_acc[q];
-#undef GEN
+#undef MAIL
+#undef B4T
+#undef XPT
+#undef B1T
 }
 
 }  // namespace
@@ -1324,16 +1364,20 @@ int sv_fast_nsub(int N, int G) {
     return s;
 }
 
-// capacity of one (destination, source) run: twice the mean plus eight standard deviations
+// capacity of one (destination, source CTA, source warp) run
 int sv_fast_pair_cap(int N, int G) {
     const int per = (N + G - 1) / G;
-    if (G == 1) return (N + 8) & ~7;
-    const double mean = (double)N / ((double)G * (double)G);
-    long long cp = (long long)(4.0 * mean + 12.0 * sqrt(mean) + 64.0);
-    if (G <= 8 && cp < 2ll * per + 64) cp = 2ll * per + 64;   // few CTAs: runs follow the parents' range
-    if (cp > N) cp = N;
-    if (cp * G < per + 1) cp = (per + G) / G + 1;   // generation 0 lives in one region
-    return (int)((cp + 7) & ~7ll);
+    const int perw = (per + kNW - 1) / kNW;   // children of one warp when the CTAs are balanced
+    long long cw;
+    if (G == 1) {
+        cw = perw + 40;
+    } else {
+        const double mean = (double)N / ((double)G * (double)G * (double)kNW);
+        cw = (long long)(4.0 * mean + 12.0 * sqrt(mean) + 32.0);
+        if (G <= 8 && cw < 2ll * perw + 40) cw = 2ll * perw + 40;   // few CTAs: runs follow the parents' range
+    }
+    if (cw * G * kNW < per + 1) cw = (per + G * kNW) / (G * kNW) + 1;   // generation 0 lives in one region
+    return (int)((cw + 7) & ~7ll);
 }
 
 // is the problem eligible (shared-memory capacity with 30 % head room)?
@@ -1342,8 +1386,8 @@ int sv_fast_eligible(int N, int G) {
     return (long long)per * 13 <= (long long)kCap * 10 && G <= kT;
 }
 
-size_t sv_fast_ws_bytes(int N, int G, int S, int CP, int RING, int LAG, int hist) {
-    return fast_ws_carve(N, G, S, CP, RING, LAG, hist, nullptr, nullptr);
+size_t sv_fast_ws_bytes(int N, int G, int S, int CW, int LAG, int hist) {
+    return fast_ws_carve(N, G, S, CW, LAG, hist, nullptr, nullptr);
 }
 
 size_t sv_fast_sync_bytes(int G, int n_teams) {
@@ -1352,8 +1396,9 @@ size_t sv_fast_sync_bytes(int G, int n_teams) {
 
 int sv_fast_smem_bytes(int N, int G, int S) {
     const int ND = S * G;
-    size_t b = (size_t)kCap * 8 + (size_t)((ND + 3) & ~1) * 8 + (size_t)kCap * 4 * 2 +
-               (size_t)(kBins + 8) * 4 + (size_t)kCap * 2 + (size_t)kLutCells * 2 + (size_t)(G + 1) * 4;
+    size_t b = (size_t)kCap * 8 + (size_t)kCap * 4 * 2 + (size_t)(kBins + 8) * 4 + (size_t)kCap * 2 +
+               (size_t)kLutCells * 2 + (size_t)(kCap / 8 + 8) * 2 + (size_t)(kPHint + 8) * 2 +
+               (size_t)(ND + 2) * 8 + (size_t)(G * kNW + 2) * 2;
     (void)N;
     return (int)(b + 64);
 }

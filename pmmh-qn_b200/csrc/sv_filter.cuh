@@ -37,7 +37,7 @@ struct SvArgs {
     int G, n_teams;
     int NB;          // sort bins (general kernel)
     int NSUB;        // exchange kernel: chunks per CTA
-    int CP;          // exchange kernel: capacity of one (destination, source) run
+    int CP;          // exchange kernel: capacity of one (destination, source CTA, source warp) run
     int only_failed; // general kernel: only run problems whose diag status is 1 (fallback pass)
     int RING;        // ring depth of the X / A / R histories (LAG + 1), or NOBS with full history
     int mode, hess;
@@ -120,7 +120,7 @@ int sv_dynamic_smem_bytes(int G);
 int sv_fast_nsub(int N, int G);
 int sv_fast_pair_cap(int N, int G);
 int sv_fast_eligible(int N, int G);
-size_t sv_fast_ws_bytes(int N, int G, int S, int CP, int RING, int LAG, int hist);
+size_t sv_fast_ws_bytes(int N, int G, int S, int CW, int LAG, int hist);
 size_t sv_fast_sync_bytes(int G, int n_teams);
 int sv_fast_smem_bytes(int N, int G, int S);
 cudaError_t sv_fast_launch(const SvArgs& a, int grid, cudaStream_t stream);
