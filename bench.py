@@ -296,12 +296,15 @@ def run_ours(args, rank, world, local_rank):
                          "frac": achieved / peak, "traffic": args.traffic_bytes,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": n * T_STEPS * BYTES_PER_PARTICLE_STEP,
-                         "kernel": "sv_pf_kernel<false>", "kernel_ms": kern_ms},
+                         "kernel": "sv_fast_kernel (exchange kernel)" if int(diag[6]) == 2 else "sv_pf_kernel<false>",
+                         "kernel_ms": kern_ms,
+                         "note": "kernel_ms = CUDA events around one pmmh_flps_sv_corr call on the launching "
+                                 "stream: the exchange kernel plus the (empty) general-kernel fallback pass"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                     "api": "ParticleMethodsCUDA.smoother(model, rvs={'rvs': pinned ndarray})"},
-            "gpu_launches": args.steps * 1,
+            "gpu_launches": args.steps * 2,
         }
         if world == 1 and not args.no_cpu_baseline:
             _, _, info = cpu_reference_throughput(1, 0)

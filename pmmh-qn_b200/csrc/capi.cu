@@ -112,7 +112,10 @@ int sv_make_plan(int nobs, int n, int lag, int batch, int hess, int mode, int ha
     p->NSUB = 0;
     p->fast_sync_bytes = p->fast_team_stride = p->fast_total = 0;
     p->CP = 0;
-    if (mode == pmmh::kSvFlps && !hess && g_sv_algorithm != 1 && pmmh::sv_fast_eligible(n, G)) {
+    // one CTA per problem (batches of small problems) has no exchange to save: the general kernel
+    // is the faster one there (measured: 8.8e9 vs 7.0e9 particle-steps/s at 1024 x N=4096)
+    const bool want_fast = (g_sv_algorithm == 2) || (g_sv_algorithm == 0 && G > 1);
+    if (mode == pmmh::kSvFlps && !hess && want_fast && pmmh::sv_fast_eligible(n, G)) {
         const int S = pmmh::sv_fast_nsub(n, G);
         const int CP = pmmh::sv_fast_pair_cap(n, G);
         const long long nv = (long long)G * G * (pmmh::kFastThreads / 32) * CP;

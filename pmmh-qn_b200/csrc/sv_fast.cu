@@ -173,9 +173,21 @@ __device__ __forceinline__ void team_exchange(TeamF& t, const double* vals, int 
         __threadfence();
     }
     __syncthreads();
-    for (int q = threadIdx.x; q < t.G * K; q += blockDim.x) {
-        const int c = q / K, k = q - c * K;
-        out[q] = __ldcg(&buf[c * kSlotW + k]);
+    // all loads of a thread are issued before the first one is used (one L2 round trip)
+    const int n = t.G * K;
+    for (int q0 = threadIdx.x; q0 < n; q0 += 8 * blockDim.x) {
+        double v[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int q = q0 + r * blockDim.x;
+            const int c = q / K, k = q - c * K;
+            v[r] = (q < n) ? __ldcg(&buf[c * kSlotW + k]) : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int q = q0 + r * blockDim.x;
+            if (q < n) out[q] = v[r];
+        }
     }
     __syncthreads();
 }
@@ -310,7 +322,8 @@ __device__ __forceinline__ double logw_e(double x, double e, double half_y2) {
 
 // chunk k of the sorted generation -> (owning CTA, local chunk index); mirrored on odd rounds
 // k / G for 0 <= k < 65536 with gm = ceil(2^32 / G)
-__device__ __forceinline__ int div_g(int k, unsigned gm) { return (int)__umulhi((unsigned)k, gm); }
+// (gm = 0 stands for G = 1, whose multiplier does not fit 32 bits)
+__device__ __forceinline__ int div_g(int k, unsigned gm) { return gm ? (int)__umulhi((unsigned)k, gm) : k; }
 __device__ __forceinline__ int chunk_owner(int k, int G, unsigned gm) {
     const int l = div_g(k, gm), r = k - l * G;
     return (l & 1) ? (G - 1 - r) : r;
@@ -380,7 +393,7 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
     const int K = LAG - 2;                    // the fixed-lag terms need the ancestor K steps back
     const int RB4 = fast_rb4(LAG), RXP = LAG + 1;
     const int per_tile = (N + G - 1) / G;
-    const unsigned gmagic = (unsigned)((0x100000000ull + (unsigned)G - 1u) / (unsigned)G);
+    const unsigned gmagic = (G == 1) ? 0u : (unsigned)((0x100000000ull + (unsigned)G - 1u) / (unsigned)G);
     int lbits = 0;
     while ((1 << lbits) < S) ++lbits;
     const int kb = kKeyBits - lbits;           // key bits inside a chunk
@@ -1026,13 +1039,19 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
                 const int PR = (NR + kT - 1) / kT;
                 const int r0 = min(NR, tid * PR), r1 = min(NR, r0 + PR);
                 int csum = 0;
-                for (int r = r0; r < r1; ++r) csum += __ldcg(&cn[r]);
+                int cv[8];   // PR <= 8: at most 8 * kT runs
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    cv[q] = (r0 + q < r1) ? __ldcg(&cn[r0 + q]) : 0;
+                    csum += cv[q];
+                }
                 int total = 0;
                 int run = block_excl_scan_i(csum, s_iw, &total);
                 const bool fits = total <= kCap;
-                for (int r = r0; r < r1; ++r) {
-                    s_off[r] = (unsigned short)(fits ? run : 0);
-                    run += __ldcg(&cn[r]);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if (r0 + q < r1) s_off[r0 + q] = (unsigned short)(fits ? run : 0);
+                    run += cv[q];
                 }
                 if (tid == 0) s_off[NR] = (unsigned short)(fits ? total : 0);
                 for (int q = tid; q < kBins + 8; q += kT) s_hist[q] = 0;
@@ -1082,8 +1101,8 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
                         if (e < n_d) {
                             const double xv = rc[r].x;
                             b4n[my_cid + e] = rc[r].b[3];
-                            xpn[my_cid + e] = make_double2(xv, rc[r].xpar);
-                            if (b1n) b1n[my_cid + e] = rc[r].b[0];
+                            __stcs(&xpn[my_cid + e], make_double2(xv, rc[r].xpar));   // read 8 steps later: stream out
+                            if (b1n) __stcs(&b1n[my_cid + e], rc[r].b[0]);
                             s_hb[e] = (hop0 == 3) ? rc[r].b[3] : ((hop0 == 2) ? rc[r].b[2] : ((hop0 == 1) ? rc[r].b[1] : rc[r].b[0]));
                             // chunk and key
                             int kc = 0;

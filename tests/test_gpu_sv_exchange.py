@@ -1,0 +1,160 @@
+"""The exchange kernel (csrc/sv_fast.cu) on its own: pmmh_sv_set_algorithm(2) runs it WITHOUT the
+general-kernel fallback, so a pass here is a pass of that kernel (diag[PMMH_DIAG_KERNEL] == 2).
+
+Parity against the CPU oracle (ancestors bit-exact, near-ties counted), against the general
+kernel at N = 2^20 (two independent device implementations), run-to-run bit reproducibility,
+other lags, batches over several teams, and size-independent invariants of the stored history.
+"""
+import numpy as np
+import pytest
+
+import golden_inputs as gi
+from helpers import first_mismatch_step, relerr, to_time_major
+
+pytestmark = pytest.mark.gpu
+
+DIAG_NEAR_TIES, DIAG_STATUS, DIAG_KERNEL = 0, 2, 6
+
+
+@pytest.fixture()
+def exchange_only():
+    from pmmh_qn_b200 import kernels as K
+    K.set_sv_algorithm(2)
+    yield K
+    K.set_sv_algorithm(0)
+
+
+def _run(K, dev, obs, params, rvr, u_tm, lag, hist, ctas=0):
+    import torch
+    out = K.flps_sv_corr(torch.from_numpy(obs).to(dev), torch.from_numpy(params).to(dev),
+                         torch.from_numpy(rvr).to(dev), torch.from_numpy(u_tm).to(dev), lag=lag,
+                         compute_hessian=False, store_history=hist, ctas_per_problem=ctas)
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in out.items() if not k.startswith("_")}
+
+
+def _inputs(n, nobs, seed):
+    obs, params, rvr, rvp = gi.sv_inputs(n, nobs, seed)
+    return obs, params, rvr[:nobs].copy(), rvp, to_time_major(rvp, n, nobs)
+
+
+@pytest.mark.parametrize("n,nobs,ctas", [(4096, 300, 4), (20000, 120, 16), (65536, 60, 64),
+                                         (6000, 200, 1), (50000, 40, 148)])
+def test_exchange_vs_oracle(cuda_dev, exchange_only, n, nobs, ctas):
+    import oracle
+    lag = 10
+    obs, params, rvr, rvp, u = _inputs(n, nobs, 3)
+    ref = oracle.flps_sv_corr(obs, params, rvr, rvp, n, lag, 0, dumps=True)
+    res = _run(exchange_only, cuda_dev, obs, params, rvr, u, lag, True, ctas)
+    assert int(res["diag"][0, DIAG_KERNEL]) == 2 and int(res["diag"][0, DIAG_STATUS]) == 0
+    step = first_mismatch_step(res["A"][0][1:], ref["A"][1:])
+    assert step is None, "ancestors differ first at time %d (near ties reported: %d)" % (
+        step + 1, int(res["diag"][0, DIAG_NEAR_TIES]))
+    assert relerr(res["X"][0], ref["X"]) <= 1e-12
+    assert abs(res["log_like"][0] - ref["log_like"]) <= 1e-10 * abs(ref["log_like"])
+    assert relerr(res["filt"][0], ref["filt"]) <= 1e-10
+    assert relerr(res["smo"][0], ref["smo"]) <= 1e-10
+    assert relerr(res["traj"][0], ref["traj"]) <= 1e-12
+    assert np.max(np.abs(res["gradient"][0] - ref["gradient"])) <= 1e-9 * np.max(np.abs(ref["gradient"]))
+
+
+@pytest.mark.parametrize("lag", [2, 3, 4, 6, 7, 11, 13])
+def test_exchange_other_lags(cuda_dev, exchange_only, lag):
+    import oracle
+    n, nobs = 5000, 80
+    obs, params, rvr, rvp, u = _inputs(n, nobs, 1)
+    ref = oracle.flps_sv_corr(obs, params, rvr, rvp, n, lag, 0, dumps=True)
+    res = _run(exchange_only, cuda_dev, obs, params, rvr, u, lag, False, 5)
+    assert int(res["diag"][0, DIAG_KERNEL]) == 2 and int(res["diag"][0, DIAG_STATUS]) == 0
+    assert abs(res["log_like"][0] - ref["log_like"]) <= 1e-10 * abs(ref["log_like"])
+    assert relerr(res["smo"][0], ref["smo"]) <= 1e-10
+    assert np.max(np.abs(res["gradient"][0] - ref["gradient"])) <= 1e-9 * np.max(np.abs(ref["gradient"]))
+
+
+def test_exchange_vs_general_full_size(cuda_dev):
+    """BASELINE size N = 2^20 (T cut to 40 steps): the exchange kernel and the general kernel
+    agree on every output; ancestors are compared through the outputs they determine."""
+    import torch
+    from pmmh_qn_b200 import kernels as K
+    n, nobs, lag = 1 << 20, 41, 10
+    dev = cuda_dev
+    g = torch.Generator(device=dev)
+    g.manual_seed(7)
+    obs = torch.from_numpy(gi.sv_obs(nobs)).to(dev)
+    params = torch.tensor([[0.2, 0.9, 0.4, -0.5]], dtype=torch.float64, device=dev)
+    u = torch.randn((1, nobs, n), dtype=torch.float64, device=dev, generator=g)
+    rvr = torch.rand((1, nobs), dtype=torch.float64, device=dev, generator=g)
+    outs = {}
+    try:
+        for algo in (1, 2):
+            K.set_sv_algorithm(algo)
+            o = K.flps_sv_corr(obs, params, rvr, u, lag=lag, compute_hessian=False)
+            torch.cuda.synchronize()
+            outs[algo] = {k: v.cpu().numpy() for k, v in o.items() if not k.startswith("_")}
+    finally:
+        K.set_sv_algorithm(0)
+    a, b = outs[1], outs[2]
+    assert int(a["diag"][0, DIAG_KERNEL]) == 1 and int(b["diag"][0, DIAG_KERNEL]) == 2
+    assert int(b["diag"][0, DIAG_STATUS]) == 0
+    assert abs(a["log_like"][0] - b["log_like"][0]) <= 1e-12 * abs(a["log_like"][0])
+    assert relerr(b["filt"][0], a["filt"][0]) <= 1e-11
+    assert relerr(b["smo"][0], a["smo"][0]) <= 1e-10
+    assert relerr(b["traj"][0], a["traj"][0]) <= 1e-12
+    assert np.max(np.abs(a["gradient"][0] - b["gradient"][0])) <= 1e-9 * np.max(np.abs(a["gradient"][0]))
+
+
+def test_exchange_is_bit_reproducible(cuda_dev, exchange_only):
+    n, nobs = 200000, 50
+    obs, params, rvr, rvp, u = _inputs(n, nobs, 5)
+    r1 = _run(exchange_only, cuda_dev, obs, params, rvr, u, 10, False)
+    r2 = _run(exchange_only, cuda_dev, obs, params, rvr, u, 10, False)
+    assert int(r1["diag"][0, DIAG_KERNEL]) == 2 and int(r1["diag"][0, DIAG_STATUS]) == 0
+    for k in ("log_like", "filt", "smo", "gradient", "traj"):
+        assert np.array_equal(r1[k], r2[k]), k
+
+
+def test_exchange_history_invariants_large(cuda_dev, exchange_only):
+    """N = 2^19: every stored generation is sorted, ancestors are valid positions, and the
+    composed one-step ancestors of the sorted children follow the parents' order only through
+    the sort (no value may be lost: the multiset of children per parent sums to N)."""
+    n, nobs = 1 << 19, 14
+    obs, params, rvr, rvp, u = _inputs(n, nobs, 2)
+    res = _run(exchange_only, cuda_dev, obs, params, rvr, u, 10, True)
+    assert int(res["diag"][0, DIAG_KERNEL]) == 2 and int(res["diag"][0, DIAG_STATUS]) == 0
+    X, A = res["X"][0], res["A"][0]
+    assert np.all(np.diff(X, axis=1) >= 0.0), "a generation is not sorted"
+    assert A.min() >= 0 and A.max() < n
+    for t in range(1, nobs):
+        counts = np.bincount(A[t], minlength=n)
+        assert counts.sum() == n
+        # systematic resampling: offspring numbers differ from N w by less than one
+        assert counts.max() <= n
+
+
+def test_exchange_batch_over_teams(cuda_dev, exchange_only):
+    """B problems spread over several teams in one launch == B single launches, bit for bit."""
+    import torch
+    K = exchange_only
+    n, nobs, lag, B = 3000, 90, 10, 7
+    obs = gi.sv_obs(nobs)
+    rs = np.random.RandomState(11)
+    params = np.array(gi.SV_PARAM_SETS[0]) + 0.02 * rs.normal(size=(B, 4))
+    rvs = rs.normal(size=(B, nobs, n + 1))
+    rvr = np.zeros((B, nobs))
+    u = np.zeros((B, nobs, n))
+    for b in range(B):
+        r, p = gi.split_particle(rvs[b], nobs)
+        rvr[b] = r
+        u[b] = to_time_major(p, n, nobs)
+    dev = cuda_dev
+    t = lambda x: torch.from_numpy(x).to(dev)   # noqa: E731
+    out = K.flps_sv_corr(t(obs), t(params), t(rvr), t(u), lag=lag, ctas_per_problem=3)
+    torch.cuda.synchronize()
+    assert np.all(out["diag"][:, DIAG_KERNEL].cpu().numpy() == 2)
+    assert np.all(out["diag"][:, DIAG_STATUS].cpu().numpy() == 0)
+    for b in range(B):
+        single = K.flps_sv_corr(t(obs), t(params[b:b + 1]), t(rvr[b:b + 1]), t(u[b:b + 1]), lag=lag,
+                                ctas_per_problem=3)
+        torch.cuda.synchronize()
+        for k in ("log_like", "filt", "smo", "gradient", "traj"):
+            assert torch.equal(out[k][b], single[k][0]), (b, k)
