@@ -59,9 +59,11 @@ constexpr int kLutCells = 2048;
 constexpr int kMaxLagF = 64;
 constexpr int kSlotW = kMaxAllgather;    // doubles per CTA in the exchange buffers
 constexpr int kNumSums = 10;             // fx, m1, m2, minx, lag[5], flag
-constexpr int kRounds = (kT >= 1024) ? 2 : 4;   // children per thread in flight (phase A)
-constexpr int kB1 = (kT >= 1024) ? 2 : 4;       // arrivals per thread in flight (phase B pass 1)
-constexpr int kB2 = (kT >= 1024) ? 4 : 8;       // look-ups per thread in flight (fixed-lag terms)
+constexpr int kRounds = 1;   // children per thread in flight (phase A)
+constexpr int kB1 = 1;       // arrivals per thread in flight (phase B pass 1)
+constexpr int kB2 = 1;       // look-ups per thread in flight (fixed-lag terms)
+// (measured on B200 at N = 2^20: 4/4/8 in flight 210 ms, 2/2/4 202 ms, 1/1/1 199 ms per evaluation -- the
+//  kernel is bound by instruction issue and code size, not by memory-level parallelism)
 constexpr int kTile = kT * kRounds;
 constexpr int kBinOccMax = 1024;         // a fuller bin means a degenerate cloud: abandon
 constexpr int kMaxSub = kFastMaxSub;
@@ -69,6 +71,7 @@ constexpr int kPHint = 2 * kCap / 32;   // parent hints cover this many blocks o
 
 static_assert(kCap <= 16384, "arrival indices are packed into 14 bits");
 static_assert(kBins % kT == 0, "bin scan layout");
+static_assert(kLutCells % kT == 0, "LUT build layout");
 
 struct __align__(32) Rec {   // one particle of one generation
     double x;      // value
@@ -230,6 +233,40 @@ __device__ __forceinline__ int block_excl_scan_i(int v, int* s_w, int* total) {
     *total = s_w[kNW];
     return r;
 }
+// exclusive prefixes of one double and one int per thread in the same three barriers
+__device__ __forceinline__ void block_excl_scan_di(double v, int c, double* s_w, int* s_iw, double& vpre,
+                                                   int& cpre, double& vtot, int& ctot) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double incl = warp_incl_scan(v, lane);
+    const int iincl = warp_incl_scan(c, lane);
+    __syncthreads();
+    if (lane == 31) {
+        s_w[warp] = incl;
+        s_iw[warp] = iincl;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const double tv = (lane < kNW) ? s_w[lane] : 0.0;
+        const int tc = (lane < kNW) ? s_iw[lane] : 0;
+        const double ti = warp_incl_scan(tv, lane);
+        const int tci = warp_incl_scan(tc, lane);
+        __syncwarp();
+        if (lane < kNW) {
+            s_w[lane] = ti - tv;
+            s_iw[lane] = tci - tc;
+        }
+        if (lane == kNW - 1) {
+            s_w[kNW] = ti;
+            s_iw[kNW] = tci;
+        }
+    }
+    __syncthreads();
+    vpre = s_w[warp] + (incl - v);
+    cpre = s_iw[warp] + (iincl - c);
+    vtot = s_w[kNW];
+    ctot = s_iw[kNW];
+}
+
 // exclusive running maximum (identity = lowest)
 __device__ __forceinline__ int block_excl_maxscan_i(int v, int* s_w, int lowest) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -350,6 +387,31 @@ __device__ __forceinline__ int first_child_above(double c, double u, int N, bool
     return fc;
 }
 
+// Same as first_child_above, written on integer-valued doubles (one conversion at the end), and
+// counting the decisions within 64 ulp of a tie on the way (diagnostics).  dN = (double)N.
+__device__ __forceinline__ int first_child_above_nt(double c, double u, double dN, bool pow2, double invN,
+                                                    long long& near_ties) {
+    if (!(c == c)) return (int)dN;
+    double jd = floor(c * dN - u);   // candidate for the last child whose threshold is <= c
+    if (!(jd >= -1.0)) jd = -1.0;
+    if (jd > dN - 1.0) jd = dN - 1.0;
+    double cpl = pow2 ? (u + jd) * invN : (u + jd) / dN;            // threshold of child jd
+    while (jd >= 0.0 && cpl > c) {
+        jd -= 1.0;
+        cpl = pow2 ? (u + jd) * invN : (u + jd) / dN;
+    }
+    double cph = pow2 ? (u + (jd + 1.0)) * invN : (u + (jd + 1.0)) / dN;   // threshold of child jd + 1
+    while (jd < dN - 1.0 && !(cph > c)) {
+        jd += 1.0;
+        cpl = cph;
+        cph = pow2 ? (u + (jd + 1.0)) * invN : (u + (jd + 1.0)) / dN;
+    }
+    const double tol = 64.0 * 2.220446049250313e-16 * c;
+    if (jd >= 0.0 && fabs(c - cpl) <= tol) near_ties++;
+    if (jd < dN - 1.0 && fabs(cph - c) <= tol) near_ties++;
+    return (int)jd + 1;
+}
+
 // arrival index -> slot inside the destination region (NR runs, CW apart).  s_hint[e >> 3] is
 // the run that holds arrival (e & ~7), so the walk below is a step or two.
 __device__ __forceinline__ int arrival_slot(const unsigned short* s_off, const unsigned short* s_hint, int CW,
@@ -410,6 +472,7 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
     unsigned short* s_phint = s_hint + (kCap / 8 + 8);                // [kPHint + 8] child block -> parent hints
     double* s_z = (double*)(s_phint + (kPHint + 8));                  // [ND + 2] splitters in z space
     unsigned short* s_off = (unsigned short*)(s_z + (ND + 2));        // [NR + 2] arrival runs
+    unsigned char* s_own = (unsigned char*)(s_off + (NR + 2));        // [ND] chunk -> owning CTA
     //   views of the s_karr region (dead between pass 2 of phase B and the next pass 1)
     double* s_gather = (double*)s_karr;                               // [G * KW] exchange output
     int* s_fc = (int*)s_karr;                                         // [kCap]  sorted position -> end of its children
@@ -461,6 +524,7 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
     const size_t my_base = (size_t)me * NR * CW;   // first mailbox slot of my region
     const int my_cid = me * kCap;                  // first compact id of my region
 
+    for (int k = tid; k < ND; k += kT) s_own[k] = (unsigned char)chunk_owner(k, G, gmagic);   // G <= 255
     for (int prob = team_id; prob < a.B; prob += a.n_teams) {
         const double* obs = a.obs + (size_t)prob * a.obs_stride;
         const double* rvr = a.rvr + (size_t)prob * NOBS;
@@ -523,6 +587,15 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
             }
         }
 
+        // the levels of the chunks this thread handles in the bookkeeping (fixed for the problem)
+        double levr[5];
+        __syncthreads();
+        {
+            const int PERT = (ND + kT - 1) / kT;
+            const int k0 = min(ND, tid * PERT);
+#pragma unroll
+            for (int q = 0; q < 5; ++q) levr[q] = __ldcg(&w.lev[min(ND, k0 + q)]);
+        }
         // ---------------- time 0 (:306-323, Q1): every particle equals mu + stDev * 0.0
         const double stdev0 = c.sigmav / sqrt(1.0 - (c.phi * c.phi));
         const double x0 = c.mu + stdev0 * 0.0;
@@ -634,42 +707,53 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
                 if (lane == 0) s_tot[q] = s;
             }
             {
-                // prefixes over the chunks in chunk order: thread t owns PERT consecutive chunks
+                // prefixes over the chunks in chunk order: thread t owns PERT (<= 4) consecutive chunks
                 const int PERT = (ND + kT - 1) / kT;
                 const int k0 = min(ND, tid * PERT), k1 = min(ND, k0 + PERT);
+                double wv4[4];
+                int cv4[4];
                 double wsum = 0.0;
                 int csum = 0, cmax = 0;
-                for (int k = k0; k < k1; ++k) {
-                    const int cta = chunk_owner(k, G, gmagic), l = div_g(k, gmagic);
-                    wsum += s_gather[cta * KW + 2 * l];
-                    const int cc = (int)s_gather[cta * KW + 2 * l + 1];
-                    csum += cc;
-                    cmax = max(cmax, cc);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    wv4[q] = 0.0;
+                    cv4[q] = 0;
+                    const int k = k0 + q;
+                    if (k < k1) {
+                        const int l = div_g(k, gmagic);
+                        const int cta = s_own[k];
+                        wv4[q] = s_gather[cta * KW + 2 * l];
+                        cv4[q] = (int)s_gather[cta * KW + 2 * l + 1];
+                    }
+                    wsum += wv4[q];
+                    csum += cv4[q];
+                    cmax = max(cmax, cv4[q]);
                 }
-                double wtot;
-                int ctot;
-                const double wpre = block_excl_scan_d(wsum, s_w, &wtot);
-                const int cpre = block_excl_scan_i(csum, s_iw, &ctot);
+                double wtot, wpre;
+                int ctot, cpre;
+                block_excl_scan_di(wsum, csum, s_w, s_iw, wpre, cpre, wtot, ctot);
                 // enforce a non-decreasing prefix across threads (tree sums may dip by an ulp)
-                double runw = wpre;
-                int runc = cpre;
                 double last = wpre;
-                for (int k = k0; k < k1; ++k) {
-                    const int cta = chunk_owner(k, G, gmagic), l = div_g(k, gmagic);
-                    last = runw;
-                    runw += s_gather[cta * KW + 2 * l];
-                    runc += (int)s_gather[cta * KW + 2 * l + 1];
+                {
+                    double runw = wpre;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (k0 + q < k1) {
+                            last = runw;
+                            runw += wv4[q];
+                        }
                 }
                 const double floorw = block_excl_maxscan_d((k1 > k0) ? last : 0.0, s_w);
-                runw = wpre;
-                runc = cpre;
-                for (int k = k0; k < k1; ++k) {
-                    const int cta = chunk_owner(k, G, gmagic), l = div_g(k, gmagic);
-                    s_P[k] = fmax(runw, floorw);
-                    s_coff[k] = runc;
-                    runw += s_gather[cta * KW + 2 * l];
-                    runc += (int)s_gather[cta * KW + 2 * l + 1];
-                }
+                double runw = wpre;
+                int runc = cpre;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (k0 + q < k1) {
+                        s_P[k0 + q] = fmax(runw, floorw);
+                        s_coff[k0 + q] = runc;
+                        runw += wv4[q];
+                        runc += cv4[q];
+                    }
                 if (tid == kT - 1) {
                     s_P[ND] = fmax(wtot, fmax(runw, floorw));
                     s_coff[ND] = ctot;
@@ -677,6 +761,7 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
                 max_occ = max(max_occ, cmax);
             }
             __syncthreads();
+            PROF_MARK(10);   // bk: sums + prefixes
             if (s_tot[9] > 0.0) {   // a CTA overflowed in phase B (uniform decision)
                 status = 1;
                 fail_info = 2 | ((long long)i << 8);
@@ -728,6 +813,7 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
                 }
             }
             if (i == NOBS - 1) break;
+            PROF_MARK(11);   // bk: outputs + dense maps
 
             // moments of the propagation mean => splitters and weight shift of step i + 1
             const double m1 = cshift + s_tot[1] / S_i;
@@ -757,12 +843,13 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
                 const int l = tid, k = chunk_of(l, me, G);
                 const int cntl = s_lstart[l + 1] - s_lstart[l];
                 int lb = 0, ub = 0;
+                long long dummy_nt = 0;   // chunk boundaries are counted by the sweep below
                 s_lP0[l] = s_P[k];
                 if (cntl > 0) {
-                    lb = (s_coff[k] == 0) ? 0 : first_child_above(s_P[k] / S_i, u, N, n_pow2, invN_exact);
+                    lb = (s_coff[k] == 0) ? 0 : first_child_above_nt(s_P[k] / S_i, u, (double)N, n_pow2, invN_exact, dummy_nt);
                     int kn = k + 1;   // next chunk that holds particles
                     while (kn < ND && s_coff[kn + 1] == s_coff[kn]) ++kn;
-                    ub = (kn >= ND) ? N : first_child_above(s_P[kn] / S_i, u, N, n_pow2, invN_exact);
+                    ub = (kn >= ND) ? N : first_child_above_nt(s_P[kn] / S_i, u, (double)N, n_pow2, invN_exact, dummy_nt);
                     if (ub < lb) ub = lb;
                 }
                 s_lLB[l] = lb;
@@ -777,6 +864,7 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
                 }
                 s_lco[S] = accn;
             }
+            PROF_MARK(12);   // bk: moments + child ranges per chunk
             // ----- splitters of step inext.  In standardised space z = (x - m1) / sdc they start
             // as normal quantiles; afterwards they follow the shape the cloud really has: the
             // chunk counts of generation i give the empirical cdf F at the current splitters.
@@ -790,73 +878,103 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
                 const int PERT = (ND + kT - 1) / kT;
                 const int k0 = min(ND, tid * PERT), k1 = min(ND, k0 + PERT);
                 double wsum = 0.0;
-                for (int k = k0; k < k1; ++k) {
-                    const double Fk = (i == 0) ? __ldcg(&w.lev[k]) : (double)s_coff[k] / (double)N;
-                    const double Fk1 = (i == 0) ? __ldcg(&w.lev[k + 1]) : (double)s_coff[k + 1] / (double)N;
-                    const double zl = (k == 0) ? s_z[1] - 0.5 : s_z[k];
-                    const double zr = (k == ND - 1) ? s_z[ND - 1] + 0.5 : s_z[k + 1];
-                    const double xm = m1 + sdc * (0.5 * (zl + zr));
-                    double wv = exp(logw_e(xm, exp(-0.5 * xm), half_y2) - shift);
-                    if (!isfinite(wv)) wv = 0.0;
-                    const double wm = (Fk1 - Fk) * wv;
-                    s_zn[k] = wm;
-                    wsum += wm;
+                double wm4[4], F4[5];
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {
+                    const int k = min(ND, k0 + q);
+                    F4[q] = (i == 0) ? levr[q] : (double)s_coff[k] / (double)N;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int k = k0 + q;
+                    wm4[q] = 0.0;
+                    if (k < k1) {
+                        const double zl = (k == 0) ? s_z[1] - 0.5 : s_z[k];
+                        const double zr = (k == ND - 1) ? s_z[ND - 1] + 0.5 : s_z[k + 1];
+                        const double xm = m1 + sdc * (0.5 * (zl + zr));
+                        // single precision is plenty here: the weights only steer the splitters
+                        // (every CTA evaluates the same instructions on the same numbers)
+                        const double eh = (double)__expf((float)(-0.5 * xm));
+                        double wv = (double)__expf((float)(logw_e(xm, eh, half_y2) - shift));
+                        if (!isfinite(wv)) wv = 0.0;
+                        wm4[q] = (F4[q + 1] - F4[q]) * wv;
+                    }
+                    wsum += wm4[q];
                 }
                 double wtot;
                 const double wpre = block_excl_scan_d(wsum, s_w, &wtot);
                 const bool use_w = (wtot > 0.0) && isfinite(wtot);
+                const double inv_wtot = use_w ? 1.0 / wtot : 0.0;
                 double runw = wpre;
-                for (int k = k0; k < k1; ++k) {
-                    const double Fk = (i == 0) ? __ldcg(&w.lev[k]) : (double)s_coff[k] / (double)N;
-                    s_H[k] = use_w ? 0.5 * (Fk + runw / wtot) : Fk;
-                    runw += s_zn[k];
-                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (k0 + q < k1) {
+                        s_H[k0 + q] = use_w ? 0.5 * (F4[q] + runw * inv_wtot) : F4[q];
+                        runw += wm4[q];
+                    }
                 if (tid == 0) s_H[ND] = 1.0;
                 __syncthreads();
-                for (int k = 1 + tid; k < ND; k += kT) {
-                    const double Tk = __ldcg(&w.lev[k]);
-                    int lo2 = 0, hi2 = ND - 1;   // largest m with H[m] <= lev[k]
-                    while (lo2 < hi2) {
-                        const int mid = (lo2 + hi2 + 1) >> 1;
-                        if (s_H[mid] <= Tk) lo2 = mid;
-                        else hi2 = mid - 1;
+                PROF_MARK(13);   // bk: blended cdf
+                int mw = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {   // consecutive levels: one search, then walk
+                    const int k = k0 + q;
+                    if (k >= 1 && k < k1) {
+                        const double Tk = levr[q];
+                        if (q == 0 || k == 1) {
+                            int hi2 = ND - 1;   // largest m with H[m] <= lev[k]
+                            while (mw < hi2) {
+                                const int mid = (mw + hi2 + 1) >> 1;
+                                if (s_H[mid] <= Tk) mw = mid;
+                                else hi2 = mid - 1;
+                            }
+                        } else {
+                            while (mw + 1 < ND && s_H[mw + 1] <= Tk) ++mw;
+                        }
+                        const int m = mw;
+                        const double Fm = s_H[m], Fm1 = s_H[m + 1];
+                        double frac = (Tk - Fm) / (Fm1 - Fm);
+                        if (!(frac >= 0.0)) frac = 0.0;
+                        if (frac > 1.0) frac = 1.0;
+                        double zn;
+                        if (m == 0) {   // unbounded chunk: exponential tail with the decay rate of a normal tail
+                            const double z1 = s_z[1];
+                            zn = z1 + log(fmax(frac, 1e-300)) / fmax(1.0, fabs(z1));
+                        } else if (m == ND - 1) {
+                            const double z9 = s_z[ND - 1];
+                            zn = z9 - log(fmax(1.0 - frac, 1e-300)) / fmax(1.0, fabs(z9));
+                        } else {
+                            zn = s_z[m] + frac * (s_z[m + 1] - s_z[m]);
+                        }
+                        s_P[k] = zn;   // s_P is free: the per-chunk values were copied out above
                     }
-                    const int m = lo2;
-                    const double Fm = s_H[m], Fm1 = s_H[m + 1];
-                    double frac = (Tk - Fm) / (Fm1 - Fm);
-                    if (!(frac >= 0.0)) frac = 0.0;
-                    if (frac > 1.0) frac = 1.0;
-                    double zn;
-                    if (m == 0) {
-                        const double pz = 0.5 * erfc(-s_z[1] * 0.70710678118654752);
-                        zn = inv_norm_cdf(fmax(frac * pz, 1e-300));
-                        if (zn > s_z[1]) zn = s_z[1];
-                    } else if (m == ND - 1) {
-                        const double pz = 0.5 * erfc(s_z[ND - 1] * 0.70710678118654752);
-                        zn = -inv_norm_cdf(fmax((1.0 - frac) * pz, 1e-300));
-                        if (zn < s_z[ND - 1]) zn = s_z[ND - 1];
-                    } else {
-                        zn = s_z[m] + frac * (s_z[m + 1] - s_z[m]);
-                    }
-                    s_P[k] = zn;   // s_P is free: the per-chunk values were copied out above
                 }
                 __syncthreads();
                 for (int k = 1 + tid; k < ND; k += kT) s_z[k] = s_P[k];
                 __syncthreads();
             }
+            PROF_MARK(14);   // bk: new splitters
             double lut_lo = -1.0, lut_scale = 0.0;
             if (ND > 1) {
                 const double zlo = s_z[1] - 1e-9, zhi = s_z[ND - 1] + 1e-9;
                 lut_lo = zlo;
                 lut_scale = (double)kLutCells / (zhi - zlo);
                 if (!isfinite(lut_scale) || !(lut_scale > 0.0)) lut_scale = 0.0;
-                for (int cidx = tid; cidx < kLutCells; cidx += kT) {
+                constexpr int PC = kLutCells / kT;   // consecutive cells per thread: one search, then walk
+                int lo2 = 0;
+#pragma unroll
+                for (int q = 0; q < PC; ++q) {
+                    const int cidx = tid * PC + q;
                     const double edge = (lut_scale > 0.0) ? lut_lo + (double)cidx / lut_scale : -INFINITY;
-                    int lo2 = 0, hi2 = ND - 1;   // largest d in [0, ND-1] with s_z[d] <= edge (s_z[0] = -inf)
-                    while (lo2 < hi2) {
-                        const int mid = (lo2 + hi2 + 1) >> 1;
-                        if (s_z[mid] <= edge) lo2 = mid;
-                        else hi2 = mid - 1;
+                    if (q == 0) {
+                        int hi2 = ND - 1;   // largest d in [0, ND-1] with s_z[d] <= edge (s_z[0] = -inf)
+                        while (lo2 < hi2) {
+                            const int mid = (lo2 + hi2 + 1) >> 1;
+                            if (s_z[mid] <= edge) lo2 = mid;
+                            else hi2 = mid - 1;
+                        }
+                    } else {
+                        while (lo2 + 1 < ND && s_z[lo2 + 1] <= edge) ++lo2;
                     }
                     s_lut[cidx] = (unsigned short)lo2;
                 }
@@ -880,11 +998,7 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
                         ub = s_lUB[lc];
                     } else {
                         const double cc = (s_lP0[lc] + (run - s_Cb[lc])) / S_i;
-                        ub = first_child_above(cc, u, N, n_pow2, invN_exact);
-                        // diagnostics: decisions within 64 ulp of a cumulative-weight tie
-                        const double tol = 64.0 * 2.220446049250313e-16 * cc;
-                        if (ub > 0 && fabs(cc - child_cp(u, ub - 1, N, n_pow2, invN_exact)) <= tol) near_ties++;
-                        if (ub < N && fabs(child_cp(u, ub, N, n_pow2, invN_exact) - cc) <= tol) near_ties++;
+                        ub = first_child_above_nt(cc, u, (double)N, n_pow2, invN_exact, near_ties);
                     }
                     m = max(m, ub);
                     s_fc[q] = m;
@@ -990,7 +1104,7 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
                                 while (kc + 1 < ND && zx >= s_z[kc + 1]) ++kc;
                                 while (kc > 0 && zx < s_z[kc]) --kc;
                             }
-                            d = chunk_owner(kc, G, gmagic);
+                            d = s_own[kc];
                         }
                         // stable rank inside the warp's run: lanes with the same destination
                         const unsigned peers = __match_any_sync(kFullMask, d);
@@ -1417,7 +1531,7 @@ int sv_fast_smem_bytes(int N, int G, int S) {
     const int ND = S * G;
     size_t b = (size_t)kCap * 8 + (size_t)kCap * 4 * 2 + (size_t)(kBins + 8) * 4 + (size_t)kCap * 2 +
                (size_t)kLutCells * 2 + (size_t)(kCap / 8 + 8) * 2 + (size_t)(kPHint + 8) * 2 +
-               (size_t)(ND + 2) * 8 + (size_t)(G * kNW + 2) * 2;
+               (size_t)(ND + 2) * 8 + (size_t)(G * kNW + 2) * 2 + (size_t)ND;
     (void)N;
     return (int)(b + 64);
 }

@@ -15,12 +15,12 @@ r = probe_sv.run(n, nobs=nobs, reps=0)
 torch.cuda.synchronize()
 _lib.load().pmmh_sv_debug_profile(None)
 c = buf.cpu().numpy().astype(np.float64)
-names = ["cumsum", "exch2", "bookkeep", "ranges", "children", "exch1", "B:pass1", "B:sort", "-", "tail"]
+names = ["cumsum", "exch2", "bk:lut", "ranges", "children", "exch1", "B:pass1", "B:sort", "-", "tail", "bk:prefix", "bk:outputs", "bk:chunks", "bk:cdf", "bk:splitters"]
 steps = nobs - 1
 tot = c.sum(axis=1)
 print("per-step microseconds at 1.9 GHz (mean / min / max over CTAs); total per CTA %.1f ms" % (tot.mean() / 1.9e6))
 for k, nm in enumerate(names):
     v = c[:, k] / steps / 1900.0
     print("  %-10s %7.2f %7.2f %7.2f" % (nm, v.mean(), v.min(), v.max()))
-work = c[:, [0, 2, 3, 4, 6, 7]].sum(axis=1) / steps / 1900.0
+work = c[:, [0, 2, 3, 4, 6, 7, 10, 11, 12, 13, 14]].sum(axis=1) / steps / 1900.0
 print("  work sum   %7.2f %7.2f %7.2f" % (work.mean(), work.min(), work.max()))
