@@ -417,7 +417,8 @@ __global__ void __launch_bounds__(256) logistic_partial_kernel(
     const double* __restrict__ x, const double* __restrict__ y, const int* __restrict__ idx, int m,
     int d, long long row_begin, long long row_end, const double* __restrict__ beta,
     double* __restrict__ partial, int stride) {
-    const int lane = threadIdx.x & 31;
+    extern __shared__ double s_acc[];   // [stride] block accumulator
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     const double bk = (lane < d) ? beta[lane] : 0.0;
@@ -425,79 +426,102 @@ __global__ void __launch_bounds__(256) logistic_partial_kernel(
     double h[HESS ? 32 : 1];
 #pragma unroll
     for (int l = 0; l < (HESS ? 32 : 1); ++l) h[l] = 0.0;
-    for (int r = gwarp; r < m; r += nwarps) {
-        const long long row = idx[r];
-        if (row < row_begin || row >= row_end) continue;   // warp-uniform
-        const size_t lrow = (size_t)(row - row_begin);
-        const double xk = (lane < d) ? x[lrow * d + lane] : 0.0;
-        const double yy = y[lrow];
-        const double xb = warp_sum(bk * xk);
-        const double en = exp(-1.0 * xb), ep = exp(xb);
-        const double eta = 1.0 / (1.0 + en);
-        double e1 = log(eta), e0 = log(1.0 - eta);
-        if (isinf(e1)) e1 = 0.0;
-        if (isinf(e0)) e0 = 0.0;
-        ll += yy * e1 + (1.0 - yy) * e0;
-        const double g1 = xk / (1.0 + ep);
-        const double g0 = -xk / (1.0 + en);
-        gk += yy * g1 + (1.0 - yy) * g0;
-        if (HESS) {
-            double s0 = -1.0 / ((1.0 + en) * (1.0 + en));
-            s0 *= en;
-            double s1 = -1.0 / ((1.0 + ep) * (1.0 + ep));
-            s1 *= ep;
-            const double s = yy * s1 + (1.0 - yy) * s0;
+    constexpr int U = HESS ? 2 : 4;   // rows in flight per warp (independent gathers)
+    for (int r0 = gwarp; r0 < m; r0 += U * nwarps) {
+        double xk[U], yy[U];
+        bool ok[U];
 #pragma unroll
-            for (int l = 0; l < 32; ++l) {
-                const double xl = __shfl_sync(kFullMask, xk, l);
-                h[l] += s * (xk * xl);
+        for (int q = 0; q < U; ++q) {
+            const int r = r0 + q * nwarps;
+            long long row = -1;
+            if (r < m) row = idx[r];
+            ok[q] = (row >= row_begin && row < row_end);   // warp-uniform
+            const size_t lrow = ok[q] ? (size_t)(row - row_begin) : 0;
+            xk[q] = (ok[q] && lane < d) ? x[lrow * d + lane] : 0.0;
+            yy[q] = ok[q] ? y[lrow] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < U; ++q) {
+            if (!ok[q]) continue;
+            const double xb = warp_sum(bk * xk[q]);
+            const double en = exp(-1.0 * xb), ep = exp(xb);
+            const double eta = 1.0 / (1.0 + en);
+            double e1 = log(eta), e0 = log(1.0 - eta);
+            if (isinf(e1)) e1 = 0.0;
+            if (isinf(e0)) e0 = 0.0;
+            ll += yy[q] * e1 + (1.0 - yy[q]) * e0;
+            const double g1 = xk[q] / (1.0 + ep);
+            const double g0 = -xk[q] / (1.0 + en);
+            gk += yy[q] * g1 + (1.0 - yy[q]) * g0;
+            if (HESS) {
+                double s0 = -1.0 / ((1.0 + en) * (1.0 + en));
+                s0 *= en;
+                double s1 = -1.0 / ((1.0 + ep) * (1.0 + ep));
+                s1 *= ep;
+                const double sv = yy[q] * s1 + (1.0 - yy[q]) * s0;
+#pragma unroll
+                for (int l = 0; l < 32; ++l) {
+                    const double xl = __shfl_sync(kFullMask, xk[q], l);
+                    h[l] += sv * (xk[q] * xl);
+                }
             }
         }
     }
-    double* out = partial + (size_t)gwarp * stride;
-    if (lane == 0) out[0] = ll;
-    if (lane < d) out[1 + lane] = gk;
-    if (HESS && lane < d) {
+    // block partial: the warps add their sums into shared memory one after the other (fixed order)
+    for (int k = threadIdx.x; k < stride; k += blockDim.x) s_acc[k] = 0.0;
+    __syncthreads();
+    for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) {
+        if (warp == wv) {
+            if (lane == 0) s_acc[0] += ll;
+            if (lane < d) s_acc[1 + lane] += gk;
+            if (HESS && lane < d) {
 #pragma unroll
-        for (int l = 0; l < 32; ++l)
-            if (l < d) out[1 + d + lane * d + l] = -h[l];
+                for (int l = 0; l < 32; ++l)
+                    if (l < d) s_acc[1 + d + lane * d + l] += -h[l];
+            }
+        }
+        __syncthreads();
     }
+    double* out = partial + (size_t)blockIdx.x * stride;
+    for (int k = threadIdx.x; k < stride; k += blockDim.x) out[k] = s_acc[k];
 }
 
-__global__ void logistic_reduce_kernel(const double* __restrict__ partial, int nwarps, int stride,
+// one warp per output: lanes stride over the block partials, then a fixed tree
+__global__ void logistic_reduce_kernel(const double* __restrict__ partial, int nparts, int stride,
                                        int nout_valid, int nout, double* __restrict__ out) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (k >= nout) return;
     double s = 0.0;
     if (k < nout_valid)
-        for (int w = 0; w < nwarps; ++w) s += partial[(size_t)w * stride + k];
-    out[k] = s;
+        for (int w = lane; w < nparts; w += 32) s += partial[(size_t)w * stride + k];
+    s = warp_sum(s);
+    if (lane == 0) out[k] = s;
 }
 
-static int logistic_grid() { return 148 * 2; }
+static int logistic_grid(int hess) { return 148 * (hess ? 2 : 8); }
 
 size_t logistic_ws_bytes(int m, int d, int hess) {
     (void)m;
-    const int nwarps = logistic_grid() * 8;
     const int stride = 1 + d + (hess ? d * d : 0);
-    return (size_t)nwarps * stride * sizeof(double);
+    return (size_t)logistic_grid(hess) * stride * sizeof(double);
 }
 
 cudaError_t launch_logistic(const double* x, const double* y, const int* idx, int m, int d,
                             long long row_begin, long long row_end, const double* beta, int hess,
                             double* out, void* ws, cudaStream_t st) {
-    const int grid = logistic_grid();
-    const int nwarps = grid * 8;
+    const int grid = logistic_grid(hess);
     const int stride = 1 + d + (hess ? d * d : 0);
+    const size_t smem = (size_t)stride * sizeof(double);
     double* partial = (double*)ws;
     if (hess)
-        logistic_partial_kernel<true><<<grid, 256, 0, st>>>(x, y, idx, m, d, row_begin, row_end, beta,
-                                                            partial, stride);
+        logistic_partial_kernel<true><<<grid, 256, smem, st>>>(x, y, idx, m, d, row_begin, row_end, beta,
+                                                               partial, stride);
     else
-        logistic_partial_kernel<false><<<grid, 256, 0, st>>>(x, y, idx, m, d, row_begin, row_end, beta,
-                                                             partial, stride);
+        logistic_partial_kernel<false><<<grid, 256, smem, st>>>(x, y, idx, m, d, row_begin, row_end, beta,
+                                                                partial, stride);
     const int nout = 1 + d + d * d;
-    logistic_reduce_kernel<<<(nout + 127) / 128, 128, 0, st>>>(partial, nwarps, stride, stride, nout, out);
+    logistic_reduce_kernel<<<(nout * 32 + 127) / 128, 128, 0, st>>>(partial, grid, stride, stride, nout, out);
     return cudaGetLastError();
 }
 
