@@ -486,6 +486,66 @@ __global__ void __launch_bounds__(256) logistic_partial_kernel(
     for (int k = threadIdx.x; k < stride; k += blockDim.x) out[k] = s_acc[k];
 }
 
+// Log-likelihood + gradient only (the call the QN sampler makes): a warp takes 32 sampled rows at
+// a time.  Lane k owns feature k for the loads and the dot products (32 independent row gathers
+// in flight), then every lane does the scalar exp / log work of ONE row, so the transcendental
+// work is shared out over the lanes instead of being repeated by all 32.
+__global__ void __launch_bounds__(256) logistic_grad_kernel(
+    const double* __restrict__ x, const double* __restrict__ y, const int* __restrict__ idx, int m,
+    int d, long long row_begin, long long row_end, const double* __restrict__ beta,
+    double* __restrict__ partial, int stride) {
+    extern __shared__ double s_acc[];   // [stride] block accumulator
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const double bk = (lane < d) ? beta[lane] : 0.0;
+    double ll = 0.0, gk = 0.0;
+    for (int r0 = gwarp * 32; r0 < m; r0 += nwarps * 32) {
+        const int r = r0 + lane;
+        long long row = -1;
+        if (r < m) row = idx[r];
+        const bool ok = (row >= row_begin && row < row_end);
+        const long long lrow = ok ? (row - row_begin) : -1;
+        const double yy = ok ? y[lrow] : 0.0;
+        double xk[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+            const long long rq = __shfl_sync(kFullMask, lrow, q);
+            xk[q] = (rq >= 0 && lane < d) ? x[(size_t)rq * d + lane] : 0.0;
+        }
+        double xb = 0.0;
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+            const double pq = warp_sum(bk * xk[q]);
+            if (lane == q) xb = pq;
+        }
+        double coef = 0.0;
+        if (ok) {
+            const double en = exp(-1.0 * xb), ep = exp(xb);
+            const double eta = 1.0 / (1.0 + en);
+            double e1 = log(eta), e0 = log(1.0 - eta);
+            if (isinf(e1)) e1 = 0.0;
+            if (isinf(e0)) e0 = 0.0;
+            ll += yy * e1 + (1.0 - yy) * e0;
+            coef = yy / (1.0 + ep) - (1.0 - yy) / (1.0 + en);
+        }
+#pragma unroll
+        for (int q = 0; q < 32; ++q) gk += __shfl_sync(kFullMask, coef, q) * xk[q];
+    }
+    ll = warp_sum(ll);   // one row per lane: the warp's log-likelihood is the sum over its lanes
+    for (int k = threadIdx.x; k < stride; k += blockDim.x) s_acc[k] = 0.0;
+    __syncthreads();
+    for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) {
+        if (warp == wv) {
+            if (lane == 0) s_acc[0] += ll;
+            if (lane < d) s_acc[1 + lane] += gk;
+        }
+        __syncthreads();
+    }
+    double* out = partial + (size_t)blockIdx.x * stride;
+    for (int k = threadIdx.x; k < stride; k += blockDim.x) out[k] = s_acc[k];
+}
+
 // one warp per output: lanes stride over the block partials, then a fixed tree
 __global__ void logistic_reduce_kernel(const double* __restrict__ partial, int nparts, int stride,
                                        int nout_valid, int nout, double* __restrict__ out) {
@@ -499,7 +559,7 @@ __global__ void logistic_reduce_kernel(const double* __restrict__ partial, int n
     if (lane == 0) out[k] = s;
 }
 
-static int logistic_grid(int hess) { return 148 * (hess ? 2 : 8); }
+static int logistic_grid(int hess) { return 148 * (hess ? 2 : 4); }
 
 size_t logistic_ws_bytes(int m, int d, int hess) {
     (void)m;
@@ -518,8 +578,8 @@ cudaError_t launch_logistic(const double* x, const double* y, const int* idx, in
         logistic_partial_kernel<true><<<grid, 256, smem, st>>>(x, y, idx, m, d, row_begin, row_end, beta,
                                                                partial, stride);
     else
-        logistic_partial_kernel<false><<<grid, 256, smem, st>>>(x, y, idx, m, d, row_begin, row_end, beta,
-                                                                partial, stride);
+        logistic_grad_kernel<<<grid, 256, smem, st>>>(x, y, idx, m, d, row_begin, row_end, beta, partial,
+                                                      stride);
     const int nout = 1 + d + d * d;
     logistic_reduce_kernel<<<(nout * 32 + 127) / 128, 128, 0, st>>>(partial, grid, stride, stride, nout, out);
     return cudaGetLastError();
