@@ -303,7 +303,9 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-                    "api": "ParticleMethodsCUDA.smoother(model, rvs={'rvs': pinned ndarray})"},
+                    "api": "ParticleMethodsCUDA.smoother(model, rvs={'rvs': pinned ndarray})",
+                    "note": "host rvs -> pmmh_flps_sv_corr_streamed: the copy engine feeds the running kernel "
+                            "in chunks of 64 time steps (no layout kernel); results read back to the host"},
             "gpu_launches": args.steps * 2,
         }
         if world == 1 and not args.no_cpu_baseline:

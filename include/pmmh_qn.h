@@ -12,6 +12,8 @@
  *                                ...stochastic_volatility.pyx:61, called at cython.py:57,63
  *   pmmh_sv_workspace_bytes      (new) the reference malloc()s scratch inside each call
  *                                (:208-238); here the caller owns one reusable workspace
+ *   pmmh_flps_sv_corr_streamed   the same call fed straight from the sampler's host array
+ *                                (copies overlap the kernel)
  *   pmmh_split_rvs               rvs.flatten() / rvs[NOBS:] of cython.py:54-56,89-91 plus
  *                                the change to the device's time-major layout
  *   pmmh_norm_cdf                scipy.stats.norm.cdf of cython.py:55,90 / standard.py:52,75
@@ -106,6 +108,26 @@ int pmmh_flps_sv_corr(const double* d_obs, long long obs_stride, const double* d
                       double* d_log_like, double* d_gradient, double* d_traj, double* d_hess1,
                       double* d_hess2, long long* d_diag, double* d_x_hist, int* d_a_hist,
                       void* d_workspace, size_t workspace_bytes, int ctas_per_problem, void* stream);
+
+/* The same evaluation (log-likelihood + gradient, one problem) with the auxiliary variables still
+ * in HOST memory -- what the samplers hand to estimator.smoother(model, rvs={'rvs': ndarray})
+ * (mh_quasi_newton.py:333, state/particle_methods/cython.py:89-91).  h_rvs is the reference's
+ * (n_obs, N+1) row-major array (pinned memory makes the copies asynchronous).  The copy engine
+ * moves it in chunks of 64 time steps on an internal stream into d_stage (particle-major chunks,
+ * no layout kernel) while the persistent kernel is already running; the kernel waits for a
+ * chunk only when it reaches it.  d_rvr = Phi of the first n_obs flat entries (computed by the
+ * caller as in cython.py:90).  Only sizes the exchange kernel takes (pmmh_sv_streamed_eligible);
+ * there is no fallback inside: if d_diag[PMMH_DIAG_STATUS] == 1 afterwards, upload the array and
+ * call pmmh_flps_sv_corr.  d_stage needs pmmh_sv_stage_bytes() bytes and must stay untouched
+ * until the kernel has finished; the workspace size is that of pmmh_sv_workspace_bytes(batch 1). */
+int pmmh_sv_stage_bytes(int n_obs, int n_particles, size_t* bytes);
+int pmmh_sv_streamed_eligible(int n_obs, int n_particles, int lag, int ctas_per_problem);
+int pmmh_flps_sv_corr_streamed(const double* h_rvs, const double* d_obs, const double* d_params,
+                               const double* d_rvr, int n_obs, int n_particles, int lag, void* d_stage,
+                               size_t stage_bytes, double* d_filt, double* d_smo, double* d_log_like,
+                               double* d_gradient, double* d_traj, double* d_hess1, double* d_hess2,
+                               long long* d_diag, void* d_workspace, size_t workspace_bytes,
+                               int ctas_per_problem, void* stream);
 
 /* Bootstrap particle filter (filter only).  read_mode: PMMH_BPF_PARITY / PMMH_BPF_INTENDED. */
 int pmmh_bpf_sv_corr(const double* d_obs, long long obs_stride, const double* d_params,

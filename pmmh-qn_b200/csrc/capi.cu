@@ -264,6 +264,130 @@ int pmmh_flps_sv_corr(const double* d_obs, long long obs_stride, const double* d
                   stream);
 }
 
+// ---- host-resident auxiliary variables, copied while the kernel runs ----------------------
+namespace {
+constexpr int kUChunk = 64;   // time steps per copy chunk (512-byte rows for the copy engine)
+struct StreamedState {
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_reset = nullptr;
+    int* h_vals = nullptr;   // pinned: h_vals[c] = time steps available after chunk c
+    int h_cap = 0;
+};
+thread_local StreamedState g_streamed[64];
+
+int streamed_chunks(int n_obs) { return (n_obs + kUChunk - 1) / kUChunk; }
+size_t streamed_data_bytes(int n_obs, int n) {
+    return (size_t)streamed_chunks(n_obs) * (size_t)n * kUChunk * sizeof(double);
+}
+}  // namespace
+
+int pmmh_sv_stage_bytes(int n_obs, int n_particles, size_t* bytes) {
+    if (!bytes || n_obs < 2 || n_particles < 1) return fail(PMMH_ERR_INVALID, "pmmh_sv_stage_bytes: bad arguments");
+    *bytes = streamed_data_bytes(n_obs, n_particles) + 256;
+    return PMMH_OK;
+}
+
+int pmmh_sv_streamed_eligible(int n_obs, int n_particles, int lag, int ctas_per_problem) {
+    SvPlan p;
+    if (sv_make_plan(n_obs, n_particles, lag, 1, 0, pmmh::kSvFlps, 0, ctas_per_problem, &p) != PMMH_OK) return 0;
+    return p.use_fast ? 1 : 0;
+}
+
+int pmmh_flps_sv_corr_streamed(const double* h_rvs, const double* d_obs, const double* d_params,
+                               const double* d_rvr, int n_obs, int n_particles, int lag, void* d_stage,
+                               size_t stage_bytes, double* d_filt, double* d_smo, double* d_log_like,
+                               double* d_gradient, double* d_traj, double* d_hess1, double* d_hess2,
+                               long long* d_diag, void* d_workspace, size_t workspace_bytes,
+                               int ctas_per_problem, void* stream) {
+    if (!h_rvs || !d_obs || !d_params || !d_rvr || !d_stage || !d_filt || !d_smo || !d_log_like || !d_gradient ||
+        !d_traj || !d_hess1 || !d_hess2 || !d_diag || !d_workspace)
+        return fail(PMMH_ERR_INVALID, "pmmh_flps_sv_corr_streamed: null pointer argument");
+    SvPlan p;
+    int rc = sv_make_plan(n_obs, n_particles, lag, 1, 0, pmmh::kSvFlps, 0, ctas_per_problem, &p);
+    if (rc != PMMH_OK) return rc;
+    if (!p.use_fast) return fail(PMMH_ERR_INVALID, "pmmh_flps_sv_corr_streamed: exchange kernel not eligible for these sizes");
+    if (workspace_bytes < p.total) return fail(PMMH_ERR_WORKSPACE, "workspace too small");
+    const size_t data_bytes = streamed_data_bytes(n_obs, n_particles);
+    if (stage_bytes < data_bytes + 256) return fail(PMMH_ERR_WORKSPACE, "staging buffer too small");
+    int dev = 0;
+    PMMH_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(PMMH_ERR_NO_DEVICE, "device ordinal out of range");
+    StreamedState& ss = g_streamed[dev];
+    const int chunks = streamed_chunks(n_obs);
+    if (!ss.copy_stream) {
+        PMMH_CUDA(cudaStreamCreateWithFlags(&ss.copy_stream, cudaStreamNonBlocking));
+        PMMH_CUDA(cudaEventCreateWithFlags(&ss.ev_start, cudaEventDisableTiming));
+        PMMH_CUDA(cudaEventCreateWithFlags(&ss.ev_reset, cudaEventDisableTiming));
+    }
+    if (ss.h_cap < chunks) {
+        if (ss.h_vals) cudaFreeHost(ss.h_vals);
+        ss.h_vals = nullptr;
+        PMMH_CUDA(cudaHostAlloc((void**)&ss.h_vals, (size_t)chunks * sizeof(int), cudaHostAllocDefault));
+        ss.h_cap = chunks;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    char* stage = (char*)d_stage;
+    int* d_flag = (int*)(stage + data_bytes);
+    // the copies may start once everything queued so far on the caller's stream has finished
+    // (the previous evaluation may still be reading the staging buffer)
+    PMMH_CUDA(cudaEventRecord(ss.ev_start, st));
+    PMMH_CUDA(cudaStreamWaitEvent(ss.copy_stream, ss.ev_start, 0));
+    PMMH_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), ss.copy_stream));
+    PMMH_CUDA(cudaEventRecord(ss.ev_reset, ss.copy_stream));
+    for (int c = 0; c < chunks; ++c) {
+        const int t0 = c * kUChunk;
+        const int wsteps = (n_obs - t0 < kUChunk) ? (n_obs - t0) : kUChunk;
+        // rows = particles: rvp[i + j * n_obs] with rvp = rvs_flat + n_obs (cython.py:89-91)
+        const double* src = h_rvs + (size_t)n_obs + (size_t)t0;
+        char* dst = stage + (size_t)c * (size_t)n_particles * kUChunk * sizeof(double);
+        PMMH_CUDA(cudaMemcpy2DAsync(dst, (size_t)kUChunk * sizeof(double), src, (size_t)n_obs * sizeof(double),
+                                    (size_t)wsteps * sizeof(double), (size_t)n_particles, cudaMemcpyHostToDevice,
+                                    ss.copy_stream));
+        ss.h_vals[c] = t0 + wsteps;
+        PMMH_CUDA(cudaMemcpyAsync(d_flag, &ss.h_vals[c], sizeof(int), cudaMemcpyHostToDevice, ss.copy_stream));
+    }
+    // the kernel must not start before the flag has been reset
+    PMMH_CUDA(cudaStreamWaitEvent(st, ss.ev_reset, 0));
+    pmmh::SvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.N = n_particles;
+    a.NOBS = n_obs;
+    a.LAG = lag;
+    a.B = 1;
+    a.G = p.G;
+    a.n_teams = p.n_teams;
+    a.NB = p.NB;
+    a.RING = p.RING;
+    a.mode = pmmh::kSvFlps;
+    a.hess = 0;
+    a.SQ = p.SQ;
+    a.SQW = p.SQW;
+    a.obs = d_obs;
+    a.obs_stride = 0;
+    a.params = d_params;
+    a.rvr = d_rvr;
+    a.U = (const double*)d_stage;
+    a.u_chunk = kUChunk;
+    a.u_ready = d_flag;
+    a.filt = d_filt;
+    a.smo = d_smo;
+    a.loglike = d_log_like;
+    a.grad = d_gradient;
+    a.traj = d_traj;
+    a.hess1 = d_hess1;
+    a.hess2 = d_hess2;
+    a.diag = d_diag;
+    a.prof = g_sv_prof;
+    a.ws = (char*)d_workspace;
+    a.NSUB = p.NSUB;
+    a.CP = p.CP;
+    a.ws_sync_bytes = p.fast_sync_bytes;
+    a.ws_team_stride = p.fast_team_stride;
+    PMMH_CUDA(cudaMemsetAsync(d_workspace, 0, p.fast_sync_bytes, st));
+    PMMH_CUDA(pmmh::sv_fast_launch(a, p.grid, st));
+    return PMMH_OK;
+}
+
 int pmmh_bpf_sv_corr(const double* d_obs, long long obs_stride, const double* d_params,
                      const double* d_rvr, const double* d_u, int n_obs, int n_particles, int batch,
                      int read_mode, double* d_filt, double* d_log_like, double* d_traj,

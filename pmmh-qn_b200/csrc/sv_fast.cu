@@ -1046,6 +1046,24 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
                     n_c = 0;
                 }
                 const double* Ui = U + (size_t)inext * N;
+                // streamed u (host copies still in flight): wait until the chunk that holds time
+                // step inext has landed.  Chunk layout: [chunk][particle][UC steps].
+                const int UC = a.u_chunk;
+                const double* Uc = nullptr;
+                if (UC > 0) {
+                    if (tid == 0 && a.u_ready != nullptr) {
+                        long long spins = 0;
+                        while (ld_acquire_sys_s32(a.u_ready) < inext + 1) {
+                            if (++spins > (1ll << 28)) {   // ~ seconds: the copies never came, give up
+                                pair_over = 1;
+                                break;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    const int ch = inext / UC;
+                    Uc = U + (size_t)ch * N * UC + (inext - ch * UC);
+                }
                 const Rec* Gi = MAIL(i);
                 Rec* Gn = MAIL(inext);
                 unsigned short* my_wh = s_wh + warp * G;
@@ -1067,7 +1085,7 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
                             int l = 0;
                             while (l + 1 < S && s_lco[l + 1] <= t) ++l;
                             const int j = s_lLB[l] + (t - s_lco[l]);
-                            un[r] = ld_stream_f64(&Ui[j]);
+                            un[r] = (UC > 0) ? __ldcg(&Uc[(size_t)j * UC]) : ld_stream_f64(&Ui[j]);
                             // parent: first sorted position of chunk l whose children end beyond j
                             int lo2 = s_lstart[l], hi2 = s_lstart[l + 1] - 1;
                             if (use_ph) {

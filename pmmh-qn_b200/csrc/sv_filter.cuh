@@ -47,7 +47,10 @@ struct SvArgs {
     long long obs_stride;     // 0: shared observations
     const double* params;     // [B][4]
     const double* rvr;        // [B][NOBS]  (already Phi-transformed)
-    const double* U;          // [B][NOBS][N] time-major
+    const double* U;          // [B][NOBS][N] time-major, or (u_chunk > 0, exchange kernel, B = 1)
+                              // [chunks][N][u_chunk]: particle-major chunks of u_chunk time steps
+    int u_chunk;              // 0 = time-major
+    const int* u_ready;       // streamed u: number of time steps that have landed (written by the copy stream)
     double *filt, *smo, *loglike, *grad, *traj, *hess1, *hess2;
     long long* diag;          // [B][kDiagCount]
     double* Xhist;            // optional [B][NOBS][N]

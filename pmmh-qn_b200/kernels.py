@@ -120,6 +120,50 @@ def flps_sv_corr(obs, params, rvr, u, lag=10, compute_hessian=False, store_histo
     return out
 
 
+def sv_streamed_eligible(n_obs, n_particles, lag=10, ctas_per_problem=0):
+    """True if pmmh_flps_sv_corr_streamed takes these sizes (the exchange kernel is eligible)."""
+    return bool(_lib.load().pmmh_sv_streamed_eligible(int(n_obs), int(n_particles), int(lag),
+                                                      int(ctas_per_problem)))
+
+
+def flps_sv_corr_streamed(rvs_host, obs, params, rvr, n_obs, n_particles, lag=10, ctas_per_problem=0,
+                          workspace=None, stage=None):
+    """Log-likelihood + gradient with the auxiliary variables still in host memory
+    (pmmh_flps_sv_corr_streamed): ``rvs_host`` is the reference's (n_obs, N+1) float64 array
+    (C-contiguous NumPy array; pinned memory makes the copies overlap the kernel).  The caller
+    must keep ``rvs_host`` alive and unchanged until the stream has been synchronised."""
+    lib = _lib.load()
+    _need_cuda(obs, params, rvr)
+    if rvs_host.dtype != "float64" or not rvs_host.flags["C_CONTIGUOUS"] or rvs_host.size != n_obs * (n_particles + 1):
+        raise _lib.PmmhError("flps_sv_corr_streamed: rvs must be a C-contiguous float64 (n_obs, N+1) array")
+    dev = obs.device
+    params = params.reshape(1, 4)
+    rvr = rvr.reshape(1, n_obs)
+    out = {
+        "filt": torch.empty((1, n_obs), dtype=_F64, device=dev),
+        "smo": torch.empty((1, n_obs), dtype=_F64, device=dev),
+        "log_like": torch.empty((1,), dtype=_F64, device=dev),
+        "gradient": torch.empty((1, 4, n_obs), dtype=_F64, device=dev),
+        "traj": torch.empty((1, n_obs), dtype=_F64, device=dev),
+        "hess1": torch.empty((1, 4, 4), dtype=_F64, device=dev),
+        "hess2": torch.empty((1, 4, 4), dtype=_F64, device=dev),
+        "diag": torch.zeros((1, _lib.DIAG_COUNT), dtype=torch.int64, device=dev),
+    }
+    nbytes = sv_workspace_bytes(n_obs, n_particles, lag, 1, 0, 0, False, ctas_per_problem)
+    ws = (workspace or Workspace()).get(nbytes, dev)
+    sb = ctypes.c_size_t()
+    _lib.check(lib.pmmh_sv_stage_bytes(n_obs, n_particles, ctypes.byref(sb)), "pmmh_sv_stage_bytes")
+    st = (stage or Workspace()).get(sb.value, dev)
+    _lib.check(lib.pmmh_flps_sv_corr_streamed(
+        ctypes.c_void_p(rvs_host.ctypes.data), _ptr(obs), _ptr(params), _ptr(rvr), n_obs, n_particles, lag,
+        _ptr(st), st.numel(), _ptr(out["filt"]), _ptr(out["smo"]), _ptr(out["log_like"]),
+        _ptr(out["gradient"]), _ptr(out["traj"]), _ptr(out["hess1"]), _ptr(out["hess2"]),
+        _ptr(out["diag"]), _ptr(ws), ws.numel(), ctas_per_problem, _stream()), "pmmh_flps_sv_corr_streamed")
+    out["_workspace"] = ws
+    out["_stage"] = st
+    return out
+
+
 def bpf_sv_corr(obs, params, rvr, u, read_mode=_lib.BPF_PARITY, store_history=False,
                 ctas_per_problem=0, workspace=None):
     """Bootstrap particle filter (pmmh_bpf_sv_corr)."""

@@ -35,6 +35,8 @@ class ParticleMethodsCUDA(BaseStateInference):
         self.bpf_read_mode = {'parity': BPF_PARITY, 'intended': BPF_INTENDED}[bpf_read_mode]
         self.ctas_per_problem = int(ctas_per_problem)
         self._workspace = K.Workspace()
+        self._stage = K.Workspace()
+        self.stream_min_particles = 1 << 15   # below this the upload is too small to be worth overlapping
         self._obs_cache = None
         self._init_particle_method(model, int(no_particles), int(fixed_lag), verbose)
         self.results = {}
@@ -67,6 +69,28 @@ class ParticleMethodsCUDA(BaseStateInference):
         _, u = K.split_rvs(d, n_obs, n)
         rvr = torch.from_numpy(rv_r).to(self.device, non_blocking=True)
         return rvr, u[0]
+
+    def _smoother_streamed(self, rvs, obs_d, params):
+        """Large host-resident rvs: let the copy engine feed the running kernel
+        (pmmh_flps_sv_corr_streamed) instead of upload -> layout kernel -> smoother.  Returns
+        None when this path does not apply or the kernel abandoned the evaluation."""
+        n_obs, n = self.no_obs, self.no_particles
+        lag = self.settings['fixed_lag']
+        if not isinstance(rvs, np.ndarray) or n < self.stream_min_particles:
+            return None
+        if rvs.dtype != np.float64 or not rvs.flags['C_CONTIGUOUS'] or rvs.size != n_obs * (n + 1):
+            return None
+        if not K.sv_streamed_eligible(n_obs, n, lag, self.ctas_per_problem):
+            return None
+        flat = rvs.reshape(-1)
+        rv_r = norm.cdf(flat[0:n_obs]).flatten()   # bit-identical to cython.py:90
+        rvr = torch.from_numpy(rv_r).to(self.device, non_blocking=True)
+        out = K.flps_sv_corr_streamed(rvs, obs_d, torch.from_numpy(params).to(self.device), rvr, n_obs, n,
+                                      lag=lag, ctas_per_problem=self.ctas_per_problem,
+                                      workspace=self._workspace, stage=self._stage)
+        if int(out['diag'][0, DIAG_STATUS].item()) != 0:   # synchronises; abandoned: use the general path
+            return None
+        return out
 
     @staticmethod
     def _to_host(tensors):
@@ -108,10 +132,14 @@ class ParticleMethodsCUDA(BaseStateInference):
         try:
             _, obs_d = self._obs_device(model)
             params = np.asarray(model.get_all_params(), dtype=np.float64)
-            rvr, u = self._rvs_device(kwargs)
-            out = K.flps_sv_corr(obs_d, torch.from_numpy(params).to(self.device), rvr, u,
-                                 lag=self.settings['fixed_lag'], compute_hessian=hessian_flag,
-                                 ctas_per_problem=self.ctas_per_problem, workspace=self._workspace)
+            out = None
+            if not hessian_flag and 'rvs' in kwargs:
+                out = self._smoother_streamed(kwargs['rvs']['rvs'], obs_d, params)
+            if out is None:
+                rvr, u = self._rvs_device(kwargs)
+                out = K.flps_sv_corr(obs_d, torch.from_numpy(params).to(self.device), rvr, u,
+                                     lag=self.settings['fixed_lag'], compute_hessian=hessian_flag,
+                                     ctas_per_problem=self.ctas_per_problem, workspace=self._workspace)
             xf, xs, ll, grad, xtraj, hess1, hess2, diag = self._to_host(
                 [out['filt'][0], out['smo'][0], out['log_like'], out['gradient'][0], out['traj'][0],
                  out['hess1'][0], out['hess2'][0], out['diag'][0]])

@@ -158,3 +158,44 @@ def test_exchange_batch_over_teams(cuda_dev, exchange_only):
         torch.cuda.synchronize()
         for k in ("log_like", "filt", "smo", "gradient", "traj"):
             assert torch.equal(out[k][b], single[k][0]), (b, k)
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+def test_streamed_host_rvs_equals_resident(cuda_dev, pinned):
+    """pmmh_flps_sv_corr_streamed (copies overlap the kernel, chunked particle-major staging) gives
+    bit-identical outputs to the upload -> split_rvs -> pmmh_flps_sv_corr path."""
+    import torch
+    from pmmh_qn_b200 import kernels as K
+    n, nobs, lag = 65536, 150, 10
+    dev = cuda_dev
+    rs = np.random.RandomState(21)
+    if pinned:
+        host = torch.empty((nobs, n + 1), dtype=torch.float64, pin_memory=True)
+        rvs = host.numpy()
+        rvs[...] = rs.normal(size=(nobs, n + 1))
+    else:
+        rvs = rs.normal(size=(nobs, n + 1))
+    assert K.sv_streamed_eligible(nobs, n, lag)
+    obs = torch.from_numpy(gi.sv_obs(nobs)).to(dev)
+    params = torch.tensor([[0.2, 0.9, 0.4, -0.5]], dtype=torch.float64, device=dev)
+    rvr_h, rvp = gi.split_particle(rvs, nobs)
+    rvr = torch.from_numpy(rvr_h).to(dev)
+    a = K.flps_sv_corr_streamed(rvs, obs, params, rvr, nobs, n, lag=lag)
+    torch.cuda.synchronize()
+    assert int(a["diag"][0, DIAG_KERNEL]) == 2 and int(a["diag"][0, DIAG_STATUS]) == 0
+    K.set_sv_algorithm(2)
+    try:
+        u = torch.from_numpy(to_time_major(rvp, n, nobs)).to(dev)
+        b = K.flps_sv_corr(obs, params, rvr, u, lag=lag, compute_hessian=False)
+        torch.cuda.synchronize()
+    finally:
+        K.set_sv_algorithm(0)
+    for k in ("log_like", "filt", "smo", "gradient", "traj"):
+        assert torch.equal(a[k], b[k]), k
+    # twice in a row on the same staging buffer (the second call must wait for the first)
+    ws, st = K.Workspace(), K.Workspace()
+    c1 = K.flps_sv_corr_streamed(rvs, obs, params, rvr, nobs, n, lag=lag, workspace=ws, stage=st)
+    c2 = K.flps_sv_corr_streamed(rvs, obs, params, rvr, nobs, n, lag=lag, workspace=ws, stage=st)
+    torch.cuda.synchronize()
+    for k in ("log_like", "gradient"):
+        assert torch.equal(c1[k], a[k]) and torch.equal(c2[k], a[k]), k
