@@ -16,16 +16,19 @@
 //     weight (exact predicate re-checked).  Children are generated in birth order from
 //     coalesced reads of u, propagated (:354-358) and routed by value to the CTA that will
 //     sort them: the chip-wide sort is a one-pass sample sort whose splitters follow the
-//     empirical cdf of the previous generation.  The child record (32 bytes = one sector: value,
-//     parent value, ids of the ancestors 1..4 steps back) is written straight into the
-//     destination's region of the generation table; its slot is deterministic
-//     (source CTA, stable rank among that source's children for that destination).
+//     empirical cdf of the previous generation blended with the predicted weight (a chunk holds
+//     neither much more than its share of the particles nor of the weight).  The child record
+//     (32 bytes = one sector: value, parent value, compact ids of the ancestors 1..4 steps back)
+//     is written straight into the destination's mailbox region; its slot is deterministic:
+//     (source CTA, source warp, stable rank among that warp's children for that destination,
+//     from __match_any_sync) -- the phase has no block-wide synchronisation.
 //   exchange 1 (barrier; the per-(destination, source) counts travel through global memory)
 //   phase B  (arrivals -> sorted generation; CTA c works on what was routed to it)
-//     Records never move again: a particle's id is its arrival slot.  The CTA reads the
-//     arrivals (coalesced runs), evaluates log-weights (:427-437), the fixed-lag score terms
-//     (:445-470; the ancestor LAG-2 steps back is reached through the carried ids in
-//     ceil((LAG-2)/4) look-ups) and all weighted sums in arrival order, and sorts (key, arrival
+//     Records never move again: a particle's id is (destination, arrival index).  The CTA reads
+//     its runs, writes the dense tables later steps look up (id 4 steps back; value + parent
+//     value), evaluates log-weights (:427-437), the fixed-lag score terms (:445-470; the ancestor
+//     LAG-2 steps back is reached through the carried ids and the id table in ceil((LAG-2)/4)
+//     look-ups) and all weighted sums in arrival order, and sorts (key, arrival
 //     index) pairs in shared memory: counting sort on the chunk-relative position followed by
 //     an all-pairs pass inside a bin.  A block scan in sorted order gives the cumulative
 //     weights.
@@ -35,9 +38,12 @@
 // fixed-order tree sums (deterministic); the weight shift is the maximum of the log-weight
 // over the predicted range (the reference's my_max, Q4, picks another element; the shift
 // cancels analytically); log N(y; 0, e^{x/2}) is evaluated as -0.9189.. - x/2 - y^2 e^{-x}/2.
-// If the arrivals of a CTA exceed its shared-memory capacity or a (destination, source) run
+// If the arrivals of a CTA exceed its shared-memory capacity or a (destination, source, warp) run
 // overflows (a degenerate cloud), the evaluation is abandoned with status 1 and the host code
 // re-runs the general kernel (sv_filter.cu) for that problem.
+//
+// u is read either time-major from device memory or, for host-resident u, from the chunked
+// staging buffer the copy engine fills while the kernel runs (pmmh_flps_sv_corr_streamed).
 #include <math.h>
 
 #include "common.cuh"
@@ -64,7 +70,6 @@ constexpr int kB1 = 1;       // arrivals per thread in flight (phase B pass 1)
 constexpr int kB2 = 1;       // look-ups per thread in flight (fixed-lag terms)
 // (measured on B200 at N = 2^20: 4/4/8 in flight 210 ms, 2/2/4 202 ms, 1/1/1 199 ms per evaluation -- the
 //  kernel is bound by instruction issue and code size, not by memory-level parallelism)
-constexpr int kTile = kT * kRounds;
 constexpr int kBinOccMax = 1024;         // a fuller bin means a degenerate cloud: abandon
 constexpr int kMaxSub = kFastMaxSub;
 constexpr int kPHint = 2 * kCap / 32;   // parent hints cover this many blocks of 32 children
@@ -102,7 +107,6 @@ __device__ __forceinline__ Rec ld_rec(const Rec* p) {
     return r;
 }
 __device__ __forceinline__ double ld_rec_x(const Rec* p) { return __ldcg(&p->x); }
-__device__ __forceinline__ int ld_rec_b(const Rec* p, int k) { return __ldcg(&p->b[k]); }
 
 struct FastWs {
     Rec* mail;       // [2][G * NR * CW]   child records by generation parity; NR = G * kNW runs per
@@ -369,26 +373,9 @@ __device__ __forceinline__ int chunk_of(int l, int rank, int G) {
     return l * G + ((l & 1) ? (G - 1 - rank) : rank);
 }
 
-// threshold of child j (:711): (u + j) / N
-__device__ __forceinline__ double child_cp(double u, int j, int N, bool pow2, double invN) {
-    return pow2 ? (u + (double)j) * invN : (u + (double)j) / (double)N;
-}
-// number of thresholds at or below c = smallest j in [0, N] whose threshold exceeds c
-__device__ __forceinline__ int first_child_above(double c, double u, int N, bool pow2, double invN) {
-    if (!(c == c)) return N;
-    double guess = c * (double)N - u;
-    if (!(guess > -1.0)) guess = -1.0;
-    if (guess > (double)N) guess = (double)N;
-    int fc = (int)floor(guess) + 1;
-    if (fc < 0) fc = 0;
-    if (fc > N) fc = N;
-    while (fc > 0 && child_cp(u, fc - 1, N, pow2, invN) > c) --fc;
-    while (fc < N && !(child_cp(u, fc, N, pow2, invN) > c)) ++fc;
-    return fc;
-}
-
-// Same as first_child_above, written on integer-valued doubles (one conversion at the end), and
-// counting the decisions within 64 ulp of a tie on the way (diagnostics).  dN = (double)N.
+// Number of thresholds (u + j) / N (:711) at or below c = smallest j in [0, N] whose threshold
+// exceeds c, written on integer-valued doubles (one conversion at the end); decisions within 64 ulp
+// of a tie are counted on the way (diagnostics).  dN = (double)N.
 __device__ __forceinline__ int first_child_above_nt(double c, double u, double dN, bool pow2, double invN,
                                                     long long& near_ties) {
     if (!(c == c)) return (int)dN;
@@ -492,7 +479,6 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
     __shared__ double s_red[12 * 32];
     __shared__ double s_w[kNW + 1];
     __shared__ int s_iw[kNW + 1];
-    __shared__ int s_misc[8];
     __shared__ double s_S[kMaxLagF];
     // per local chunk
     __shared__ int s_lstart[kMaxSub + 1];    // first sorted position
