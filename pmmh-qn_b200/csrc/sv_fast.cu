@@ -199,6 +199,58 @@ __device__ __forceinline__ void team_exchange(TeamF& t, const double* vals, int 
     __syncthreads();
 }
 
+// The same exchange in two halves, so that work that does not depend on the other CTAs can run
+// between publishing (team_arrive) and waiting for everybody (team_finish).
+__device__ __forceinline__ void team_arrive(TeamF& t, const double* vals, int K) {
+    if (t.G == 1) {
+        __syncthreads();
+        return;
+    }
+    t.epoch++;
+    double* buf = t.slots + (size_t)(t.epoch & 1u) * t.G * kSlotW;
+    __syncthreads();
+    if ((int)threadIdx.x < K) __stcg(&buf[t.rank * kSlotW + threadIdx.x], vals[threadIdx.x]);
+    __syncthreads();
+    // the last warp signals (and later polls): it takes no part in the work between the two
+    // halves, so the fence (which drains the CTA's stores) and the atomic overlap with that work
+    if (threadIdx.x == blockDim.x - 32) {
+        __threadfence();
+        atomicAdd(t.ctr, 1u);
+    }
+}
+__device__ __forceinline__ void team_finish(TeamF& t, const double* vals, int K, double* out) {
+    if (t.G == 1) {
+        __syncthreads();
+        if ((int)threadIdx.x < K) out[threadIdx.x] = vals[threadIdx.x];
+        __syncthreads();
+        return;
+    }
+    const double* buf = t.slots + (size_t)(t.epoch & 1u) * t.G * kSlotW;
+    if (threadIdx.x == blockDim.x - 32) {
+        const unsigned target = t.epoch * (unsigned)t.G;
+        while (ld_acquire_u32(t.ctr) < target) {
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    const int n = t.G * K;
+    for (int q0 = threadIdx.x; q0 < n; q0 += 8 * blockDim.x) {
+        double v[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int q = q0 + r * blockDim.x;
+            const int c = q / K, k = q - c * K;
+            v[r] = (q < n) ? __ldcg(&buf[c * kSlotW + k]) : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int q = q0 + r * blockDim.x;
+            if (q < n) out[q] = v[r];
+        }
+    }
+    __syncthreads();
+}
+
 // ---- block-wide scans (kT threads; fixed order => deterministic) ---------------------------
 // exclusive prefix of one value per thread; *total = sum over the block.  s_w: shared [kNW + 1].
 __device__ __forceinline__ double block_excl_scan_d(double v, double* s_w, double* total) {
@@ -471,8 +523,6 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
     double* s_g1 = (double*)s_k32;                                    // [G * 8]  small exchanges
     //   views of the s_hist region (phase A)
     unsigned short* s_wh = (unsigned short*)s_hist;                   // [kNW][G] per-warp destination counts
-    //   views of the s_k32 region (phase B pass 1)
-    int* s_hb = (int*)s_k32;                                          // [kCap]  arrival order: first look-up id
 
     __shared__ double s_vals[kSlotW];
     __shared__ double s_tot[16];
@@ -480,6 +530,7 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
     __shared__ double s_w[kNW + 1];
     __shared__ int s_iw[kNW + 1];
     __shared__ double s_S[kMaxLagF];
+    __shared__ double s_lag[5];              // fixed-lag sums of the previous generation (published one step late)
     // per local chunk
     __shared__ int s_lstart[kMaxSub + 1];    // first sorted position
     __shared__ double s_Cb[kMaxSub + 1];     // CTA-wide cumulative weight in front of it
@@ -630,6 +681,41 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
         int max_occ = 0, status = 0, max_arr = 0;
         long long fail_info = 0;
 
+        // ---- fixed-lag terms (:445-470) of generation g for my arrivals [e_lo, e_hi): the ancestor
+        // K = LAG - 2 steps back through the compact tables (the carried id reaches generation
+        // g - ((K-1) % 4 + 1), then 4 at a time).  These sums only feed outputs, so they are
+        // evaluated while the CTA waits for the exchanges and published one step late.
+        double lacc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        if (tid < 5) s_lag[tid] = 0.0;
+        auto lag_sweep = [&](int g, int e_lo, int e_hi) {
+            if (g < LAG) return;
+            const double ylg = obs[g - LAG];   // Q5
+            const int hop0 = (K >= 1) ? ((K - 1) & 3) : 0;
+            const int g1 = g - (hop0 + 1);
+            const int nh = (K >= 1) ? ((K - 1) >> 2) : 0;
+            const double2* xpk = XPT(g - K);
+            const int* b4g = B4T(g);
+            const Rec* Mg = MAIL(g);
+            // (the last warp is busy with the exchange when a team has more than one CTA)
+            const int nsw = (G > 1) ? kT - 32 : kT;
+            if (tid >= nsw) return;
+            for (int e = e_lo + tid; e < e_hi; e += nsw) {
+                int id;
+                if (K == 0) id = my_cid + e;   // the pair is the record itself
+                else if (hop0 == 3) id = __ldcg(&b4g[my_cid + e]);
+                else id = __ldcg(&Mg[my_base + arrival_slot(s_off, s_hint, CW, e)].b[hop0]);
+                for (int h = 0; h < nh; ++h) id = __ldcg(&B4T(g1 - 4 * h)[id]);
+                const double2 pv = __ldcg(&xpk[id]);
+                const double shv = s_sh[e];
+                double sq, gq[4];
+                sv_score_main(c, pv.y, pv.x, ylg, sq, gq);
+                lacc[0] += shv * pv.y;
+                lacc[1] += gq[0] * shv;
+                lacc[2] += gq[1] * shv;
+                lacc[3] += gq[2] * shv;
+                lacc[4] += gq[3] * shv;
+            }
+        };
         for (int i = 0; i < NOBS; ++i) {
             // =========== cumulative weights of generation i in sorted order (CTA-local), publish
             const int R = (n_d + kT - 1) / kT;
@@ -654,8 +740,8 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
                     }
                 }
                 __syncthreads();
-                double sums[8] = {acc[0], acc[1], acc[2], acc[4], acc[5], acc[6], acc[7], acc[8]};
-                block_sum<8>(sums, s_red);
+                double sums[3] = {acc[0], acc[1], acc[2]};
+                block_sum<3>(sums, s_red);
                 minx = warp_min(minx);
                 if (lane == 0) s_w[warp] = minx;
                 chunk_over = __syncthreads_or(chunk_over);
@@ -672,17 +758,19 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
                     s_vals[2 * S + 0] = sums[0];
                     s_vals[2 * S + 1] = sums[1];
                     s_vals[2 * S + 2] = sums[2];
-                    s_vals[2 * S + 4] = sums[3];
-                    s_vals[2 * S + 5] = sums[4];
-                    s_vals[2 * S + 6] = sums[5];
-                    s_vals[2 * S + 7] = sums[6];
-                    s_vals[2 * S + 8] = sums[7];
+                    s_vals[2 * S + 4] = s_lag[0];   // fixed-lag sums of generation i - 1
+                    s_vals[2 * S + 5] = s_lag[1];
+                    s_vals[2 * S + 6] = s_lag[2];
+                    s_vals[2 * S + 7] = s_lag[3];
+                    s_vals[2 * S + 8] = s_lag[4];
                     s_vals[2 * S + 9] = (double)chunk_over;
                 }
             }
             PROF_MARK(0);   // cumulative weights + block sums
-            team_exchange(tm, s_vals, KW, s_gather);   // exchange 2
-            PROF_MARK(1);   // exchange 2 (wait + gather)
+            team_arrive(tm, s_vals, KW);   // exchange 2 ...
+            lag_sweep(i, 0, n_d >> 1);     // ... first half of the fixed-lag terms while the others arrive
+            team_finish(tm, s_vals, KW, s_gather);
+            PROF_MARK(1);   // exchange 2 (wait + gather) + half of the fixed-lag terms
 
             // =========== bookkeeping for generation i (just gathered)
             for (int q = warp; q < kNumSums; q += kNW) {
@@ -764,13 +852,14 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
             if (lead && tid == 0) {
                 o_filt[i] = s_tot[0] / S_i;
                 o_traj[i] = s_tot[3];   // Q11: traj[i] = X_i[0] (time 0: x0)
-                if (i >= LAG) {
-                    const int tt = i - LAG + 1;
-                    o_smo[tt] = s_tot[4] / S_i;
-                    o_grad[tt] = s_tot[5] / S_i;
-                    o_grad[NOBS + tt] = s_tot[6] / S_i;
-                    o_grad[2 * NOBS + tt] = s_tot[7] / S_i;
-                    o_grad[3 * NOBS + tt] = s_tot[8] / S_i;
+                if (i - 1 >= LAG) {   // the fixed-lag sums travel one step late
+                    const int tt = i - LAG;
+                    const double S_p = s_S[(i - 1) % kMaxLagF];
+                    o_smo[tt] = s_tot[4] / S_p;
+                    o_grad[tt] = s_tot[5] / S_p;
+                    o_grad[NOBS + tt] = s_tot[6] / S_p;
+                    o_grad[2 * NOBS + tt] = s_tot[7] / S_p;
+                    o_grad[3 * NOBS + tt] = s_tot[8] / S_p;
                 }
             }
             if (tid < S) s_lcoff[tid] = s_coff[chunk_of(tid, me, G)];
@@ -1137,7 +1226,14 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
             pair_over = __syncthreads_or(pair_over);
             PROF_MARK(4);   // children: propagate + route + write
             if (tid == 0) s_vals[0] = (double)pair_over;
-            team_exchange(tm, s_vals, 1, s_g1);   // exchange 1
+            team_arrive(tm, s_vals, 1);   // exchange 1 ...
+            // ... second half of the fixed-lag terms of generation i while the others arrive
+            lag_sweep(i, n_d >> 1, n_d);
+            block_sum<5>(lacc, s_red);
+            if (tid < 5) s_lag[tid] = s_red[tid * 32];   // block_sum leaves the totals there
+#pragma unroll
+            for (int q = 0; q < 5; ++q) lacc[q] = 0.0;
+            team_finish(tm, s_vals, 1, s_g1);
             {
                 double f = 0.0;
                 for (int cc = tid; cc < G; cc += kT) f = fmax(f, s_g1[cc]);
@@ -1194,9 +1290,6 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
             }
             __syncthreads();
             const Rec* Gn = MAIL(inext);
-            const double yl = (inext >= LAG) ? obs[inext - LAG] : 0.0;   // Q5
-            const bool lagged = inext >= LAG;
-            const int hop0 = (K >= 1) ? ((K - 1) & 3) : 0;   // carried id that starts the look-ups
 #pragma unroll
             for (int q = 0; q < 9; ++q) acc[q] = 0.0;
             minx = INFINITY;
@@ -1221,7 +1314,6 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
                             b4n[my_cid + e] = rc[r].b[3];
                             __stcs(&xpn[my_cid + e], make_double2(xv, rc[r].xpar));   // read 8 steps later: stream out
                             if (b1n) __stcs(&b1n[my_cid + e], rc[r].b[0]);
-                            s_hb[e] = (hop0 == 3) ? rc[r].b[3] : ((hop0 == 2) ? rc[r].b[2] : ((hop0 == 1) ? rc[r].b[1] : rc[r].b[0]));
                             // chunk and key
                             int kc = 0;
                             const double zx = (xv - m1) * inv_sdc;
@@ -1255,52 +1347,6 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
                                 acc[1] += sdf;
                                 acc[2] += sdf * df;
                             }
-                            if (lagged && K == 0) {   // the pair is the record itself
-                                double sq, g[4];
-                                sv_score_main(c, rc[r].xpar, xv, yl, sq, g);
-                                acc[4] += shv * rc[r].xpar;
-                                acc[5] += g[0] * shv;
-                                acc[6] += g[1] * shv;
-                                acc[7] += g[2] * shv;
-                                acc[8] += g[3] * shv;
-                            }
-                        }
-                    }
-                }
-            }
-            // ---- fixed-lag terms (:445-470): ancestor K = LAG - 2 steps back through the compact
-            //      tables: the carried id reaches generation inext - ((K-1) % 4 + 1), then 4 at a time
-            if (lagged && K >= 1) {
-                const int g1 = inext - (hop0 + 1);
-                const int nh = (K - 1) >> 2;
-                const double2* xpk = XPT(inext - K);
-                for (int e0 = 0; e0 < n_d; e0 += kB2 * kT) {
-                    int hb[kB2];
-#pragma unroll
-                    for (int r = 0; r < kB2; ++r) {
-                        const int e = e0 + r * kT + tid;
-                        hb[r] = (e < n_d) ? s_hb[e] : 0;
-                    }
-                    for (int h = 0; h < nh; ++h) {
-                        const int* bt = B4T(g1 - 4 * h);
-#pragma unroll
-                        for (int r = 0; r < kB2; ++r) hb[r] = __ldcg(&bt[hb[r]]);
-                    }
-                    double2 pv[kB2];
-#pragma unroll
-                    for (int r = 0; r < kB2; ++r) pv[r] = __ldcg(&xpk[hb[r]]);
-#pragma unroll
-                    for (int r = 0; r < kB2; ++r) {
-                        const int e = e0 + r * kT + tid;
-                        if (e < n_d) {
-                            const double shv = s_sh[e];
-                            double sq, g[4];
-                            sv_score_main(c, pv[r].y, pv[r].x, yl, sq, g);
-                            acc[4] += shv * pv[r].y;
-                            acc[5] += g[0] * shv;
-                            acc[6] += g[1] * shv;
-                            acc[7] += g[2] * shv;
-                            acc[8] += g[3] * shv;
                         }
                     }
                 }
@@ -1378,6 +1424,29 @@ __global__ void __launch_bounds__(kT, 1) sv_fast_kernel(SvArgs a) {
         }   // time loop
         PROF_MARK(8);
 
+        // ---------------- fixed-lag terms of the last generation (they travel one step late)
+        if (status == 0) {
+            const int T = NOBS - 1;
+            lag_sweep(T, n_d >> 1, n_d);   // the first half ran while waiting for the last exchange
+            block_sum<5>(lacc, s_red);
+            if (tid < 5) s_vals[tid] = s_red[tid * 32];
+            team_exchange(tm, s_vals, 5, s_g1);
+            if (warp < 5) {
+                const double sv = gathered_sum(s_g1, 5, warp, G, lane);
+                if (lane == 0) s_tot[warp] = sv;
+            }
+            __syncthreads();
+            if (lead && tid == 0 && T >= LAG) {
+                const int tt = T - LAG + 1;
+                const double S_T = s_S[T % kMaxLagF];
+                o_smo[tt] = s_tot[0] / S_T;
+                o_grad[tt] = s_tot[1] / S_T;
+                o_grad[NOBS + tt] = s_tot[2] / S_T;
+                o_grad[2 * NOBS + tt] = s_tot[3] / S_T;
+                o_grad[3 * NOBS + tt] = s_tot[4] / S_T;
+            }
+            __syncthreads();
+        }
         // ---------------- tail (:540-562, Q6), dense positions
         if (status == 0) {
             const int T = NOBS - 1;

@@ -15,7 +15,7 @@ r = probe_sv.run(n, nobs=nobs, reps=0)
 torch.cuda.synchronize()
 _lib.load().pmmh_sv_debug_profile(None)
 c = buf.cpu().numpy().astype(np.float64)
-names = ["cumsum", "exch2", "bk:lut", "ranges", "children", "exch1", "B:pass1", "B:sort", "-", "tail", "bk:prefix", "bk:outputs", "bk:chunks", "bk:cdf", "bk:splitters"]
+names = ["cumsum", "exch2+lag/2", "bk:lut", "ranges", "children", "exch1+lag/2", "B:pass1", "B:sort", "-", "tail", "bk:prefix", "bk:outputs", "bk:chunks", "bk:cdf", "bk:splitters"]
 steps = nobs - 1
 tot = c.sum(axis=1)
 print("per-step microseconds at 1.9 GHz (mean / min / max over CTAs); total per CTA %.1f ms" % (tot.mean() / 1.9e6))
