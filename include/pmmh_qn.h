@@ -62,7 +62,7 @@ extern "C" {
 #define PMMH_DIAG_KEY_TIES 3    /* equal keys met while sorting */
 #define PMMH_DIAG_WAVEFRONT 4   /* bpf parity mode: deepest dependency chain */
 #define PMMH_DIAG_TRAJ_IDX 5    /* bpf: sampled trajectory index */
-#define PMMH_DIAG_KERNEL 6      /* kernel that produced the outputs: 1 general, 2 exchange */
+#define PMMH_DIAG_KERNEL 6      /* kernel that produced the outputs: 1 general, 2 exchange, 3 chain */
 #define PMMH_DIAG_FAST_INFO 7   /* exchange kernel: abandon reason (1 run / 2 chunk overflow) |
                                    step << 8 | longest mailbox run << 32 */
 #define PMMH_DIAG_COUNT 8
@@ -75,11 +75,13 @@ int pmmh_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* ---------------------------------------------------------------- SV particle methods -- */
 
 /* Kernel selection for pmmh_flps_sv_corr (process-wide; default 0).
- *   0  automatic: the two-barrier "exchange" kernel for log-likelihood + gradient
- *      (compute_hessian == 0), the general kernel for everything else and as the fallback
- *      for problems the exchange kernel abandons (degenerate particle clouds)
+ *   0  automatic, for log-likelihood + gradient (compute_hessian == 0): the "chain" kernel (one
+ *      CTA per problem, everything in shared memory) when n_particles <= 4096 and lag <= 10, the
+ *      two-exchange "exchange" kernel for teams of CTAs; the general kernel for everything else
+ *      and as the fallback for problems those abandon (degenerate particle clouds)
  *   1  general kernel only
- *   2  diagnostics: like 0 but without the fallback pass (abandoned problems keep status 1)
+ *   2  diagnostics: exchange kernel where eligible, without the fallback pass
+ *   3  diagnostics: chain kernel where eligible, without the fallback pass
  * Call before pmmh_sv_workspace_bytes: the workspace size depends on it. */
 int pmmh_sv_set_algorithm(int algorithm);
 

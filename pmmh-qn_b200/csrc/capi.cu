@@ -60,11 +60,15 @@ struct SvPlan {
     size_t stamp_bytes, sync_bytes, team_stride, total;
     // exchange kernel (sv_fast.cu); use_fast = 0 when the problem is not eligible
     int use_fast, NSUB, CP;
+    int use_chain;
+    size_t chain_stride, chain_total;
     size_t fast_sync_bytes, fast_team_stride, fast_total, general_total;
 };
 
-// 0 = automatic (exchange kernel where eligible, general kernel otherwise and as its fallback),
-// 1 = general kernel only, 2 = exchange kernel where eligible WITHOUT the fallback pass (diagnostics)
+// 0 = automatic (chain kernel for problems that fit one CTA, exchange kernel for teams of CTAs,
+//     general kernel otherwise and as their fallback),
+// 1 = general kernel only, 2 = exchange kernel where eligible WITHOUT the fallback pass (diagnostics),
+// 3 = chain kernel where eligible WITHOUT the fallback pass (diagnostics)
 int g_sv_algorithm = 0;
 long long* g_sv_prof = nullptr;   // development: per-CTA phase clocks of the exchange kernel
 constexpr int kMaxDynSmem = 227 * 1024;
@@ -84,8 +88,13 @@ int sv_make_plan(int nobs, int n, int lag, int batch, int hess, int mode, int ha
     if (rc != PMMH_OK) return rc;
     if (di.major < 10) return fail(PMMH_ERR_NO_DEVICE, "an sm_100 (B200) device is required");
     if (!di.coop) return fail(PMMH_ERR_NO_DEVICE, "device lacks cooperative launch");
+    // log-likelihood + gradient of a problem that fits one CTA: the chain kernel (everything in
+    // shared memory, no exchanges)
+    const bool chain_ok = (mode == pmmh::kSvFlps) && !hess && pmmh::sv_chain_eligible(n, lag) &&
+                          (g_sv_algorithm == 0 || g_sv_algorithm == 3) && (ctas <= 1);
     int G;
     if (ctas > 0) G = ctas;
+    else if (chain_ok) G = 1;
     else if (batch > 1) G = (n + 4095) / 4096;
     else G = (n + 1023) / 1024;
     if (G < 1) G = 1;
@@ -108,13 +117,21 @@ int sv_make_plan(int nobs, int n, int lag, int batch, int hess, int mode, int ha
                                         have_hist, nullptr, nullptr);
     p->general_total = p->sync_bytes + (size_t)n_teams * p->team_stride;
     p->total = p->general_total;
+    p->use_chain = 0;
+    p->chain_stride = p->chain_total = 0;
+    if (chain_ok && G == 1 && pmmh::sv_chain_smem_bytes(n) <= kMaxDynSmem) {
+        p->use_chain = 1;
+        p->chain_stride = pmmh::sv_chain_ws_bytes(n, lag);
+        p->chain_total = (size_t)p->grid * p->chain_stride;
+        if (p->chain_total > p->total) p->total = p->chain_total;
+    }
     p->use_fast = 0;
     p->NSUB = 0;
     p->fast_sync_bytes = p->fast_team_stride = p->fast_total = 0;
     p->CP = 0;
     // one CTA per problem (batches of small problems) has no exchange to save: the general kernel
     // is the faster one there (measured: 8.8e9 vs 7.0e9 particle-steps/s at 1024 x N=4096)
-    const bool want_fast = (g_sv_algorithm == 2) || (g_sv_algorithm == 0 && G > 1);
+    const bool want_fast = !p->use_chain && ((g_sv_algorithm == 2) || (g_sv_algorithm == 0 && G > 1));
     if (mode == pmmh::kSvFlps && !hess && want_fast && pmmh::sv_fast_eligible(n, G)) {
         const int S = pmmh::sv_fast_nsub(n, G);
         const int CP = pmmh::sv_fast_pair_cap(n, G);
@@ -180,6 +197,14 @@ int sv_run(int mode, const double* d_obs, long long obs_stride, const double* d_
     a.Ahist = d_ah;
     a.prof = g_sv_prof;
     a.ws = (char*)d_ws;
+    if (p.use_chain) {
+        // chain kernel first; problems it abandons (diag status 1) are re-run by the general kernel
+        a.ws_sync_bytes = 0;
+        a.ws_team_stride = p.chain_stride;
+        PMMH_CUDA(pmmh::sv_chain_launch(a, p.grid, st));
+        if (g_sv_algorithm == 3) return PMMH_OK;   // diagnostics: no fallback pass
+        a.only_failed = 1;
+    }
     if (p.use_fast) {
         // exchange kernel first; problems it abandons (diag status 1) are re-run by the general
         // kernel in the same stream, reusing the workspace
@@ -230,7 +255,7 @@ int pmmh_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 }
 
 int pmmh_sv_set_algorithm(int algorithm) {
-    if (algorithm < 0 || algorithm > 2) return fail(PMMH_ERR_INVALID, "algorithm must be 0, 1 or 2");
+    if (algorithm < 0 || algorithm > 3) return fail(PMMH_ERR_INVALID, "algorithm must be 0, 1, 2 or 3");
     g_sv_algorithm = algorithm;
     return PMMH_OK;
 }

@@ -15,6 +15,9 @@ constexpr int kFastThreads = 512;        // exchange kernel: threads per CTA (12
 constexpr int kFastCap = 10240;          // exchange kernel: arrivals per CTA and generation (smem capacity)
 constexpr int kFastMaxSub = 8;           // exchange kernel: at most this many chunks per CTA
 
+constexpr int kChainThreads = 1024;      // chain kernel: threads per CTA (one CTA per problem)
+constexpr int kChainMaxN = 4096;         // chain kernel: particles per problem (all in shared memory)
+
 constexpr int kProfSlots = 16;
 
 enum SvMode { kSvFlps = 0, kSvBpfParity = 1, kSvBpfIntended = 2 };
@@ -27,7 +30,7 @@ enum SvDiag {
     kDiagKeyTies = 3,      // equal adjacent keys after sorting
     kDiagWavefront = 4,    // bpf parity mode: max dependency-chain depth
     kDiagTrajIdx = 5,      // bpf: sampled trajectory index (Q10)
-    kDiagKernel = 6,       // which kernel produced the outputs: 1 general, 2 exchange
+    kDiagKernel = 6,       // which kernel produced the outputs: 1 general, 2 exchange, 3 chain
     kDiagFastInfo = 7,     // exchange kernel: reason (1 run, 2 CTA overflow, 3 weights) | step << 8 | most arrivals << 32
     kDiagCount = 8
 };
@@ -118,6 +121,12 @@ __host__ __device__ inline size_t sv_ws_layout(int N, int NOBS, int LAG, int NB,
 // Host-side launcher (sv_filter.cu)
 cudaError_t sv_launch(const SvArgs& a, int grid, cudaStream_t stream);
 int sv_dynamic_smem_bytes(int G);
+
+// chain kernel (sv_chain.cu): one CTA per problem, N <= kChainMaxN
+int sv_chain_eligible(int N, int LAG);
+size_t sv_chain_ws_bytes(int N, int LAG);
+int sv_chain_smem_bytes(int N);
+cudaError_t sv_chain_launch(const SvArgs& a, int grid, cudaStream_t stream);
 
 // exchange kernel (sv_fast.cu)
 int sv_fast_nsub(int N, int G);

@@ -52,7 +52,8 @@ def device_info():
 
 
 def set_sv_algorithm(algorithm):
-    """0 = automatic (exchange kernel where eligible), 1 = general kernel only (pmmh_sv_set_algorithm)."""
+    """0 = automatic (chain / exchange kernel where eligible), 1 = general kernel only, 2 / 3 = exchange /
+    chain kernel without the general-kernel fallback (pmmh_sv_set_algorithm)."""
     lib = _lib.load()
     _lib.check(lib.pmmh_sv_set_algorithm(int(algorithm)), "pmmh_sv_set_algorithm")
 

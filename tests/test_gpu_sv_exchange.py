@@ -199,3 +199,63 @@ def test_streamed_host_rvs_equals_resident(cuda_dev, pinned):
     torch.cuda.synchronize()
     for k in ("log_like", "gradient"):
         assert torch.equal(c1[k], a[k]) and torch.equal(c2[k], a[k]), k
+
+
+# ------------------------------------------------------------------ chain kernel (one CTA per problem)
+@pytest.fixture()
+def chain_only():
+    from pmmh_qn_b200 import kernels as K
+    K.set_sv_algorithm(3)
+    yield K
+    K.set_sv_algorithm(0)
+
+
+@pytest.mark.parametrize("n,nobs,lag", [(75, 361, 10), (1024, 301, 10), (3000, 200, 10), (4096, 1001, 10),
+                                        (4096, 120, 2), (2500, 120, 3), (2500, 120, 6), (2500, 120, 7)])
+def test_chain_vs_oracle(cuda_dev, chain_only, n, nobs, lag):
+    import oracle
+    obs, params, rvr, rvp, u = _inputs(n, nobs, 4)
+    ref = oracle.flps_sv_corr(obs, params, rvr, rvp, n, lag, 0, dumps=True)
+    res = _run(chain_only, cuda_dev, obs, params, rvr, u, lag, True)
+    assert int(res["diag"][0, DIAG_KERNEL]) == 3 and int(res["diag"][0, DIAG_STATUS]) == 0
+    step = first_mismatch_step(res["A"][0][1:], ref["A"][1:])
+    assert step is None, "ancestors differ first at time %d" % (step + 1)
+    assert relerr(res["X"][0], ref["X"]) <= 1e-12
+    assert abs(res["log_like"][0] - ref["log_like"]) <= 1e-10 * abs(ref["log_like"])
+    assert relerr(res["filt"][0], ref["filt"]) <= 1e-10
+    assert relerr(res["smo"][0], ref["smo"]) <= 1e-10
+    assert relerr(res["traj"][0], ref["traj"]) <= 1e-12
+    assert np.max(np.abs(res["gradient"][0] - ref["gradient"])) <= 1e-9 * np.max(np.abs(ref["gradient"]))
+
+
+def test_chain_batch_equals_singles_and_general(cuda_dev, chain_only):
+    """A batch of chains (more problems than CTAs) == single launches bit for bit, and agrees with
+    the general kernel within the tolerances."""
+    import torch
+    K = chain_only
+    n, nobs, lag, B = 2048, 100, 10, 200
+    obs = gi.sv_obs(nobs)
+    rs = np.random.RandomState(13)
+    params = np.array(gi.SV_PARAM_SETS[0]) + 0.02 * rs.normal(size=(B, 4))
+    dev = cuda_dev
+    g = torch.Generator(device=dev)
+    g.manual_seed(3)
+    u = torch.randn((B, nobs, n), dtype=torch.float64, device=dev, generator=g)
+    rvr = torch.rand((B, nobs), dtype=torch.float64, device=dev, generator=g)
+    t = lambda x: torch.from_numpy(x).to(dev)   # noqa: E731
+    out = K.flps_sv_corr(t(obs), t(params), rvr, u, lag=lag)
+    torch.cuda.synchronize()
+    assert np.all(out["diag"][:, DIAG_KERNEL].cpu().numpy() == 3)
+    assert np.all(out["diag"][:, DIAG_STATUS].cpu().numpy() == 0)
+    for b in (0, 57, 148, 199):
+        single = K.flps_sv_corr(t(obs), t(params[b:b + 1]), rvr[b:b + 1].contiguous(), u[b:b + 1].contiguous(), lag=lag)
+        torch.cuda.synchronize()
+        for k in ("log_like", "filt", "smo", "gradient", "traj"):
+            assert torch.equal(out[k][b], single[k][0]), (b, k)
+    K.set_sv_algorithm(1)
+    gen = K.flps_sv_corr(t(obs), t(params), rvr, u, lag=lag)
+    torch.cuda.synchronize()
+    a, b_ = out["log_like"].cpu().numpy(), gen["log_like"].cpu().numpy()
+    assert np.max(np.abs(a - b_) / np.abs(b_)) <= 1e-12
+    ga, gb = out["gradient"].cpu().numpy(), gen["gradient"].cpu().numpy()
+    assert np.max(np.abs(ga - gb)) <= 1e-9 * np.max(np.abs(gb))
