@@ -258,12 +258,20 @@ __global__ void __launch_bounds__(kCT, 1) sv_chain_kernel(SvArgs a) {
                         if (s_cum[mid] < cps) l = mid + 1;
                         else h = mid;
                     }
-                    while (l > 0 && !(s_cum[l - 1] / S_prev < cp)) --l;
-                    while (l < N - 1 && (s_cum[l] / S_prev < cp)) ++l;
+                    double cv_hi = s_cum[l] / S_prev;
+                    double cv_lo = (l > 0) ? s_cum[l - 1] / S_prev : -1.0;
+                    while (l > 0 && !(cv_lo < cp)) {   // (rare: the two quotients settle the probe result)
+                        --l;
+                        cv_hi = cv_lo;
+                        cv_lo = (l > 0) ? s_cum[l - 1] / S_prev : -1.0;
+                    }
+                    while (l < N - 1 && (cv_hi < cp)) {
+                        ++l;
+                        cv_lo = cv_hi;
+                        cv_hi = s_cum[l] / S_prev;
+                    }
                     {   // diagnostics: decisions within 64 ulp of a cumulative-weight tie
                         const double tol = 64.0 * 2.220446049250313e-16 * cp;
-                        const double cv_hi = s_cum[l] / S_prev;
-                        const double cv_lo = (l > 0) ? s_cum[l - 1] / S_prev : -1.0;
                         if (fabs(cv_hi - cp) <= tol || (cv_lo >= 0.0 && fabs(cp - cv_lo) <= tol)) near_ties++;
                     }
                     const double xpv = s_x[l];
