@@ -25,6 +25,8 @@
  *                                state/direct/standard.py:52-53,75-76, subsampling.pyx:34-51
  *   pmmh_logistic_loglike        LogisticRegressionModel.get_loglike_gradient
  *                                models/logistic_regression.py:108-176
+ *   pmmh_svsplit_*               (new) the same smoother with its particles split over the GPUs of
+ *                                one box; phases of one time step, see below
  *   pmmh_*_host                  the same calls with HOST buffers in the reference's own
  *                                layouts (what a cgo/ctypes/Cython stub would bind 1:1)
  *
@@ -62,7 +64,7 @@ extern "C" {
 #define PMMH_DIAG_KEY_TIES 3    /* equal keys met while sorting */
 #define PMMH_DIAG_WAVEFRONT 4   /* bpf parity mode: deepest dependency chain */
 #define PMMH_DIAG_TRAJ_IDX 5    /* bpf: sampled trajectory index */
-#define PMMH_DIAG_KERNEL 6      /* kernel that produced the outputs: 1 general, 2 exchange, 3 chain */
+#define PMMH_DIAG_KERNEL 6      /* kernel that produced the outputs: 1 general, 2 exchange, 3 chain, 4 split */
 #define PMMH_DIAG_FAST_INFO 7   /* exchange kernel: abandon reason (1 run / 2 chunk overflow) |
                                    step << 8 | longest mailbox run << 32 */
 #define PMMH_DIAG_COUNT 8
@@ -190,6 +192,82 @@ int pmmh_logistic_loglike(const double* d_x, const double* d_y, const int* d_idx
                           long long row_begin, long long row_end, const double* d_beta,
                           int compute_hessian, double* d_out, void* d_workspace,
                           size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------- one SV particle filter split over several GPUs -- */
+
+/* BASELINE.json configs[4] / SURVEY.md 8e: a single flps_sv_corr evaluation
+ * (state/particle_methods/stochastic_volatility.pyx:205-655; called at
+ * state/particle_methods/cython.py:97) whose N particles do not fit, or are not wanted, on one
+ * GPU.  NEW API -- the reference has no multi-device call.  Rank r of `world` owns a contiguous
+ * value range of the sorted generation.  The library provides the device phases of one time step;
+ * the three exchanges between them are issued by the host layer on the same stream (NCCL through
+ * torch.distributed in pmmh-qn_b200/state/particle_methods/split.py):
+ *
+ *   weights(t) -> all-gather [world][4] -> children(t+1) -> all-gather [world][4096] int ->
+ *   plan (+ counts to pinned host memory) -> pack -> all-to-all-v of records -> sort -> weights(t+1)
+ *
+ * Buffers the caller owns (per rank): d_xs [cap] sorted values, d_perm [cap] sorted position ->
+ * arrival row, two record buffers [cap][LR] (current / next generation, LR = lag, or 1 when
+ * lag == 0 = log-likelihood and filter means only), d_send [cap_children][LR], d_sums [n_obs][8],
+ * d_shift [n_obs], d_xmin [n_obs], and the workspace.  cap_particles / cap_children bound the
+ * arrivals and the children of one rank; exceeding them sets diag[PMMH_DIAG_STATUS] (4 = children,
+ * 8 = arrivals, 16 = degenerate sort bin, 1/2 = non-finite weights) and the evaluation must be
+ * abandoned (the estimator returns False, as state/particle_methods/cython.py:71-75 does).
+ * u: d_u = [n_obs][N] time-major on every rank, or NULL = Philox stream (seed, philox_offset),
+ * element t*N + j as pmmh_crank_nicolson draws it. */
+int pmmh_svsplit_workspace_bytes(long long cap_particles, long long cap_children, size_t* bytes);
+/* generation 0 (Q1: every particle = mu); n_local = particles this rank starts with */
+int pmmh_svsplit_init(void* d_ws, size_t ws_bytes, long long n_total, int n_obs, int world, int rank,
+                      int lag, long long cap_particles, long long cap_children, int n_local,
+                      const double* h_params, double* d_xs, int* d_perm, double* d_rec, void* stream);
+/* weights of generation t (:427-470): d_sums[t][0..6] = local sums of sh, sh x, sh curr, sh g_0..3;
+ * d_gather_send[4] = (sum sh, n_local, min x, max x); d_sh_save (optional, [n_local]) keeps sh */
+int pmmh_svsplit_weights(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
+                         int t, int n_local, int lag, int n_obs, const double* h_obs,
+                         const double* d_params, const double* d_xs, const int* d_perm,
+                         const double* d_rec, double* d_sums, double* d_gather_send, double* d_sh_save,
+                         void* stream);
+/* resampling + propagation of the children of the local parents for time t (:694-715, :354-358);
+ * d_gather = all-gathered [world][4]; d_hist_send [4096] = local value histogram of the children */
+int pmmh_svsplit_children(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
+                          int t, int n_local, const double* d_obs, const double* d_params,
+                          const double* d_rvr, const double* d_u, unsigned long long seed,
+                          unsigned long long philox_offset, const double* d_gather, const double* d_xs,
+                          int* d_hist_send, double* d_shift, double* d_xmin, void* stream);
+/* splitters and counts from the all-gathered histograms [world][4096]; h_counts (pinned host,
+ * 2*world + 4 ints, valid after the stream is synchronised) = send counts per destination, receive
+ * counts per source, arrivals, children, fine sort bins, status */
+int pmmh_svsplit_plan(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
+                      int world, const int* d_hist, int* h_counts, void* stream);
+/* records of the children grouped by destination rank -> d_send (rows of LR doubles) */
+int pmmh_svsplit_pack(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
+                      const int* d_perm, const double* d_rec, double* d_send, void* stream);
+/* argsort of the arrivals (:392-424): d_xs / d_perm of the new generation */
+int pmmh_svsplit_sort(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
+                      int n_arrivals, int n_fine, int lag, const double* d_rec_new, double* d_xs,
+                      int* d_perm, void* stream);
+/* d_w[p] = d_sh[p] / *d_total (normalised weights of a kept generation, for the tail) */
+int pmmh_svsplit_normalise(const double* d_sh, int n_local, const double* d_total, double* d_w,
+                           void* stream);
+/* tail terms (:540-562, Q6) of the final generation.  d_w_lagged[irel][p] = normalised weight of
+ * generation n_obs - lag + irel at the GLOBAL sorted position of local particle p (redistributed
+ * by the host layer), irel < lag - 1.  d_tail [lag][8]: [irel][0] = smo term of time
+ * n_obs - lag + irel, [irel][1..4] = gradient terms of slot n_obs - 2 lag + 1 + irel (local sums) */
+int pmmh_svsplit_tail(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
+                      int n_local, int lag, int n_obs, const double* d_obs, const double* d_params,
+                      const int* d_perm, const double* d_rec, const double* d_w_final,
+                      const double* d_w_lagged, long long w_lagged_stride, double* d_tail,
+                      void* stream);
+/* O(T) assembly from the rank-summed d_sums / d_tail: log-likelihood (:537), filter and smoother
+ * means, gradient [4][n_obs], trajectory (Q10/Q11) */
+int pmmh_svsplit_finish(const double* d_sums, const double* d_shift, const double* d_xmin,
+                        const double* d_tail, const double* d_gather_last, int world,
+                        const double* d_params, int n_obs, int lag, long long n_total,
+                        double* d_log_like, double* d_filt, double* d_smo, double* d_gradient,
+                        double* d_traj, void* stream);
+/* h_diag[PMMH_DIAG_COUNT] of this rank (synchronises) */
+int pmmh_svsplit_diag(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
+                      long long* h_diag);
 
 /* ------------------------------------------------------------------- host-buffer wrappers -- */
 

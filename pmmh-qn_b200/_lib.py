@@ -49,6 +49,22 @@ SIGNATURES = {
     "pmmh_logistic_workspace_bytes": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_size)]),
     "pmmh_logistic_loglike": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_ll, c_ll, c_vp, c_int,
                                       c_vp, c_vp, c_size, c_vp]),
+    "pmmh_svsplit_workspace_bytes": (c_int, [c_ll, c_ll, ctypes.POINTER(c_size)]),
+    "pmmh_svsplit_init": (c_int, [c_vp, c_size, c_ll, c_int, c_int, c_int, c_int, c_ll, c_ll, c_int,
+                                  c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "pmmh_svsplit_weights": (c_int, [c_vp, c_size, c_ll, c_ll, c_int, c_int, c_int, c_int, c_vp,
+                                     c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "pmmh_svsplit_children": (c_int, [c_vp, c_size, c_ll, c_ll, c_int, c_int, c_vp, c_vp, c_vp, c_vp,
+                                      c_ull, c_ull, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "pmmh_svsplit_plan": (c_int, [c_vp, c_size, c_ll, c_ll, c_int, c_vp, c_vp, c_vp]),
+    "pmmh_svsplit_pack": (c_int, [c_vp, c_size, c_ll, c_ll, c_vp, c_vp, c_vp, c_vp]),
+    "pmmh_svsplit_sort": (c_int, [c_vp, c_size, c_ll, c_ll, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "pmmh_svsplit_normalise": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp]),
+    "pmmh_svsplit_tail": (c_int, [c_vp, c_size, c_ll, c_ll, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp,
+                                  c_vp, c_vp, c_ll, c_vp, c_vp]),
+    "pmmh_svsplit_finish": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_int, c_ll,
+                                    c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "pmmh_svsplit_diag": (c_int, [c_vp, c_size, c_ll, c_ll, c_vp]),
     "pmmh_flps_sv_corr_host": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int,
                                        c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "pmmh_bpf_sv_corr_host": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int,

@@ -8,6 +8,7 @@
 // All of it is HBM/L2-bound integer and fp64 streaming work: coalesced loads, shared-memory
 // tiles where a transpose or a reduction needs them, no tensor cores.  -fmad=false.
 #include "aux_kernels.cuh"
+#include "philox.cuh"
 
 #include <math.h>
 
@@ -80,28 +81,6 @@ cudaError_t launch_norm_cdf(const double* in, double* out, long long n, cudaStre
     const int grid = (int)min((long long)148 * 8, (n + 255) / 256);
     norm_cdf_kernel<<<grid, 256, 0, st>>>(in, out, n);
     return cudaGetLastError();
-}
-
-// Philox4x32-10 (Salmon et al. 2011), counter-based so every element is reproducible
-__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
-    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
-        const uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
-        const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
-        c[0] = n0;
-        c[1] = n1;
-        c[2] = n2;
-        c[3] = n3;
-        k0 += W0;
-        k1 += W1;
-    }
-}
-
-__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
-    const unsigned long long v = (((unsigned long long)hi << 32) | lo) >> 11;
-    return ((double)v + 0.5) * 1.1102230246251565e-16;   // (0, 1)
 }
 
 // parameter/mcmc/base_class.py:231-233:  out = sqrt(1 - s^2) * u + s * xi   (two roundings)

@@ -32,6 +32,16 @@ int fail_cuda(cudaError_t err, const char* where) {
         if (e__ != cudaSuccess) return fail_cuda(e__, #call); \
     } while (0)
 
+}  // namespace
+
+namespace pmmh {
+// error plumbing for the other translation units (sv_split.cu)
+int set_error(int code, const char* what) { return fail(code, what); }
+int set_cuda_error(cudaError_t err, const char* where) { return fail_cuda(err, where); }
+}  // namespace pmmh
+
+namespace {
+
 struct DeviceInfo {
     int sm = 0, major = 0, minor = 0, coop = 0;
     bool ok = false;

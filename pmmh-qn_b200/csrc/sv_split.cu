@@ -1,0 +1,1104 @@
+// sv_split.cu -- ONE stochastic-volatility particle filter / fixed-lag smoother whose particles
+// are split over the GPUs of a box (BASELINE.json configs[4], SURVEY.md 8e "single large PF").
+//
+// Same algorithm as flps_sv_corr (/root/reference/python/state/particle_methods/
+// stochastic_volatility.pyx:205-655: sort -> correlated systematic resampling -> propagate ->
+// weights -> fixed-lag score terms); what is new is the partition.  Rank r of `world` owns a
+// contiguous VALUE range of the sorted generation (n_r particles, every value on rank r <= every
+// value on rank r+1).  One time step is a sequence of device phases with three exchanges between
+// them; the exchanges themselves are issued by the host layer (torch.distributed / NCCL):
+//
+//   weights    log-weights, sh_j = exp(lw_j - shift), tiled inclusive scan of sh over the local
+//              generation, local sums for the outputs              -> 4 doubles per rank
+//   [all-gather of (sum sh, n_r, min x, max x)]   <- the "per-shard weight totals"
+//   children   global offset of this rank's cumulative weights; the children of LOCAL parents
+//              form a contiguous range [jlo, jhi) of the N resampling points (:694-715 evaluated
+//              parent-side, so no parent is ever fetched from another GPU); vectorised binary
+//              search of every child in the local cumulative weights, propagation (:354-358),
+//              coarse value histogram (4096 bins)                  -> 4096 ints per rank
+//   [all-gather of the histograms]
+//   plan       splitters on histogram-bin boundaries that give every rank ~N/world arrivals,
+//              send / receive counts, fine sort bins for the local value range
+//   pack       records (value + lagged ancestor values) grouped by destination rank
+//   [all-to-all-v of the records]
+//   sort       counting sort of the arrivals into fine bins (~8 per bin) + exact in-bin ranking
+//              = the reference's argsort (:392-424, :23-52) restricted to this value range
+//
+// Deviations from the reference's operation order are confined to summation order (parallel
+// scans / reductions instead of one sequential loop) and the choice of the log-weight shift
+// (any shift cancels analytically; Q4).  Resampling decisions that fall within 64 ulp of a
+// cumulative-weight tie are counted (diag[0]).  fp64, -fmad=false.  HBM/L2-bound streaming and
+// gather work: no tensor cores.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/pmmh_qn.h"
+#include "common.cuh"
+#include "philox.cuh"
+#include "sv_math.cuh"
+
+namespace pmmh {
+
+int set_error(int code, const char* what);           // capi.cu
+int set_cuda_error(cudaError_t err, const char* where);
+
+namespace {
+
+constexpr int kBins = 4096;         // coarse value bins of the routing histogram
+constexpr int kTile = 2048;         // particles per scan tile (256 threads x 8)
+constexpr int kFine = 8;            // target occupancy of a fine sort bin
+constexpr int kMaxWorld = 16;
+constexpr int kStage = 4096;        // cumulative weights staged in shared memory per child tile
+constexpr int kChildTile = 1024;    // children per tile (256 threads x 4)
+constexpr int kMaxRounds = 64;      // child tiles whose boundaries one block resolves at once
+constexpr int kScanTile = 4096;     // ints per block of the fine-bin scan
+constexpr int kMaxBinRank = 8192;   // a fine bin larger than this abandons the evaluation
+constexpr double kChildNsd = 6.5;   // histogram range: extreme propagation means +- 6.5 sd
+
+struct SplitState {
+    long long N;
+    int world, rank, LR, nobs;
+    long long cap, capc;
+    // step scalars (children kernel)
+    long long jlo, jhi;
+    int nc;
+    double S, off, lo, scale, shift;
+    // plan
+    int n_arrivals, NF;
+    int send_cnt[kMaxWorld], send_off[kMaxWorld], recv_cnt[kMaxWorld], cursor[kMaxWorld];
+    // diagnostics
+    unsigned long long near_ties, key_ties;
+    int max_bin, status;
+};
+
+struct Layout {
+    size_t state, cumblk, boff, btot, bpart, xc, pa, cb, dest, nfc, fstart, counts, fcnt, fst, ftot,
+        rnk, fb, tkey, tidx, tfb, total;
+    long long ntiles_max, nf_max;
+};
+
+size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+
+Layout make_layout(long long cap, long long capc) {
+    Layout L;
+    L.ntiles_max = (cap + kTile - 1) / kTile + 1;
+    L.nf_max = cap / kFine + kBins + 64;
+    size_t o = 0;
+    L.state = o;   o += al(sizeof(SplitState));
+    L.cumblk = o;  o += al((size_t)cap * 8);
+    L.boff = o;    o += al((size_t)(L.ntiles_max + 1) * 8);
+    L.btot = o;    o += al((size_t)L.ntiles_max * 8);
+    L.bpart = o;   o += al((size_t)L.ntiles_max * 8 * 8);
+    L.xc = o;      o += al((size_t)capc * 8);
+    L.pa = o;      o += al((size_t)capc * 4);
+    L.cb = o;      o += al((size_t)capc * 2);
+    L.dest = o;    o += al((size_t)kBins * 4);
+    L.nfc = o;     o += al((size_t)kBins * 4);
+    L.fstart = o;  o += al((size_t)(kBins + 1) * 4);
+    L.counts = o;  o += al((size_t)(2 * kMaxWorld + 4) * 4);
+    L.fcnt = o;    o += al((size_t)(L.nf_max + 1) * 4);
+    L.fst = o;     o += al((size_t)(L.nf_max + 1) * 4);
+    L.ftot = o;    o += al((size_t)(L.nf_max / kScanTile + 2) * 4);
+    L.rnk = o;     o += al((size_t)cap * 4);
+    L.fb = o;      o += al((size_t)cap * 4);
+    L.tkey = o;    o += al((size_t)cap * 8);
+    L.tidx = o;    o += al((size_t)cap * 4);
+    L.tfb = o;     o += al((size_t)cap * 4);
+    L.total = o;
+    return L;
+}
+
+// ---------------------------------------------------------------------------------------------
+// generation 0: every particle = mu (Q1, :306-323), identity order, history rows (mu, 0, ...)
+// ---------------------------------------------------------------------------------------------
+__global__ void split_init_kernel(double* __restrict__ xs, int* __restrict__ perm,
+                                  double* __restrict__ rec, int n, int LR, double mu) {
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        xs[p] = mu;
+        perm[p] = p;
+        rec[(size_t)p * LR] = mu;
+        for (int m = 1; m < LR; ++m) rec[(size_t)p * LR + m] = 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weights: one block per tile of 2048 sorted particles (thread = 8 consecutive particles)
+//   sh_j = exp(norm_logpdf(y_t; 0, exp(x_j / 2)) - shift)          (:427-437, :659-664)
+//   cumblk[p] = inclusive sum of sh inside the tile, btot[tile] = tile total
+//   bpart[tile][0..6] = sum sh x | sum sh curr | sum sh g_0..3     (:439-470, unnormalised)
+// ---------------------------------------------------------------------------------------------
+template <bool GRAD>
+__global__ void __launch_bounds__(256) split_weights_kernel(
+    SplitState* __restrict__ st, const double* __restrict__ xs, const int* __restrict__ perm,
+    const double* __restrict__ rec, int n, int LR, double y, double ylag,
+    const double* __restrict__ params, int uniform, double* __restrict__ cumblk,
+    double* __restrict__ btot, double* __restrict__ bpart, double* __restrict__ shsave) {
+    __shared__ double red[7 * 32];
+    __shared__ double s_wtot[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    SvConst c;
+    sv_const_init(c, params);
+    const double shift = uniform ? 0.0 : st->shift;
+    const int base = blockIdx.x * kTile + tid * 8;
+    double loc[8];
+    double acc[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    double run = 0.0;
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int p = base + k;
+        if (p < n) {
+            const double x = xs[p];
+            double s = uniform ? 1.0 : exp(sv_logw(x, y) - shift);
+            if (!isfinite(s)) {
+                bad = true;
+                s = 0.0;
+            }
+            if (shsave) shsave[p] = s;
+            run = run + s;
+            acc[0] += s * x;
+            if (GRAD) {
+                const size_t row = (size_t)perm[p] * LR;
+                const double curr = rec[row + LR - 1], next = rec[row + LR - 2];
+                double sq, g[4];
+                sv_score_main(c, curr, next, ylag, sq, g);
+                acc[1] += s * curr;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[2 + q] += g[q] * s;
+            }
+        }
+        loc[k] = run;
+    }
+    if (bad) atomicOr(&st->status, 2);
+    const double incl = warp_incl_scan(run, lane);
+    double excl = __shfl_up_sync(kFullMask, incl, 1);
+    if (lane == 0) excl = 0.0;
+    if (lane == 31) s_wtot[warp] = incl;
+    __syncthreads();
+    double woff = 0.0;
+    for (int w = 0; w < warp; ++w) woff = woff + s_wtot[w];
+    const double toff = woff + excl;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int p = base + k;
+        if (p < n) cumblk[p] = toff + loc[k];
+    }
+    if (tid == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < 8; ++w) tot = tot + s_wtot[w];
+        btot[blockIdx.x] = tot;
+    }
+    block_sum<7>(acc, red);
+    if (tid < 7) bpart[(size_t)blockIdx.x * 8 + tid] = acc[tid];
+}
+
+// one block: sequential-in-chunks exclusive scan of the tile totals, fixed-order sums of the
+// tile partials, the 4 doubles this rank contributes to the all-gather
+__global__ void __launch_bounds__(256) split_weights_finalize_kernel(
+    SplitState* __restrict__ st, const double* __restrict__ xs, int n, int ntiles,
+    const double* __restrict__ btot, const double* __restrict__ bpart, double* __restrict__ boff,
+    double* __restrict__ sums_t, double* __restrict__ gather_send) {
+    __shared__ double red[7 * 32];
+    __shared__ double s_lane[33];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (ntiles + 31) / 32;
+    if (warp == 0) {
+        const int b = min(ntiles, lane * per), e = min(ntiles, b + per);
+        double s = 0.0;
+        for (int q = b; q < e; ++q) s = s + btot[q];
+        s_lane[lane + 1] = s;
+        __syncwarp();
+        if (lane == 0) {
+            s_lane[0] = 0.0;
+            for (int q = 1; q <= 32; ++q) s_lane[q] = s_lane[q - 1] + s_lane[q];
+        }
+        __syncwarp();
+        double r = s_lane[lane];
+        for (int q = b; q < e; ++q) {
+            boff[q] = r;
+            r = r + btot[q];
+        }
+        if (lane == 31) boff[ntiles] = s_lane[32];
+    }
+    double acc[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int q = tid; q < ntiles; q += 256)
+#pragma unroll
+        for (int k = 0; k < 7; ++k) acc[k] += bpart[(size_t)q * 8 + k];
+    block_sum<7>(acc, red);
+    __syncthreads();
+    if (tid == 0) {
+        const double tot = s_lane[32];
+        sums_t[0] = tot;
+        for (int k = 0; k < 7; ++k) sums_t[1 + k] = acc[k];
+        gather_send[0] = tot;
+        gather_send[1] = (double)n;
+        gather_send[2] = n > 0 ? xs[0] : INFINITY;
+        gather_send[3] = n > 0 ? xs[n - 1] : -INFINITY;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// children
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double cum_at(int p, double off, double S, const double* __restrict__ boff,
+                                         const double* __restrict__ cumblk) {
+    return ((off + boff[p / kTile]) + cumblk[p]) / S;
+}
+
+// first p in [lo, hi) with cum(p) >= cp, hi if none
+__device__ __forceinline__ int cum_search(double cp, int lo, int hi, double off, double S,
+                                          const double* __restrict__ boff,
+                                          const double* __restrict__ cumblk) {
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (cum_at(mid, off, S, boff, cumblk) < cp) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// #{ j in [0, N) : (u + j) / N <= c }, the exact predicate of :703-711 re-checked
+__device__ long long count_le(double c, double u, long long N) {
+    const double dn = (double)N;
+    const double e = c * dn - u;
+    long long est = (e < 0.0) ? 0 : (e >= dn ? N : (long long)floor(e) + 1);
+    if (est < 0) est = 0;
+    if (est > N) est = N;
+    while (est > 0 && (u + (double)(est - 1)) / dn > c) --est;
+    while (est < N && (u + (double)est) / dn <= c) ++est;
+    return est;
+}
+
+struct ChildScalars {
+    long long jlo, jhi;
+    double S, off, lo, scale, cprev;
+    int nc;
+};
+
+__global__ void __launch_bounds__(256) split_children_kernel(
+    SplitState* __restrict__ st, int t, int n, const double* __restrict__ obs,
+    const double* __restrict__ params, const double* __restrict__ rvr, const double* __restrict__ u,
+    unsigned long long seed, unsigned long long philox_offset, const double* __restrict__ gather,
+    const double* __restrict__ xs, const double* __restrict__ cumblk, const double* __restrict__ boff,
+    double* __restrict__ xc, int* __restrict__ pa, unsigned short* __restrict__ cb,
+    int* __restrict__ hist_out, double* __restrict__ shift_out, double* __restrict__ xmin_out) {
+    extern __shared__ unsigned char smem_raw[];
+    double* s_cum = (double*)smem_raw;                       // [kStage]
+    int* s_hist = (int*)(smem_raw + (size_t)kStage * 8);     // [kBins]
+    __shared__ ChildScalars sc;
+    __shared__ int s_tp[2 * kMaxRounds];
+    __shared__ int s_near[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    SvConst c;
+    sv_const_init(c, params);
+    const long long N = st->N;
+    const double uu = rvr[t], y1 = obs[t - 1];
+    for (int b = tid; b < kBins; b += 256) s_hist[b] = 0;
+    if (tid == 0) {
+        const int G = st->world, r = st->rank;
+        double S = 0.0, off = 0.0, xmin = INFINITY, xmax = -INFINITY, tot_r = 0.0;
+        int last_nonempty = -1, prev_nonempty = -1;
+        for (int q = 0; q < G; ++q) {
+            const double tot = gather[q * 4];
+            const int nq = (int)gather[q * 4 + 1];
+            if (q == r) {
+                off = S;
+                tot_r = tot;
+            }
+            S = S + tot;
+            if (nq > 0) {
+                xmin = fmin(xmin, gather[q * 4 + 2]);
+                xmax = fmax(xmax, gather[q * 4 + 3]);
+                last_nonempty = q;
+                if (q < r) prev_nonempty = q;
+            }
+        }
+        long long jlo = 0, jhi = 0;
+        if (n > 0) {
+            jlo = (prev_nonempty < 0) ? 0 : count_le(off / S, uu, N);
+            jhi = (r == last_nonempty) ? N : count_le((off + tot_r) / S, uu, N);
+            if (jhi < jlo) jhi = jlo;
+        }
+        long long nc = jhi - jlo;
+        double lo, hi;
+        sv_child_range(c, xmin, xmax, y1, kChildNsd, lo, hi);
+        const double scale = (double)kBins / (hi - lo);
+        const double y = obs[t];
+        double xstar = (y != 0.0) ? log(y * y) : lo;
+        xstar = fmin(fmax(xstar, lo), hi);
+        const double shift = sv_logw(xstar, y);
+        int bad = 0;
+        if (!(S > 0.0) || !isfinite(S) || !isfinite(scale) || !(scale > 0.0) || !isfinite(shift)) bad = 1;
+        if (nc > st->capc) {
+            bad = 4;
+            nc = st->capc;
+        }
+        sc.jlo = jlo;
+        sc.jhi = jhi;
+        sc.S = S;
+        sc.off = off;
+        sc.lo = lo;
+        sc.scale = scale;
+        sc.cprev = off / S;
+        sc.nc = (int)nc;
+        if (bad) sc.nc = (bad == 4) ? sc.nc : 0;
+        if (blockIdx.x == 0) {
+            st->jlo = jlo;
+            st->jhi = jhi;
+            st->nc = sc.nc;
+            st->S = S;
+            st->off = off;
+            st->lo = lo;
+            st->scale = scale;
+            st->shift = shift;
+            if (bad) atomicOr(&st->status, bad == 4 ? 4 : 1);
+            shift_out[t] = shift;
+            xmin_out[t - 1] = xmin;
+        }
+    }
+    __syncthreads();
+    const int nc = sc.nc;
+    const double S = sc.S, off = sc.off, lo = sc.lo, scale = sc.scale;
+    const long long jlo = sc.jlo;
+    const double dn = (double)N;
+    const int ntl = (nc + kChildTile - 1) / kChildTile;
+    int near = 0;
+    for (int r0 = 0; blockIdx.x + (long long)r0 * gridDim.x < ntl; r0 += kMaxRounds) {
+        // boundaries (first and last parent) of up to kMaxRounds of this block's tiles at once
+        if (tid < 2 * kMaxRounds) {
+            const long long tile = blockIdx.x + (long long)(r0 + (tid >> 1)) * gridDim.x;
+            if (tile < ntl) {
+                long long k = tile * kChildTile;
+                if (tid & 1) k = min((long long)nc, k + kChildTile) - 1;
+                const double cp = (uu + (double)(jlo + k)) / dn;
+                s_tp[tid] = min(n - 1, cum_search(cp, 0, n, off, S, boff, cumblk));
+            }
+        }
+        __syncthreads();
+        for (int rr = 0; rr < kMaxRounds; ++rr) {
+            const long long tile = blockIdx.x + (long long)(r0 + rr) * gridDim.x;
+            if (tile >= ntl) break;
+            const int pf = s_tp[2 * rr], pl = max(pf, s_tp[2 * rr + 1]);
+            const int cnt = pl - pf + 1;
+            const bool staged = cnt <= kStage;
+            if (staged)
+                for (int q = tid; q < cnt; q += 256) s_cum[q] = cum_at(pf + q, off, S, boff, cumblk);
+            __syncthreads();
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const long long k = tile * kChildTile + tid + 256 * m;
+                if (k < nc) {
+                    const long long j = jlo + k;
+                    const double cp = (uu + (double)j) / dn;
+                    int a;
+                    double ca;
+                    if (staged) {
+                        int l = 0, h = cnt;
+                        while (l < h) {
+                            const int mid = (l + h) >> 1;
+                            if (s_cum[mid] < cp) l = mid + 1;
+                            else h = mid;
+                        }
+                        l = min(l, cnt - 1);
+                        a = pf + l;
+                        ca = s_cum[l];
+                    } else {
+                        a = min(pl, cum_search(cp, pf, pl + 1, off, S, boff, cumblk));
+                        ca = cum_at(a, off, S, boff, cumblk);
+                    }
+                    const double cprev = (a > 0) ? ((staged && a > pf) ? s_cum[a - pf - 1]
+                                                                        : cum_at(a - 1, off, S, boff, cumblk))
+                                                 : sc.cprev;
+                    const double tol = 1.4210854715202004e-14 * cp;   // 64 ulp
+                    if (fabs(ca - cp) <= tol || fabs(cprev - cp) <= tol) ++near;
+                    const double x = xs[a];
+                    double mean = c.mu + c.phi * (x - c.mu);
+                    mean += c.sr * exp(-0.5 * x) * y1;
+                    const double uv = u ? ld_stream_f64(u + (size_t)t * (size_t)N + (size_t)j)
+                                        : philox_normal(seed, philox_offset,
+                                                        (unsigned long long)t * (unsigned long long)N +
+                                                            (unsigned long long)j);
+                    const double xn = mean + c.sd * uv;
+                    const int bin = sv_bin(xn, lo, scale, kBins);
+                    atomicAdd(&s_hist[bin], 1);
+                    xc[k] = xn;
+                    pa[k] = a;
+                    cb[k] = (unsigned short)bin;
+                }
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    for (int b = tid; b < kBins; b += 256) {
+        const int v = s_hist[b];
+        if (v) atomicAdd(&hist_out[b], v);
+    }
+    near = near + __shfl_xor_sync(kFullMask, near, 16);
+    near = near + __shfl_xor_sync(kFullMask, near, 8);
+    near = near + __shfl_xor_sync(kFullMask, near, 4);
+    near = near + __shfl_xor_sync(kFullMask, near, 2);
+    near = near + __shfl_xor_sync(kFullMask, near, 1);
+    if (lane == 0) s_near[warp] = near;
+    __syncthreads();
+    if (tid == 0) {
+        int tot = 0;
+        for (int w = 0; w < 8; ++w) tot += s_near[w];
+        if (tot) atomicAdd(&st->near_ties, (unsigned long long)tot);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// plan: one block of 1024 threads over the 4096 coarse bins (thread = 4 consecutive bins)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) split_plan_kernel(SplitState* __restrict__ st,
+                                                          const int* __restrict__ H,
+                                                          int* __restrict__ dest, int* __restrict__ nfc,
+                                                          int* __restrict__ fstart,
+                                                          int* __restrict__ counts) {
+    __shared__ long long s_w[32];
+    __shared__ int s_wi[32];
+    __shared__ int s_send[kMaxWorld], s_recv[kMaxWorld];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = st->world, me = st->rank;
+    if (tid < kMaxWorld) {
+        s_send[tid] = 0;
+        s_recv[tid] = 0;
+    }
+    long long gc[4], run = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int b = tid * 4 + k;
+        long long s = 0;
+        for (int r = 0; r < G; ++r) s += H[r * kBins + b];
+        gc[k] = s;
+        run += s;
+    }
+    // block-wide exclusive scan of `run`
+    long long incl = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const long long o = __shfl_up_sync(kFullMask, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    long long woff = 0, total = 0;
+    for (int w = 0; w < 32; ++w) {
+        if (w < warp) woff += s_w[w];
+        total += s_w[w];
+    }
+    long long before = woff + incl - run;
+    int mydest[4], mynf[4], nfrun = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int b = tid * 4 + k;
+        long long d = (total > 0) ? (before * G) / total : 0;
+        if (d > G - 1) d = G - 1;
+        mydest[k] = (int)d;
+        dest[b] = (int)d;
+        const int hs = H[me * kBins + b];
+        if (hs) atomicAdd(&s_send[d], hs);
+        int nf = 0;
+        if ((int)d == me) {
+            for (int r = 0; r < G; ++r) {
+                const int h = H[r * kBins + b];
+                if (h) atomicAdd(&s_recv[r], h);
+            }
+            nf = (int)((gc[k] + kFine - 1) / kFine);
+            if (nf < 1) nf = 1;
+        }
+        mynf[k] = nf;
+        nfrun += nf;
+        before += gc[k];
+    }
+    __syncthreads();
+    int iincl = warp_incl_scan(nfrun, lane);
+    if (lane == 31) s_wi[warp] = iincl;
+    __syncthreads();
+    int iwoff = 0, nftot = 0;
+    for (int w = 0; w < 32; ++w) {
+        if (w < warp) iwoff += s_wi[w];
+        nftot += s_wi[w];
+    }
+    int fbefore = iwoff + iincl - nfrun;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int b = tid * 4 + k;
+        nfc[b] = mynf[k];
+        fstart[b] = fbefore;
+        fbefore += mynf[k];
+    }
+    if (tid == 0) {
+        fstart[kBins] = nftot;
+        int so = 0, narr = 0;
+        for (int d = 0; d < G; ++d) {
+            st->send_cnt[d] = s_send[d];
+            st->send_off[d] = so;
+            st->recv_cnt[d] = s_recv[d];
+            st->cursor[d] = 0;
+            counts[d] = s_send[d];
+            counts[G + d] = s_recv[d];
+            so += s_send[d];
+            narr += s_recv[d];
+        }
+        if (narr > st->cap) atomicOr(&st->status, 8);
+        st->n_arrivals = narr;
+        st->NF = nftot;
+        counts[2 * G] = narr;
+        counts[2 * G + 1] = st->nc;
+        counts[2 * G + 2] = nftot;
+        counts[2 * G + 3] = st->status;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pack: children grouped by destination rank; record = (value, parent's value, parent's lagged
+// ancestors ...) -- the particle_history shift of :334-341 carried with the particle
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) split_pack_kernel(
+    SplitState* __restrict__ st, const double* __restrict__ xc, const int* __restrict__ pa,
+    const unsigned short* __restrict__ cb, const int* __restrict__ dest, const int* __restrict__ perm,
+    const double* __restrict__ rec, double* __restrict__ send) {
+    __shared__ int s_cnt[kMaxWorld], s_base[kMaxWorld];
+    const int tid = threadIdx.x;
+    const int nc = st->nc, G = st->world, LR = st->LR;
+    for (long long base = (long long)blockIdx.x * 256; base < nc; base += (long long)gridDim.x * 256) {
+        const long long k = base + tid;
+        const bool valid = k < nc;
+        if (tid < G) s_cnt[tid] = 0;
+        __syncthreads();
+        int d = 0, r = 0;
+        if (valid) {
+            d = dest[cb[k]];
+            r = atomicAdd(&s_cnt[d], 1);
+        }
+        __syncthreads();
+        if (tid < G && s_cnt[tid] > 0) s_base[tid] = atomicAdd(&st->cursor[tid], s_cnt[tid]);
+        __syncthreads();
+        if (valid) {
+            const size_t slot = (size_t)(st->send_off[d] + s_base[d] + r) * LR;
+            send[slot] = xc[k];
+            if (LR > 1) {
+                const size_t row = (size_t)perm[pa[k]] * LR;
+                for (int m = 1; m < LR; ++m) send[slot + m] = rec[row + m - 1];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// sort of the arrivals
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int fine_bin(double x, double lo, double scale, const int* __restrict__ nfc,
+                                        const int* __restrict__ fstart) {
+    const int cbin = sv_bin(x, lo, scale, kBins);
+    const double tt = (x - lo) * scale;
+    double frac = tt - (double)cbin;
+    const int nf = nfc[cbin];
+    int sub = (!(frac > 0.0)) ? 0 : (int)(frac * (double)nf);
+    if (sub > nf - 1) sub = nf - 1;
+    if (sub < 0) sub = 0;
+    return fstart[cbin] + sub;
+}
+
+__global__ void split_fine_hist_kernel(const SplitState* __restrict__ st, const double* __restrict__ recn,
+                                       int n, int LR, const int* __restrict__ nfc,
+                                       const int* __restrict__ fstart, int* __restrict__ fcnt,
+                                       int* __restrict__ rnk, int* __restrict__ fb) {
+    const double lo = st->lo, scale = st->scale;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const double x = recn[(size_t)e * LR];
+        const int f = fine_bin(x, lo, scale, nfc, fstart);
+        rnk[e] = atomicAdd(&fcnt[f], 1);
+        fb[e] = f;
+    }
+}
+
+// exclusive scan of ints in three launches (tile totals, scan of totals, apply)
+__device__ __forceinline__ int block_excl_scan_1024(int v, int* s_w, int& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int incl = warp_incl_scan(v, lane);
+    __syncthreads();
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    int woff = 0, tot = 0;
+    for (int w = 0; w < 32; ++w) {
+        if (w < warp) woff += s_w[w];
+        tot += s_w[w];
+    }
+    total = tot;
+    return woff + incl - v;
+}
+
+__global__ void __launch_bounds__(1024) iscan_totals_kernel(const int* __restrict__ in, int n,
+                                                            int* __restrict__ tot) {
+    __shared__ int s_w[32];
+    const int base = blockIdx.x * kScanTile + threadIdx.x * 4;
+    int v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (base + k < n) v += in[base + k];
+    int total;
+    block_excl_scan_1024(v, s_w, total);
+    if (threadIdx.x == 0) tot[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) iscan_offsets_kernel(int* __restrict__ tot, int nt) {
+    // single block: exclusive scan of tot[0..nt) in place (nt <= 64K handled in chunks of 4096)
+    __shared__ int s_w[32];
+    int carry = 0;
+    for (int c0 = 0; c0 < nt; c0 += kScanTile) {
+        const int base = c0 + threadIdx.x * 4;
+        int v[4], s = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            v[k] = (base + k < nt) ? tot[base + k] : 0;
+            s += v[k];
+        }
+        int total;
+        int ex = carry + block_excl_scan_1024(s, s_w, total);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (base + k < nt) tot[base + k] = ex;
+            ex += v[k];
+        }
+        carry += total;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(1024) iscan_apply_kernel(const int* __restrict__ in, int n,
+                                                           const int* __restrict__ tot,
+                                                           int* __restrict__ out) {
+    __shared__ int s_w[32];
+    const int base = blockIdx.x * kScanTile + threadIdx.x * 4;
+    int v[4], s = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        v[k] = (base + k < n) ? in[base + k] : 0;
+        s += v[k];
+    }
+    int total;
+    int ex = tot[blockIdx.x] + block_excl_scan_1024(s, s_w, total);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (base + k < n) out[base + k] = ex;
+        ex += v[k];
+    }
+}
+
+__global__ void split_scatter_kernel(const double* __restrict__ recn, int n, int LR,
+                                     const int* __restrict__ fst, const int* __restrict__ rnk,
+                                     const int* __restrict__ fb, double* __restrict__ tkey,
+                                     int* __restrict__ tidx, int* __restrict__ tfb) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const int f = fb[e];
+        const int slot = fst[f] + rnk[e];
+        tkey[slot] = recn[(size_t)e * LR];
+        tidx[slot] = e;
+        tfb[slot] = f;
+    }
+}
+
+// exact order inside each fine bin: (value, arrival index); any correct sort reproduces the
+// reference's qsort order when values are distinct (SURVEY 7 "hard parts"); equal values counted
+__global__ void split_rank_kernel(SplitState* __restrict__ st, const double* __restrict__ tkey,
+                                  const int* __restrict__ tidx, const int* __restrict__ tfb,
+                                  const int* __restrict__ fst, int n, int nf_total,
+                                  double* __restrict__ xs, int* __restrict__ perm) {
+    int mx = 0, ties = 0;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+        const int f = tfb[s];
+        const int b = fst[f], e = (f + 1 < nf_total) ? fst[f + 1] : n;
+        const double v = tkey[s];
+        const int oi = tidx[s];
+        int rank = 0;
+        if (e - b <= kMaxBinRank) {
+            for (int q = b; q < e; ++q) {
+                const double k2 = tkey[q];
+                if (k2 < v) ++rank;
+                else if (k2 == v && q != s) {
+                    ++ties;
+                    if (tidx[q] < oi) ++rank;
+                }
+            }
+        } else {
+            rank = s - b;
+            atomicOr(&st->status, 16);
+        }
+        xs[b + rank] = v;
+        perm[b + rank] = oi;
+        mx = max(mx, e - b);
+    }
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(&st->max_bin, mx);
+    if (ties) atomicAdd(&st->key_ties, (unsigned long long)ties);
+}
+
+// ---------------------------------------------------------------------------------------------
+// tail (:540-562, Q6) on the final generation: wt[k][p] = normalised weight at global position
+// (gstart + p) of generation nobs-1-k... see pmmh_svsplit_tail
+//   part[i_rel][0] = sum_j W_T[j] ph[idx][j];  part[i_rel][1..4] = sum_j g_p W_i[j]
+// one block per (i_rel, tile)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) split_tail_kernel(
+    const int* __restrict__ perm, const double* __restrict__ rec, int n, int LR, int nobs,
+    const double* __restrict__ obs, const double* __restrict__ params, const double* __restrict__ wfinal,
+    const double* __restrict__ wlag, long long wlag_stride, double* __restrict__ part, int ntiles) {
+    __shared__ double red[5 * 32];
+    const int tid = threadIdx.x;
+    const int irel = blockIdx.y;                 // i = nobs - LR + irel, idx = LR - 1 - irel
+    const int i = nobs - LR + irel, idx = LR - 1 - irel;
+    SvConst c;
+    sv_const_init(c, params);
+    const double y1 = obs_wrap(obs, i - 1, nobs);
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    const int base = blockIdx.x * kTile;
+    for (int p = base + tid; p < min(n, base + kTile); p += 256) {
+        const size_t row = (size_t)perm[p] * LR;
+        const double curr = rec[row + idx];
+        acc[0] += wfinal[p] * curr;
+        if (idx >= 1) {
+            const double next = rec[row + idx - 1];
+            const double wi = wlag[(size_t)irel * wlag_stride + p];
+            double sq, g[4];
+            sv_score_tail(c, curr, next, y1, sq, g);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[1 + q] += g[q] * wi;
+        }
+    }
+    block_sum<5>(acc, red);
+    if (tid < 5) part[((size_t)irel * ntiles + blockIdx.x) * 8 + tid] = acc[tid];
+}
+
+__global__ void __launch_bounds__(256) split_tail_reduce_kernel(const double* __restrict__ part,
+                                                                int ntiles, double* __restrict__ out) {
+    __shared__ double red[5 * 32];
+    const int irel = blockIdx.x, tid = threadIdx.x;
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int q = tid; q < ntiles; q += 256)
+#pragma unroll
+        for (int k = 0; k < 5; ++k) acc[k] += part[((size_t)irel * ntiles + q) * 8 + k];
+    block_sum<5>(acc, red);
+    if (tid < 5) out[irel * 8 + tid] = acc[tid];
+}
+
+// normalised weights of the local generation (for the tail): w[p] = sh[p] / S
+__global__ void split_normalise_kernel(const double* __restrict__ sh, int n,
+                                       const double* __restrict__ S_ptr, double* __restrict__ w) {
+    const double S = *S_ptr;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x)
+        w[p] = sh[p] / S;
+}
+
+// ---------------------------------------------------------------------------------------------
+// finish: O(T) assembly of the outputs from the rank-summed per-step sums
+//   sums[t][0] = sum sh, [1] = sum sh x, [2] = sum sh curr, [3..6] = sum sh g
+//   tail[irel][0] = smo term, [1..4] = gradient terms (already normalised weights)
+// ---------------------------------------------------------------------------------------------
+__global__ void split_finish_kernel(const double* __restrict__ sums, const double* __restrict__ shift,
+                                    const double* __restrict__ xmin, const double* __restrict__ tail,
+                                    const double* __restrict__ gather_last, int world,
+                                    const double* __restrict__ params, int nobs, int LR, double n_total,
+                                    double* __restrict__ log_like, double* __restrict__ filt,
+                                    double* __restrict__ smo, double* __restrict__ grad,
+                                    double* __restrict__ traj) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid == 0) {
+        double ll = 0.0;
+        const double logn = log(n_total);
+        for (int t = 1; t < nobs; ++t) ll += shift[t] + log(sums[t * 8]) - logn;   // :537
+        log_like[0] = ll;
+    }
+    for (int t = tid; t < nobs; t += gridDim.x * blockDim.x) {
+        filt[t] = sums[t * 8 + 1] / sums[t * 8];
+        // Q10/Q11: traj[t] = X_t[0] for t >= 1, X_0 == mu
+        double tr = (t == 0) ? params[0] : xmin[t];
+        if (t == nobs - 1) {
+            tr = INFINITY;
+            for (int q = 0; q < world; ++q)
+                if (gather_last[q * 4 + 1] > 0.0) tr = fmin(tr, gather_last[q * 4 + 2]);
+        }
+        traj[t] = tr;
+        if (LR > 1) {
+            // main loop terms land at tt = t - LR + 1 (:445-470); the tail adds to the same slots
+            double s = 0.0, g[4] = {0.0, 0.0, 0.0, 0.0};
+            const int src = t + LR - 1;   // time step whose weights produced slot t
+            if (t >= 1 && src < nobs) {
+                const double S = sums[src * 8];
+                s = sums[src * 8 + 2] / S;
+                for (int q = 0; q < 4; ++q) g[q] = sums[src * 8 + 3 + q] / S;
+            }
+            // tail (:540-562): i = nobs-LR+irel adds smo[i] and gradient[.][i-LR+1]
+            if (tail) {
+                const int irel_s = t - (nobs - LR);
+                if (irel_s >= 0 && irel_s < LR) s += tail[irel_s * 8];
+                const int irel_g = t + LR - 1 - (nobs - LR);
+                if (irel_g >= 0 && irel_g < LR - 1)
+                    for (int q = 0; q < 4; ++q) g[q] += tail[irel_g * 8 + 1 + q];
+            }
+            smo[t] = s;
+            for (int q = 0; q < 4; ++q) grad[(size_t)q * nobs + t] = g[q];
+        }
+    }
+}
+
+int check_ws(void* ws, size_t bytes, long long cap, long long capc, Layout* L) {
+    if (!ws) return set_error(PMMH_ERR_INVALID, "svsplit: null workspace");
+    *L = make_layout(cap, capc);
+    if (bytes < L->total) return set_error(PMMH_ERR_WORKSPACE, "svsplit: workspace too small");
+    return PMMH_OK;
+}
+
+#define SPLIT_CUDA(call)                                                \
+    do {                                                                \
+        cudaError_t e__ = (call);                                       \
+        if (e__ != cudaSuccess) return pmmh::set_cuda_error(e__, #call); \
+    } while (0)
+
+int grid_for(long long n, int per_block) {
+    long long g = (n + per_block - 1) / per_block;
+    if (g < 1) g = 1;
+    if (g > 148 * 8) g = 148 * 8;
+    return (int)g;
+}
+
+}  // namespace
+}  // namespace pmmh
+
+using namespace pmmh;
+
+extern "C" {
+
+int pmmh_svsplit_workspace_bytes(long long cap_particles, long long cap_children, size_t* bytes) {
+    if (cap_particles < 1 || cap_children < 1 || cap_particles >= (1ll << 31) - 4096 ||
+        cap_children >= (1ll << 31) - 4096 || !bytes)
+        return set_error(PMMH_ERR_INVALID, "svsplit: capacities must be in [1, 2^31)");
+    *bytes = make_layout(cap_particles, cap_children).total;
+    return PMMH_OK;
+}
+
+int pmmh_svsplit_init(void* d_ws, size_t ws_bytes, long long n_total, int n_obs, int world, int rank,
+                      int lag, long long cap_particles, long long cap_children, int n_local,
+                      const double* h_params, double* d_xs, int* d_perm, double* d_rec, void* stream) {
+    Layout L;
+    if (int rc = check_ws(d_ws, ws_bytes, cap_particles, cap_children, &L)) return rc;
+    if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world || n_total < 1 || n_obs < 2 ||
+        (lag != 0 && (lag < 2 || lag > 63)) || n_local < 0 || n_local > cap_particles)
+        return set_error(PMMH_ERR_INVALID, "svsplit_init: bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    SplitState h;
+    memset(&h, 0, sizeof(h));
+    h.N = n_total;
+    h.world = world;
+    h.rank = rank;
+    h.LR = lag == 0 ? 1 : lag;
+    h.nobs = n_obs;
+    h.cap = cap_particles;
+    h.capc = cap_children;
+    SPLIT_CUDA(cudaMemcpyAsync((char*)d_ws + L.state, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+    SPLIT_CUDA(cudaStreamSynchronize(st));   // h lives on this stack frame
+    if (n_local > 0)
+        split_init_kernel<<<grid_for(n_local, 256), 256, 0, st>>>(d_xs, d_perm, d_rec, n_local, h.LR,
+                                                                   h_params[0]);
+    SPLIT_CUDA(cudaGetLastError());
+    return PMMH_OK;
+}
+
+int pmmh_svsplit_weights(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
+                         int t, int n_local, int lag, int n_obs, const double* h_obs,
+                         const double* d_params, const double* d_xs, const int* d_perm,
+                         const double* d_rec, double* d_sums, double* d_gather_send, double* d_sh_save,
+                         void* stream) {
+    Layout L;
+    if (int rc = check_ws(d_ws, ws_bytes, cap_particles, cap_children, &L)) return rc;
+    if (t < 0 || t >= n_obs || n_local < 0 || n_local > cap_particles)
+        return set_error(PMMH_ERR_INVALID, "svsplit_weights: bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)d_ws;
+    SplitState* state = (SplitState*)(ws + L.state);
+    const int LR = lag == 0 ? 1 : lag;
+    const int ntiles = (n_local + kTile - 1) / kTile;
+    const bool grad = lag > 0 && t >= lag;
+    const double y = h_obs[t], ylag = grad ? h_obs[t - lag] : 0.0;   // Q5: obs[i - LAG]
+    double* cumblk = (double*)(ws + L.cumblk);
+    double* btot = (double*)(ws + L.btot);
+    double* bpart = (double*)(ws + L.bpart);
+    double* boff = (double*)(ws + L.boff);
+    if (ntiles > 0) {
+        if (grad)
+            split_weights_kernel<true><<<ntiles, 256, 0, st>>>(state, d_xs, d_perm, d_rec, n_local, LR, y,
+                                                               ylag, d_params, t == 0, cumblk, btot,
+                                                               bpart, d_sh_save);
+        else
+            split_weights_kernel<false><<<ntiles, 256, 0, st>>>(state, d_xs, d_perm, d_rec, n_local, LR,
+                                                                y, ylag, d_params, t == 0, cumblk, btot,
+                                                                bpart, d_sh_save);
+    }
+    split_weights_finalize_kernel<<<1, 256, 0, st>>>(state, d_xs, n_local, ntiles, btot, bpart, boff,
+                                                     d_sums + (size_t)t * 8, d_gather_send);
+    SPLIT_CUDA(cudaGetLastError());
+    return PMMH_OK;
+}
+
+int pmmh_svsplit_children(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
+                          int t, int n_local, const double* d_obs, const double* d_params,
+                          const double* d_rvr, const double* d_u, unsigned long long seed,
+                          unsigned long long philox_offset, const double* d_gather, const double* d_xs,
+                          int* d_hist_send, double* d_shift, double* d_xmin, void* stream) {
+    Layout L;
+    if (int rc = check_ws(d_ws, ws_bytes, cap_particles, cap_children, &L)) return rc;
+    if (t < 1 || n_local < 0) return set_error(PMMH_ERR_INVALID, "svsplit_children: bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)d_ws;
+    SplitState* state = (SplitState*)(ws + L.state);
+    static thread_local bool attr_set[64] = {false};
+    int dev = 0;
+    SPLIT_CUDA(cudaGetDevice(&dev));
+    const int smem = kStage * 8 + kBins * 4;
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        SPLIT_CUDA(cudaFuncSetAttribute(split_children_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        smem));
+        attr_set[dev] = true;
+    }
+    SPLIT_CUDA(cudaMemsetAsync(d_hist_send, 0, (size_t)kBins * 4, st));
+    split_children_kernel<<<148 * 4, 256, smem, st>>>(
+        state, t, n_local, d_obs, d_params, d_rvr, d_u, seed, philox_offset, d_gather, d_xs,
+        (const double*)(ws + L.cumblk), (const double*)(ws + L.boff), (double*)(ws + L.xc),
+        (int*)(ws + L.pa), (unsigned short*)(ws + L.cb), d_hist_send, d_shift, d_xmin);
+    SPLIT_CUDA(cudaGetLastError());
+    return PMMH_OK;
+}
+
+int pmmh_svsplit_plan(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
+                      int world, const int* d_hist, int* h_counts, void* stream) {
+    Layout L;
+    if (int rc = check_ws(d_ws, ws_bytes, cap_particles, cap_children, &L)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)d_ws;
+    SplitState* state = (SplitState*)(ws + L.state);
+    split_plan_kernel<<<1, 1024, 0, st>>>(state, d_hist, (int*)(ws + L.dest), (int*)(ws + L.nfc),
+                                          (int*)(ws + L.fstart), (int*)(ws + L.counts));
+    SPLIT_CUDA(cudaGetLastError());
+    SPLIT_CUDA(cudaMemcpyAsync(h_counts, ws + L.counts, (size_t)(2 * world + 4) * 4,
+                               cudaMemcpyDeviceToHost, st));
+    return PMMH_OK;
+}
+
+int pmmh_svsplit_pack(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
+                      const int* d_perm, const double* d_rec, double* d_send, void* stream) {
+    Layout L;
+    if (int rc = check_ws(d_ws, ws_bytes, cap_particles, cap_children, &L)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)d_ws;
+    SplitState* state = (SplitState*)(ws + L.state);
+    split_pack_kernel<<<148 * 8, 256, 0, st>>>(state, (const double*)(ws + L.xc), (const int*)(ws + L.pa),
+                                               (const unsigned short*)(ws + L.cb),
+                                               (const int*)(ws + L.dest), d_perm, d_rec, d_send);
+    SPLIT_CUDA(cudaGetLastError());
+    return PMMH_OK;
+}
+
+int pmmh_svsplit_sort(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
+                      int n_arrivals, int n_fine, int lag, const double* d_rec_new, double* d_xs,
+                      int* d_perm, void* stream) {
+    Layout L;
+    if (int rc = check_ws(d_ws, ws_bytes, cap_particles, cap_children, &L)) return rc;
+    if (n_arrivals < 0 || n_arrivals > cap_particles || n_fine < 0 || n_fine > L.nf_max)
+        return set_error(PMMH_ERR_INVALID, "svsplit_sort: bad sizes");
+    if (n_arrivals == 0) return PMMH_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)d_ws;
+    SplitState* state = (SplitState*)(ws + L.state);
+    const int LR = lag == 0 ? 1 : lag;
+    int* fcnt = (int*)(ws + L.fcnt);
+    int* fst = (int*)(ws + L.fst);
+    int* ftot = (int*)(ws + L.ftot);
+    int* rnk = (int*)(ws + L.rnk);
+    int* fb = (int*)(ws + L.fb);
+    double* tkey = (double*)(ws + L.tkey);
+    int* tidx = (int*)(ws + L.tidx);
+    int* tfb = (int*)(ws + L.tfb);
+    SPLIT_CUDA(cudaMemsetAsync(fcnt, 0, (size_t)(n_fine + 1) * 4, st));
+    const int g = grid_for(n_arrivals, 256);
+    split_fine_hist_kernel<<<g, 256, 0, st>>>(state, d_rec_new, n_arrivals, LR, (const int*)(ws + L.nfc),
+                                              (const int*)(ws + L.fstart), fcnt, rnk, fb);
+    const int nt = (n_fine + kScanTile - 1) / kScanTile;
+    iscan_totals_kernel<<<nt, 1024, 0, st>>>(fcnt, n_fine, ftot);
+    iscan_offsets_kernel<<<1, 1024, 0, st>>>(ftot, nt);
+    iscan_apply_kernel<<<nt, 1024, 0, st>>>(fcnt, n_fine, ftot, fst);
+    split_scatter_kernel<<<g, 256, 0, st>>>(d_rec_new, n_arrivals, LR, fst, rnk, fb, tkey, tidx, tfb);
+    split_rank_kernel<<<g, 256, 0, st>>>(state, tkey, tidx, tfb, fst, n_arrivals, n_fine, d_xs, d_perm);
+    SPLIT_CUDA(cudaGetLastError());
+    return PMMH_OK;
+}
+
+int pmmh_svsplit_normalise(const double* d_sh, int n_local, const double* d_total, double* d_w,
+                           void* stream) {
+    if (n_local <= 0) return PMMH_OK;
+    split_normalise_kernel<<<grid_for(n_local, 256), 256, 0, (cudaStream_t)stream>>>(d_sh, n_local, d_total,
+                                                                                      d_w);
+    SPLIT_CUDA(cudaGetLastError());
+    return PMMH_OK;
+}
+
+int pmmh_svsplit_tail(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
+                      int n_local, int lag, int n_obs, const double* d_obs, const double* d_params,
+                      const int* d_perm, const double* d_rec, const double* d_w_final,
+                      const double* d_w_lagged, long long w_lagged_stride, double* d_tail,
+                      void* stream) {
+    Layout L;
+    if (int rc = check_ws(d_ws, ws_bytes, cap_particles, cap_children, &L)) return rc;
+    if (lag < 2 || n_local < 0) return set_error(PMMH_ERR_INVALID, "svsplit_tail: bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)d_ws;
+    const int ntiles = (n_local + kTile - 1) / kTile;
+    // scratch: tkey is free after the last sort (needs lag * ntiles * 8 doubles)
+    double* part = (double*)(ws + L.tkey);
+    if ((size_t)lag * (size_t)max(ntiles, 1) * 8 > (size_t)cap_particles)
+        return set_error(PMMH_ERR_WORKSPACE, "svsplit_tail: scratch too small");
+    SPLIT_CUDA(cudaMemsetAsync(d_tail, 0, (size_t)lag * 8 * 8, st));
+    if (ntiles > 0) {
+        dim3 grid(ntiles, lag);
+        split_tail_kernel<<<grid, 256, 0, st>>>(d_perm, d_rec, n_local, lag, n_obs, d_obs, d_params,
+                                                d_w_final, d_w_lagged, w_lagged_stride, part, ntiles);
+        split_tail_reduce_kernel<<<lag, 256, 0, st>>>(part, ntiles, d_tail);
+    }
+    SPLIT_CUDA(cudaGetLastError());
+    return PMMH_OK;
+}
+
+int pmmh_svsplit_finish(const double* d_sums, const double* d_shift, const double* d_xmin,
+                        const double* d_tail, const double* d_gather_last, int world,
+                        const double* d_params, int n_obs, int lag,
+                        long long n_total, double* d_log_like, double* d_filt, double* d_smo,
+                        double* d_gradient, double* d_traj, void* stream) {
+    const int LR = lag == 0 ? 1 : lag;
+    split_finish_kernel<<<grid_for(n_obs, 256), 256, 0, (cudaStream_t)stream>>>(
+        d_sums, d_shift, d_xmin, d_tail, d_gather_last, world, d_params, n_obs, LR, (double)n_total,
+        d_log_like, d_filt, d_smo, d_gradient, d_traj);
+    SPLIT_CUDA(cudaGetLastError());
+    return PMMH_OK;
+}
+
+int pmmh_svsplit_diag(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
+                      long long* h_diag) {
+    Layout L;
+    if (int rc = check_ws(d_ws, ws_bytes, cap_particles, cap_children, &L)) return rc;
+    SplitState h;
+    SPLIT_CUDA(cudaMemcpy(&h, (char*)d_ws + L.state, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < PMMH_DIAG_COUNT; ++k) h_diag[k] = 0;
+    h_diag[PMMH_DIAG_NEAR_TIES] = (long long)h.near_ties;
+    h_diag[PMMH_DIAG_MAX_BIN] = h.max_bin;
+    h_diag[PMMH_DIAG_STATUS] = h.status;
+    h_diag[PMMH_DIAG_KEY_TIES] = (long long)h.key_ties;
+    h_diag[PMMH_DIAG_KERNEL] = 4;
+    return PMMH_OK;
+}
+
+}  // extern "C"

@@ -85,3 +85,26 @@ def subsample_partial_sums(x_shard, y_shard, idx, beta, row_begin, compute_hessi
             s = y * (-ep / (1.0 + ep) ** 2) + (1.0 - y) * (-en / (1.0 + en) ** 2)
             out[1 + d:] = (-(x.T * s).dot(x)).reshape(-1)
     return out
+
+
+def interval_exchange_counts(n_src, n_dst, rank):
+    """A vector of length sum(n_src) is stored as consecutive blocks, block r (n_src[r] entries) on
+    rank r; it is wanted as consecutive blocks of n_dst[r] entries.  Returns (send_counts,
+    recv_counts) of `rank` for one all_to_all_single: what it sends to every destination is a
+    run of its block in destination order, what it receives arrives in source order -- so both
+    buffers are contiguous and no index list travels.  Used by the split particle filter to put
+    the weights of generation i where the tail terms of the final generation need them
+    (state/particle_methods/split.py)."""
+    n_src = np.asarray(n_src, dtype=np.int64)
+    n_dst = np.asarray(n_dst, dtype=np.int64)
+    assert n_src.sum() == n_dst.sum()
+    s0 = np.concatenate([[0], np.cumsum(n_src)])
+    d0 = np.concatenate([[0], np.cumsum(n_dst)])
+    world = len(n_src)
+
+    def overlap(a0, a1, b0, b1):
+        return int(max(0, min(a1, b1) - max(a0, b0)))
+
+    send = [overlap(s0[rank], s0[rank + 1], d0[d], d0[d + 1]) for d in range(world)]
+    recv = [overlap(s0[s], s0[s + 1], d0[rank], d0[rank + 1]) for s in range(world)]
+    return send, recv

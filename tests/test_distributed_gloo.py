@@ -1,7 +1,8 @@
 """CPU, world_size = 2, gloo: the two multi-GPU decompositions of the path.
 
 (1) subsampling estimator: row-sharded partial sums + ONE all-reduce == unsharded oracle;
-(2) chain-batched sharding: block shards of a batch of problems, results all-gathered."""
+(2) chain-batched sharding: block shards of a batch of problems, results all-gathered;
+(3) split particle filter: the interval plan of the tail exchange and the communicator wrapper."""
 import os
 import sys
 
@@ -53,7 +54,28 @@ def _worker(rank, world, port, ret):
         rvr, rvp = gi.split_particle(gi.sv_rvs(n, nobs, s), nobs)
         want.append(oracle.flps_sv_corr(obs, np.array(gi.SV_PARAM_SETS[0]), rvr, rvp, n, 4, 0)["log_like"])
     ok2 = np.array_equal(allv, np.array(want))
-    ret[rank] = bool(ok1 and ok2)
+
+    # (3) split particle filter, host side of the tail exchange: weights of generation i live in
+    # blocks of n_src[r] sorted positions, the final generation wants blocks of n_dst[r]; one
+    # all_to_all_single with the interval plan must deliver exactly the wanted slice, in order
+    from pmmh_qn_b200.state.particle_methods.split import DistComm
+    comm = DistComm()
+    n_src, n_dst = [700, 324], [301, 723]
+    full = np.arange(1024, dtype=np.float64) * 0.5
+    s0, d0 = sum(n_src[:rank]), sum(n_dst[:rank])
+    mine = torch.from_numpy(full[s0:s0 + n_src[rank]].copy())
+    got = torch.zeros(800, dtype=torch.float64)
+    sc, rc = S.interval_exchange_counts(n_src, n_dst, rank)
+    comm.all_to_all([mine], [sc], [got], [rc])
+    ok3 = np.array_equal(got[:n_dst[rank]].numpy(), full[d0:d0 + n_dst[rank]])
+    # and the small all-gather / all-reduce the time loop uses
+    g_out = torch.zeros((world, 4), dtype=torch.float64)
+    comm.all_gather([torch.full((4,), float(rank + 1), dtype=torch.float64)], [g_out])
+    ok3 = ok3 and g_out[:, 0].tolist() == [1.0, 2.0]
+    red = torch.full((3, 8), float(rank + 1), dtype=torch.float64)
+    comm.all_reduce_sum([red])
+    ok3 = ok3 and bool((red == 3.0).all())
+    ret[rank] = bool(ok1 and ok2 and ok3)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -1,0 +1,129 @@
+"""GPU parity of the split particle filter / smoother (pmmh_svsplit_*, BASELINE configs[4]) against
+the CPU oracle.  The ranks run in ONE process on one GPU (LocalComm): same device phases and
+the same partition logic as the NCCL path, exchanges as device copies.
+
+Bar: every sorted generation, gathered over the ranks, equals the oracle's bit for bit (that is
+ancestors + propagation + sort); log-likelihood rel <= 1e-10, filter / smoother means rel <= 1e-10,
+gradient <= 1e-9 * max|g| (summation order differs from the reference's sequential loops).
+"""
+import numpy as np
+import pytest
+
+import golden_inputs as gi
+from helpers import relerr, to_time_major
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(dev, world, obs, params, rvr, rvp, n, nobs, lag, cap=None, capc=None, history=True):
+    import torch
+    from pmmh_qn_b200.state.particle_methods import split as SP
+    u = torch.from_numpy(to_time_major(rvp, n, nobs)).to(dev)
+    rvr_d = torch.from_numpy(rvr[:nobs].copy()).to(dev)
+    out = SP.run_split_smoother(SP.LocalComm(world), obs, params, n, lag, rvr_d, u_d=u, device=dev,
+                                cap=cap, capc=capc, keep_history=history)
+    torch.cuda.synchronize()
+    return out
+
+
+def _check(out, ref, nobs, lag, history=True):
+    for o in out["per_rank"]:
+        assert o["diag"][2] == 0, "status %d" % o["diag"][2]
+    if history:
+        for t in range(nobs):
+            x = np.concatenate([c.cpu().numpy() for c in out["x_hist"][t]])
+            assert x.shape[0] == ref["X"].shape[1]
+            assert np.array_equal(x, ref["X"][t]), "generation %d differs from the oracle" % t
+    ll = float(out["log_like"].item())
+    assert abs(ll - ref["log_like"]) <= 1e-10 * abs(ref["log_like"]), (ll, ref["log_like"])
+    assert relerr(out["filt"].cpu().numpy(), ref["filt"]) <= 1e-10
+    assert relerr(out["traj"].cpu().numpy(), ref["traj"]) <= 1e-12
+    if lag:
+        assert relerr(out["smo"].cpu().numpy(), ref["smo"]) <= 1e-10
+        g, gr = out["gradient"].cpu().numpy(), ref["gradient"]
+        assert np.max(np.abs(g - gr)) <= 1e-9 * np.max(np.abs(gr))
+    # every rank assembles the same outputs
+    for o in out["per_rank"][1:]:
+        assert float(o["log_like"].item()) == ll
+        assert np.array_equal(o["gradient"].cpu().numpy(), out["gradient"].cpu().numpy())
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4])
+@pytest.mark.parametrize("n,nobs,lag,seed", [(2000, 61, 10, 0), (777, 45, 4, 1), (5000, 40, 10, 2)])
+def test_split_smoother_vs_oracle(cuda_dev, world, n, nobs, lag, seed):
+    import oracle
+    obs, params, rvr, rvp = gi.sv_inputs(n, nobs, seed)
+    ref = oracle.flps_sv_corr(obs, params, rvr, rvp, n, lag, 0, dumps=True)
+    out = _run(cuda_dev, world, obs, params, rvr, rvp, n, nobs, lag, cap=n, capc=n)
+    _check(out, ref, nobs, lag)
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_split_filter_only_and_balance(cuda_dev, world):
+    """lag = 0: records are the bare values.  Arrivals per rank stay within one histogram bin of
+    N / world."""
+    import oracle
+    n, nobs = 1 << 17, 40
+    obs, params, rvr, rvp = gi.sv_inputs(n, nobs, 3)
+    ref = oracle.flps_sv_corr(obs, params, rvr, rvp, n, 10, 0, dumps=True)
+    out = _run(cuda_dev, world, obs, params, rvr, rvp, n, nobs, 0)
+    _check(out, ref, nobs, 0)
+    counts = out["counts"][1:]
+    assert counts.sum(axis=1).tolist() == [n] * (nobs - 1)
+    assert counts.max() <= n / world * 1.05 + 64
+
+
+def test_split_smoother_default_capacities_large(cuda_dev):
+    """N = 2^19 over 4 ranks, T = 30, default capacities, gradient: against the oracle."""
+    import oracle
+    n, nobs, lag = 1 << 19, 31, 10
+    obs, params, rvr, rvp = gi.sv_inputs(n, nobs, 5)
+    ref = oracle.flps_sv_corr(obs, params, rvr, rvp, n, lag, 0, dumps=True)
+    out = _run(cuda_dev, 4, obs, params, rvr, rvp, n, nobs, lag)
+    _check(out, ref, nobs, lag)
+
+
+def test_philox_stream_equals_the_array(cuda_dev):
+    """u regenerated from the Philox stream inside the kernel == the same stream materialised."""
+    import torch
+    from pmmh_qn_b200 import kernels as K
+    from pmmh_qn_b200.state.particle_methods import split as SP
+    n, nobs, lag = 30000, 50, 10
+    obs = gi.sv_obs(nobs)
+    params = np.array(gi.SV_PARAM_SETS[0], dtype=np.float64)
+    ph = SP.PhiloxRVS(seed=1234, offset=77)
+    rvr = K.norm_cdf(ph.resampling_normals(nobs, n, cuda_dev))
+    u = ph.materialise(nobs, n, cuda_dev)
+    a = SP.run_split_smoother(SP.LocalComm(2), obs, params, n, lag, rvr, u_d=u, device=cuda_dev)
+    b = SP.run_split_smoother(SP.LocalComm(2), obs, params, n, lag, rvr, philox=(ph.seed, ph.offset),
+                              device=cuda_dev)
+    torch.cuda.synchronize()
+    assert float(a["log_like"].item()) == float(b["log_like"].item())
+    assert np.array_equal(a["gradient"].cpu().numpy(), b["gradient"].cpu().numpy())
+    # and against the oracle on the materialised numbers
+    import oracle
+    rvp = np.ascontiguousarray(u.cpu().numpy().T).reshape(-1)
+    ref = oracle.flps_sv_corr(obs, params, rvr.cpu().numpy(), rvp, n, lag, 0)
+    assert abs(float(a["log_like"].item()) - ref["log_like"]) <= 1e-10 * abs(ref["log_like"])
+
+
+def test_split_estimator_contract(cuda_dev):
+    """SplitParticleMethodsCUDA keeps the estimator contract and agrees with ParticleMethodsCUDA."""
+    from pmmh_qn_b200 import DeviceRVS, ParticleMethodsCUDA
+    from pmmh_qn_b200.state.particle_methods.split import SplitParticleMethodsCUDA
+    from toy_models import ToySVModel
+    n, nobs = 3000, 80
+    model = ToySVModel(gi.sv_obs(nobs), gi.SV_PARAM_SETS[0])
+    rvs = gi.sv_rvs(n, nobs, 7)
+    handle = DeviceRVS.from_numpy_particle(rvs, cuda_dev)
+    one = ParticleMethodsCUDA(model, no_particles=n, fixed_lag=10)
+    assert one.smoother(model, rvs={'rvs': handle})
+    sp = SplitParticleMethodsCUDA(model, n, fixed_lag=10, local_world=3)
+    assert sp.dim_rvs == one.dim_rvs and sp.alg_type == 'particle'
+    assert sp.smoother(model, rvs={'rvs': handle})
+    assert abs(sp.results['log_like'] - one.results['log_like']) <= 1e-10 * abs(one.results['log_like'])
+    g1, g2 = one.results['gradient_internal'], sp.results['gradient_internal']
+    assert np.max(np.abs(g1 - g2)) <= 1e-9 * np.max(np.abs(g1))
+    assert relerr(sp.results['smo_state_est'], one.results['smo_state_est']) <= 1e-10
+    assert sp.filter(model, rvs={'rvs': handle})
+    assert abs(sp.results['log_like'] - one.results['log_like']) <= 1e-10 * abs(one.results['log_like'])

@@ -65,3 +65,25 @@ def test_block_ranges_cover_everything():
             if n < 5000:
                 assert seen == list(range(n))
             assert sum(block_range(n, r, world)[1] - block_range(n, r, world)[0] for r in range(world)) == n
+
+
+def test_interval_exchange_counts_cover_every_position_once():
+    from pmmh_qn_b200 import sharding as S
+    rng = np.random.RandomState(3)
+    for world in (1, 2, 3, 8):
+        for _ in range(20):
+            n_src = rng.multinomial(1000, np.ones(world) / world)
+            n_dst = rng.multinomial(1000, rng.dirichlet(np.ones(world)))
+            plans = [S.interval_exchange_counts(n_src, n_dst, r) for r in range(world)]
+            for r in range(world):
+                assert sum(plans[r][0]) == n_src[r] and sum(plans[r][1]) == n_dst[r]
+                for d in range(world):
+                    assert plans[r][0][d] == plans[d][1][r]
+
+
+def test_split_default_capacities():
+    from pmmh_qn_b200.state.particle_methods.split import default_capacities
+    assert default_capacities(1 << 20, 1) == (1 << 20, 1 << 20)
+    for world in (2, 4, 8):
+        cap, capc = default_capacities(1 << 24, world)
+        assert (1 << 24) // world < cap <= (1 << 24) and cap <= capc <= (1 << 24)
