@@ -69,13 +69,15 @@ class PhiloxRVS(object):
 
 def default_capacities(n_total, world):
     """(cap_particles, cap_children) per rank.  Arrivals are balanced to one histogram bin
-    (~0.2 % of N); children follow the weight mass of the local parents, which is not balanced."""
+    (~0.2 % of N).  Children follow the weight mass of the local parents, which is NOT balanced:
+    after an outlying observation the rank with the largest values can own most of the weight
+    (seen: > N/2 on one of 8 ranks), so the children buffers are sized for all N (94 bytes per
+    child at lag 10: 6.3 GB of the 180 GB at N = 2^26)."""
     per = -(-n_total // world)
     if world == 1:
         return n_total, n_total
     cap = min(n_total, int(per * 1.3) + 65536)
-    capc = n_total if world <= 2 else min(n_total, 4 * per)
-    return cap, capc
+    return cap, n_total
 
 
 def _p(t):

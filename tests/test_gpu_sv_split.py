@@ -2,8 +2,8 @@
 the CPU oracle.  The ranks run in ONE process on one GPU (LocalComm): same device phases and
 the same partition logic as the NCCL path, exchanges as device copies.
 
-Bar: every sorted generation, gathered over the ranks, equals the oracle's bit for bit (that is
-ancestors + propagation + sort); log-likelihood rel <= 1e-10, filter / smoother means rel <= 1e-10,
+Bar: every sorted generation, gathered over the ranks, equals the oracle's to 1e-12 (that is
+ancestors + propagation + sort: one wrong ancestor would move a value by ~1e-6); log-likelihood rel <= 1e-10, filter / smoother means rel <= 1e-10,
 gradient <= 1e-9 * max|g| (summation order differs from the reference's sequential loops).
 """
 import numpy as np
@@ -33,7 +33,9 @@ def _check(out, ref, nobs, lag, history=True):
         for t in range(nobs):
             x = np.concatenate([c.cpu().numpy() for c in out["x_hist"][t]])
             assert x.shape[0] == ref["X"].shape[1]
-            assert np.array_equal(x, ref["X"][t]), "generation %d differs from the oracle" % t
+            # a single wrong ancestor moves one value by ~ the parent spacing (>> 1e-12); libm and
+            # CUDA exp() differ in the last ulp, so bit equality of the values is not the bar
+            assert relerr(x, ref["X"][t]) <= 1e-12, "generation %d differs from the oracle" % t
     ll = float(out["log_like"].item())
     assert abs(ll - ref["log_like"]) <= 1e-10 * abs(ref["log_like"]), (ll, ref["log_like"])
     assert relerr(out["filt"].cpu().numpy(), ref["filt"]) <= 1e-10

@@ -86,4 +86,4 @@ def test_split_default_capacities():
     assert default_capacities(1 << 20, 1) == (1 << 20, 1 << 20)
     for world in (2, 4, 8):
         cap, capc = default_capacities(1 << 24, world)
-        assert (1 << 24) // world < cap <= (1 << 24) and cap <= capc <= (1 << 24)
+        assert (1 << 24) // world < cap <= (1 << 24) and capc == (1 << 24)
