@@ -84,6 +84,9 @@ int pmmh_device_info(int* sm_count, int* cc_major, int* cc_minor);
  *   1  general kernel only
  *   2  diagnostics: exchange kernel where eligible, without the fallback pass
  *   3  diagnostics: chain kernel where eligible, without the fallback pass
+ *   4  streaming kernels (sv_split.cu driven on one device: ~11 launches per time step, no
+ *      persistent kernel) for one problem with compute_hessian == 0 and no history output,
+ *      without the fallback pass
  * Call before pmmh_sv_workspace_bytes: the workspace size depends on it. */
 int pmmh_sv_set_algorithm(int algorithm);
 
@@ -219,11 +222,11 @@ int pmmh_svsplit_workspace_bytes(long long cap_particles, long long cap_children
 /* generation 0 (Q1: every particle = mu); n_local = particles this rank starts with */
 int pmmh_svsplit_init(void* d_ws, size_t ws_bytes, long long n_total, int n_obs, int world, int rank,
                       int lag, long long cap_particles, long long cap_children, int n_local,
-                      const double* h_params, double* d_xs, int* d_perm, double* d_rec, void* stream);
+                      const double* d_params, double* d_xs, int* d_perm, double* d_rec, void* stream);
 /* weights of generation t (:427-470): d_sums[t][0..6] = local sums of sh, sh x, sh curr, sh g_0..3;
  * d_gather_send[4] = (sum sh, n_local, min x, max x); d_sh_save (optional, [n_local]) keeps sh */
 int pmmh_svsplit_weights(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
-                         int t, int n_local, int lag, int n_obs, const double* h_obs,
+                         int t, int n_local, int lag, int n_obs, const double* d_obs,
                          const double* d_params, const double* d_xs, const int* d_perm,
                          const double* d_rec, double* d_sums, double* d_gather_send, double* d_sh_save,
                          void* stream);
@@ -235,17 +238,18 @@ int pmmh_svsplit_children(void* d_ws, size_t ws_bytes, long long cap_particles, 
                           unsigned long long philox_offset, const double* d_gather, const double* d_xs,
                           int* d_hist_send, double* d_shift, double* d_xmin, void* stream);
 /* splitters and counts from the all-gathered histograms [world][4096]; h_counts (pinned host,
- * 2*world + 4 ints, valid after the stream is synchronised) = send counts per destination, receive
+ * 2*world + 4 ints, valid after the stream is synchronised; may be NULL when world == 1) = send counts per destination, receive
  * counts per source, arrivals, children, fine sort bins, status */
 int pmmh_svsplit_plan(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
                       int world, const int* d_hist, int* h_counts, void* stream);
 /* records of the children grouped by destination rank -> d_send (rows of LR doubles) */
 int pmmh_svsplit_pack(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
                       const int* d_perm, const double* d_rec, double* d_send, void* stream);
-/* argsort of the arrivals (:392-424): d_xs / d_perm of the new generation */
+/* argsort of the arrivals (:392-424): d_xs / d_perm of the new generation.  keys_are_children = 1
+ * (world == 1 only): arrival e is child e, its value is read from the dense child array */
 int pmmh_svsplit_sort(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
-                      int n_arrivals, int n_fine, int lag, const double* d_rec_new, double* d_xs,
-                      int* d_perm, void* stream);
+                      int n_arrivals, int n_fine, int lag, const double* d_rec_new,
+                      int keys_are_children, double* d_xs, int* d_perm, void* stream);
 /* d_w[p] = d_sh[p] / *d_total (normalised weights of a kept generation, for the tail) */
 int pmmh_svsplit_normalise(const double* d_sh, int n_local, const double* d_total, double* d_w,
                            void* stream);

@@ -11,6 +11,7 @@
 #include "../../include/pmmh_qn.h"
 #include "aux_kernels.cuh"
 #include "sv_filter.cuh"
+#include "sv_split.cuh"
 
 namespace {
 
@@ -72,6 +73,8 @@ struct SvPlan {
     int use_fast, NSUB, CP;
     int use_chain;
     size_t chain_stride, chain_total;
+    int use_split;           // streaming kernels (sv_split.cu), one problem, log-likelihood + gradient
+    size_t split_total;
     size_t fast_sync_bytes, fast_team_stride, fast_total, general_total;
 };
 
@@ -80,6 +83,7 @@ struct SvPlan {
 // 1 = general kernel only, 2 = exchange kernel where eligible WITHOUT the fallback pass (diagnostics),
 // 3 = chain kernel where eligible WITHOUT the fallback pass (diagnostics)
 int g_sv_algorithm = 0;
+int g_split_min_particles = 1 << 30;   // automatic selection of the streaming kernels from this N on
 long long* g_sv_prof = nullptr;   // development: per-CTA phase clocks of the exchange kernel
 constexpr int kMaxDynSmem = 227 * 1024;
 
@@ -135,13 +139,24 @@ int sv_make_plan(int nobs, int n, int lag, int batch, int hess, int mode, int ha
         p->chain_total = (size_t)p->grid * p->chain_stride;
         if (p->chain_total > p->total) p->total = p->chain_total;
     }
+    // one large problem, log-likelihood + gradient, no history dump: the streaming kernels
+    p->use_split = 0;
+    p->split_total = 0;
+    if (mode == pmmh::kSvFlps && !hess && batch == 1 && !have_hist && ctas == 0 && !p->use_chain &&
+        (g_sv_algorithm == 4 || (g_sv_algorithm == 0 && n >= g_split_min_particles)) &&
+        pmmh::sv_split_single_eligible(nobs, n, lag)) {
+        p->use_split = 1;
+        p->split_total = pmmh::sv_split_single_ws_bytes(nobs, n, lag);
+        // the general kernel (fallback pass) reuses the head of the same workspace
+        if (p->split_total > p->total) p->total = p->split_total;
+    }
     p->use_fast = 0;
     p->NSUB = 0;
     p->fast_sync_bytes = p->fast_team_stride = p->fast_total = 0;
     p->CP = 0;
     // one CTA per problem (batches of small problems) has no exchange to save: the general kernel
     // is the faster one there (measured: 8.8e9 vs 7.0e9 particle-steps/s at 1024 x N=4096)
-    const bool want_fast = !p->use_chain && ((g_sv_algorithm == 2) || (g_sv_algorithm == 0 && G > 1));
+    const bool want_fast = !p->use_chain && !p->use_split && ((g_sv_algorithm == 2) || (g_sv_algorithm == 0 && G > 1));
     if (mode == pmmh::kSvFlps && !hess && want_fast && pmmh::sv_fast_eligible(n, G)) {
         const int S = pmmh::sv_fast_nsub(n, G);
         const int CP = pmmh::sv_fast_pair_cap(n, G);
@@ -215,6 +230,17 @@ int sv_run(int mode, const double* d_obs, long long obs_stride, const double* d_
         if (g_sv_algorithm == 3) return PMMH_OK;   // diagnostics: no fallback pass
         a.only_failed = 1;
     }
+    if (p.use_split) {
+        // streaming kernels first; an abandoned evaluation (diag status 1) is re-run by the general
+        // kernel in the same stream
+        rc = pmmh::sv_split_single_run(d_obs, d_params, d_rvr, d_u, nobs, n, lag, d_filt, d_smo, d_ll, d_grad,
+                                       d_traj, d_diag, d_ws, ws_bytes, st);
+        if (rc != PMMH_OK) return rc;
+        PMMH_CUDA(cudaMemsetAsync(d_h1, 0, 16 * sizeof(double), st));
+        PMMH_CUDA(cudaMemsetAsync(d_h2, 0, 16 * sizeof(double), st));
+        if (g_sv_algorithm == 4) return PMMH_OK;   // diagnostics: no fallback pass
+        a.only_failed = 1;
+    }
     if (p.use_fast) {
         // exchange kernel first; problems it abandons (diag status 1) are re-run by the general
         // kernel in the same stream, reusing the workspace
@@ -265,7 +291,7 @@ int pmmh_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 }
 
 int pmmh_sv_set_algorithm(int algorithm) {
-    if (algorithm < 0 || algorithm > 3) return fail(PMMH_ERR_INVALID, "algorithm must be 0, 1, 2 or 3");
+    if (algorithm < 0 || algorithm > 4) return fail(PMMH_ERR_INVALID, "algorithm must be 0 .. 4");
     g_sv_algorithm = algorithm;
     return PMMH_OK;
 }

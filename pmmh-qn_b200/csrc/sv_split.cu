@@ -47,7 +47,8 @@ int set_cuda_error(cudaError_t err, const char* where);
 namespace {
 
 constexpr int kBins = 4096;         // coarse value bins of the routing histogram
-constexpr int kTile = 2048;         // particles per scan tile (256 threads x 8)
+constexpr int kTile = 1024;         // particles per scan tile (128 threads x 8)
+constexpr int kTileThreads = kTile / 8;
 constexpr int kFine = 8;            // target occupancy of a fine sort bin
 constexpr int kMaxWorld = 16;
 constexpr int kStage = 4096;        // cumulative weights staged in shared memory per child tile
@@ -74,7 +75,7 @@ struct SplitState {
 };
 
 struct Layout {
-    size_t state, cumblk, boff, btot, bpart, xc, pa, cb, dest, nfc, fstart, counts, fcnt, fst, ftot,
+    size_t state, cumblk, boff, btot, tlast, bpart, xc, pa, cb, dest, nfc, fstart, counts, fcnt, fst, ftot,
         rnk, fb, tkey, tidx, tfb, total;
     long long ntiles_max, nf_max;
 };
@@ -90,6 +91,7 @@ Layout make_layout(long long cap, long long capc) {
     L.cumblk = o;  o += al((size_t)cap * 8);
     L.boff = o;    o += al((size_t)(L.ntiles_max + 1) * 8);
     L.btot = o;    o += al((size_t)L.ntiles_max * 8);
+    L.tlast = o;   o += al((size_t)L.ntiles_max * 8);
     L.bpart = o;   o += al((size_t)L.ntiles_max * 8 * 8);
     L.xc = o;      o += al((size_t)capc * 8);
     L.pa = o;      o += al((size_t)capc * 4);
@@ -103,7 +105,7 @@ Layout make_layout(long long cap, long long capc) {
     L.ftot = o;    o += al((size_t)(L.nf_max / kScanTile + 2) * 4);
     L.rnk = o;     o += al((size_t)cap * 4);
     L.fb = o;      o += al((size_t)cap * 4);
-    L.tkey = o;    o += al((size_t)cap * 8);
+    L.tkey = o;    o += al((size_t)cap * 16);   // SortEntry[cap]
     L.tidx = o;    o += al((size_t)cap * 4);
     L.tfb = o;     o += al((size_t)cap * 4);
     L.total = o;
@@ -114,7 +116,9 @@ Layout make_layout(long long cap, long long capc) {
 // generation 0: every particle = mu (Q1, :306-323), identity order, history rows (mu, 0, ...)
 // ---------------------------------------------------------------------------------------------
 __global__ void split_init_kernel(double* __restrict__ xs, int* __restrict__ perm,
-                                  double* __restrict__ rec, int n, int LR, double mu) {
+                                  double* __restrict__ rec, int n, int LR,
+                                  const double* __restrict__ params) {
+    const double mu = params[0];
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
         xs[p] = mu;
         perm[p] = p;
@@ -130,17 +134,19 @@ __global__ void split_init_kernel(double* __restrict__ xs, int* __restrict__ per
 //   bpart[tile][0..6] = sum sh x | sum sh curr | sum sh g_0..3     (:439-470, unnormalised)
 // ---------------------------------------------------------------------------------------------
 template <bool GRAD>
-__global__ void __launch_bounds__(256) split_weights_kernel(
+__global__ void __launch_bounds__(kTileThreads) split_weights_kernel(
     SplitState* __restrict__ st, const double* __restrict__ xs, const int* __restrict__ perm,
-    const double* __restrict__ rec, int n, int LR, double y, double ylag,
+    const double* __restrict__ rec, int n, int LR, const double* __restrict__ obs, int t, int lag,
     const double* __restrict__ params, int uniform, double* __restrict__ cumblk,
-    double* __restrict__ btot, double* __restrict__ bpart, double* __restrict__ shsave) {
+    double* __restrict__ btot, double* __restrict__ tlast, double* __restrict__ bpart,
+    double* __restrict__ shsave) {
     __shared__ double red[7 * 32];
-    __shared__ double s_wtot[8];
+    __shared__ double s_wtot[kTileThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     SvConst c;
     sv_const_init(c, params);
     const double shift = uniform ? 0.0 : st->shift;
+    const double y = obs[t], ylag = GRAD ? obs[t - lag] : 0.0;   // Q5: obs[i - LAG]
     const int base = blockIdx.x * kTile + tid * 8;
     double loc[8];
     double acc[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
@@ -183,11 +189,15 @@ __global__ void __launch_bounds__(256) split_weights_kernel(
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int p = base + k;
-        if (p < n) cumblk[p] = toff + loc[k];
+        if (p < n) {
+            const double v = toff + loc[k];
+            cumblk[p] = v;
+            if (p == n - 1 || p == (int)(blockIdx.x + 1) * kTile - 1) tlast[blockIdx.x] = v;
+        }
     }
     if (tid == 0) {
         double tot = 0.0;
-        for (int w = 0; w < 8; ++w) tot = tot + s_wtot[w];
+        for (int w = 0; w < kTileThreads / 32; ++w) tot = tot + s_wtot[w];
         btot[blockIdx.x] = tot;
     }
     block_sum<7>(acc, red);
@@ -259,6 +269,23 @@ __device__ __forceinline__ int cum_search(double cp, int lo, int hi, double off,
     return lo;
 }
 
+// the same search in two levels: first over the last element of every tile (two small dense
+// arrays, cache resident), then inside one tile
+__device__ __forceinline__ int cum_search2(double cp, int n, double off, double S,
+                                           const double* __restrict__ boff,
+                                           const double* __restrict__ tlast,
+                                           const double* __restrict__ cumblk) {
+    const int ntiles = (n + kTile - 1) / kTile;
+    int lo = 0, hi = ntiles;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (((off + boff[mid]) + tlast[mid]) / S < cp) lo = mid + 1;
+        else hi = mid;
+    }
+    if (lo >= ntiles) return n;
+    return cum_search(cp, lo * kTile, min(n, (lo + 1) * kTile), off, S, boff, cumblk);
+}
+
 // #{ j in [0, N) : (u + j) / N <= c }, the exact predicate of :703-711 re-checked
 __device__ long long count_le(double c, double u, long long N) {
     const double dn = (double)N;
@@ -282,7 +309,7 @@ __global__ void __launch_bounds__(256) split_children_kernel(
     const double* __restrict__ params, const double* __restrict__ rvr, const double* __restrict__ u,
     unsigned long long seed, unsigned long long philox_offset, const double* __restrict__ gather,
     const double* __restrict__ xs, const double* __restrict__ cumblk, const double* __restrict__ boff,
-    double* __restrict__ xc, int* __restrict__ pa, unsigned short* __restrict__ cb,
+    const double* __restrict__ tlast, double* __restrict__ xc, int* __restrict__ pa, unsigned short* __restrict__ cb,
     int* __restrict__ hist_out, double* __restrict__ shift_out, double* __restrict__ xmin_out) {
     extern __shared__ unsigned char smem_raw[];
     double* s_cum = (double*)smem_raw;                       // [kStage]
@@ -373,7 +400,7 @@ __global__ void __launch_bounds__(256) split_children_kernel(
                 long long k = tile * kChildTile;
                 if (tid & 1) k = min((long long)nc, k + kChildTile) - 1;
                 const double cp = (uu + (double)(jlo + k)) / dn;
-                s_tp[tid] = min(n - 1, cum_search(cp, 0, n, off, S, boff, cumblk));
+                s_tp[tid] = min(n - 1, cum_search2(cp, n, off, S, boff, tlast, cumblk));
             }
         }
         __syncthreads();
@@ -564,30 +591,43 @@ __global__ void __launch_bounds__(256) split_pack_kernel(
     const unsigned short* __restrict__ cb, const int* __restrict__ dest, const int* __restrict__ perm,
     const double* __restrict__ rec, double* __restrict__ send) {
     __shared__ int s_cnt[kMaxWorld], s_base[kMaxWorld];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int nc = st->nc, G = st->world, LR = st->LR;
     for (long long base = (long long)blockIdx.x * 256; base < nc; base += (long long)gridDim.x * 256) {
         const long long k = base + tid;
         const bool valid = k < nc;
-        if (tid < G) s_cnt[tid] = 0;
-        __syncthreads();
-        int d = 0, r = 0;
-        if (valid) {
-            d = dest[cb[k]];
-            r = atomicAdd(&s_cnt[d], 1);
-        }
-        __syncthreads();
-        if (tid < G && s_cnt[tid] > 0) s_base[tid] = atomicAdd(&st->cursor[tid], s_cnt[tid]);
-        __syncthreads();
-        if (valid) {
-            const size_t slot = (size_t)(st->send_off[d] + s_base[d] + r) * LR;
-            send[slot] = xc[k];
-            if (LR > 1) {
-                const size_t row = (size_t)perm[pa[k]] * LR;
-                for (int m = 1; m < LR; ++m) send[slot + m] = rec[row + m - 1];
+        long long slot = -1;
+        if (G == 1) {
+            slot = valid ? k : -1;                  // one rank: birth order is arrival order
+        } else {
+            if (tid < G) s_cnt[tid] = 0;
+            __syncthreads();
+            int d = 0, r = 0;
+            if (valid) {
+                d = dest[cb[k]];
+                r = atomicAdd(&s_cnt[d], 1);
             }
+            __syncthreads();
+            if (tid < G && s_cnt[tid] > 0) s_base[tid] = atomicAdd(&st->cursor[tid], s_cnt[tid]);
+            __syncthreads();
+            if (valid) slot = st->send_off[d] + s_base[d] + r;
+            __syncthreads();
         }
-        __syncthreads();
+        const double xv = valid ? xc[k] : 0.0;
+        if (LR == 1) {
+            if (valid) send[slot] = xv;
+            continue;
+        }
+        // the warp copies its 32 records together: consecutive lanes move consecutive doubles of
+        // a record, so both the parent-row reads and the record writes are 72 / 80-byte runs
+        const long long row = valid ? (long long)perm[pa[k]] : 0;
+        for (int idx = lane; idx < 32 * LR; idx += 32) {
+            const int cc = idx / LR, m = idx - cc * LR;
+            const long long sc = __shfl_sync(kFullMask, slot, cc);
+            const long long rc = __shfl_sync(kFullMask, row, cc);
+            const double xvc = __shfl_sync(kFullMask, xv, cc);
+            if (sc >= 0) send[(size_t)sc * LR + m] = (m == 0) ? xvc : rec[(size_t)rc * LR + m - 1];
+        }
     }
 }
 
@@ -607,12 +647,13 @@ __device__ __forceinline__ int fine_bin(double x, double lo, double scale, const
 }
 
 __global__ void split_fine_hist_kernel(const SplitState* __restrict__ st, const double* __restrict__ recn,
-                                       int n, int LR, const int* __restrict__ nfc,
+                                       const double* __restrict__ keys, int n, int LR,
+                                       const int* __restrict__ nfc,
                                        const int* __restrict__ fstart, int* __restrict__ fcnt,
                                        int* __restrict__ rnk, int* __restrict__ fb) {
     const double lo = st->lo, scale = st->scale;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-        const double x = recn[(size_t)e * LR];
+        const double x = keys ? keys[e] : recn[(size_t)e * LR];
         const int f = fine_bin(x, lo, scale, nfc, fstart);
         rnk[e] = atomicAdd(&fcnt[f], 1);
         fb[e] = f;
@@ -692,39 +733,45 @@ __global__ void __launch_bounds__(1024) iscan_apply_kernel(const int* __restrict
     }
 }
 
-__global__ void split_scatter_kernel(const double* __restrict__ recn, int n, int LR,
-                                     const int* __restrict__ fst, const int* __restrict__ rnk,
-                                     const int* __restrict__ fb, double* __restrict__ tkey,
-                                     int* __restrict__ tidx, int* __restrict__ tfb) {
+struct __align__(16) SortEntry {
+    double key;
+    int idx, fb;
+};
+
+__global__ void split_scatter_kernel(const double* __restrict__ recn, const double* __restrict__ keys,
+                                     int n, int LR, const int* __restrict__ fst,
+                                     const int* __restrict__ rnk, const int* __restrict__ fb,
+                                     SortEntry* __restrict__ ent) {
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
         const int f = fb[e];
-        const int slot = fst[f] + rnk[e];
-        tkey[slot] = recn[(size_t)e * LR];
-        tidx[slot] = e;
-        tfb[slot] = f;
+        SortEntry v;
+        v.key = keys ? keys[e] : recn[(size_t)e * LR];
+        v.idx = e;
+        v.fb = f;
+        ent[fst[f] + rnk[e]] = v;   // one 16-byte store: one sector per particle
     }
 }
 
 // exact order inside each fine bin: (value, arrival index); any correct sort reproduces the
 // reference's qsort order when values are distinct (SURVEY 7 "hard parts"); equal values counted
-__global__ void split_rank_kernel(SplitState* __restrict__ st, const double* __restrict__ tkey,
-                                  const int* __restrict__ tidx, const int* __restrict__ tfb,
+__global__ void split_rank_kernel(SplitState* __restrict__ st, const SortEntry* __restrict__ ent,
                                   const int* __restrict__ fst, int n, int nf_total,
                                   double* __restrict__ xs, int* __restrict__ perm) {
     int mx = 0, ties = 0;
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
-        const int f = tfb[s];
+        const SortEntry me = ent[s];
+        const int f = me.fb;
         const int b = fst[f], e = (f + 1 < nf_total) ? fst[f + 1] : n;
-        const double v = tkey[s];
-        const int oi = tidx[s];
+        const double v = me.key;
+        const int oi = me.idx;
         int rank = 0;
         if (e - b <= kMaxBinRank) {
             for (int q = b; q < e; ++q) {
-                const double k2 = tkey[q];
-                if (k2 < v) ++rank;
-                else if (k2 == v && q != s) {
+                const SortEntry o = ent[q];
+                if (o.key < v) ++rank;
+                else if (o.key == v && q != s) {
                     ++ties;
-                    if (tidx[q] < oi) ++rank;
+                    if (o.idx < oi) ++rank;
                 }
             }
         } else {
@@ -759,7 +806,7 @@ __global__ void __launch_bounds__(256) split_tail_kernel(
     const double y1 = obs_wrap(obs, i - 1, nobs);
     double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     const int base = blockIdx.x * kTile;
-    for (int p = base + tid; p < min(n, base + kTile); p += 256) {
+    for (int p = base + tid; p < min(n, base + kTile); p += blockDim.x) {
         const size_t row = (size_t)perm[p] * LR;
         const double curr = rec[row + idx];
         acc[0] += wfinal[p] * curr;
@@ -848,6 +895,19 @@ __global__ void split_finish_kernel(const double* __restrict__ sums, const doubl
     }
 }
 
+// diag[] of a one-rank evaluation without a host round trip
+__global__ void split_diag_kernel(const SplitState* __restrict__ st, long long* __restrict__ diag) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        for (int k = 0; k < PMMH_DIAG_COUNT; ++k) diag[k] = 0;
+        diag[PMMH_DIAG_NEAR_TIES] = (long long)st->near_ties;
+        diag[PMMH_DIAG_MAX_BIN] = st->max_bin;
+        diag[PMMH_DIAG_STATUS] = st->status ? 1 : 0;
+        diag[PMMH_DIAG_KEY_TIES] = (long long)st->key_ties;
+        diag[PMMH_DIAG_KERNEL] = 4;
+        diag[PMMH_DIAG_FAST_INFO] = st->status;
+    }
+}
+
 int check_ws(void* ws, size_t bytes, long long cap, long long capc, Layout* L) {
     if (!ws) return set_error(PMMH_ERR_INVALID, "svsplit: null workspace");
     *L = make_layout(cap, capc);
@@ -868,10 +928,164 @@ int grid_for(long long n, int per_block) {
     return (int)g;
 }
 
+struct SingleLayout {
+    size_t split, xs, perm, xs2, perm2, recA, recB, sums, shift, xmin, gather, hist, keep, tail, total;
+    size_t split_bytes;
+};
+
+SingleLayout make_single_layout(int nobs, long long n, int lag) {
+    SingleLayout S;
+    const size_t LR = lag;
+    size_t o = 0;
+    S.split_bytes = make_layout(n, n).total;
+    S.split = o;   o += al(S.split_bytes);
+    S.xs = o;      o += al((size_t)n * 8);
+    S.perm = o;    o += al((size_t)n * 4);
+    S.xs2 = o;     o += al((size_t)n * 8);
+    S.perm2 = o;   o += al((size_t)n * 4);
+    S.recA = o;    o += al((size_t)n * LR * 8);
+    S.recB = o;    o += al((size_t)n * LR * 8);
+    S.sums = o;    o += al((size_t)nobs * 8 * 8);
+    S.shift = o;   o += al((size_t)nobs * 8);
+    S.xmin = o;    o += al((size_t)nobs * 8);
+    S.gather = o;  o += al(4 * 8);
+    S.hist = o;    o += al((size_t)kBins * 4);
+    S.keep = o;    o += al((size_t)n * LR * 8);
+    S.tail = o;    o += al((size_t)LR * 8 * 8);
+    S.total = o;
+    return S;
+}
+
 }  // namespace
+
+size_t sv_split_single_ws_bytes(int nobs, int n, int lag) { return make_single_layout(nobs, n, lag).total; }
+bool sv_split_single_eligible(int nobs, int n, int lag) {
+    return lag >= 2 && lag <= 63 && nobs >= 2 * lag && n >= 1;
+}
+
 }  // namespace pmmh
 
 using namespace pmmh;
+
+extern "C" {
+int pmmh_svsplit_init(void*, size_t, long long, int, int, int, int, long long, long long, int, const double*,
+                      double*, int*, double*, void*);
+int pmmh_svsplit_weights(void*, size_t, long long, long long, int, int, int, int, const double*, const double*,
+                         const double*, const int*, const double*, double*, double*, double*, void*);
+int pmmh_svsplit_children(void*, size_t, long long, long long, int, int, const double*, const double*,
+                          const double*, const double*, unsigned long long, unsigned long long, const double*,
+                          const double*, int*, double*, double*, void*);
+int pmmh_svsplit_plan(void*, size_t, long long, long long, int, const int*, int*, void*);
+int pmmh_svsplit_pack(void*, size_t, long long, long long, const int*, const double*, double*, void*);
+int pmmh_svsplit_sort(void*, size_t, long long, long long, int, int, int, const double*, int, double*, int*,
+                      void*);
+int pmmh_svsplit_normalise(const double*, int, const double*, double*, void*);
+int pmmh_svsplit_tail(void*, size_t, long long, long long, int, int, int, const double*, const double*,
+                      const int*, const double*, const double*, const double*, long long, double*, void*);
+int pmmh_svsplit_finish(const double*, const double*, const double*, const double*, const double*, int,
+                        const double*, int, int, long long, double*, double*, double*, double*, double*,
+                        void*);
+}
+
+namespace pmmh {
+
+// The whole evaluation on ONE device (world = 1): the same phases, no exchange, no host
+// synchronisation -- T x 11 kernel launches on `st`.  Returns a PMMH_* status.
+int sv_split_single_run(const double* d_obs, const double* d_params, const double* d_rvr, const double* d_u,
+                        int nobs, int n, int lag, double* d_filt, double* d_smo, double* d_ll,
+                        double* d_grad, double* d_traj, long long* d_diag, void* d_ws, size_t ws_bytes,
+                        cudaStream_t st) {
+    if (!sv_split_single_eligible(nobs, n, lag)) return set_error(PMMH_ERR_INVALID, "split kernels: sizes not eligible");
+    const SingleLayout S = make_single_layout(nobs, n, lag);
+    if (ws_bytes < S.total) return set_error(PMMH_ERR_WORKSPACE, "split kernels: workspace too small");
+    char* ws = (char*)d_ws;
+    void* sws = ws + S.split;
+    const size_t sb = S.split_bytes;
+    double* xs = (double*)(ws + S.xs);
+    int* perm = (int*)(ws + S.perm);
+    double* xs_next = (double*)(ws + S.xs2);
+    int* perm_next = (int*)(ws + S.perm2);
+    double* rec = (double*)(ws + S.recA);
+    double* rec_next = (double*)(ws + S.recB);
+    double* sums = (double*)(ws + S.sums);
+    double* shift = (double*)(ws + S.shift);
+    double* xmin = (double*)(ws + S.xmin);
+    double* gather = (double*)(ws + S.gather);
+    int* hist = (int*)(ws + S.hist);
+    double* keep = (double*)(ws + S.keep);
+    double* tail = (double*)(ws + S.tail);
+    const Layout L = make_layout(n, n);
+    const int nf_bound = (int)(n / kFine + kBins);
+    int rc;
+    // pack (record traffic, DRAM bound) and the sort (latency / L2 bound) both depend only on
+    // the plan: they run side by side on two streams
+    static thread_local cudaStream_t side[64] = {nullptr};
+    static thread_local cudaEvent_t ev_fork[64] = {nullptr}, ev_join[64] = {nullptr};
+    int dev = 0;
+    SPLIT_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return set_error(PMMH_ERR_NO_DEVICE, "device ordinal out of range");
+    if (!side[dev]) {
+        SPLIT_CUDA(cudaStreamCreateWithFlags(&side[dev], cudaStreamNonBlocking));
+        SPLIT_CUDA(cudaEventCreateWithFlags(&ev_fork[dev], cudaEventDisableTiming));
+        SPLIT_CUDA(cudaEventCreateWithFlags(&ev_join[dev], cudaEventDisableTiming));
+    }
+    SPLIT_CUDA(cudaMemsetAsync(sums, 0, (size_t)nobs * 8 * 8, st));
+    if ((rc = pmmh_svsplit_init(sws, sb, n, nobs, 1, 0, lag, n, n, n, d_params, xs, perm, rec, st))) return rc;
+    if ((rc = pmmh_svsplit_weights(sws, sb, n, n, 0, n, lag, nobs, d_obs, d_params, xs, perm, rec, sums, gather,
+                                   nullptr, st)))
+        return rc;
+    for (int t = 1; t < nobs; ++t) {
+        if ((rc = pmmh_svsplit_children(sws, sb, n, n, t, n, d_obs, d_params, d_rvr, d_u, 0, 0, gather, xs, hist,
+                                        shift, xmin, st)))
+            return rc;
+        if ((rc = pmmh_svsplit_plan(sws, sb, n, n, 1, hist, nullptr, st))) return rc;
+        SPLIT_CUDA(cudaEventRecord(ev_fork[dev], st));
+        SPLIT_CUDA(cudaStreamWaitEvent(side[dev], ev_fork[dev], 0));
+        if ((rc = pmmh_svsplit_pack(sws, sb, n, n, perm, rec, rec_next, side[dev]))) return rc;
+        SPLIT_CUDA(cudaEventRecord(ev_join[dev], side[dev]));
+        double* tmp = rec;
+        rec = rec_next;
+        rec_next = tmp;
+        // the sort reads the dense child values and writes xs / perm of the NEW generation: pack
+        // still reads perm of the OLD one, so the new order goes to the alternate buffers
+        if ((rc = pmmh_svsplit_sort(sws, sb, n, n, n, nf_bound, lag, rec, 1, xs_next, perm_next, st))) return rc;
+        SPLIT_CUDA(cudaStreamWaitEvent(st, ev_join[dev], 0));
+        { double* tx = xs; xs = xs_next; xs_next = tx; int* tp = perm; perm = perm_next; perm_next = tp; }
+        double* kp = (t >= nobs - lag) ? keep + (size_t)(t % lag) * n : nullptr;
+        if ((rc = pmmh_svsplit_weights(sws, sb, n, n, t, n, lag, nobs, d_obs, d_params, xs, perm, rec, sums,
+                                       gather, kp, st)))
+            return rc;
+    }
+    // tail: normalised weights of the last `lag` generations, in place (same global positions)
+    for (int irel = 0; irel < lag; ++irel) {
+        const int i = nobs - lag + irel;
+        double* kp = keep + (size_t)(i % lag) * n;
+        if ((rc = pmmh_svsplit_normalise(kp, n, sums + (size_t)i * 8, kp, st))) return rc;
+    }
+    // the tail kernel indexes lagged weights as [irel][p]: slot of generation nobs-lag+irel is
+    // (nobs - lag + irel) % lag = a rotation of irel; pass the rotated base per call through a view
+    // by copying nothing: rotation r0 = (nobs - lag) % lag, so slot(irel) = (r0 + irel) % lag.
+    // The kernel takes one base + stride, so rotate into rec_next (free now) when r0 != 0.
+    const int r0 = (nobs - lag) % lag;
+    double* wl = keep;
+    if (r0 != 0) {
+        wl = rec_next;
+        for (int irel = 0; irel < lag; ++irel)
+            SPLIT_CUDA(cudaMemcpyAsync(wl + (size_t)irel * n, keep + (size_t)((r0 + irel) % lag) * n,
+                                       (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    if ((rc = pmmh_svsplit_tail(sws, sb, n, n, n, lag, nobs, d_obs, d_params, perm, rec,
+                                wl + (size_t)(lag - 1) * n, wl, n, tail, st)))
+        return rc;
+    if ((rc = pmmh_svsplit_finish(sums, shift, xmin, tail, gather, 1, d_params, nobs, lag, n, d_ll, d_filt, d_smo,
+                                  d_grad, d_traj, st)))
+        return rc;
+    split_diag_kernel<<<1, 32, 0, st>>>((const SplitState*)((char*)sws + L.state), d_diag);
+    SPLIT_CUDA(cudaGetLastError());
+    return PMMH_OK;
+}
+
+}  // namespace pmmh
 
 extern "C" {
 
@@ -885,7 +1099,7 @@ int pmmh_svsplit_workspace_bytes(long long cap_particles, long long cap_children
 
 int pmmh_svsplit_init(void* d_ws, size_t ws_bytes, long long n_total, int n_obs, int world, int rank,
                       int lag, long long cap_particles, long long cap_children, int n_local,
-                      const double* h_params, double* d_xs, int* d_perm, double* d_rec, void* stream) {
+                      const double* d_params, double* d_xs, int* d_perm, double* d_rec, void* stream) {
     Layout L;
     if (int rc = check_ws(d_ws, ws_bytes, cap_particles, cap_children, &L)) return rc;
     if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world || n_total < 1 || n_obs < 2 ||
@@ -905,13 +1119,13 @@ int pmmh_svsplit_init(void* d_ws, size_t ws_bytes, long long n_total, int n_obs,
     SPLIT_CUDA(cudaStreamSynchronize(st));   // h lives on this stack frame
     if (n_local > 0)
         split_init_kernel<<<grid_for(n_local, 256), 256, 0, st>>>(d_xs, d_perm, d_rec, n_local, h.LR,
-                                                                   h_params[0]);
+                                                                   d_params);
     SPLIT_CUDA(cudaGetLastError());
     return PMMH_OK;
 }
 
 int pmmh_svsplit_weights(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
-                         int t, int n_local, int lag, int n_obs, const double* h_obs,
+                         int t, int n_local, int lag, int n_obs, const double* d_obs,
                          const double* d_params, const double* d_xs, const int* d_perm,
                          const double* d_rec, double* d_sums, double* d_gather_send, double* d_sh_save,
                          void* stream) {
@@ -925,20 +1139,20 @@ int pmmh_svsplit_weights(void* d_ws, size_t ws_bytes, long long cap_particles, l
     const int LR = lag == 0 ? 1 : lag;
     const int ntiles = (n_local + kTile - 1) / kTile;
     const bool grad = lag > 0 && t >= lag;
-    const double y = h_obs[t], ylag = grad ? h_obs[t - lag] : 0.0;   // Q5: obs[i - LAG]
     double* cumblk = (double*)(ws + L.cumblk);
     double* btot = (double*)(ws + L.btot);
     double* bpart = (double*)(ws + L.bpart);
     double* boff = (double*)(ws + L.boff);
+    double* tlast = (double*)(ws + L.tlast);
     if (ntiles > 0) {
         if (grad)
-            split_weights_kernel<true><<<ntiles, 256, 0, st>>>(state, d_xs, d_perm, d_rec, n_local, LR, y,
-                                                               ylag, d_params, t == 0, cumblk, btot,
-                                                               bpart, d_sh_save);
+            split_weights_kernel<true><<<ntiles, kTileThreads, 0, st>>>(state, d_xs, d_perm, d_rec, n_local, LR, d_obs,
+                                                               t, lag, d_params, t == 0, cumblk, btot,
+                                                               tlast, bpart, d_sh_save);
         else
-            split_weights_kernel<false><<<ntiles, 256, 0, st>>>(state, d_xs, d_perm, d_rec, n_local, LR,
-                                                                y, ylag, d_params, t == 0, cumblk, btot,
-                                                                bpart, d_sh_save);
+            split_weights_kernel<false><<<ntiles, kTileThreads, 0, st>>>(state, d_xs, d_perm, d_rec, n_local, LR,
+                                                                d_obs, t, lag, d_params, t == 0, cumblk, btot,
+                                                                tlast, bpart, d_sh_save);
     }
     split_weights_finalize_kernel<<<1, 256, 0, st>>>(state, d_xs, n_local, ntiles, btot, bpart, boff,
                                                      d_sums + (size_t)t * 8, d_gather_send);
@@ -969,7 +1183,8 @@ int pmmh_svsplit_children(void* d_ws, size_t ws_bytes, long long cap_particles, 
     SPLIT_CUDA(cudaMemsetAsync(d_hist_send, 0, (size_t)kBins * 4, st));
     split_children_kernel<<<148 * 4, 256, smem, st>>>(
         state, t, n_local, d_obs, d_params, d_rvr, d_u, seed, philox_offset, d_gather, d_xs,
-        (const double*)(ws + L.cumblk), (const double*)(ws + L.boff), (double*)(ws + L.xc),
+        (const double*)(ws + L.cumblk), (const double*)(ws + L.boff), (const double*)(ws + L.tlast),
+        (double*)(ws + L.xc),
         (int*)(ws + L.pa), (unsigned short*)(ws + L.cb), d_hist_send, d_shift, d_xmin);
     SPLIT_CUDA(cudaGetLastError());
     return PMMH_OK;
@@ -985,8 +1200,9 @@ int pmmh_svsplit_plan(void* d_ws, size_t ws_bytes, long long cap_particles, long
     split_plan_kernel<<<1, 1024, 0, st>>>(state, d_hist, (int*)(ws + L.dest), (int*)(ws + L.nfc),
                                           (int*)(ws + L.fstart), (int*)(ws + L.counts));
     SPLIT_CUDA(cudaGetLastError());
-    SPLIT_CUDA(cudaMemcpyAsync(h_counts, ws + L.counts, (size_t)(2 * world + 4) * 4,
-                               cudaMemcpyDeviceToHost, st));
+    if (h_counts)
+        SPLIT_CUDA(cudaMemcpyAsync(h_counts, ws + L.counts, (size_t)(2 * world + 4) * 4,
+                                   cudaMemcpyDeviceToHost, st));
     return PMMH_OK;
 }
 
@@ -1005,8 +1221,8 @@ int pmmh_svsplit_pack(void* d_ws, size_t ws_bytes, long long cap_particles, long
 }
 
 int pmmh_svsplit_sort(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
-                      int n_arrivals, int n_fine, int lag, const double* d_rec_new, double* d_xs,
-                      int* d_perm, void* stream) {
+                      int n_arrivals, int n_fine, int lag, const double* d_rec_new,
+                      int keys_are_children, double* d_xs, int* d_perm, void* stream) {
     Layout L;
     if (int rc = check_ws(d_ws, ws_bytes, cap_particles, cap_children, &L)) return rc;
     if (n_arrivals < 0 || n_arrivals > cap_particles || n_fine < 0 || n_fine > L.nf_max)
@@ -1021,19 +1237,19 @@ int pmmh_svsplit_sort(void* d_ws, size_t ws_bytes, long long cap_particles, long
     int* ftot = (int*)(ws + L.ftot);
     int* rnk = (int*)(ws + L.rnk);
     int* fb = (int*)(ws + L.fb);
-    double* tkey = (double*)(ws + L.tkey);
-    int* tidx = (int*)(ws + L.tidx);
-    int* tfb = (int*)(ws + L.tfb);
+    SortEntry* ent = (SortEntry*)(ws + L.tkey);
     SPLIT_CUDA(cudaMemsetAsync(fcnt, 0, (size_t)(n_fine + 1) * 4, st));
     const int g = grid_for(n_arrivals, 256);
-    split_fine_hist_kernel<<<g, 256, 0, st>>>(state, d_rec_new, n_arrivals, LR, (const int*)(ws + L.nfc),
+    // one rank: the arrivals ARE the children in birth order, their values are a dense array
+    const double* keys = keys_are_children ? (const double*)(ws + L.xc) : nullptr;
+    split_fine_hist_kernel<<<g, 256, 0, st>>>(state, d_rec_new, keys, n_arrivals, LR, (const int*)(ws + L.nfc),
                                               (const int*)(ws + L.fstart), fcnt, rnk, fb);
     const int nt = (n_fine + kScanTile - 1) / kScanTile;
     iscan_totals_kernel<<<nt, 1024, 0, st>>>(fcnt, n_fine, ftot);
     iscan_offsets_kernel<<<1, 1024, 0, st>>>(ftot, nt);
     iscan_apply_kernel<<<nt, 1024, 0, st>>>(fcnt, n_fine, ftot, fst);
-    split_scatter_kernel<<<g, 256, 0, st>>>(d_rec_new, n_arrivals, LR, fst, rnk, fb, tkey, tidx, tfb);
-    split_rank_kernel<<<g, 256, 0, st>>>(state, tkey, tidx, tfb, fst, n_arrivals, n_fine, d_xs, d_perm);
+    split_scatter_kernel<<<g, 256, 0, st>>>(d_rec_new, keys, n_arrivals, LR, fst, rnk, fb, ent);
+    split_rank_kernel<<<g, 256, 0, st>>>(state, ent, fst, n_arrivals, n_fine, d_xs, d_perm);
     SPLIT_CUDA(cudaGetLastError());
     return PMMH_OK;
 }

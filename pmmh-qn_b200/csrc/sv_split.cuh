@@ -1,0 +1,13 @@
+// sv_split.cuh -- the streaming ("split") SV kernels driven on one device (sv_split.cu)
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace pmmh {
+size_t sv_split_single_ws_bytes(int nobs, int n, int lag);
+bool sv_split_single_eligible(int nobs, int n, int lag);
+int sv_split_single_run(const double* d_obs, const double* d_params, const double* d_rvr, const double* d_u,
+                        int nobs, int n, int lag, double* d_filt, double* d_smo, double* d_ll,
+                        double* d_grad, double* d_traj, long long* d_diag, void* d_ws, size_t ws_bytes,
+                        cudaStream_t st);
+}  // namespace pmmh

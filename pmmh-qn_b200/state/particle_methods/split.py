@@ -127,24 +127,24 @@ class _Rank(object):
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def init(self, params_host):
+    def init(self, params_d):
         b, e = block_range(self.N, self.rank, self.world)
         self.n_local = e - b
         if self.n_local > self.cap:
             raise _lib.PmmhError("cap_particles too small for the initial split")
         _lib.check(self.lib.pmmh_svsplit_init(_p(self.ws), self.ws_bytes, self.N, self.n_obs, self.world,
                                               self.rank, self.lag, self.cap, self.capc, self.n_local,
-                                              params_host.ctypes.data_as(ctypes.c_void_p), _p(self.xs),
+                                              _p(params_d), _p(self.xs),
                                               _p(self.perm), _p(self.rec), self._stream()),
                    "pmmh_svsplit_init")
 
-    def weights(self, t, obs_host, params_d):
+    def weights(self, t, obs_d, params_d):
         keep = None
         if self.sh_keep is not None and t >= self.n_obs - self.lag:
             keep = self.sh_keep[t % self.lag]
             self.n_keep[t] = self.n_local
         _lib.check(self.lib.pmmh_svsplit_weights(*self._c(), t, self.n_local, self.lag, self.n_obs,
-                                                 obs_host.ctypes.data_as(ctypes.c_void_p), _p(params_d),
+                                                 _p(obs_d), _p(params_d),
                                                  _p(self.xs), _p(self.perm), _p(self.rec), _p(self.sums),
                                                  _p(self.gather_send), None if keep is None else _p(keep),
                                                  self._stream()), "pmmh_svsplit_weights")
@@ -173,7 +173,8 @@ class _Rank(object):
         self.rec, self.rec_next = self.rec_next, self.rec
         self.n_local = n_arrivals
         _lib.check(self.lib.pmmh_svsplit_sort(*self._c(), n_arrivals, n_fine, self.lag, _p(self.rec),
-                                              _p(self.xs), _p(self.perm), self._stream()), "pmmh_svsplit_sort")
+                                              1 if self.world == 1 else 0, _p(self.xs), _p(self.perm),
+                                              self._stream()), "pmmh_svsplit_sort")
 
     def diag(self):
         out = (ctypes.c_longlong * _lib.DIAG_COUNT)()
@@ -255,8 +256,8 @@ def run_split_smoother(comm, obs, params, n_total, lag, rvr_d, u_d=None, philox=
     hist = [] if keep_history else None
 
     for rk in ranks:
-        rk.init(params)
-        rk.weights(0, obs, params_d)
+        rk.init(params_d)
+        rk.weights(0, obs_d, params_d)
     comm.all_gather([rk.gather_send for rk in ranks], [rk.gather for rk in ranks])
     if keep_history:
         hist.append([rk.xs[:rk.n_local].clone() for rk in ranks])
@@ -282,7 +283,7 @@ def run_split_smoother(comm, obs, params, n_total, lag, rvr_d, u_d=None, philox=
                             [rk.rec_next for rk in ranks], [c[1] for c in cnt])
         for rk, c in zip(ranks, cnt):
             rk.sort(c[2], c[4])
-            rk.weights(t, obs, params_d)
+            rk.weights(t, obs_d, params_d)
         comm.all_gather([rk.gather_send for rk in ranks], [rk.gather for rk in ranks])
         if keep_history:
             hist.append([rk.xs[:rk.n_local].clone() for rk in ranks])

@@ -129,3 +129,30 @@ def test_split_estimator_contract(cuda_dev):
     assert relerr(sp.results['smo_state_est'], one.results['smo_state_est']) <= 1e-10
     assert sp.filter(model, rvs={'rvs': handle})
     assert abs(sp.results['log_like'] - one.results['log_like']) <= 1e-10 * abs(one.results['log_like'])
+
+
+@pytest.mark.parametrize("n,nobs,lag,seed", [(20000, 61, 10, 1), (3000, 47, 4, 2), (1 << 17, 45, 10, 4)])
+def test_streaming_kernels_behind_flps_sv_corr(cuda_dev, n, nobs, lag, seed):
+    """pmmh_flps_sv_corr with algorithm 4: the same phases driven from C++ on one device."""
+    import torch
+    import oracle
+    from pmmh_qn_b200 import kernels as K
+    obs, params, rvr, rvp = gi.sv_inputs(n, nobs, seed)
+    ref = oracle.flps_sv_corr(obs, params, rvr, rvp, n, lag, 0)
+    u = torch.from_numpy(to_time_major(rvp, n, nobs)).to(cuda_dev)
+    K.set_sv_algorithm(4)
+    try:
+        out = K.flps_sv_corr(torch.from_numpy(obs).to(cuda_dev), torch.from_numpy(params).to(cuda_dev),
+                             torch.from_numpy(rvr[:nobs].copy()).to(cuda_dev), u, lag=lag)
+        torch.cuda.synchronize()
+    finally:
+        K.set_sv_algorithm(0)
+    diag = out["diag"][0].cpu().numpy()
+    assert int(diag[6]) == 4 and int(diag[2]) == 0
+    ll = float(out["log_like"][0])
+    assert abs(ll - ref["log_like"]) <= 1e-10 * abs(ref["log_like"])
+    assert relerr(out["filt"][0].cpu().numpy(), ref["filt"]) <= 1e-10
+    assert relerr(out["smo"][0].cpu().numpy(), ref["smo"]) <= 1e-10
+    assert relerr(out["traj"][0].cpu().numpy(), ref["traj"]) <= 1e-12
+    g, gr = out["gradient"][0].cpu().numpy(), ref["gradient"]
+    assert np.max(np.abs(g - gr)) <= 1e-9 * np.max(np.abs(gr))
