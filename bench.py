@@ -192,6 +192,46 @@ class BenchSVModel(object):
         return {k: 0.0 for k in self.params}
 
 
+def run_split_pf(args, rank, world, dev, dist):
+    """Secondary measurement (not the headline): one SV smoother with N = 2^24 particles split over
+    all ranks (pmmh_svsplit_* phases + NCCL all-gather / all-to-all per time step), T = 100,
+    log-likelihood + gradient, u from a Philox stream.  Fixed N => strong scaling over --gpus."""
+    import torch
+    import golden_inputs as gi
+    from pmmh_qn_b200 import kernels as K
+    from pmmh_qn_b200.state.particle_methods import split as SP
+    n, T = args.split_particles, args.split_steps
+    nobs = T + 1
+    obs = gi.sv_obs(nobs)
+    comm = SP.DistComm() if dist is not None else SP.LocalComm(1)
+    ph = SP.PhiloxRVS(seed=5, offset=0)
+    rvr = K.norm_cdf(ph.resampling_normals(nobs, n, dev))
+    secs, out = [], None
+    try:
+        for rep in range(2):
+            torch.cuda.synchronize()
+            if dist is not None:
+                dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = SP.run_split_smoother(comm, obs, np.array(PARAMS), n, LAG, rvr, philox=(5, 0), device=dev)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+            if dist is not None:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            secs.append(float(ms.item()) * 1e-3)
+    except Exception as e:     # reported, never silently replaced by another path
+        return {"error": str(e)[:200]}
+    return {"workload": "sv_flps_split_T%d_N2^%d_grad" % (T, int(np.log2(n))), "N": n, "T": T, "lag": LAG,
+            "value": n * T / secs[-1], "unit": UNIT, "seconds": secs[-1], "scaling": "strong",
+            "n_gpus": world, "log_like": float(out["log_like"].item()),
+            "near_ties_rank0": int(out["diag"][0]), "status": int(out["diag"][2]),
+            "max_particles_per_rank": int(out["counts"].max()),
+            "exchange": "none (one rank)" if world == 1 else
+                        "per step: all_gather 32 B + all_gather 16 KB + all_to_all of 80-byte records (NCCL)"}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import golden_inputs as gi
@@ -278,6 +318,11 @@ def run_ours(args, rank, world, local_rank):
     h2d = rvs_np.nbytes + (NOBS + 4 + NOBS) * 8
     d2h = (NOBS * 3 + 4 * NOBS + 1 + 32 + 8) * 8
 
+    # ---- BASELINE configs[4]: ONE particle filter split over the ranks (strong scaling, fixed N)
+    split_line = None
+    if not args.no_split:
+        split_line = run_split_pf(args, rank, world, dev, dist)
+
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
         achieved = n * T_STEPS * BYTES_PER_PARTICLE_STEP / (kern_ms * 1e-3) / 1e9
@@ -308,6 +353,8 @@ def run_ours(args, rank, world, local_rank):
                             "in chunks of 64 time steps (no layout kernel); results read back to the host"},
             "gpu_launches": args.steps * 2,
         }
+        if split_line is not None:
+            line["config5_split_pf"] = split_line
         if world == 1 and not args.no_cpu_baseline:
             _, _, info = cpu_reference_throughput(1, 0)
             line["cpu_baseline"] = info
@@ -326,6 +373,9 @@ def main():
     ap.add_argument("--particles", type=int, default=1 << 20)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-split", action="store_true", help="skip the config-5 split particle filter block")
+    ap.add_argument("--split-particles", type=int, default=1 << 24)
+    ap.add_argument("--split-steps", type=int, default=100)
     ap.add_argument("--traffic-bytes", type=float, default=None,
                     help="dram bytes per launch from the committed ncu capture (profiles/)")
     args = ap.parse_args()

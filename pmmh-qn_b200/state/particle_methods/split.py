@@ -254,6 +254,7 @@ def run_split_smoother(comm, obs, params, n_total, lag, rvr_d, u_d=None, philox=
     if u_d is None and philox is None:
         raise _lib.PmmhError("either u or a Philox stream is needed")
     hist = [] if keep_history else None
+    nc_hist = []
 
     for rk in ranks:
         rk.init(params_d)
@@ -270,6 +271,7 @@ def run_split_smoother(comm, obs, params, n_total, lag, rvr_d, u_d=None, philox=
             rk.plan_and_pack()
         torch.cuda.current_stream(device).synchronize()      # the counts are on the host now
         cnt = [rk.counts() for rk in ranks]
+        nc_hist.append([c[3] for c in cnt])
         for rk, c in zip(ranks, cnt):
             if c[5] != 0:
                 raise FloatingPointError("split particle filter abandoned at t=%d on rank %d (status %d: "
@@ -338,6 +340,7 @@ def run_split_smoother(comm, obs, params, n_total, lag, rvr_d, u_d=None, philox=
     res = dict(outs[0])
     res["per_rank"] = outs
     res["counts"] = ranks[0].gather_hist[:, :, 1].cpu().numpy().astype(np.int64)
+    res["children"] = np.array(nc_hist, dtype=np.int64)     # [T][local ranks] children generated per step
     if keep_history:
         res["x_hist"] = hist
     return res

@@ -31,4 +31,6 @@ for rep in range(2):
                       "particle_steps_per_s": n * T / dt, "log_like": float(out["log_like"].item()),
                       "near_ties": sum(o["diag"][0] for o in out["per_rank"]),
                       "max_bin": max(o["diag"][1] for o in out["per_rank"]),
-                      "max_arrivals": int(out["counts"].max())}), flush=True)
+                      "max_arrivals": int(out["counts"].max()),
+                      "children_max_over_mean": float((out["children"].max(axis=1) / (n / world)).mean()),
+                      "children_worst_step": float(out["children"].max() / (n / world))}), flush=True)
