@@ -54,7 +54,6 @@ constexpr int kMaxWorld = 16;
 constexpr int kStage = 4096;        // cumulative weights staged in shared memory per child tile
 constexpr int kChildTile = 1024;    // children per tile (256 threads x 4)
 constexpr int kMaxRounds = 64;      // child tiles whose boundaries one block resolves at once
-constexpr int kScanTile = 4096;     // ints per block of the fine-bin scan
 constexpr int kMaxBinRank = 8192;   // a fine bin larger than this abandons the evaluation
 constexpr double kChildNsd = 6.5;   // histogram range: extreme propagation means +- 6.5 sd
 
@@ -75,7 +74,7 @@ struct SplitState {
 };
 
 struct Layout {
-    size_t state, cumblk, boff, btot, tlast, bpart, xc, pa, cb, dest, nfc, fstart, counts, fcnt, fst, ftot,
+    size_t state, cumblk, boff, btot, tlast, bpart, cstart, xc, pa, cb, dest, nfc, fstart, counts, fcnt, fst,
         rnk, fb, tkey, tidx, tfb, total;
     long long ntiles_max, nf_max;
 };
@@ -93,6 +92,7 @@ Layout make_layout(long long cap, long long capc) {
     L.btot = o;    o += al((size_t)L.ntiles_max * 8);
     L.tlast = o;   o += al((size_t)L.ntiles_max * 8);
     L.bpart = o;   o += al((size_t)L.ntiles_max * 8 * 8);
+    L.cstart = o;  o += al((size_t)kBins * 4);
     L.xc = o;      o += al((size_t)capc * 8);
     L.pa = o;      o += al((size_t)capc * 4);
     L.cb = o;      o += al((size_t)capc * 2);
@@ -102,7 +102,6 @@ Layout make_layout(long long cap, long long capc) {
     L.counts = o;  o += al((size_t)(2 * kMaxWorld + 4) * 4);
     L.fcnt = o;    o += al((size_t)(L.nf_max + 1) * 4);
     L.fst = o;     o += al((size_t)(L.nf_max + 1) * 4);
-    L.ftot = o;    o += al((size_t)(L.nf_max / kScanTile + 2) * 4);
     L.rnk = o;     o += al((size_t)cap * 4);
     L.fb = o;      o += al((size_t)cap * 4);
     L.tkey = o;    o += al((size_t)cap * 16);   // SortEntry[cap]
@@ -485,7 +484,9 @@ __global__ void __launch_bounds__(1024) split_plan_kernel(SplitState* __restrict
                                                           const int* __restrict__ H,
                                                           int* __restrict__ dest, int* __restrict__ nfc,
                                                           int* __restrict__ fstart,
+                                                          int* __restrict__ cstart,
                                                           int* __restrict__ counts) {
+    __shared__ unsigned long long s_first;
     __shared__ long long s_w[32];
     __shared__ int s_wi[32];
     __shared__ int s_send[kMaxWorld], s_recv[kMaxWorld];
@@ -495,7 +496,8 @@ __global__ void __launch_bounds__(1024) split_plan_kernel(SplitState* __restrict
         s_send[tid] = 0;
         s_recv[tid] = 0;
     }
-    long long gc[4], run = 0;
+    if (tid == 0) s_first = ~0ull;
+    long long gc[4], bef[4], run = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int b = tid * 4 + k;
@@ -527,6 +529,8 @@ __global__ void __launch_bounds__(1024) split_plan_kernel(SplitState* __restrict
         if (d > G - 1) d = G - 1;
         mydest[k] = (int)d;
         dest[b] = (int)d;
+        bef[k] = before;
+        if ((int)d == me) atomicMin(&s_first, (unsigned long long)before);
         const int hs = H[me * kBins + b];
         if (hs) atomicAdd(&s_send[d], hs);
         int nf = 0;
@@ -557,6 +561,7 @@ __global__ void __launch_bounds__(1024) split_plan_kernel(SplitState* __restrict
         const int b = tid * 4 + k;
         nfc[b] = mynf[k];
         fstart[b] = fbefore;
+        cstart[b] = (mydest[k] == me) ? (int)(bef[k] - (long long)s_first) : 0;
         fbefore += mynf[k];
     }
     if (tid == 0) {
@@ -660,77 +665,27 @@ __global__ void split_fine_hist_kernel(const SplitState* __restrict__ st, const 
     }
 }
 
-// exclusive scan of ints in three launches (tile totals, scan of totals, apply)
-__device__ __forceinline__ int block_excl_scan_1024(int v, int* s_w, int& total) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int incl = warp_incl_scan(v, lane);
-    __syncthreads();
-    if (lane == 31) s_w[warp] = incl;
-    __syncthreads();
-    int woff = 0, tot = 0;
-    for (int w = 0; w < 32; ++w) {
-        if (w < warp) woff += s_w[w];
-        tot += s_w[w];
+// start slot of every fine bin: arrivals before its coarse bin (known exactly from the gathered
+// histograms) + a warp scan over the fine bins of that coarse bin.  One warp per coarse bin.
+__global__ void __launch_bounds__(256) split_fine_offsets_kernel(const int* __restrict__ nfc,
+                                                                 const int* __restrict__ fstart,
+                                                                 const int* __restrict__ cstart,
+                                                                 const int* __restrict__ fcnt,
+                                                                 int* __restrict__ fst) {
+    const int cbin = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (cbin >= kBins) return;
+    const int nf = nfc[cbin];
+    if (nf == 0) return;
+    const int f0 = fstart[cbin];
+    int carry = cstart[cbin];
+    for (int i0 = 0; i0 < nf; i0 += 32) {
+        const int i = i0 + lane;
+        const int v = (i < nf) ? fcnt[f0 + i] : 0;
+        const int incl = warp_incl_scan(v, lane);
+        if (i < nf) fst[f0 + i] = carry + incl - v;
+        carry += __shfl_sync(kFullMask, incl, 31);
     }
-    total = tot;
-    return woff + incl - v;
-}
-
-__global__ void __launch_bounds__(1024) iscan_totals_kernel(const int* __restrict__ in, int n,
-                                                            int* __restrict__ tot) {
-    __shared__ int s_w[32];
-    const int base = blockIdx.x * kScanTile + threadIdx.x * 4;
-    int v = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-        if (base + k < n) v += in[base + k];
-    int total;
-    block_excl_scan_1024(v, s_w, total);
-    if (threadIdx.x == 0) tot[blockIdx.x] = total;
-}
-
-__global__ void __launch_bounds__(1024) iscan_offsets_kernel(int* __restrict__ tot, int nt) {
-    // single block: exclusive scan of tot[0..nt) in place (nt <= 64K handled in chunks of 4096)
-    __shared__ int s_w[32];
-    int carry = 0;
-    for (int c0 = 0; c0 < nt; c0 += kScanTile) {
-        const int base = c0 + threadIdx.x * 4;
-        int v[4], s = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            v[k] = (base + k < nt) ? tot[base + k] : 0;
-            s += v[k];
-        }
-        int total;
-        int ex = carry + block_excl_scan_1024(s, s_w, total);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (base + k < nt) tot[base + k] = ex;
-            ex += v[k];
-        }
-        carry += total;
-        __syncthreads();
-    }
-}
-
-__global__ void __launch_bounds__(1024) iscan_apply_kernel(const int* __restrict__ in, int n,
-                                                           const int* __restrict__ tot,
-                                                           int* __restrict__ out) {
-    __shared__ int s_w[32];
-    const int base = blockIdx.x * kScanTile + threadIdx.x * 4;
-    int v[4], s = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        v[k] = (base + k < n) ? in[base + k] : 0;
-        s += v[k];
-    }
-    int total;
-    int ex = tot[blockIdx.x] + block_excl_scan_1024(s, s_w, total);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (base + k < n) out[base + k] = ex;
-        ex += v[k];
-    }
+    if (lane == 0) fst[f0 + nf] = carry;   // == first slot of the next coarse bin (same value)
 }
 
 struct __align__(16) SortEntry {
@@ -755,13 +710,13 @@ __global__ void split_scatter_kernel(const double* __restrict__ recn, const doub
 // exact order inside each fine bin: (value, arrival index); any correct sort reproduces the
 // reference's qsort order when values are distinct (SURVEY 7 "hard parts"); equal values counted
 __global__ void split_rank_kernel(SplitState* __restrict__ st, const SortEntry* __restrict__ ent,
-                                  const int* __restrict__ fst, int n, int nf_total,
+                                  const int* __restrict__ fst, int* __restrict__ fcnt, int n,
                                   double* __restrict__ xs, int* __restrict__ perm) {
     int mx = 0, ties = 0;
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
         const SortEntry me = ent[s];
         const int f = me.fb;
-        const int b = fst[f], e = (f + 1 < nf_total) ? fst[f + 1] : n;
+        const int b = fst[f], e = fst[f + 1];
         const double v = me.key;
         const int oi = me.idx;
         int rank = 0;
@@ -781,6 +736,7 @@ __global__ void split_rank_kernel(SplitState* __restrict__ st, const SortEntry* 
         xs[b + rank] = v;
         perm[b + rank] = oi;
         mx = max(mx, e - b);
+        fcnt[f] = 0;   // every counter that was touched is reset for the next step (no memset)
     }
     mx = warp_max(mx);
     if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(&st->max_bin, mx);
@@ -1116,6 +1072,7 @@ int pmmh_svsplit_init(void* d_ws, size_t ws_bytes, long long n_total, int n_obs,
     h.cap = cap_particles;
     h.capc = cap_children;
     SPLIT_CUDA(cudaMemcpyAsync((char*)d_ws + L.state, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+    SPLIT_CUDA(cudaMemsetAsync((char*)d_ws + L.fcnt, 0, (size_t)(L.nf_max + 1) * 4, st));
     SPLIT_CUDA(cudaStreamSynchronize(st));   // h lives on this stack frame
     if (n_local > 0)
         split_init_kernel<<<grid_for(n_local, 256), 256, 0, st>>>(d_xs, d_perm, d_rec, n_local, h.LR,
@@ -1198,7 +1155,8 @@ int pmmh_svsplit_plan(void* d_ws, size_t ws_bytes, long long cap_particles, long
     char* ws = (char*)d_ws;
     SplitState* state = (SplitState*)(ws + L.state);
     split_plan_kernel<<<1, 1024, 0, st>>>(state, d_hist, (int*)(ws + L.dest), (int*)(ws + L.nfc),
-                                          (int*)(ws + L.fstart), (int*)(ws + L.counts));
+                                          (int*)(ws + L.fstart), (int*)(ws + L.cstart),
+                                          (int*)(ws + L.counts));
     SPLIT_CUDA(cudaGetLastError());
     if (h_counts)
         SPLIT_CUDA(cudaMemcpyAsync(h_counts, ws + L.counts, (size_t)(2 * world + 4) * 4,
@@ -1234,22 +1192,19 @@ int pmmh_svsplit_sort(void* d_ws, size_t ws_bytes, long long cap_particles, long
     const int LR = lag == 0 ? 1 : lag;
     int* fcnt = (int*)(ws + L.fcnt);
     int* fst = (int*)(ws + L.fst);
-    int* ftot = (int*)(ws + L.ftot);
     int* rnk = (int*)(ws + L.rnk);
     int* fb = (int*)(ws + L.fb);
     SortEntry* ent = (SortEntry*)(ws + L.tkey);
-    SPLIT_CUDA(cudaMemsetAsync(fcnt, 0, (size_t)(n_fine + 1) * 4, st));
     const int g = grid_for(n_arrivals, 256);
     // one rank: the arrivals ARE the children in birth order, their values are a dense array
     const double* keys = keys_are_children ? (const double*)(ws + L.xc) : nullptr;
     split_fine_hist_kernel<<<g, 256, 0, st>>>(state, d_rec_new, keys, n_arrivals, LR, (const int*)(ws + L.nfc),
                                               (const int*)(ws + L.fstart), fcnt, rnk, fb);
-    const int nt = (n_fine + kScanTile - 1) / kScanTile;
-    iscan_totals_kernel<<<nt, 1024, 0, st>>>(fcnt, n_fine, ftot);
-    iscan_offsets_kernel<<<1, 1024, 0, st>>>(ftot, nt);
-    iscan_apply_kernel<<<nt, 1024, 0, st>>>(fcnt, n_fine, ftot, fst);
+    split_fine_offsets_kernel<<<kBins * 32 / 256, 256, 0, st>>>((const int*)(ws + L.nfc),
+                                                                (const int*)(ws + L.fstart),
+                                                                (const int*)(ws + L.cstart), fcnt, fst);
     split_scatter_kernel<<<g, 256, 0, st>>>(d_rec_new, keys, n_arrivals, LR, fst, rnk, fb, ent);
-    split_rank_kernel<<<g, 256, 0, st>>>(state, ent, fst, n_arrivals, n_fine, d_xs, d_perm);
+    split_rank_kernel<<<g, 256, 0, st>>>(state, ent, fst, fcnt, n_arrivals, d_xs, d_perm);
     SPLIT_CUDA(cudaGetLastError());
     return PMMH_OK;
 }

@@ -24,6 +24,9 @@ u = torch.randn((nobs, n), dtype=torch.float64, device=dev, generator=g)
 rvr = torch.rand((nobs,), dtype=torch.float64, device=dev, generator=g)
 K.set_sv_algorithm(alg)
 ws = K.Workspace()
+stream = torch.cuda.Stream() if os.environ.get("PMMH_SPLIT_GRAPH") else torch.cuda.current_stream()
+torch.cuda.synchronize()
+torch.cuda.set_stream(stream)
 for rep in range(reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
