@@ -79,14 +79,14 @@ int pmmh_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* Kernel selection for pmmh_flps_sv_corr (process-wide; default 0).
  *   0  automatic, for log-likelihood + gradient (compute_hessian == 0): the "chain" kernel (one
  *      CTA per problem, everything in shared memory) when n_particles <= 4096 and lag <= 10, the
- *      two-exchange "exchange" kernel for teams of CTAs; the general kernel for everything else
- *      and as the fallback for problems those abandon (degenerate particle clouds)
+ *      two-exchange "exchange" kernel for teams of CTAs; the streaming kernels (see 4) for one
+ *      problem too large for the exchange kernel (N > ~1.16 M particles); the general kernel
+ *      for everything else and as the fallback for problems those abandon (degenerate clouds)
  *   1  general kernel only
  *   2  diagnostics: exchange kernel where eligible, without the fallback pass
  *   3  diagnostics: chain kernel where eligible, without the fallback pass
  *   4  streaming kernels (sv_split.cu driven on one device: ~11 launches per time step, no
- *      persistent kernel) for one problem with compute_hessian == 0 and no history output,
- *      without the fallback pass
+ *      persistent kernel) for one problem with compute_hessian == 0 and no history output
  * Call before pmmh_sv_workspace_bytes: the workspace size depends on it. */
 int pmmh_sv_set_algorithm(int algorithm);
 
@@ -242,13 +242,17 @@ int pmmh_svsplit_children(void* d_ws, size_t ws_bytes, long long cap_particles, 
  * counts per source, arrivals, children, fine sort bins, status */
 int pmmh_svsplit_plan(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
                       int world, const int* d_hist, int* h_counts, void* stream);
-/* records of the children grouped by destination rank -> d_send (rows of LR doubles) */
+/* records of the children grouped by destination rank -> d_send (rows of LR doubles); d_send_keys
+ * (optional, [cap_children]) receives the values alone in the same order, so that they can be
+ * exchanged first and sorted while the records are still in flight */
 int pmmh_svsplit_pack(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
-                      const int* d_perm, const double* d_rec, double* d_send, void* stream);
-/* argsort of the arrivals (:392-424): d_xs / d_perm of the new generation.  keys_are_children = 1
- * (world == 1 only): arrival e is child e, its value is read from the dense child array */
+                      const int* d_perm, const double* d_rec, double* d_send, double* d_send_keys,
+                      void* stream);
+/* argsort of the arrivals (:392-424): d_xs / d_perm of the new generation.  The values come from
+ * d_keys [n_arrivals] if given, else from column 0 of d_rec_new; keys_are_children = 1 (world == 1
+ * only): arrival e is child e, its value is read from the dense child array in the workspace */
 int pmmh_svsplit_sort(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
-                      int n_arrivals, int n_fine, int lag, const double* d_rec_new,
+                      int n_arrivals, int n_fine, int lag, const double* d_rec_new, const double* d_keys,
                       int keys_are_children, double* d_xs, int* d_perm, void* stream);
 /* d_w[p] = d_sh[p] / *d_total (normalised weights of a kept generation, for the tail) */
 int pmmh_svsplit_normalise(const double* d_sh, int n_local, const double* d_total, double* d_w,

@@ -83,7 +83,7 @@ struct SvPlan {
 // 1 = general kernel only, 2 = exchange kernel where eligible WITHOUT the fallback pass (diagnostics),
 // 3 = chain kernel where eligible WITHOUT the fallback pass (diagnostics)
 int g_sv_algorithm = 0;
-int g_split_min_particles = 1 << 30;   // automatic selection of the streaming kernels from this N on
+int g_split_min_particles = 1 << 20;   // automatic selection of the streaming kernels from this N on
 long long* g_sv_prof = nullptr;   // development: per-CTA phase clocks of the exchange kernel
 constexpr int kMaxDynSmem = 227 * 1024;
 
@@ -139,24 +139,15 @@ int sv_make_plan(int nobs, int n, int lag, int batch, int hess, int mode, int ha
         p->chain_total = (size_t)p->grid * p->chain_stride;
         if (p->chain_total > p->total) p->total = p->chain_total;
     }
-    // one large problem, log-likelihood + gradient, no history dump: the streaming kernels
     p->use_split = 0;
     p->split_total = 0;
-    if (mode == pmmh::kSvFlps && !hess && batch == 1 && !have_hist && ctas == 0 && !p->use_chain &&
-        (g_sv_algorithm == 4 || (g_sv_algorithm == 0 && n >= g_split_min_particles)) &&
-        pmmh::sv_split_single_eligible(nobs, n, lag)) {
-        p->use_split = 1;
-        p->split_total = pmmh::sv_split_single_ws_bytes(nobs, n, lag);
-        // the general kernel (fallback pass) reuses the head of the same workspace
-        if (p->split_total > p->total) p->total = p->split_total;
-    }
     p->use_fast = 0;
     p->NSUB = 0;
     p->fast_sync_bytes = p->fast_team_stride = p->fast_total = 0;
     p->CP = 0;
     // one CTA per problem (batches of small problems) has no exchange to save: the general kernel
     // is the faster one there (measured: 8.8e9 vs 7.0e9 particle-steps/s at 1024 x N=4096)
-    const bool want_fast = !p->use_chain && !p->use_split && ((g_sv_algorithm == 2) || (g_sv_algorithm == 0 && G > 1));
+    const bool want_fast = !p->use_chain && g_sv_algorithm != 4 && ((g_sv_algorithm == 2) || (g_sv_algorithm == 0 && G > 1));
     if (mode == pmmh::kSvFlps && !hess && want_fast && pmmh::sv_fast_eligible(n, G)) {
         const int S = pmmh::sv_fast_nsub(n, G);
         const int CP = pmmh::sv_fast_pair_cap(n, G);
@@ -171,6 +162,17 @@ int sv_make_plan(int nobs, int n, int lag, int batch, int hess, int mode, int ha
             p->fast_total = p->fast_sync_bytes + (size_t)n_teams * p->fast_team_stride;
             if (p->fast_total > p->total) p->total = p->fast_total;
         }
+    }
+    // one large problem, log-likelihood + gradient, no history dump: the streaming kernels -- on
+    // request (algorithm 4), or automatically where the exchange kernel does not take the size
+    // (N > ~1.16 M on 148 SMs; the general kernel is ~4x slower there)
+    if (mode == pmmh::kSvFlps && !hess && batch == 1 && !have_hist && ctas == 0 && !p->use_chain &&
+        (g_sv_algorithm == 4 || (g_sv_algorithm == 0 && !p->use_fast && n >= g_split_min_particles)) &&
+        pmmh::sv_split_single_eligible(nobs, n, lag)) {
+        p->use_split = 1;
+        p->split_total = pmmh::sv_split_single_ws_bytes(nobs, n, lag);
+        // the general kernel (fallback pass) reuses the head of the same workspace
+        if (p->split_total > p->total) p->total = p->split_total;
     }
     return PMMH_OK;
 }

@@ -594,7 +594,7 @@ __global__ void __launch_bounds__(1024) split_plan_kernel(SplitState* __restrict
 __global__ void __launch_bounds__(256) split_pack_kernel(
     SplitState* __restrict__ st, const double* __restrict__ xc, const int* __restrict__ pa,
     const unsigned short* __restrict__ cb, const int* __restrict__ dest, const int* __restrict__ perm,
-    const double* __restrict__ rec, double* __restrict__ send) {
+    const double* __restrict__ rec, double* __restrict__ send, double* __restrict__ send_keys) {
     __shared__ int s_cnt[kMaxWorld], s_base[kMaxWorld];
     const int tid = threadIdx.x, lane = tid & 31;
     const int nc = st->nc, G = st->world, LR = st->LR;
@@ -619,6 +619,7 @@ __global__ void __launch_bounds__(256) split_pack_kernel(
             __syncthreads();
         }
         const double xv = valid ? xc[k] : 0.0;
+        if (send_keys && valid) send_keys[slot] = xv;   // values alone, for the receiver's sort
         if (LR == 1) {
             if (valid) send[slot] = xv;
             continue;
@@ -932,9 +933,9 @@ int pmmh_svsplit_children(void*, size_t, long long, long long, int, int, const d
                           const double*, const double*, unsigned long long, unsigned long long, const double*,
                           const double*, int*, double*, double*, void*);
 int pmmh_svsplit_plan(void*, size_t, long long, long long, int, const int*, int*, void*);
-int pmmh_svsplit_pack(void*, size_t, long long, long long, const int*, const double*, double*, void*);
-int pmmh_svsplit_sort(void*, size_t, long long, long long, int, int, int, const double*, int, double*, int*,
-                      void*);
+int pmmh_svsplit_pack(void*, size_t, long long, long long, const int*, const double*, double*, double*, void*);
+int pmmh_svsplit_sort(void*, size_t, long long, long long, int, int, int, const double*, const double*, int,
+                      double*, int*, void*);
 int pmmh_svsplit_normalise(const double*, int, const double*, double*, void*);
 int pmmh_svsplit_tail(void*, size_t, long long, long long, int, int, int, const double*, const double*,
                       const int*, const double*, const double*, const double*, long long, double*, void*);
@@ -997,14 +998,14 @@ int sv_split_single_run(const double* d_obs, const double* d_params, const doubl
         if ((rc = pmmh_svsplit_plan(sws, sb, n, n, 1, hist, nullptr, st))) return rc;
         SPLIT_CUDA(cudaEventRecord(ev_fork[dev], st));
         SPLIT_CUDA(cudaStreamWaitEvent(side[dev], ev_fork[dev], 0));
-        if ((rc = pmmh_svsplit_pack(sws, sb, n, n, perm, rec, rec_next, side[dev]))) return rc;
+        if ((rc = pmmh_svsplit_pack(sws, sb, n, n, perm, rec, rec_next, nullptr, side[dev]))) return rc;
         SPLIT_CUDA(cudaEventRecord(ev_join[dev], side[dev]));
         double* tmp = rec;
         rec = rec_next;
         rec_next = tmp;
         // the sort reads the dense child values and writes xs / perm of the NEW generation: pack
         // still reads perm of the OLD one, so the new order goes to the alternate buffers
-        if ((rc = pmmh_svsplit_sort(sws, sb, n, n, n, nf_bound, lag, rec, 1, xs_next, perm_next, st))) return rc;
+        if ((rc = pmmh_svsplit_sort(sws, sb, n, n, n, nf_bound, lag, rec, nullptr, 1, xs_next, perm_next, st))) return rc;
         SPLIT_CUDA(cudaStreamWaitEvent(st, ev_join[dev], 0));
         { double* tx = xs; xs = xs_next; xs_next = tx; int* tp = perm; perm = perm_next; perm_next = tp; }
         double* kp = (t >= nobs - lag) ? keep + (size_t)(t % lag) * n : nullptr;
@@ -1165,7 +1166,8 @@ int pmmh_svsplit_plan(void* d_ws, size_t ws_bytes, long long cap_particles, long
 }
 
 int pmmh_svsplit_pack(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
-                      const int* d_perm, const double* d_rec, double* d_send, void* stream) {
+                      const int* d_perm, const double* d_rec, double* d_send, double* d_send_keys,
+                      void* stream) {
     Layout L;
     if (int rc = check_ws(d_ws, ws_bytes, cap_particles, cap_children, &L)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
@@ -1173,13 +1175,14 @@ int pmmh_svsplit_pack(void* d_ws, size_t ws_bytes, long long cap_particles, long
     SplitState* state = (SplitState*)(ws + L.state);
     split_pack_kernel<<<148 * 8, 256, 0, st>>>(state, (const double*)(ws + L.xc), (const int*)(ws + L.pa),
                                                (const unsigned short*)(ws + L.cb),
-                                               (const int*)(ws + L.dest), d_perm, d_rec, d_send);
+                                               (const int*)(ws + L.dest), d_perm, d_rec, d_send,
+                                               d_send_keys);
     SPLIT_CUDA(cudaGetLastError());
     return PMMH_OK;
 }
 
 int pmmh_svsplit_sort(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
-                      int n_arrivals, int n_fine, int lag, const double* d_rec_new,
+                      int n_arrivals, int n_fine, int lag, const double* d_rec_new, const double* d_keys,
                       int keys_are_children, double* d_xs, int* d_perm, void* stream) {
     Layout L;
     if (int rc = check_ws(d_ws, ws_bytes, cap_particles, cap_children, &L)) return rc;
@@ -1197,7 +1200,7 @@ int pmmh_svsplit_sort(void* d_ws, size_t ws_bytes, long long cap_particles, long
     SortEntry* ent = (SortEntry*)(ws + L.tkey);
     const int g = grid_for(n_arrivals, 256);
     // one rank: the arrivals ARE the children in birth order, their values are a dense array
-    const double* keys = keys_are_children ? (const double*)(ws + L.xc) : nullptr;
+    const double* keys = keys_are_children ? (const double*)(ws + L.xc) : d_keys;
     split_fine_hist_kernel<<<g, 256, 0, st>>>(state, d_rec_new, keys, n_arrivals, LR, (const int*)(ws + L.nfc),
                                               (const int*)(ws + L.fstart), fcnt, rnk, fb);
     split_fine_offsets_kernel<<<kBins * 32 / 256, 256, 0, st>>>((const int*)(ws + L.nfc),

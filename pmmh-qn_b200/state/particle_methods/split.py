@@ -107,6 +107,11 @@ class _Rank(object):
         self.rec = torch.empty((rows, self.LR), dtype=_F64, device=dev)
         self.rec_next = torch.empty((rows, self.LR), dtype=_F64, device=dev)
         self.send = torch.empty((max(self.capc, rows if world == 1 else 0), self.LR), dtype=_F64, device=dev)
+        # values alone (8 bytes per particle): exchanged first so that the sort can start while the
+        # 8 * lag byte records are still crossing NVLink
+        split_keys = world > 1 and self.LR > 1
+        self.send_keys = torch.empty(self.capc, dtype=_F64, device=dev) if split_keys else None
+        self.recv_keys = torch.empty(self.cap, dtype=_F64, device=dev) if split_keys else None
         self.sums = torch.zeros((self.n_obs, 8), dtype=_F64, device=dev)
         self.shift = torch.zeros(self.n_obs, dtype=_F64, device=dev)
         self.xmin = torch.zeros(self.n_obs, dtype=_F64, device=dev)
@@ -161,6 +166,7 @@ class _Rank(object):
                                               ctypes.c_void_p(self.h_counts.data_ptr()), self._stream()),
                    "pmmh_svsplit_plan")
         _lib.check(self.lib.pmmh_svsplit_pack(*self._c(), _p(self.perm), _p(self.rec), _p(self.send),
+                                              None if self.send_keys is None else _p(self.send_keys),
                                               self._stream()), "pmmh_svsplit_pack")
 
     def counts(self):
@@ -173,6 +179,7 @@ class _Rank(object):
         self.rec, self.rec_next = self.rec_next, self.rec
         self.n_local = n_arrivals
         _lib.check(self.lib.pmmh_svsplit_sort(*self._c(), n_arrivals, n_fine, self.lag, _p(self.rec),
+                                              None if self.recv_keys is None else _p(self.recv_keys),
                                               1 if self.world == 1 else 0, _p(self.xs), _p(self.perm),
                                               self._stream()), "pmmh_svsplit_sort")
 
@@ -205,6 +212,10 @@ class LocalComm(object):
                 if n:
                     recvs[d][roff[d][s]:roff[d][s] + n].copy_(sends[s][soff[s][d]:soff[s][d] + n])
 
+    def all_to_all_async(self, sends, send_counts, recvs, recv_counts):
+        self.all_to_all(sends, send_counts, recvs, recv_counts)
+        return None
+
     def all_reduce_sum(self, tensors):
         tot = torch.stack(tensors).sum(dim=0) if len(tensors) > 1 else tensors[0]
         for t in tensors:
@@ -228,6 +239,13 @@ class DistComm(object):
         nrecv, nsend = int(sum(recv_counts[0])), int(sum(send_counts[0]))
         self.dist.all_to_all_single(recvs[0][:nrecv], sends[0][:nsend], list(recv_counts[0]),
                                     list(send_counts[0]), group=self.group)
+
+    def all_to_all_async(self, sends, send_counts, recvs, recv_counts):
+        """Enqueued behind the current stream's work; later kernels on the current stream overlap
+        it until ``handle.wait()`` (which makes the current stream wait, not the host)."""
+        nrecv, nsend = int(sum(recv_counts[0])), int(sum(send_counts[0]))
+        return self.dist.all_to_all_single(recvs[0][:nrecv], sends[0][:nsend], list(recv_counts[0]),
+                                           list(send_counts[0]), group=self.group, async_op=True)
 
     def all_reduce_sum(self, tensors):
         self.dist.all_reduce(tensors[0], op=self.dist.ReduceOp.SUM, group=self.group)
@@ -280,11 +298,23 @@ def run_split_smoother(comm, obs, params, n_total, lag, rvr_d, u_d=None, philox=
         if G == 1:
             rk = ranks[0]
             rk.rec_next, rk.send = rk.send, rk.rec_next       # the exchange is the identity
+            pending = None
+        elif ranks[0].send_keys is not None:
+            # values first (8 B per particle), then the records asynchronously: the sort needs only
+            # the values and runs while the records are in flight
+            comm.all_to_all([rk.send_keys for rk in ranks], [c[0] for c in cnt],
+                            [rk.recv_keys for rk in ranks], [c[1] for c in cnt])
+            pending = comm.all_to_all_async([rk.send for rk in ranks], [c[0] for c in cnt],
+                                            [rk.rec_next for rk in ranks], [c[1] for c in cnt])
         else:
             comm.all_to_all([rk.send for rk in ranks], [c[0] for c in cnt],
                             [rk.rec_next for rk in ranks], [c[1] for c in cnt])
+            pending = None
         for rk, c in zip(ranks, cnt):
             rk.sort(c[2], c[4])
+        if pending is not None:
+            pending.wait()
+        for rk in ranks:
             rk.weights(t, obs_d, params_d)
         comm.all_gather([rk.gather_send for rk in ranks], [rk.gather for rk in ranks])
         if keep_history:

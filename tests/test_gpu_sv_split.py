@@ -156,3 +156,24 @@ def test_streaming_kernels_behind_flps_sv_corr(cuda_dev, n, nobs, lag, seed):
     assert relerr(out["traj"][0].cpu().numpy(), ref["traj"]) <= 1e-12
     g, gr = out["gradient"][0].cpu().numpy(), ref["gradient"]
     assert np.max(np.abs(g - gr)) <= 1e-9 * np.max(np.abs(gr))
+
+
+def test_automatic_selection_beyond_the_exchange_kernel(cuda_dev):
+    """Default algorithm, N = 1.5 M (the exchange kernel takes at most ~1.16 M on 148 SMs): the
+    streaming kernels run and match the oracle."""
+    import torch
+    import oracle
+    from pmmh_qn_b200 import kernels as K
+    n, nobs, lag = 1500000, 26, 10
+    obs, params, rvr, rvp = gi.sv_inputs(n, nobs, 6)
+    ref = oracle.flps_sv_corr(obs, params, rvr, rvp, n, lag, 0)
+    u = torch.from_numpy(to_time_major(rvp, n, nobs)).to(cuda_dev)
+    out = K.flps_sv_corr(torch.from_numpy(obs).to(cuda_dev), torch.from_numpy(params).to(cuda_dev),
+                         torch.from_numpy(rvr[:nobs].copy()).to(cuda_dev), u, lag=lag)
+    torch.cuda.synchronize()
+    diag = out["diag"][0].cpu().numpy()
+    assert int(diag[6]) == 4 and int(diag[2]) == 0
+    assert abs(float(out["log_like"][0]) - ref["log_like"]) <= 1e-10 * abs(ref["log_like"])
+    g, gr = out["gradient"][0].cpu().numpy(), ref["gradient"]
+    assert np.max(np.abs(g - gr)) <= 1e-9 * np.max(np.abs(gr))
+    assert relerr(out["smo"][0].cpu().numpy(), ref["smo"]) <= 1e-10
