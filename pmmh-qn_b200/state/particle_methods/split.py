@@ -109,7 +109,9 @@ class _Rank(object):
         self.send = torch.empty((max(self.capc, rows if world == 1 else 0), self.LR), dtype=_F64, device=dev)
         # values alone (8 bytes per particle): exchanged first so that the sort can start while the
         # 8 * lag byte records are still crossing NVLink
-        split_keys = world > 1 and self.LR > 1
+        # (measured, N = 2^24, lag 10: 2 GPUs 4.8e9 -> 6.4e9 particle-steps/s; 8 GPUs 1.29e10 -> 1.17e10,
+        # where a second all-to-all per step costs more than the overlap returns: used up to 4 ranks)
+        split_keys = 1 < world <= 4 and self.LR > 1
         self.send_keys = torch.empty(self.capc, dtype=_F64, device=dev) if split_keys else None
         self.recv_keys = torch.empty(self.cap, dtype=_F64, device=dev) if split_keys else None
         self.sums = torch.zeros((self.n_obs, 8), dtype=_F64, device=dev)

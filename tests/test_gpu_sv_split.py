@@ -177,3 +177,37 @@ def test_automatic_selection_beyond_the_exchange_kernel(cuda_dev):
     g, gr = out["gradient"][0].cpu().numpy(), ref["gradient"]
     assert np.max(np.abs(g - gr)) <= 1e-9 * np.max(np.abs(gr))
     assert relerr(out["smo"][0].cpu().numpy(), ref["smo"]) <= 1e-10
+
+
+@pytest.mark.parametrize("par", [(0.2, 0.9, 0.4, -0.5), (2.0, 0.9, 0.4, -0.2), (-0.3, 0.97, 0.15, 0.3),
+                                 (0.0, 0.995, 0.05, -0.8), (1.0, 0.5, 1.2, 0.0)])
+def test_streaming_kernels_agree_with_the_general_kernel_over_parameter_sets(cuda_dev, par):
+    """Two independent implementations (persistent general kernel, streaming kernels) on the same
+    inputs over the parameter sets of the robustness sweep, N = 60 000, T = 300: identical
+    near-tie counts are not required, the estimates must agree to the parity tolerances."""
+    import torch
+    from pmmh_qn_b200 import kernels as K
+    n, nobs, lag = 60000, 301, 10
+    obs = torch.from_numpy(gi.sv_obs(nobs, params=par)).to(cuda_dev)
+    params = torch.tensor([par], dtype=torch.float64, device=cuda_dev)
+    g = torch.Generator(device=cuda_dev)
+    g.manual_seed(99)
+    u = torch.randn((1, nobs, n), dtype=torch.float64, device=cuda_dev, generator=g)
+    rvr = torch.rand((1, nobs), dtype=torch.float64, device=cuda_dev, generator=g)
+    res = {}
+    try:
+        for alg in (1, 4):
+            K.set_sv_algorithm(alg)
+            res[alg] = K.flps_sv_corr(obs, params, rvr, u, lag=lag)
+            torch.cuda.synchronize()
+    finally:
+        K.set_sv_algorithm(0)
+    a, b = res[1], res[4]
+    assert int(b["diag"][0, 6]) == 4 and int(b["diag"][0, 2]) == 0 and int(a["diag"][0, 2]) == 0
+    la, lb = float(a["log_like"][0]), float(b["log_like"][0])
+    assert abs(la - lb) <= 1e-10 * abs(la), (la, lb)
+    ga, gb = a["gradient"][0].cpu().numpy(), b["gradient"][0].cpu().numpy()
+    assert np.max(np.abs(ga - gb)) <= 1e-9 * np.max(np.abs(ga))
+    assert relerr(b["filt"][0].cpu().numpy(), a["filt"][0].cpu().numpy()) <= 1e-10
+    assert relerr(b["smo"][0].cpu().numpy(), a["smo"][0].cpu().numpy()) <= 1e-10
+    assert relerr(b["traj"][0].cpu().numpy(), a["traj"][0].cpu().numpy()) <= 1e-12
