@@ -47,9 +47,13 @@ def main():
     rep, lib, kern = sys.argv[1], sys.argv[2], sys.argv[3]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
     maps = line_map(lib, kern)
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], stdout=subprocess.PIPE,
-                         stderr=subprocess.DEVNULL, text=True).stdout
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kern],
+                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
+    # several launches may match: keep the first block
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+    if len(starts) > 1:
+        rows = rows[:starts[1]]
     kname = rows[0][1]
     mangled = [k for k in maps if kern in k]
     # pick the map whose instruction count matches best
@@ -77,7 +81,8 @@ def main():
         text = ""
         if src:
             path = None
-            for root in (os.path.dirname(os.path.abspath(lib)) + "/../csrc",):
+            for root in (os.path.dirname(os.path.abspath(lib)) + "/../csrc",
+                         os.path.dirname(os.path.abspath(lib)) + "/pmmh-qn_b200/csrc"):
                 p = os.path.join(root, src[0])
                 if os.path.exists(p):
                     path = p
