@@ -87,6 +87,8 @@ int pmmh_device_info(int* sm_count, int* cc_major, int* cc_minor);
  *   3  diagnostics: chain kernel where eligible, without the fallback pass
  *   4  streaming kernels (sv_split.cu driven on one device: ~11 launches per time step, no
  *      persistent kernel) for one problem with compute_hessian == 0 and no history output
+ *   5  the same with path storage: a generation is stored once in birth order (value + parent
+ *      row), no records are copied; the lagged ancestors are reached through jump tables
  * Call before pmmh_sv_workspace_bytes: the workspace size depends on it. */
 int pmmh_sv_set_algorithm(int algorithm);
 

@@ -147,7 +147,7 @@ int sv_make_plan(int nobs, int n, int lag, int batch, int hess, int mode, int ha
     p->CP = 0;
     // one CTA per problem (batches of small problems) has no exchange to save: the general kernel
     // is the faster one there (measured: 8.8e9 vs 7.0e9 particle-steps/s at 1024 x N=4096)
-    const bool want_fast = !p->use_chain && g_sv_algorithm != 4 && ((g_sv_algorithm == 2) || (g_sv_algorithm == 0 && G > 1));
+    const bool want_fast = !p->use_chain && g_sv_algorithm != 4 && g_sv_algorithm != 5 && ((g_sv_algorithm == 2) || (g_sv_algorithm == 0 && G > 1));
     if (mode == pmmh::kSvFlps && !hess && want_fast && pmmh::sv_fast_eligible(n, G)) {
         const int S = pmmh::sv_fast_nsub(n, G);
         const int CP = pmmh::sv_fast_pair_cap(n, G);
@@ -167,10 +167,12 @@ int sv_make_plan(int nobs, int n, int lag, int batch, int hess, int mode, int ha
     // request (algorithm 4), or automatically where the exchange kernel does not take the size
     // (N > ~1.16 M on 148 SMs; the general kernel is ~4x slower there)
     if (mode == pmmh::kSvFlps && !hess && batch == 1 && !have_hist && ctas == 0 && !p->use_chain &&
-        (g_sv_algorithm == 4 || (g_sv_algorithm == 0 && !p->use_fast && n >= g_split_min_particles)) &&
+        (g_sv_algorithm == 4 || g_sv_algorithm == 5 ||
+         (g_sv_algorithm == 0 && !p->use_fast && n >= g_split_min_particles)) &&
         pmmh::sv_split_single_eligible(nobs, n, lag)) {
         p->use_split = 1;
-        p->split_total = pmmh::sv_split_single_ws_bytes(nobs, n, lag);
+        p->split_total = (g_sv_algorithm == 5) ? pmmh::sv_split_path_ws_bytes(nobs, n, lag)
+                                               : pmmh::sv_split_single_ws_bytes(nobs, n, lag);
         // the general kernel (fallback pass) reuses the head of the same workspace
         if (p->split_total > p->total) p->total = p->split_total;
     }
@@ -235,12 +237,15 @@ int sv_run(int mode, const double* d_obs, long long obs_stride, const double* d_
     if (p.use_split) {
         // streaming kernels first; an abandoned evaluation (diag status 1) is re-run by the general
         // kernel in the same stream
-        rc = pmmh::sv_split_single_run(d_obs, d_params, d_rvr, d_u, nobs, n, lag, d_filt, d_smo, d_ll, d_grad,
-                                       d_traj, d_diag, d_ws, ws_bytes, st);
+        rc = (g_sv_algorithm == 5)
+                 ? pmmh::sv_split_path_run(d_obs, d_params, d_rvr, d_u, nobs, n, lag, d_filt, d_smo, d_ll,
+                                           d_grad, d_traj, d_diag, d_ws, ws_bytes, st)
+                 : pmmh::sv_split_single_run(d_obs, d_params, d_rvr, d_u, nobs, n, lag, d_filt, d_smo, d_ll,
+                                             d_grad, d_traj, d_diag, d_ws, ws_bytes, st);
         if (rc != PMMH_OK) return rc;
         PMMH_CUDA(cudaMemsetAsync(d_h1, 0, 16 * sizeof(double), st));
         PMMH_CUDA(cudaMemsetAsync(d_h2, 0, 16 * sizeof(double), st));
-        if (g_sv_algorithm == 4) return PMMH_OK;   // diagnostics: no fallback pass
+        if (g_sv_algorithm == 4 || g_sv_algorithm == 5) return PMMH_OK;   // no fallback pass
         a.only_failed = 1;
     }
     if (p.use_fast) {
@@ -293,7 +298,7 @@ int pmmh_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 }
 
 int pmmh_sv_set_algorithm(int algorithm) {
-    if (algorithm < 0 || algorithm > 4) return fail(PMMH_ERR_INVALID, "algorithm must be 0 .. 4");
+    if (algorithm < 0 || algorithm > 5) return fail(PMMH_ERR_INVALID, "algorithm must be 0 .. 5");
     g_sv_algorithm = algorithm;
     return PMMH_OK;
 }

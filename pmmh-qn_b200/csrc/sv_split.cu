@@ -55,6 +55,7 @@ constexpr int kStage = 4096;        // cumulative weights staged in shared memor
 constexpr int kChildTile = 1024;    // children per tile (256 threads x 4)
 constexpr int kMaxRounds = 64;      // child tiles whose boundaries one block resolves at once
 constexpr int kMaxBinRank = 8192;   // a fine bin larger than this abandons the evaluation
+constexpr int kLineageGrid = 148 * 8;   // blocks of the lineage kernel (one partial-sum row each)
 constexpr double kChildNsd = 6.5;   // histogram range: extreme propagation means +- 6.5 sd
 
 struct SplitState {
@@ -74,7 +75,7 @@ struct SplitState {
 };
 
 struct Layout {
-    size_t state, cumblk, boff, btot, tlast, bpart, cstart, xc, pa, cb, dest, nfc, fstart, counts, fcnt, fst,
+    size_t state, cumblk, boff, btot, tlast, bpart, gpart, cstart, xc, pa, cb, dest, nfc, fstart, counts, fcnt, fst,
         rnk, fb, tkey, tidx, tfb, total;
     long long ntiles_max, nf_max;
 };
@@ -92,6 +93,7 @@ Layout make_layout(long long cap, long long capc) {
     L.btot = o;    o += al((size_t)L.ntiles_max * 8);
     L.tlast = o;   o += al((size_t)L.ntiles_max * 8);
     L.bpart = o;   o += al((size_t)L.ntiles_max * 8 * 8);
+    L.gpart = o;   o += al((size_t)kLineageGrid * 8 * 8);
     L.cstart = o;  o += al((size_t)kBins * 4);
     L.xc = o;      o += al((size_t)capc * 8);
     L.pa = o;      o += al((size_t)capc * 4);
@@ -207,8 +209,8 @@ __global__ void __launch_bounds__(kTileThreads) split_weights_kernel(
 // tile partials, the 4 doubles this rank contributes to the all-gather
 __global__ void __launch_bounds__(256) split_weights_finalize_kernel(
     SplitState* __restrict__ st, const double* __restrict__ xs, int n, int ntiles,
-    const double* __restrict__ btot, const double* __restrict__ bpart, double* __restrict__ boff,
-    double* __restrict__ sums_t, double* __restrict__ gather_send) {
+    const double* __restrict__ btot, const double* __restrict__ bpart, const double* __restrict__ gpart,
+    double* __restrict__ boff, double* __restrict__ sums_t, double* __restrict__ gather_send) {
     __shared__ double red[7 * 32];
     __shared__ double s_lane[33];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -235,6 +237,10 @@ __global__ void __launch_bounds__(256) split_weights_finalize_kernel(
     for (int q = tid; q < ntiles; q += 256)
 #pragma unroll
         for (int k = 0; k < 7; ++k) acc[k] += bpart[(size_t)q * 8 + k];
+    if (gpart)   // path storage: sum sh curr, sum sh g_0..3 come from the lineage kernel
+        for (int q = tid; q < kLineageGrid; q += 256)
+#pragma unroll
+            for (int k = 0; k < 5; ++k) acc[1 + k] += gpart[(size_t)q * 8 + k];
     block_sum<7>(acc, red);
     __syncthreads();
     if (tid == 0) {
@@ -303,13 +309,14 @@ struct ChildScalars {
     int nc;
 };
 
-__global__ void __launch_bounds__(256) split_children_kernel(
+__global__ void __launch_bounds__(256, 4) split_children_kernel(
     SplitState* __restrict__ st, int t, int n, const double* __restrict__ obs,
     const double* __restrict__ params, const double* __restrict__ rvr, const double* __restrict__ u,
     unsigned long long seed, unsigned long long philox_offset, const double* __restrict__ gather,
     const double* __restrict__ xs, const double* __restrict__ cumblk, const double* __restrict__ boff,
     const double* __restrict__ tlast, double* __restrict__ xc, int* __restrict__ pa, unsigned short* __restrict__ cb,
-    int* __restrict__ hist_out, double* __restrict__ shift_out, double* __restrict__ xmin_out) {
+    int* __restrict__ hist_out, double* __restrict__ shift_out, double* __restrict__ xmin_out,
+    const int* __restrict__ perm, int* __restrict__ par_out) {
     extern __shared__ unsigned char smem_raw[];
     double* s_cum = (double*)smem_raw;                       // [kStage]
     int* s_hist = (int*)(smem_raw + (size_t)kStage * 8);     // [kBins]
@@ -451,6 +458,7 @@ __global__ void __launch_bounds__(256) split_children_kernel(
                     atomicAdd(&s_hist[bin], 1);
                     xc[k] = xn;
                     pa[k] = a;
+                    if (par_out) par_out[k] = perm[a];   // path storage: birth row of the parent
                     cb[k] = (unsigned short)bin;
                 }
             }
@@ -745,6 +753,86 @@ __global__ void split_rank_kernel(SplitState* __restrict__ st, const SortEntry* 
 }
 
 // ---------------------------------------------------------------------------------------------
+// path storage (one device): a generation is stored ONCE, in birth order, as value X[g][k] and
+// parent row J[0][g][k]; nothing is copied when a particle has children.  Jump tables
+// J[q][g][k] = row (in generation g - 2^q) of the ancestor 2^q steps back are extended by one
+// random 4-byte read per table per particle-step.  The fixed-lag terms (:445-470) reach the
+// ancestors lag-2 / lag-1 steps back through them.  Rings of depth R over the generations.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) split_lineage_kernel(
+    const SplitState* __restrict__ st, int t, int n, int lag, int R, int Q, const double* __restrict__ X,
+    int* __restrict__ J, const double* __restrict__ obs, const double* __restrict__ params,
+    double* __restrict__ gpart) {
+    __shared__ double red[5 * 32];
+    const int tid = threadIdx.x;
+    const size_t N = (size_t)n;
+    SvConst c;
+    sv_const_init(c, params);
+    const bool grad = t >= lag;
+    const double shift = st->shift, y = obs[t], ylag = grad ? obs[t - lag] : 0.0;   // Q5: obs[i - LAG]
+    const int m = lag - 2;
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    bool bad = false;
+    for (int k = blockIdx.x * 256 + tid; k < n; k += gridDim.x * 256) {
+        // extend the jump tables of generation t
+        int jq[6];
+        jq[0] = J[((size_t)0 * R + (t % R)) * N + k];
+        for (int q = 1; q <= Q; ++q) {
+            const int b = 1 << q, h = b >> 1;
+            if (t >= b) {
+                jq[q] = J[((size_t)(q - 1) * R + ((t - h) % R)) * N + jq[q - 1]];
+                J[((size_t)q * R + (t % R)) * N + k] = jq[q];
+            } else {
+                jq[q] = 0;
+            }
+        }
+        if (!grad) continue;
+        // ancestor m = lag - 2 steps back: binary decomposition of m over the tables
+        int r = k, g = t;
+        for (int q = Q; q >= 0; --q) {
+            const int b = 1 << q;
+            if (m & b) {
+                r = (g == t) ? jq[q] : J[((size_t)q * R + (g % R)) * N + r];
+                g -= b;
+            }
+        }
+        const double next = X[(size_t)(g % R) * N + r];
+        const int rp = (g == t) ? jq[0] : J[((size_t)0 * R + (g % R)) * N + r];
+        const double curr = X[(size_t)((g - 1) % R) * N + rp];
+        double sh = exp(sv_logw(X[(size_t)(t % R) * N + k], y) - shift);
+        if (!isfinite(sh)) {
+            bad = true;
+            sh = 0.0;
+        }
+        double sq, gg[4];
+        sv_score_main(c, curr, next, ylag, sq, gg);
+        acc[0] += sh * curr;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[1 + q] += gg[q] * sh;
+    }
+    if (bad) atomicOr(&((SplitState*)st)->status, 2);
+    block_sum<5>(acc, red);
+    if (tid < 5) gpart[(size_t)blockIdx.x * 8 + tid] = acc[tid];
+}
+
+// records [n][lag] of the FINAL generation (row = birth row): rec[k][idx] = value of the ancestor
+// idx steps back -- what the tail terms (:540-562) read; built once by walking the parent rows
+__global__ void split_build_records_kernel(int T, int n, int lag, int R, const double* __restrict__ X,
+                                           const int* __restrict__ J, double* __restrict__ rec) {
+    const size_t N = (size_t)n;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        int r = k, g = T;
+        for (int idx = 0; idx < lag; ++idx) {
+            rec[(size_t)k * lag + idx] = X[(size_t)(g % R) * N + r];
+            if (idx + 1 < lag) {
+                r = J[(size_t)(g % R) * N + r];
+                --g;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // tail (:540-562, Q6) on the final generation: wt[k][p] = normalised weight at global position
 // (gstart + p) of generation nobs-1-k... see pmmh_svsplit_tail
 //   part[i_rel][0] = sum_j W_T[j] ph[idx][j];  part[i_rel][1..4] = sum_j g_p W_i[j]
@@ -932,6 +1020,11 @@ int pmmh_svsplit_weights(void*, size_t, long long, long long, int, int, int, int
 int pmmh_svsplit_children(void*, size_t, long long, long long, int, int, const double*, const double*,
                           const double*, const double*, unsigned long long, unsigned long long, const double*,
                           const double*, int*, double*, double*, void*);
+static int children_impl(void*, size_t, long long, long long, int, int, const double*, const double*,
+                         const double*, const double*, unsigned long long, unsigned long long, const double*,
+                         const double*, int*, double*, double*, void*, double*, const int*, int*);
+static int weights_impl(void*, size_t, long long, long long, int, int, int, int, const double*, const double*,
+                        const double*, const int*, const double*, double*, double*, double*, void*, int);
 int pmmh_svsplit_plan(void*, size_t, long long, long long, int, const int*, int*, void*);
 int pmmh_svsplit_pack(void*, size_t, long long, long long, const int*, const double*, double*, double*, void*);
 int pmmh_svsplit_sort(void*, size_t, long long, long long, int, int, int, const double*, const double*, int,
@@ -1042,6 +1135,129 @@ int sv_split_single_run(const double* d_obs, const double* d_params, const doubl
     return PMMH_OK;
 }
 
+// ---- path storage on one device (algorithm 5) ------------------------------------------------
+namespace {
+struct PathLayout {
+    size_t split, xs, perm, X, J, sums, shift, xmin, gather, hist, keep, tail, rec, total, split_bytes;
+    int R, Q;
+};
+
+PathLayout make_path_layout(int nobs, long long n, int lag) {
+    PathLayout P;
+    P.R = lag + 1;
+    P.Q = 0;
+    while ((2 << P.Q) <= lag - 2) ++P.Q;      // largest q with 2^q <= lag - 2 (0 when lag <= 3)
+    size_t o = 0;
+    P.split_bytes = make_layout(n, n).total;
+    P.split = o;   o += al(P.split_bytes);
+    P.xs = o;      o += al((size_t)n * 8);
+    P.perm = o;    o += al((size_t)n * 4);
+    P.X = o;       o += al((size_t)P.R * n * 8);
+    P.J = o;       o += al((size_t)(P.Q + 1) * P.R * n * 4);
+    P.sums = o;    o += al((size_t)nobs * 8 * 8);
+    P.shift = o;   o += al((size_t)nobs * 8);
+    P.xmin = o;    o += al((size_t)nobs * 8);
+    P.gather = o;  o += al(4 * 8);
+    P.hist = o;    o += al((size_t)kBins * 4);
+    P.keep = o;    o += al((size_t)n * lag * 8);
+    P.tail = o;    o += al((size_t)lag * 8 * 8);
+    P.rec = o;     o += al((size_t)n * lag * 8);
+    P.total = o;
+    return P;
+}
+}  // namespace
+
+size_t sv_split_path_ws_bytes(int nobs, int n, int lag) { return make_path_layout(nobs, n, lag).total; }
+
+int sv_split_path_run(const double* d_obs, const double* d_params, const double* d_rvr, const double* d_u,
+                      int nobs, int n, int lag, double* d_filt, double* d_smo, double* d_ll, double* d_grad,
+                      double* d_traj, long long* d_diag, void* d_ws, size_t ws_bytes, cudaStream_t st) {
+    if (!sv_split_single_eligible(nobs, n, lag)) return set_error(PMMH_ERR_INVALID, "split kernels: sizes not eligible");
+    const PathLayout P = make_path_layout(nobs, n, lag);
+    if (ws_bytes < P.total) return set_error(PMMH_ERR_WORKSPACE, "split kernels: workspace too small");
+    char* ws = (char*)d_ws;
+    void* sws = ws + P.split;
+    const size_t sb = P.split_bytes;
+    const int R = P.R, Q = P.Q;
+    double* xs = (double*)(ws + P.xs);
+    int* perm = (int*)(ws + P.perm);
+    double* X = (double*)(ws + P.X);
+    int* J = (int*)(ws + P.J);
+    double* sums = (double*)(ws + P.sums);
+    double* shift = (double*)(ws + P.shift);
+    double* xmin = (double*)(ws + P.xmin);
+    double* gather = (double*)(ws + P.gather);
+    int* hist = (int*)(ws + P.hist);
+    double* keep = (double*)(ws + P.keep);
+    double* tail = (double*)(ws + P.tail);
+    double* rec = (double*)(ws + P.rec);
+    const Layout L = make_layout(n, n);
+    SplitState* state = (SplitState*)((char*)sws + L.state);
+    const int nf_bound = (int)(n / kFine + kBins);
+    int rc;
+    static thread_local cudaStream_t side[64] = {nullptr};
+    static thread_local cudaEvent_t ev_fork[64] = {nullptr}, ev_join[64] = {nullptr};
+    int dev = 0;
+    SPLIT_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return set_error(PMMH_ERR_NO_DEVICE, "device ordinal out of range");
+    if (!side[dev]) {
+        SPLIT_CUDA(cudaStreamCreateWithFlags(&side[dev], cudaStreamNonBlocking));
+        SPLIT_CUDA(cudaEventCreateWithFlags(&ev_fork[dev], cudaEventDisableTiming));
+        SPLIT_CUDA(cudaEventCreateWithFlags(&ev_join[dev], cudaEventDisableTiming));
+    }
+    SPLIT_CUDA(cudaMemsetAsync(sums, 0, (size_t)nobs * 8 * 8, st));
+    // generation 0: xs = mu, perm = identity, X[0] = mu (the LR = 1 "records" of init are X[0])
+    if ((rc = pmmh_svsplit_init(sws, sb, n, nobs, 1, 0, 0, n, n, n, d_params, xs, perm, X, st))) return rc;
+    if ((rc = weights_impl(sws, sb, n, n, 0, n, lag, nobs, d_obs, d_params, xs, perm, nullptr, sums, gather,
+                           nullptr, st, 1)))
+        return rc;
+    for (int t = 1; t < nobs; ++t) {
+        double* Xt = X + (size_t)(t % R) * n;
+        int* J1t = J + (size_t)(t % R) * n;
+        if ((rc = children_impl(sws, sb, n, n, t, n, d_obs, d_params, d_rvr, d_u, 0, 0, gather, xs, hist, shift,
+                                xmin, st, Xt, perm, J1t)))
+            return rc;
+        if ((rc = pmmh_svsplit_plan(sws, sb, n, n, 1, hist, nullptr, st))) return rc;
+        // jump tables + fixed-lag sums (birth order) beside the sort: both depend only on the children
+        SPLIT_CUDA(cudaEventRecord(ev_fork[dev], st));
+        SPLIT_CUDA(cudaStreamWaitEvent(side[dev], ev_fork[dev], 0));
+        split_lineage_kernel<<<kLineageGrid, 256, 0, side[dev]>>>(state, t, n, lag, R, Q, X, J, d_obs, d_params,
+                                                                  (double*)((char*)sws + L.gpart));
+        SPLIT_CUDA(cudaEventRecord(ev_join[dev], side[dev]));
+        if ((rc = pmmh_svsplit_sort(sws, sb, n, n, n, nf_bound, 0, Xt, Xt, 0, xs, perm, st))) return rc;
+        SPLIT_CUDA(cudaStreamWaitEvent(st, ev_join[dev], 0));
+        double* kp = (t >= nobs - lag) ? keep + (size_t)(t % lag) * n : nullptr;
+        if ((rc = weights_impl(sws, sb, n, n, t, n, lag, nobs, d_obs, d_params, xs, perm, nullptr, sums, gather,
+                               kp, st, 1)))
+            return rc;
+    }
+    for (int irel = 0; irel < lag; ++irel) {
+        const int i = nobs - lag + irel;
+        double* kp = keep + (size_t)(i % lag) * n;
+        if ((rc = pmmh_svsplit_normalise(kp, n, sums + (size_t)i * 8, kp, st))) return rc;
+    }
+    // the tail reads records of the final generation: built once from the stored paths
+    split_build_records_kernel<<<grid_for(n, 256), 256, 0, st>>>(nobs - 1, n, lag, R, X, J, rec);
+    const int r0 = (nobs - lag) % lag;
+    double* wl = keep;
+    if (r0 != 0) {
+        // rotate the kept weights into [irel][p] order; X is free now and large enough (R > lag rows)
+        wl = X;
+        for (int irel = 0; irel < lag; ++irel)
+            SPLIT_CUDA(cudaMemcpyAsync(wl + (size_t)irel * n, keep + (size_t)((r0 + irel) % lag) * n,
+                                       (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    if ((rc = pmmh_svsplit_tail(sws, sb, n, n, n, lag, nobs, d_obs, d_params, perm, rec,
+                                wl + (size_t)(lag - 1) * n, wl, n, tail, st)))
+        return rc;
+    if ((rc = pmmh_svsplit_finish(sums, shift, xmin, tail, gather, 1, d_params, nobs, lag, n, d_ll, d_filt, d_smo,
+                                  d_grad, d_traj, st)))
+        return rc;
+    split_diag_kernel<<<1, 32, 0, st>>>(state, d_diag);
+    SPLIT_CUDA(cudaGetLastError());
+    return PMMH_OK;
+}
+
 }  // namespace pmmh
 
 extern "C" {
@@ -1082,11 +1298,11 @@ int pmmh_svsplit_init(void* d_ws, size_t ws_bytes, long long n_total, int n_obs,
     return PMMH_OK;
 }
 
-int pmmh_svsplit_weights(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
-                         int t, int n_local, int lag, int n_obs, const double* d_obs,
-                         const double* d_params, const double* d_xs, const int* d_perm,
-                         const double* d_rec, double* d_sums, double* d_gather_send, double* d_sh_save,
-                         void* stream) {
+static int weights_impl(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
+                        int t, int n_local, int lag, int n_obs, const double* d_obs,
+                        const double* d_params, const double* d_xs, const int* d_perm,
+                        const double* d_rec, double* d_sums, double* d_gather_send, double* d_sh_save,
+                        void* stream, int path_storage) {
     Layout L;
     if (int rc = check_ws(d_ws, ws_bytes, cap_particles, cap_children, &L)) return rc;
     if (t < 0 || t >= n_obs || n_local < 0 || n_local > cap_particles)
@@ -1096,7 +1312,8 @@ int pmmh_svsplit_weights(void* d_ws, size_t ws_bytes, long long cap_particles, l
     SplitState* state = (SplitState*)(ws + L.state);
     const int LR = lag == 0 ? 1 : lag;
     const int ntiles = (n_local + kTile - 1) / kTile;
-    const bool grad = lag > 0 && t >= lag;
+    const bool grad_t = lag > 0 && t >= lag;
+    const bool grad = grad_t && !path_storage;   // gather variant; path storage: sums from the lineage kernel
     double* cumblk = (double*)(ws + L.cumblk);
     double* btot = (double*)(ws + L.btot);
     double* bpart = (double*)(ws + L.bpart);
@@ -1112,17 +1329,29 @@ int pmmh_svsplit_weights(void* d_ws, size_t ws_bytes, long long cap_particles, l
                                                                 d_obs, t, lag, d_params, t == 0, cumblk, btot,
                                                                 tlast, bpart, d_sh_save);
     }
-    split_weights_finalize_kernel<<<1, 256, 0, st>>>(state, d_xs, n_local, ntiles, btot, bpart, boff,
-                                                     d_sums + (size_t)t * 8, d_gather_send);
+    split_weights_finalize_kernel<<<1, 256, 0, st>>>(
+        state, d_xs, n_local, ntiles, btot, bpart,
+        (path_storage && grad_t) ? (const double*)(ws + L.gpart) : nullptr, boff, d_sums + (size_t)t * 8,
+        d_gather_send);
     SPLIT_CUDA(cudaGetLastError());
     return PMMH_OK;
 }
 
-int pmmh_svsplit_children(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
-                          int t, int n_local, const double* d_obs, const double* d_params,
-                          const double* d_rvr, const double* d_u, unsigned long long seed,
-                          unsigned long long philox_offset, const double* d_gather, const double* d_xs,
-                          int* d_hist_send, double* d_shift, double* d_xmin, void* stream) {
+int pmmh_svsplit_weights(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
+                         int t, int n_local, int lag, int n_obs, const double* d_obs,
+                         const double* d_params, const double* d_xs, const int* d_perm,
+                         const double* d_rec, double* d_sums, double* d_gather_send, double* d_sh_save,
+                         void* stream) {
+    return weights_impl(d_ws, ws_bytes, cap_particles, cap_children, t, n_local, lag, n_obs, d_obs, d_params,
+                        d_xs, d_perm, d_rec, d_sums, d_gather_send, d_sh_save, stream, 0);
+}
+
+static int children_impl(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
+                         int t, int n_local, const double* d_obs, const double* d_params,
+                         const double* d_rvr, const double* d_u, unsigned long long seed,
+                         unsigned long long philox_offset, const double* d_gather, const double* d_xs,
+                         int* d_hist_send, double* d_shift, double* d_xmin, void* stream,
+                         double* xc_override, const int* perm, int* par_out) {
     Layout L;
     if (int rc = check_ws(d_ws, ws_bytes, cap_particles, cap_children, &L)) return rc;
     if (t < 1 || n_local < 0) return set_error(PMMH_ERR_INVALID, "svsplit_children: bad sizes");
@@ -1142,10 +1371,20 @@ int pmmh_svsplit_children(void* d_ws, size_t ws_bytes, long long cap_particles, 
     split_children_kernel<<<148 * 4, 256, smem, st>>>(
         state, t, n_local, d_obs, d_params, d_rvr, d_u, seed, philox_offset, d_gather, d_xs,
         (const double*)(ws + L.cumblk), (const double*)(ws + L.boff), (const double*)(ws + L.tlast),
-        (double*)(ws + L.xc),
-        (int*)(ws + L.pa), (unsigned short*)(ws + L.cb), d_hist_send, d_shift, d_xmin);
+        xc_override ? xc_override : (double*)(ws + L.xc),
+        (int*)(ws + L.pa), (unsigned short*)(ws + L.cb), d_hist_send, d_shift, d_xmin, perm, par_out);
     SPLIT_CUDA(cudaGetLastError());
     return PMMH_OK;
+}
+
+int pmmh_svsplit_children(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
+                          int t, int n_local, const double* d_obs, const double* d_params,
+                          const double* d_rvr, const double* d_u, unsigned long long seed,
+                          unsigned long long philox_offset, const double* d_gather, const double* d_xs,
+                          int* d_hist_send, double* d_shift, double* d_xmin, void* stream) {
+    return children_impl(d_ws, ws_bytes, cap_particles, cap_children, t, n_local, d_obs, d_params, d_rvr, d_u,
+                         seed, philox_offset, d_gather, d_xs, d_hist_send, d_shift, d_xmin, stream, nullptr,
+                         nullptr, nullptr);
 }
 
 int pmmh_svsplit_plan(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,

@@ -52,8 +52,9 @@ def device_info():
 
 
 def set_sv_algorithm(algorithm):
-    """0 = automatic (chain / exchange kernel where eligible), 1 = general kernel only, 2 / 3 = exchange /
-    chain kernel without the general-kernel fallback (pmmh_sv_set_algorithm)."""
+    """0 = automatic (chain / exchange / streaming kernels where eligible), 1 = general kernel only,
+    2 / 3 = exchange / chain kernel without the general-kernel fallback, 4 / 5 = streaming kernels with
+    records / with path storage (pmmh_sv_set_algorithm)."""
     lib = _lib.load()
     _lib.check(lib.pmmh_sv_set_algorithm(int(algorithm)), "pmmh_sv_set_algorithm")
 

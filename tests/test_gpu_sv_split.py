@@ -131,16 +131,20 @@ def test_split_estimator_contract(cuda_dev):
     assert abs(sp.results['log_like'] - one.results['log_like']) <= 1e-10 * abs(one.results['log_like'])
 
 
-@pytest.mark.parametrize("n,nobs,lag,seed", [(20000, 61, 10, 1), (3000, 47, 4, 2), (1 << 17, 45, 10, 4)])
-def test_streaming_kernels_behind_flps_sv_corr(cuda_dev, n, nobs, lag, seed):
-    """pmmh_flps_sv_corr with algorithm 4: the same phases driven from C++ on one device."""
+@pytest.mark.parametrize("alg", [4, 5])
+@pytest.mark.parametrize("n,nobs,lag,seed", [(20000, 61, 10, 1), (3000, 47, 4, 2), (1 << 17, 45, 10, 4),
+                                             (5000, 50, 7, 3), (4000, 40, 2, 5), (4000, 40, 3, 6),
+                                             (2500, 70, 13, 7)])
+def test_streaming_kernels_behind_flps_sv_corr(cuda_dev, alg, n, nobs, lag, seed):
+    """pmmh_flps_sv_corr with algorithm 4 (records) / 5 (path storage + jump tables): the same
+    phases driven from C++ on one device; several lags exercise the jump-table decomposition."""
     import torch
     import oracle
     from pmmh_qn_b200 import kernels as K
     obs, params, rvr, rvp = gi.sv_inputs(n, nobs, seed)
     ref = oracle.flps_sv_corr(obs, params, rvr, rvp, n, lag, 0)
     u = torch.from_numpy(to_time_major(rvp, n, nobs)).to(cuda_dev)
-    K.set_sv_algorithm(4)
+    K.set_sv_algorithm(alg)
     try:
         out = K.flps_sv_corr(torch.from_numpy(obs).to(cuda_dev), torch.from_numpy(params).to(cuda_dev),
                              torch.from_numpy(rvr[:nobs].copy()).to(cuda_dev), u, lag=lag)
