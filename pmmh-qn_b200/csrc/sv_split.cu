@@ -32,7 +32,12 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <algorithm>
+#include <vector>
 
 #include "../../include/pmmh_qn.h"
 #include "common.cuh"
@@ -55,7 +60,7 @@ constexpr int kStage = 4096;        // cumulative weights staged in shared memor
 constexpr int kChildTile = 1024;    // children per tile (256 threads x 4)
 constexpr int kMaxRounds = 64;      // child tiles whose boundaries one block resolves at once
 constexpr int kMaxBinRank = 8192;   // a fine bin larger than this abandons the evaluation
-constexpr int kLineageGrid = 148 * 8;   // blocks of the lineage kernel (one partial-sum row each)
+constexpr int kLineageGrid = 148 * 4;   // blocks of the lineage kernel (one partial-sum row each)
 constexpr double kChildNsd = 6.5;   // histogram range: extreme propagation means +- 6.5 sd
 
 struct SplitState {
@@ -72,6 +77,7 @@ struct SplitState {
     // diagnostics
     unsigned long long near_ties, key_ties;
     int max_bin, status;
+    unsigned int ticket_c;   // last-block-done counter of the children kernel (fused plan)
 };
 
 struct Layout {
@@ -207,7 +213,7 @@ __global__ void __launch_bounds__(kTileThreads) split_weights_kernel(
 
 // one block: sequential-in-chunks exclusive scan of the tile totals, fixed-order sums of the
 // tile partials, the 4 doubles this rank contributes to the all-gather
-__global__ void __launch_bounds__(256) split_weights_finalize_kernel(
+__global__ void __launch_bounds__(1024) split_weights_finalize_kernel(
     SplitState* __restrict__ st, const double* __restrict__ xs, int n, int ntiles,
     const double* __restrict__ btot, const double* __restrict__ bpart, const double* __restrict__ gpart,
     double* __restrict__ boff, double* __restrict__ sums_t, double* __restrict__ gather_send) {
@@ -234,11 +240,11 @@ __global__ void __launch_bounds__(256) split_weights_finalize_kernel(
         if (lane == 31) boff[ntiles] = s_lane[32];
     }
     double acc[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    for (int q = tid; q < ntiles; q += 256)
+    for (int q = tid; q < ntiles; q += blockDim.x)
 #pragma unroll
         for (int k = 0; k < 7; ++k) acc[k] += bpart[(size_t)q * 8 + k];
     if (gpart)   // path storage: sum sh curr, sum sh g_0..3 come from the lineage kernel
-        for (int q = tid; q < kLineageGrid; q += 256)
+        for (int q = tid; q < kLineageGrid; q += blockDim.x)
 #pragma unroll
             for (int k = 0; k < 5; ++k) acc[1 + k] += gpart[(size_t)q * 8 + k];
     block_sum<7>(acc, red);
@@ -316,7 +322,8 @@ __global__ void __launch_bounds__(256, 4) split_children_kernel(
     const double* __restrict__ xs, const double* __restrict__ cumblk, const double* __restrict__ boff,
     const double* __restrict__ tlast, double* __restrict__ xc, int* __restrict__ pa, unsigned short* __restrict__ cb,
     int* __restrict__ hist_out, double* __restrict__ shift_out, double* __restrict__ xmin_out,
-    const int* __restrict__ perm, int* __restrict__ par_out) {
+    const int* __restrict__ perm, int* __restrict__ par_out, int fuse_plan, int* __restrict__ nfc,
+    int* __restrict__ fstart, int* __restrict__ cstart) {
     extern __shared__ unsigned char smem_raw[];
     double* s_cum = (double*)smem_raw;                       // [kStage]
     int* s_hist = (int*)(smem_raw + (size_t)kStage * 8);     // [kBins]
@@ -396,15 +403,19 @@ __global__ void __launch_bounds__(256, 4) split_children_kernel(
     const double S = sc.S, off = sc.off, lo = sc.lo, scale = sc.scale;
     const long long jlo = sc.jlo;
     const double dn = (double)N;
-    const int ntl = (nc + kChildTile - 1) / kChildTile;
+    // tile size chosen so that every block handles the same number of (equal) tiles
+    const int per_blk = (nc + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int rounds_blk = max(1, (per_blk + kChildTile - 1) / kChildTile);
+    const int ctile = max(1, (per_blk + rounds_blk - 1) / rounds_blk);
+    const int ntl = (nc + ctile - 1) / ctile;
     int near = 0;
     for (int r0 = 0; blockIdx.x + (long long)r0 * gridDim.x < ntl; r0 += kMaxRounds) {
         // boundaries (first and last parent) of up to kMaxRounds of this block's tiles at once
         if (tid < 2 * kMaxRounds) {
             const long long tile = blockIdx.x + (long long)(r0 + (tid >> 1)) * gridDim.x;
             if (tile < ntl) {
-                long long k = tile * kChildTile;
-                if (tid & 1) k = min((long long)nc, k + kChildTile) - 1;
+                long long k = tile * ctile;
+                if (tid & 1) k = min((long long)nc, k + ctile) - 1;
                 const double cp = (uu + (double)(jlo + k)) / dn;
                 s_tp[tid] = min(n - 1, cum_search2(cp, n, off, S, boff, tlast, cumblk));
             }
@@ -421,8 +432,8 @@ __global__ void __launch_bounds__(256, 4) split_children_kernel(
             __syncthreads();
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
-                const long long k = tile * kChildTile + tid + 256 * m;
-                if (k < nc) {
+                const long long k = tile * ctile + tid + 256 * m;
+                if (tid + 256 * m < ctile && k < nc) {
                     const long long j = jlo + k;
                     const double cp = (uu + (double)j) / dn;
                     int a;
@@ -482,6 +493,66 @@ __global__ void __launch_bounds__(256, 4) split_children_kernel(
         int tot = 0;
         for (int w = 0; w < 8; ++w) tot += s_near[w];
         if (tot) atomicAdd(&st->near_ties, (unsigned long long)tot);
+    }
+    if (!fuse_plan) return;
+    // One rank: every child stays here, so the plan is two exclusive scans over the 4096 bins
+    // (arrivals before a bin, fine bins before a bin).  The last block to finish does it
+    // instead of a launch of its own (split_plan_kernel).
+    __shared__ int s_lastc;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int tk = atomicAdd(&st->ticket_c, 1u);
+        s_lastc = (tk == gridDim.x - 1) ? 1 : 0;
+        if (s_lastc) st->ticket_c = 0;
+    }
+    __syncthreads();
+    if (!s_lastc) return;
+    __threadfence();
+    constexpr int BPT = kBins / 256;
+    int run = 0, nfrun = 0;
+    const int b0 = tid * BPT;
+    for (int k = 0; k < BPT; ++k) {
+        const int g = __ldcg(&hist_out[b0 + k]);
+        run += g;
+        nfrun += max(1, (g + kFine - 1) / kFine);
+    }
+    const int incl = warp_incl_scan(run, lane), fincl = warp_incl_scan(nfrun, lane);
+    int* s_wa = s_hist;          // the block's own histogram has been flushed
+    int* s_wb = s_hist + 8;
+    __syncthreads();
+    if (lane == 31) {
+        s_wa[warp] = incl;
+        s_wb[warp] = fincl;
+    }
+    __syncthreads();
+    int before = incl - run, fbefore = fincl - nfrun, total = 0, ftotal = 0;
+    for (int w = 0; w < 8; ++w) {
+        if (w < warp) {
+            before += s_wa[w];
+            fbefore += s_wb[w];
+        }
+        total += s_wa[w];
+        ftotal += s_wb[w];
+    }
+    for (int k = 0; k < BPT; ++k) {
+        const int g = __ldcg(&hist_out[b0 + k]);
+        const int nf = max(1, (g + kFine - 1) / kFine);
+        cstart[b0 + k] = before;
+        nfc[b0 + k] = nf;
+        fstart[b0 + k] = fbefore;
+        before += g;
+        fbefore += nf;
+    }
+    if (tid == 0) {
+        fstart[kBins] = ftotal;
+        st->send_cnt[0] = total;
+        st->send_off[0] = 0;
+        st->recv_cnt[0] = total;
+        st->cursor[0] = 0;
+        if (total > st->cap) atomicOr(&st->status, 8);
+        st->n_arrivals = total;
+        st->NF = ftotal;
     }
 }
 
@@ -1022,7 +1093,7 @@ int pmmh_svsplit_children(void*, size_t, long long, long long, int, int, const d
                           const double*, int*, double*, double*, void*);
 static int children_impl(void*, size_t, long long, long long, int, int, const double*, const double*,
                          const double*, const double*, unsigned long long, unsigned long long, const double*,
-                         const double*, int*, double*, double*, void*, double*, const int*, int*);
+                         const double*, int*, double*, double*, void*, double*, const int*, int*, int);
 static int weights_impl(void*, size_t, long long, long long, int, int, int, int, const double*, const double*,
                         const double*, const int*, const double*, double*, double*, double*, void*, int);
 int pmmh_svsplit_plan(void*, size_t, long long, long long, int, const int*, int*, void*);
@@ -1211,13 +1282,34 @@ int sv_split_path_run(const double* d_obs, const double* d_params, const double*
     if ((rc = weights_impl(sws, sb, n, n, 0, n, lag, nobs, d_obs, d_params, xs, perm, nullptr, sums, gather,
                            nullptr, st, 1)))
         return rc;
+    // development: PMMH_SPLIT_TIMING=1 prints the average time of every phase of a step (events on
+    // the main stream; the lineage kernel runs beside the sort on the second stream)
+    static int timing = -1;
+    if (timing < 0) {
+        const char* e = getenv("PMMH_SPLIT_TIMING");
+        timing = e ? atoi(e) : 0;
+    }
+    const int kEv = 5;
+    std::vector<cudaEvent_t> evs;
+    int t_first = 0, t_last = 0;
+    if (timing) {
+        t_first = nobs / 2;
+        t_last = std::min(nobs - 1, t_first + 100);
+        evs.resize((size_t)(t_last - t_first) * kEv);
+        for (auto& e : evs) cudaEventCreate(&e);
+    }
+#define PMMH_MARK(slot)                                                                      \
+    do {                                                                                     \
+        if (timing && t >= t_first && t < t_last) cudaEventRecord(evs[(size_t)(t - t_first) * kEv + (slot)], st); \
+    } while (0)
     for (int t = 1; t < nobs; ++t) {
         double* Xt = X + (size_t)(t % R) * n;
         int* J1t = J + (size_t)(t % R) * n;
+        PMMH_MARK(0);
         if ((rc = children_impl(sws, sb, n, n, t, n, d_obs, d_params, d_rvr, d_u, 0, 0, gather, xs, hist, shift,
-                                xmin, st, Xt, perm, J1t)))
+                                xmin, st, Xt, perm, J1t, 1)))
             return rc;
-        if ((rc = pmmh_svsplit_plan(sws, sb, n, n, 1, hist, nullptr, st))) return rc;
+        PMMH_MARK(1);
         // jump tables + fixed-lag sums (birth order) beside the sort: both depend only on the children
         SPLIT_CUDA(cudaEventRecord(ev_fork[dev], st));
         SPLIT_CUDA(cudaStreamWaitEvent(side[dev], ev_fork[dev], 0));
@@ -1225,11 +1317,37 @@ int sv_split_path_run(const double* d_obs, const double* d_params, const double*
                                                                   (double*)((char*)sws + L.gpart));
         SPLIT_CUDA(cudaEventRecord(ev_join[dev], side[dev]));
         if ((rc = pmmh_svsplit_sort(sws, sb, n, n, n, nf_bound, 0, Xt, Xt, 0, xs, perm, st))) return rc;
+        PMMH_MARK(2);
         SPLIT_CUDA(cudaStreamWaitEvent(st, ev_join[dev], 0));
+        PMMH_MARK(3);
         double* kp = (t >= nobs - lag) ? keep + (size_t)(t % lag) * n : nullptr;
         if ((rc = weights_impl(sws, sb, n, n, t, n, lag, nobs, d_obs, d_params, xs, perm, nullptr, sums, gather,
                                kp, st, 1)))
             return rc;
+        PMMH_MARK(4);
+    }
+#undef PMMH_MARK
+    if (timing) {
+        SPLIT_CUDA(cudaStreamSynchronize(st));
+        double acc[kEv] = {0, 0, 0, 0, 0};
+        const int cnt = t_last - t_first;
+        for (int q = 0; q < cnt; ++q) {
+            for (int k = 0; k + 1 < kEv; ++k) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, evs[(size_t)q * kEv + k], evs[(size_t)q * kEv + k + 1]);
+                acc[k] += ms;
+            }
+            if (q + 1 < cnt) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, evs[(size_t)q * kEv + kEv - 1], evs[(size_t)(q + 1) * kEv]);
+                acc[kEv - 1] += ms;
+            }
+        }
+        fprintf(stderr, "[pmmh split] us per step: children(+plan) %.1f | sort %.1f | wait for lineage %.1f | "
+                        "weights+finalize %.1f | gap to next step %.1f\n",
+                acc[0] / cnt * 1e3, acc[1] / cnt * 1e3, acc[2] / cnt * 1e3, acc[3] / cnt * 1e3,
+                acc[4] / std::max(1, cnt - 1) * 1e3);
+        for (auto& e : evs) cudaEventDestroy(e);
     }
     for (int irel = 0; irel < lag; ++irel) {
         const int i = nobs - lag + irel;
@@ -1329,7 +1447,7 @@ static int weights_impl(void* d_ws, size_t ws_bytes, long long cap_particles, lo
                                                                 d_obs, t, lag, d_params, t == 0, cumblk, btot,
                                                                 tlast, bpart, d_sh_save);
     }
-    split_weights_finalize_kernel<<<1, 256, 0, st>>>(
+    split_weights_finalize_kernel<<<1, 1024, 0, st>>>(
         state, d_xs, n_local, ntiles, btot, bpart,
         (path_storage && grad_t) ? (const double*)(ws + L.gpart) : nullptr, boff, d_sums + (size_t)t * 8,
         d_gather_send);
@@ -1351,7 +1469,7 @@ static int children_impl(void* d_ws, size_t ws_bytes, long long cap_particles, l
                          const double* d_rvr, const double* d_u, unsigned long long seed,
                          unsigned long long philox_offset, const double* d_gather, const double* d_xs,
                          int* d_hist_send, double* d_shift, double* d_xmin, void* stream,
-                         double* xc_override, const int* perm, int* par_out) {
+                         double* xc_override, const int* perm, int* par_out, int fuse_plan = 0) {
     Layout L;
     if (int rc = check_ws(d_ws, ws_bytes, cap_particles, cap_children, &L)) return rc;
     if (t < 1 || n_local < 0) return set_error(PMMH_ERR_INVALID, "svsplit_children: bad sizes");
@@ -1372,7 +1490,8 @@ static int children_impl(void* d_ws, size_t ws_bytes, long long cap_particles, l
         state, t, n_local, d_obs, d_params, d_rvr, d_u, seed, philox_offset, d_gather, d_xs,
         (const double*)(ws + L.cumblk), (const double*)(ws + L.boff), (const double*)(ws + L.tlast),
         xc_override ? xc_override : (double*)(ws + L.xc),
-        (int*)(ws + L.pa), (unsigned short*)(ws + L.cb), d_hist_send, d_shift, d_xmin, perm, par_out);
+        (int*)(ws + L.pa), (unsigned short*)(ws + L.cb), d_hist_send, d_shift, d_xmin, perm, par_out,
+        fuse_plan, (int*)(ws + L.nfc), (int*)(ws + L.fstart), (int*)(ws + L.cstart));
     SPLIT_CUDA(cudaGetLastError());
     return PMMH_OK;
 }

@@ -186,7 +186,8 @@ def test_automatic_selection_beyond_the_exchange_kernel(cuda_dev):
 @pytest.mark.parametrize("par", [(0.2, 0.9, 0.4, -0.5), (2.0, 0.9, 0.4, -0.2), (-0.3, 0.97, 0.15, 0.3),
                                  (0.0, 0.995, 0.05, -0.8), (1.0, 0.5, 1.2, 0.0)])
 def test_streaming_kernels_agree_with_the_general_kernel_over_parameter_sets(cuda_dev, par):
-    """Two independent implementations (persistent general kernel, streaming kernels) on the same
+    """Independent implementations (persistent general kernel, streaming kernels with records and
+    with path storage) on the same
     inputs over the parameter sets of the robustness sweep, N = 60 000, T = 300: identical
     near-tie counts are not required, the estimates must agree to the parity tolerances."""
     import torch
@@ -200,18 +201,21 @@ def test_streaming_kernels_agree_with_the_general_kernel_over_parameter_sets(cud
     rvr = torch.rand((1, nobs), dtype=torch.float64, device=cuda_dev, generator=g)
     res = {}
     try:
-        for alg in (1, 4):
+        for alg in (1, 4, 5):
             K.set_sv_algorithm(alg)
             res[alg] = K.flps_sv_corr(obs, params, rvr, u, lag=lag)
             torch.cuda.synchronize()
     finally:
         K.set_sv_algorithm(0)
-    a, b = res[1], res[4]
-    assert int(b["diag"][0, 6]) == 4 and int(b["diag"][0, 2]) == 0 and int(a["diag"][0, 2]) == 0
-    la, lb = float(a["log_like"][0]), float(b["log_like"][0])
-    assert abs(la - lb) <= 1e-10 * abs(la), (la, lb)
-    ga, gb = a["gradient"][0].cpu().numpy(), b["gradient"][0].cpu().numpy()
-    assert np.max(np.abs(ga - gb)) <= 1e-9 * np.max(np.abs(ga))
-    assert relerr(b["filt"][0].cpu().numpy(), a["filt"][0].cpu().numpy()) <= 1e-10
-    assert relerr(b["smo"][0].cpu().numpy(), a["smo"][0].cpu().numpy()) <= 1e-10
-    assert relerr(b["traj"][0].cpu().numpy(), a["traj"][0].cpu().numpy()) <= 1e-12
+    a = res[1]
+    assert int(a["diag"][0, 2]) == 0
+    for alg in (4, 5):
+        b = res[alg]
+        assert int(b["diag"][0, 6]) == 4 and int(b["diag"][0, 2]) == 0
+        la, lb = float(a["log_like"][0]), float(b["log_like"][0])
+        assert abs(la - lb) <= 1e-10 * abs(la), (alg, la, lb)
+        ga, gb = a["gradient"][0].cpu().numpy(), b["gradient"][0].cpu().numpy()
+        assert np.max(np.abs(ga - gb)) <= 1e-9 * np.max(np.abs(ga)), alg
+        assert relerr(b["filt"][0].cpu().numpy(), a["filt"][0].cpu().numpy()) <= 1e-10
+        assert relerr(b["smo"][0].cpu().numpy(), a["smo"][0].cpu().numpy()) <= 1e-10
+        assert relerr(b["traj"][0].cpu().numpy(), a["traj"][0].cpu().numpy()) <= 1e-12
