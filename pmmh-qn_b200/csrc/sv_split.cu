@@ -99,7 +99,7 @@ Layout make_layout(long long cap, long long capc) {
     L.btot = o;    o += al((size_t)L.ntiles_max * 8);
     L.tlast = o;   o += al((size_t)L.ntiles_max * 8);
     L.bpart = o;   o += al((size_t)L.ntiles_max * 8 * 8);
-    L.gpart = o;   o += al((size_t)kLineageGrid * 8 * 8);
+    L.gpart = o;   o += 2 * al((size_t)kLineageGrid * 8 * 8);   // two generations in flight
     L.cstart = o;  o += al((size_t)kBins * 4);
     L.xc = o;      o += al((size_t)capc * 8);
     L.pa = o;      o += al((size_t)capc * 4);
@@ -216,7 +216,8 @@ __global__ void __launch_bounds__(kTileThreads) split_weights_kernel(
 __global__ void __launch_bounds__(1024) split_weights_finalize_kernel(
     SplitState* __restrict__ st, const double* __restrict__ xs, int n, int ntiles,
     const double* __restrict__ btot, const double* __restrict__ bpart, const double* __restrict__ gpart,
-    double* __restrict__ boff, double* __restrict__ sums_t, double* __restrict__ gather_send) {
+    double* __restrict__ sums_prev, double* __restrict__ boff, double* __restrict__ sums_t,
+    double* __restrict__ gather_send) {
     __shared__ double red[7 * 32];
     __shared__ double s_lane[33];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -243,13 +244,20 @@ __global__ void __launch_bounds__(1024) split_weights_finalize_kernel(
     for (int q = tid; q < ntiles; q += blockDim.x)
 #pragma unroll
         for (int k = 0; k < 7; ++k) acc[k] += bpart[(size_t)q * 8 + k];
-    if (gpart)   // path storage: sum sh curr, sum sh g_0..3 come from the lineage kernel
+    block_sum<7>(acc, red);
+    // path storage: sum sh curr, sum sh g_0..3 of the PREVIOUS generation come from the lineage
+    // kernel, which runs one step behind on the second stream (these sums only feed outputs)
+    double late[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    if (gpart) {
         for (int q = tid; q < kLineageGrid; q += blockDim.x)
 #pragma unroll
-            for (int k = 0; k < 5; ++k) acc[1 + k] += gpart[(size_t)q * 8 + k];
-    block_sum<7>(acc, red);
+            for (int k = 0; k < 5; ++k) late[k] += gpart[(size_t)q * 8 + k];
+        block_sum<5>(late, red);
+    }
     __syncthreads();
     if (tid == 0) {
+        if (gpart)
+            for (int k = 0; k < 5; ++k) sums_prev[2 + k] = late[k];
         const double tot = s_lane[32];
         sums_t[0] = tot;
         for (int k = 0; k < 7; ++k) sums_t[1 + k] = acc[k];
@@ -833,14 +841,16 @@ __global__ void split_rank_kernel(SplitState* __restrict__ st, const SortEntry* 
 __global__ void __launch_bounds__(256) split_lineage_kernel(
     const SplitState* __restrict__ st, int t, int n, int lag, int R, int Q, const double* __restrict__ X,
     int* __restrict__ J, const double* __restrict__ obs, const double* __restrict__ params,
-    double* __restrict__ gpart) {
+    const double* __restrict__ shift_arr, double* __restrict__ gpart) {
     __shared__ double red[5 * 32];
     const int tid = threadIdx.x;
     const size_t N = (size_t)n;
     SvConst c;
     sv_const_init(c, params);
     const bool grad = t >= lag;
-    const double shift = st->shift, y = obs[t], ylag = grad ? obs[t - lag] : 0.0;   // Q5: obs[i - LAG]
+    // (the shift of step t from the per-step array: the state's copy is overwritten by the
+    // children kernel of step t + 1, which may already have run)
+    const double shift = shift_arr[t], y = obs[t], ylag = grad ? obs[t - lag] : 0.0;   // Q5: obs[i - LAG]
     const int m = lag - 2;
     double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     bool bad = false;
@@ -884,6 +894,18 @@ __global__ void __launch_bounds__(256) split_lineage_kernel(
     if (bad) atomicOr(&((SplitState*)st)->status, 2);
     block_sum<5>(acc, red);
     if (tid < 5) gpart[(size_t)blockIdx.x * 8 + tid] = acc[tid];
+}
+
+// the last generation's lineage sums (no later weights phase picks them up)
+__global__ void __launch_bounds__(256) split_lineage_reduce_kernel(const double* __restrict__ gpart,
+                                                                   double* __restrict__ sums_row) {
+    __shared__ double red[5 * 32];
+    double late[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int q = threadIdx.x; q < kLineageGrid; q += 256)
+#pragma unroll
+        for (int k = 0; k < 5; ++k) late[k] += gpart[(size_t)q * 8 + k];
+    block_sum<5>(late, red);
+    if (threadIdx.x < 5) sums_row[2 + threadIdx.x] = late[threadIdx.x];
 }
 
 // records [n][lag] of the FINAL generation (row = birth row): rec[k][idx] = value of the ancestor
@@ -1267,15 +1289,17 @@ int sv_split_path_run(const double* d_obs, const double* d_params, const double*
     const int nf_bound = (int)(n / kFine + kBins);
     int rc;
     static thread_local cudaStream_t side[64] = {nullptr};
-    static thread_local cudaEvent_t ev_fork[64] = {nullptr}, ev_join[64] = {nullptr};
+    static thread_local cudaEvent_t ev_fork[64] = {nullptr}, ev_join[64][2] = {{nullptr, nullptr}};
     int dev = 0;
     SPLIT_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return set_error(PMMH_ERR_NO_DEVICE, "device ordinal out of range");
     if (!side[dev]) {
         SPLIT_CUDA(cudaStreamCreateWithFlags(&side[dev], cudaStreamNonBlocking));
         SPLIT_CUDA(cudaEventCreateWithFlags(&ev_fork[dev], cudaEventDisableTiming));
-        SPLIT_CUDA(cudaEventCreateWithFlags(&ev_join[dev], cudaEventDisableTiming));
+        SPLIT_CUDA(cudaEventCreateWithFlags(&ev_join[dev][0], cudaEventDisableTiming));
+        SPLIT_CUDA(cudaEventCreateWithFlags(&ev_join[dev][1], cudaEventDisableTiming));
     }
+    const size_t gstride = al((size_t)kLineageGrid * 8 * 8);
     SPLIT_CUDA(cudaMemsetAsync(sums, 0, (size_t)nobs * 8 * 8, st));
     // generation 0: xs = mu, perm = identity, X[0] = mu (the LR = 1 "records" of init are X[0])
     if ((rc = pmmh_svsplit_init(sws, sb, n, nobs, 1, 0, 0, n, n, n, d_params, xs, perm, X, st))) return rc;
@@ -1310,15 +1334,18 @@ int sv_split_path_run(const double* d_obs, const double* d_params, const double*
                                 xmin, st, Xt, perm, J1t, 1)))
             return rc;
         PMMH_MARK(1);
-        // jump tables + fixed-lag sums (birth order) beside the sort: both depend only on the children
+        // jump tables + fixed-lag sums (birth order) on the second stream.  They depend only on the
+        // children and feed only outputs, so they get a whole step of slack: the weights phase of
+        // step t picks up the sums of generation t - 1 (its ring slots stay untouched until t + lag)
         SPLIT_CUDA(cudaEventRecord(ev_fork[dev], st));
         SPLIT_CUDA(cudaStreamWaitEvent(side[dev], ev_fork[dev], 0));
-        split_lineage_kernel<<<kLineageGrid, 256, 0, side[dev]>>>(state, t, n, lag, R, Q, X, J, d_obs, d_params,
-                                                                  (double*)((char*)sws + L.gpart));
-        SPLIT_CUDA(cudaEventRecord(ev_join[dev], side[dev]));
+        split_lineage_kernel<<<kLineageGrid, 256, 0, side[dev]>>>(
+            state, t, n, lag, R, Q, X, J, d_obs, d_params, shift,
+            (double*)((char*)sws + L.gpart + (size_t)(t & 1) * gstride));
+        SPLIT_CUDA(cudaEventRecord(ev_join[dev][t & 1], side[dev]));
         if ((rc = pmmh_svsplit_sort(sws, sb, n, n, n, nf_bound, 0, Xt, Xt, 0, xs, perm, st))) return rc;
         PMMH_MARK(2);
-        SPLIT_CUDA(cudaStreamWaitEvent(st, ev_join[dev], 0));
+        if (t > 1) SPLIT_CUDA(cudaStreamWaitEvent(st, ev_join[dev][(t - 1) & 1], 0));
         PMMH_MARK(3);
         double* kp = (t >= nobs - lag) ? keep + (size_t)(t % lag) * n : nullptr;
         if ((rc = weights_impl(sws, sb, n, n, t, n, lag, nobs, d_obs, d_params, xs, perm, nullptr, sums, gather,
@@ -1354,6 +1381,12 @@ int sv_split_path_run(const double* d_obs, const double* d_params, const double*
         double* kp = keep + (size_t)(i % lag) * n;
         if ((rc = pmmh_svsplit_normalise(kp, n, sums + (size_t)i * 8, kp, st))) return rc;
     }
+    // sums of the last generation's lineage kernel
+    SPLIT_CUDA(cudaStreamWaitEvent(st, ev_join[dev][(nobs - 1) & 1], 0));
+    if (nobs - 1 >= lag)
+        split_lineage_reduce_kernel<<<1, 256, 0, st>>>(
+            (const double*)((char*)sws + L.gpart + (size_t)((nobs - 1) & 1) * gstride),
+            sums + (size_t)(nobs - 1) * 8);
     // the tail reads records of the final generation: built once from the stored paths
     split_build_records_kernel<<<grid_for(n, 256), 256, 0, st>>>(nobs - 1, n, lag, R, X, J, rec);
     const int r0 = (nobs - lag) % lag;
@@ -1447,10 +1480,13 @@ static int weights_impl(void* d_ws, size_t ws_bytes, long long cap_particles, lo
                                                                 d_obs, t, lag, d_params, t == 0, cumblk, btot,
                                                                 tlast, bpart, d_sh_save);
     }
+    const bool late = path_storage && lag > 0 && t - 1 >= lag;
+    const size_t gstride = al((size_t)kLineageGrid * 8 * 8);
     split_weights_finalize_kernel<<<1, 1024, 0, st>>>(
         state, d_xs, n_local, ntiles, btot, bpart,
-        (path_storage && grad_t) ? (const double*)(ws + L.gpart) : nullptr, boff, d_sums + (size_t)t * 8,
-        d_gather_send);
+        late ? (const double*)(ws + L.gpart + (size_t)((t - 1) & 1) * gstride) : nullptr,
+        late ? d_sums + (size_t)(t - 1) * 8 : nullptr, boff, d_sums + (size_t)t * 8, d_gather_send);
+    (void)grad_t;
     SPLIT_CUDA(cudaGetLastError());
     return PMMH_OK;
 }
