@@ -24,6 +24,12 @@
 //   sort       counting sort of the arrivals into fine bins (~8 per bin) + exact in-bin ranking
 //              = the reference's argsort (:392-424, :23-52) restricted to this value range
 //
+// On ONE device the same phases are driven from C++ without any host synchronisation
+// (sv_split_single_run: records as above; sv_split_path_run: "path storage" -- a generation is
+// stored once in birth order as (value, parent row), nothing is copied when a particle has
+// children, jump tables reach the lagged ancestors); pmmh_flps_sv_corr selects the latter for
+// problems larger than the persistent exchange kernel takes (N > 2^20).
+//
 // Deviations from the reference's operation order are confined to summation order (parallel
 // scans / reductions instead of one sequential loop) and the choice of the log-weight shift
 // (any shift cancels analytically; Q4).  Resampling decisions that fall within 64 ulp of a
@@ -89,7 +95,7 @@ struct Layout {
 size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
 
 Layout make_layout(long long cap, long long capc) {
-    Layout L;
+    Layout L = Layout();
     L.ntiles_max = (cap + kTile - 1) / kTile + 1;
     L.nf_max = cap / kFine + kBins + 64;
     size_t o = 0;
@@ -220,13 +226,25 @@ __global__ void __launch_bounds__(1024) split_weights_finalize_kernel(
     double* __restrict__ gather_send) {
     __shared__ double red[7 * 32];
     __shared__ double s_lane[33];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int per = (ntiles + 31) / 32;
+    __shared__ double s_part[1024], s_off[1024];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
+    // exclusive scan of the tile totals in a fixed order: every thread sums a short run of tiles
+    // (independent loads), warp 0 scans the 1024 partial sums in shared memory, every thread
+    // writes the offsets of its run
+    const int per = (ntiles + nthr - 1) / nthr;
+    const int qb = min(ntiles, tid * per), qe = min(ntiles, qb + per);
+    {
+        double sp = 0.0;
+        for (int q = qb; q < qe; ++q) sp = sp + btot[q];
+        s_part[tid] = sp;
+    }
+    __syncthreads();
     if (warp == 0) {
-        const int b = min(ntiles, lane * per), e = min(ntiles, b + per);
-        double s = 0.0;
-        for (int q = b; q < e; ++q) s = s + btot[q];
-        s_lane[lane + 1] = s;
+        const int chunk = (nthr + 31) / 32;
+        const int cb0 = min(nthr, lane * chunk), ce0 = min(nthr, cb0 + chunk);
+        double sl = 0.0;
+        for (int q = cb0; q < ce0; ++q) sl = sl + s_part[q];
+        s_lane[lane + 1] = sl;
         __syncwarp();
         if (lane == 0) {
             s_lane[0] = 0.0;
@@ -234,11 +252,19 @@ __global__ void __launch_bounds__(1024) split_weights_finalize_kernel(
         }
         __syncwarp();
         double r = s_lane[lane];
-        for (int q = b; q < e; ++q) {
+        for (int q = cb0; q < ce0; ++q) {
+            s_off[q] = r;
+            r = r + s_part[q];
+        }
+    }
+    __syncthreads();
+    {
+        double r = s_off[tid];
+        for (int q = qb; q < qe; ++q) {
             boff[q] = r;
             r = r + btot[q];
         }
-        if (lane == 31) boff[ntiles] = s_lane[32];
+        if (tid == 0) boff[ntiles] = s_lane[32];
     }
     double acc[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     for (int q = tid; q < ntiles; q += blockDim.x)
@@ -288,21 +314,41 @@ __device__ __forceinline__ int cum_search(double cp, int lo, int hi, double off,
     return lo;
 }
 
-// the same search in two levels: first over the last element of every tile (two small dense
-// arrays, cache resident), then inside one tile
-__device__ __forceinline__ int cum_search2(double cp, int n, double off, double S,
-                                           const double* __restrict__ boff,
-                                           const double* __restrict__ tlast,
-                                           const double* __restrict__ cumblk) {
-    const int ntiles = (n + kTile - 1) / kTile;
-    int lo = 0, hi = ntiles;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (((off + boff[mid]) + tlast[mid]) / S < cp) lo = mid + 1;
-        else hi = mid;
+// Warp-cooperative search: every round the 32 lanes probe 32 evenly spaced positions of
+// [lo, hi) and a ballot narrows the range 32-fold -- 2 + 2 dependent rounds of loads for 1024
+// tiles x 1024 particles instead of ~20 dependent probes by one thread.  pred must be
+// monotone (false ... false true ... true); returns the first true position, hi if none.
+template <typename Pred>
+__device__ __forceinline__ int warp_first_true(int lo, int hi, int lane, Pred pred) {
+    while (hi > lo) {
+        const int span = hi - lo, step = (span + 31) >> 5;
+        const int pos = lo + lane * step;
+        const bool ge = (pos < hi) ? pred(pos) : true;
+        const unsigned m = __ballot_sync(kFullMask, ge);
+        if (m == 0) {                      // all 32 probes false: the answer lies behind the last one
+            lo = lo + 31 * step + 1;
+            continue;
+        }
+        const int f = __ffs(m) - 1;
+        if (f == 0) return lo;
+        hi = min(hi, lo + f * step);       // first probed true position (or the old end)
+        lo = lo + (f - 1) * step + 1;      // one behind the last probed false position
     }
-    if (lo >= ntiles) return n;
-    return cum_search(cp, lo * kTile, min(n, (lo + 1) * kTile), off, S, boff, cumblk);
+    return lo;
+}
+
+__device__ __forceinline__ int cum_search_warp(double cp, int n, double off, double S,
+                                               const double* __restrict__ boff,
+                                               const double* __restrict__ tlast,
+                                               const double* __restrict__ cumblk, int lane) {
+    const int ntiles = (n + kTile - 1) / kTile;
+    const int tl = warp_first_true(0, ntiles, lane, [&](int q) {
+        return !(((off + boff[q]) + tlast[q]) / S < cp);
+    });
+    if (tl >= ntiles) return n;
+    return warp_first_true(tl * kTile, min(n, (tl + 1) * kTile), lane, [&](int q) {
+        return !(cum_at(q, off, S, boff, cumblk) < cp);
+    });
 }
 
 // #{ j in [0, N) : (u + j) / N <= c }, the exact predicate of :703-711 re-checked
@@ -419,14 +465,15 @@ __global__ void __launch_bounds__(256, 4) split_children_kernel(
     int near = 0;
     for (int r0 = 0; blockIdx.x + (long long)r0 * gridDim.x < ntl; r0 += kMaxRounds) {
         // boundaries (first and last parent) of up to kMaxRounds of this block's tiles at once
-        if (tid < 2 * kMaxRounds) {
-            const long long tile = blockIdx.x + (long long)(r0 + (tid >> 1)) * gridDim.x;
-            if (tile < ntl) {
-                long long k = tile * ctile;
-                if (tid & 1) k = min((long long)nc, k + ctile) - 1;
-                const double cp = (uu + (double)(jlo + k)) / dn;
-                s_tp[tid] = min(n - 1, cum_search2(cp, n, off, S, boff, tlast, cumblk));
-            }
+        // (one warp per boundary)
+        for (int bq = warp; bq < 2 * kMaxRounds; bq += 8) {
+            const long long tile = blockIdx.x + (long long)(r0 + (bq >> 1)) * gridDim.x;
+            if (tile >= ntl) break;
+            long long k = tile * ctile;
+            if (bq & 1) k = min((long long)nc, k + ctile) - 1;
+            const double cp = (uu + (double)(jlo + k)) / dn;
+            const int pos = cum_search_warp(cp, n, off, S, boff, tlast, cumblk, lane);
+            if (lane == 0) s_tp[bq] = min(n - 1, pos);
         }
         __syncthreads();
         for (int rr = 0; rr < kMaxRounds; ++rr) {
@@ -518,17 +565,19 @@ __global__ void __launch_bounds__(256, 4) split_children_kernel(
     if (!s_lastc) return;
     __threadfence();
     constexpr int BPT = kBins / 256;
+    // the global histogram into shared memory with coalesced, independent loads (the block's own
+    // histogram has been flushed), then every thread takes BPT consecutive bins
+    for (int b = tid; b < kBins; b += 256) s_hist[b] = __ldcg(&hist_out[b]);
+    __shared__ int s_wa[8], s_wb[8];
+    __syncthreads();
     int run = 0, nfrun = 0;
     const int b0 = tid * BPT;
     for (int k = 0; k < BPT; ++k) {
-        const int g = __ldcg(&hist_out[b0 + k]);
+        const int g = s_hist[b0 + k];
         run += g;
         nfrun += max(1, (g + kFine - 1) / kFine);
     }
     const int incl = warp_incl_scan(run, lane), fincl = warp_incl_scan(nfrun, lane);
-    int* s_wa = s_hist;          // the block's own histogram has been flushed
-    int* s_wb = s_hist + 8;
-    __syncthreads();
     if (lane == 31) {
         s_wa[warp] = incl;
         s_wb[warp] = fincl;
@@ -544,7 +593,7 @@ __global__ void __launch_bounds__(256, 4) split_children_kernel(
         ftotal += s_wb[w];
     }
     for (int k = 0; k < BPT; ++k) {
-        const int g = __ldcg(&hist_out[b0 + k]);
+        const int g = s_hist[b0 + k];
         const int nf = max(1, (g + kFine - 1) / kFine);
         cstart[b0 + k] = before;
         nfc[b0 + k] = nf;
@@ -1424,7 +1473,7 @@ int pmmh_svsplit_workspace_bytes(long long cap_particles, long long cap_children
 int pmmh_svsplit_init(void* d_ws, size_t ws_bytes, long long n_total, int n_obs, int world, int rank,
                       int lag, long long cap_particles, long long cap_children, int n_local,
                       const double* d_params, double* d_xs, int* d_perm, double* d_rec, void* stream) {
-    Layout L;
+    Layout L = Layout();
     if (int rc = check_ws(d_ws, ws_bytes, cap_particles, cap_children, &L)) return rc;
     if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world || n_total < 1 || n_obs < 2 ||
         (lag != 0 && (lag < 2 || lag > 63)) || n_local < 0 || n_local > cap_particles)
@@ -1454,7 +1503,7 @@ static int weights_impl(void* d_ws, size_t ws_bytes, long long cap_particles, lo
                         const double* d_params, const double* d_xs, const int* d_perm,
                         const double* d_rec, double* d_sums, double* d_gather_send, double* d_sh_save,
                         void* stream, int path_storage) {
-    Layout L;
+    Layout L = Layout();
     if (int rc = check_ws(d_ws, ws_bytes, cap_particles, cap_children, &L)) return rc;
     if (t < 0 || t >= n_obs || n_local < 0 || n_local > cap_particles)
         return set_error(PMMH_ERR_INVALID, "svsplit_weights: bad sizes");
@@ -1506,7 +1555,7 @@ static int children_impl(void* d_ws, size_t ws_bytes, long long cap_particles, l
                          unsigned long long philox_offset, const double* d_gather, const double* d_xs,
                          int* d_hist_send, double* d_shift, double* d_xmin, void* stream,
                          double* xc_override, const int* perm, int* par_out, int fuse_plan = 0) {
-    Layout L;
+    Layout L = Layout();
     if (int rc = check_ws(d_ws, ws_bytes, cap_particles, cap_children, &L)) return rc;
     if (t < 1 || n_local < 0) return set_error(PMMH_ERR_INVALID, "svsplit_children: bad sizes");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1544,7 +1593,7 @@ int pmmh_svsplit_children(void* d_ws, size_t ws_bytes, long long cap_particles, 
 
 int pmmh_svsplit_plan(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
                       int world, const int* d_hist, int* h_counts, void* stream) {
-    Layout L;
+    Layout L = Layout();
     if (int rc = check_ws(d_ws, ws_bytes, cap_particles, cap_children, &L)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)d_ws;
@@ -1562,7 +1611,7 @@ int pmmh_svsplit_plan(void* d_ws, size_t ws_bytes, long long cap_particles, long
 int pmmh_svsplit_pack(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
                       const int* d_perm, const double* d_rec, double* d_send, double* d_send_keys,
                       void* stream) {
-    Layout L;
+    Layout L = Layout();
     if (int rc = check_ws(d_ws, ws_bytes, cap_particles, cap_children, &L)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)d_ws;
@@ -1578,7 +1627,7 @@ int pmmh_svsplit_pack(void* d_ws, size_t ws_bytes, long long cap_particles, long
 int pmmh_svsplit_sort(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
                       int n_arrivals, int n_fine, int lag, const double* d_rec_new, const double* d_keys,
                       int keys_are_children, double* d_xs, int* d_perm, void* stream) {
-    Layout L;
+    Layout L = Layout();
     if (int rc = check_ws(d_ws, ws_bytes, cap_particles, cap_children, &L)) return rc;
     if (n_arrivals < 0 || n_arrivals > cap_particles || n_fine < 0 || n_fine > L.nf_max)
         return set_error(PMMH_ERR_INVALID, "svsplit_sort: bad sizes");
@@ -1620,7 +1669,7 @@ int pmmh_svsplit_tail(void* d_ws, size_t ws_bytes, long long cap_particles, long
                       const int* d_perm, const double* d_rec, const double* d_w_final,
                       const double* d_w_lagged, long long w_lagged_stride, double* d_tail,
                       void* stream) {
-    Layout L;
+    Layout L = Layout();
     if (int rc = check_ws(d_ws, ws_bytes, cap_particles, cap_children, &L)) return rc;
     if (lag < 2 || n_local < 0) return set_error(PMMH_ERR_INVALID, "svsplit_tail: bad sizes");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1656,7 +1705,7 @@ int pmmh_svsplit_finish(const double* d_sums, const double* d_shift, const doubl
 
 int pmmh_svsplit_diag(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
                       long long* h_diag) {
-    Layout L;
+    Layout L = Layout();
     if (int rc = check_ws(d_ws, ws_bytes, cap_particles, cap_children, &L)) return rc;
     SplitState h;
     SPLIT_CUDA(cudaMemcpy(&h, (char*)d_ws + L.state, sizeof(h), cudaMemcpyDeviceToHost));
