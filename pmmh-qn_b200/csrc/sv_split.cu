@@ -482,6 +482,15 @@ __global__ void __launch_bounds__(256, 4) split_children_kernel(
             const int pf = s_tp[2 * rr], pl = max(pf, s_tp[2 * rr + 1]);
             const int cnt = pl - pf + 1;
             const bool staged = cnt <= kStage;
+            // u comes from DRAM and is read exactly once: its loads are issued before the staging
+            double uvp[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const long long k = tile * ctile + tid + 256 * m;
+                uvp[m] = (u && tid + 256 * m < ctile && k < nc)
+                             ? ld_stream_f64(u + (size_t)t * (size_t)N + (size_t)(jlo + k))
+                             : 0.0;
+            }
             if (staged)
                 for (int q = tid; q < cnt; q += 256) s_cum[q] = cum_at(pf + q, off, S, boff, cumblk);
             __syncthreads();
@@ -515,7 +524,7 @@ __global__ void __launch_bounds__(256, 4) split_children_kernel(
                     const double x = xs[a];
                     double mean = c.mu + c.phi * (x - c.mu);
                     mean += c.sr * exp(-0.5 * x) * y1;
-                    const double uv = u ? ld_stream_f64(u + (size_t)t * (size_t)N + (size_t)j)
+                    const double uv = u ? uvp[m]
                                         : philox_normal(seed, philox_offset,
                                                         (unsigned long long)t * (unsigned long long)N +
                                                             (unsigned long long)j);
