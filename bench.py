@@ -294,6 +294,31 @@ def run_ours(args, rank, world, local_rank):
     ll = float(out["log_like"][0])
     diag = out["diag"][0].tolist()
 
+    # ---- the same workload on the other implementation of the path (not the headline): streaming
+    # kernels with path storage (pmmh_sv_set_algorithm(5)), which is what N > 2^20 runs on
+    alt = None
+    try:
+        K.set_sv_algorithm(5)
+        ws5 = K.Workspace()
+        o5 = K.flps_sv_corr(obs, params, rvr, u, lag=LAG, compute_hessian=False, workspace=ws5)   # warm-up
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(2):
+            o5 = K.flps_sv_corr(obs, params, rvr, u, lag=LAG, compute_hessian=False, workspace=ws5)
+        a1.record()
+        torch.cuda.synchronize()
+        ms5 = a0.elapsed_time(a1) / 2
+        alt = {"kernel": "streaming kernels with path storage (algorithm 5)", "ms_per_step": ms5,
+               "value": n * T_STEPS / (ms5 * 1e-3), "unit": UNIT + " (this rank)",
+               "log_like": float(o5["log_like"][0]), "status": int(o5["diag"][0, 2]),
+               "rel_diff_log_like": abs(float(o5["log_like"][0]) - ll) / abs(ll)}
+        del ws5, o5
+    except Exception as e:   # reported, never silently replaced
+        alt = {"error": str(e)[:200]}
+    finally:
+        K.set_sv_algorithm(0)
+
     # ---- end to end through the public estimator API with HOST (pinned) buffers
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     model = BenchSVModel(obs_h, PARAMS)
@@ -353,6 +378,8 @@ def run_ours(args, rank, world, local_rank):
                             "in chunks of 64 time steps (no layout kernel); results read back to the host"},
             "gpu_launches": args.steps * 2,
         }
+        if alt is not None:
+            line["alt_kernel_same_workload"] = alt
         if split_line is not None:
             line["config5_split_pf"] = split_line
         if world == 1 and not args.no_cpu_baseline:
