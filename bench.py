@@ -32,6 +32,9 @@ NOBS = T_STEPS + 1
 LAG = 10
 PARAMS = (0.2, 0.9, 0.4, -0.5)
 BYTES_PER_PARTICLE_STEP = 96          # 7s + 40 at s = 8 (filter + fixed-lag gradient)
+KERNEL_NAMES = {1: "sv_pf_kernel<false> (general kernel)", 2: "sv_fast_kernel (exchange kernel)",
+                3: "sv_chain_kernel", 4: "streaming kernels with path storage (sv_split.cu: children, "
+                                         "lineage, fine histogram, offsets, scatter, rank, weights, finalize per time step)"}
 METRIC = "particle_timesteps_per_sec"
 UNIT = "particle-timesteps/s"
 
@@ -294,11 +297,13 @@ def run_ours(args, rank, world, local_rank):
     ll = float(out["log_like"][0])
     diag = out["diag"][0].tolist()
 
-    # ---- the same workload on the other implementation of the path (not the headline): streaming
-    # kernels with path storage (pmmh_sv_set_algorithm(5)), which is what N > 2^20 runs on
+    # ---- the same workload on the other implementation of the path (not the headline): the
+    # persistent exchange kernel (pmmh_sv_set_algorithm(2)) when the headline ran on the streaming
+    # kernels, and the other way round
     alt = None
+    alt_alg = 2 if int(diag[6]) == 4 else 5
     try:
-        K.set_sv_algorithm(5)
+        K.set_sv_algorithm(alt_alg)
         ws5 = K.Workspace()
         o5 = K.flps_sv_corr(obs, params, rvr, u, lag=LAG, compute_hessian=False, workspace=ws5)   # warm-up
         torch.cuda.synchronize()
@@ -309,7 +314,8 @@ def run_ours(args, rank, world, local_rank):
         a1.record()
         torch.cuda.synchronize()
         ms5 = a0.elapsed_time(a1) / 2
-        alt = {"kernel": "streaming kernels with path storage (algorithm 5)", "ms_per_step": ms5,
+        alt = {"kernel": KERNEL_NAMES.get(int(o5["diag"][0, 6]), "?") + " (pmmh_sv_set_algorithm(%d))" % alt_alg,
+               "ms_per_step": ms5,
                "value": n * T_STEPS / (ms5 * 1e-3), "unit": UNIT + " (this rank)",
                "log_like": float(o5["log_like"][0]), "status": int(o5["diag"][0, 2]),
                "rel_diff_log_like": abs(float(o5["log_like"][0]) - ll) / abs(ll)}
@@ -349,6 +355,12 @@ def run_ours(args, rank, world, local_rank):
         split_line = run_split_pf(args, rank, world, dev, dist)
 
     if rank == 0:
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+                tj = json.load(fh)
+            args.traffic_bytes = float(tj["by_kernel"][str(int(diag[6]))]["dram_bytes_per_launch"])
+        except Exception:
+            pass
         peak, peak_src = measured_hbm_peak()
         achieved = n * T_STEPS * BYTES_PER_PARTICLE_STEP / (kern_ms * 1e-3) / 1e9
         line = {
@@ -366,17 +378,19 @@ def run_ours(args, rank, world, local_rank):
                          "frac": achieved / peak, "traffic": args.traffic_bytes,
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": n * T_STEPS * BYTES_PER_PARTICLE_STEP,
-                         "kernel": "sv_fast_kernel (exchange kernel)" if int(diag[6]) == 2 else "sv_pf_kernel<false>",
+                         "kernel": KERNEL_NAMES.get(int(diag[6]), "sv_pf_kernel<false>"),
                          "kernel_ms": kern_ms,
                          "note": "kernel_ms = CUDA events around one pmmh_flps_sv_corr call on the launching "
-                                 "stream: the exchange kernel plus the (empty) general-kernel fallback pass"},
+                                 "stream (all its launches plus the empty general-kernel fallback pass); for the "
+                                 "streaming kernels one call is 8 launches per time step, and achieved = algorithmic "
+                                 "bytes of the evaluation / that time"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                     "api": "ParticleMethodsCUDA.smoother(model, rvs={'rvs': pinned ndarray})",
                     "note": "host rvs -> pmmh_flps_sv_corr_streamed: the copy engine feeds the running kernel "
                             "in chunks of 64 time steps (no layout kernel); results read back to the host"},
-            "gpu_launches": args.steps * 2,
+            "gpu_launches": args.steps * (8 * T_STEPS + 21 if int(diag[6]) == 4 else 2),
         }
         if alt is not None:
             line["alt_kernel_same_workload"] = alt

@@ -73,6 +73,7 @@ struct SvPlan {
     int use_fast, NSUB, CP;
     int use_chain;
     size_t chain_stride, chain_total;
+    int skip_fast;           // the exchange kernel is eligible but the streaming kernels are preferred
     int use_split;           // streaming kernels (sv_split.cu), one problem, log-likelihood + gradient
     size_t split_total;
     size_t fast_sync_bytes, fast_team_stride, fast_total, general_total;
@@ -88,7 +89,7 @@ long long* g_sv_prof = nullptr;   // development: per-CTA phase clocks of the ex
 constexpr int kMaxDynSmem = 227 * 1024;
 
 int sv_make_plan(int nobs, int n, int lag, int batch, int hess, int mode, int have_hist, int ctas,
-                 SvPlan* p) {
+                 SvPlan* p, bool for_host_streamed = false) {
     if (nobs < 2 || n < 1 || batch < 1) return fail(PMMH_ERR_INVALID, "sizes must be positive");
     if (mode == pmmh::kSvFlps) {
         if (lag < 2 || lag >= 64) return fail(PMMH_ERR_INVALID, "lag must be in [2, 63]");
@@ -164,13 +165,17 @@ int sv_make_plan(int nobs, int n, int lag, int batch, int hess, int mode, int ha
         }
     }
     // one large problem, log-likelihood + gradient, no history dump: the streaming kernels -- on
-    // request (algorithm 4), or automatically where the exchange kernel does not take the size
-    // (N > ~1.16 M on 148 SMs; the general kernel is ~4x slower there)
+    // request (algorithm 4 / 5), or automatically from N = 2^20 on: there they are as fast as the
+    // exchange kernel or faster (174.7 vs 181.0 ms at N = 2^20, T = 1000) and they have no size
+    // limit (the exchange kernel stops at ~1.16 M particles; the general kernel is ~4x slower).
+    // The host-streamed entry point (pmmh_flps_sv_corr_streamed) stays on the exchange kernel.
+    p->skip_fast = 0;
     if (mode == pmmh::kSvFlps && !hess && batch == 1 && !have_hist && ctas == 0 && !p->use_chain &&
         (g_sv_algorithm == 4 || g_sv_algorithm == 5 ||
-         (g_sv_algorithm == 0 && !p->use_fast && n >= g_split_min_particles)) &&
+         (g_sv_algorithm == 0 && !for_host_streamed && n >= g_split_min_particles)) &&
         pmmh::sv_split_single_eligible(nobs, n, lag)) {
         p->use_split = 1;
+        p->skip_fast = 1;
         // automatic selection takes the path-storage variant (measured faster: 6.9e9 vs 6.4e9 at 2^22)
         p->split_total = (g_sv_algorithm != 4) ? pmmh::sv_split_path_ws_bytes(nobs, n, lag)
                                                : pmmh::sv_split_single_ws_bytes(nobs, n, lag);
@@ -249,7 +254,7 @@ int sv_run(int mode, const double* d_obs, long long obs_stride, const double* d_
         if (g_sv_algorithm == 4 || g_sv_algorithm == 5) return PMMH_OK;   // no fallback pass
         a.only_failed = 1;
     }
-    if (p.use_fast) {
+    if (p.use_fast && !p.skip_fast) {
         // exchange kernel first; problems it abandons (diag status 1) are re-run by the general
         // kernel in the same stream, reusing the workspace
         a.NSUB = p.NSUB;
@@ -358,7 +363,7 @@ int pmmh_sv_stage_bytes(int n_obs, int n_particles, size_t* bytes) {
 
 int pmmh_sv_streamed_eligible(int n_obs, int n_particles, int lag, int ctas_per_problem) {
     SvPlan p;
-    if (sv_make_plan(n_obs, n_particles, lag, 1, 0, pmmh::kSvFlps, 0, ctas_per_problem, &p) != PMMH_OK) return 0;
+    if (sv_make_plan(n_obs, n_particles, lag, 1, 0, pmmh::kSvFlps, 0, ctas_per_problem, &p, true) != PMMH_OK) return 0;
     return p.use_fast ? 1 : 0;
 }
 
@@ -372,7 +377,7 @@ int pmmh_flps_sv_corr_streamed(const double* h_rvs, const double* d_obs, const d
         !d_traj || !d_hess1 || !d_hess2 || !d_diag || !d_workspace)
         return fail(PMMH_ERR_INVALID, "pmmh_flps_sv_corr_streamed: null pointer argument");
     SvPlan p;
-    int rc = sv_make_plan(n_obs, n_particles, lag, 1, 0, pmmh::kSvFlps, 0, ctas_per_problem, &p);
+    int rc = sv_make_plan(n_obs, n_particles, lag, 1, 0, pmmh::kSvFlps, 0, ctas_per_problem, &p, true);
     if (rc != PMMH_OK) return rc;
     if (!p.use_fast) return fail(PMMH_ERR_INVALID, "pmmh_flps_sv_corr_streamed: exchange kernel not eligible for these sizes");
     if (workspace_bytes < p.total) return fail(PMMH_ERR_WORKSPACE, "workspace too small");
