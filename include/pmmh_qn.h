@@ -126,7 +126,9 @@ int pmmh_flps_sv_corr(const double* d_obs, long long obs_stride, const double* d
  * moves it in chunks of 64 time steps on an internal stream into d_stage (particle-major chunks,
  * no layout kernel) while the persistent kernel is already running; the kernel waits for a
  * chunk only when it reaches it.  d_rvr = Phi of the first n_obs flat entries (computed by the
- * caller as in cython.py:90).  Only sizes the exchange kernel takes (pmmh_sv_streamed_eligible);
+ * caller as in cython.py:90).  Sizes the exchange kernel takes run on it; larger N (>= 2^20) runs
+ * on the streaming kernels, whose host-driven step loop waits for a chunk's event when it enters
+ * it (pmmh_sv_streamed_eligible tells whether a size is taken at all);
  * there is no fallback inside: if d_diag[PMMH_DIAG_STATUS] == 1 afterwards, upload the array and
  * call pmmh_flps_sv_corr.  d_stage needs pmmh_sv_stage_bytes() bytes and must stay untouched
  * until the kernel has finished; the workspace size is that of pmmh_sv_workspace_bytes(batch 1). */

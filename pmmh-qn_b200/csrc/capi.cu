@@ -342,6 +342,7 @@ int pmmh_flps_sv_corr(const double* d_obs, long long obs_stride, const double* d
 namespace {
 constexpr int kUChunk = 64;   // time steps per copy chunk (512-byte rows for the copy engine)
 struct StreamedState {
+    std::vector<cudaEvent_t> ev_chunk;   // streaming kernels: one event per landed chunk
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_reset = nullptr;
     int* h_vals = nullptr;   // pinned: h_vals[c] = time steps available after chunk c
@@ -361,10 +362,18 @@ int pmmh_sv_stage_bytes(int n_obs, int n_particles, size_t* bytes) {
     return PMMH_OK;
 }
 
+namespace {
+// the streaming kernels take host-resident u as well (and are the preferred kernels from N = 2^20)
+bool streamed_prefers_split(int n_obs, int n, int lag, int ctas) {
+    return (g_sv_algorithm == 0 || g_sv_algorithm == 5) && ctas == 0 && n >= g_split_min_particles &&
+           pmmh::sv_split_single_eligible(n_obs, n, lag);
+}
+}  // namespace
+
 int pmmh_sv_streamed_eligible(int n_obs, int n_particles, int lag, int ctas_per_problem) {
     SvPlan p;
     if (sv_make_plan(n_obs, n_particles, lag, 1, 0, pmmh::kSvFlps, 0, ctas_per_problem, &p, true) != PMMH_OK) return 0;
-    return p.use_fast ? 1 : 0;
+    return (p.use_fast || streamed_prefers_split(n_obs, n_particles, lag, ctas_per_problem)) ? 1 : 0;
 }
 
 int pmmh_flps_sv_corr_streamed(const double* h_rvs, const double* d_obs, const double* d_params,
@@ -376,6 +385,56 @@ int pmmh_flps_sv_corr_streamed(const double* h_rvs, const double* d_obs, const d
     if (!h_rvs || !d_obs || !d_params || !d_rvr || !d_stage || !d_filt || !d_smo || !d_log_like || !d_gradient ||
         !d_traj || !d_hess1 || !d_hess2 || !d_diag || !d_workspace)
         return fail(PMMH_ERR_INVALID, "pmmh_flps_sv_corr_streamed: null pointer argument");
+    // Host-resident u runs on the exchange kernel where it takes the size (measured at N = 2^20:
+    // 206 ms per call against 242 ms on the streaming kernels, whose strided reads of the
+    // particle-major chunks cost more than they save) and on the streaming kernels beyond it.
+    bool exchange_ok = false;
+    {
+        SvPlan p0;
+        if (sv_make_plan(n_obs, n_particles, lag, 1, 0, pmmh::kSvFlps, 0, ctas_per_problem, &p0, true) == PMMH_OK)
+            exchange_ok = p0.use_fast != 0;
+    }
+    if (!exchange_ok && streamed_prefers_split(n_obs, n_particles, lag, ctas_per_problem)) {
+        // streaming kernels with path storage: the copy engine fills particle-major chunks of 64
+        // time steps; the (host-driven) step loop waits for a chunk's event when it enters it
+        if (workspace_bytes < pmmh::sv_split_path_ws_bytes(n_obs, n_particles, lag))
+            return fail(PMMH_ERR_WORKSPACE, "workspace too small");
+        const size_t data_bytes2 = streamed_data_bytes(n_obs, n_particles);
+        if (stage_bytes < data_bytes2 + 256) return fail(PMMH_ERR_WORKSPACE, "staging buffer too small");
+        int dev2 = 0;
+        PMMH_CUDA(cudaGetDevice(&dev2));
+        if (dev2 < 0 || dev2 >= 64) return fail(PMMH_ERR_NO_DEVICE, "device ordinal out of range");
+        StreamedState& s2 = g_streamed[dev2];
+        const int chunks2 = streamed_chunks(n_obs);
+        if (!s2.copy_stream) {
+            PMMH_CUDA(cudaStreamCreateWithFlags(&s2.copy_stream, cudaStreamNonBlocking));
+            PMMH_CUDA(cudaEventCreateWithFlags(&s2.ev_start, cudaEventDisableTiming));
+            PMMH_CUDA(cudaEventCreateWithFlags(&s2.ev_reset, cudaEventDisableTiming));
+        }
+        while ((int)s2.ev_chunk.size() < chunks2) {
+            cudaEvent_t e;
+            PMMH_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            s2.ev_chunk.push_back(e);
+        }
+        cudaStream_t st2 = (cudaStream_t)stream;
+        PMMH_CUDA(cudaEventRecord(s2.ev_start, st2));
+        PMMH_CUDA(cudaStreamWaitEvent(s2.copy_stream, s2.ev_start, 0));
+        for (int c = 0; c < chunks2; ++c) {
+            const int t0 = c * kUChunk;
+            const int wsteps = (n_obs - t0 < kUChunk) ? (n_obs - t0) : kUChunk;
+            const double* src = h_rvs + (size_t)n_obs + (size_t)t0;   // rvp[i + j * n_obs], cython.py:89-91
+            char* dst = (char*)d_stage + (size_t)c * (size_t)n_particles * kUChunk * sizeof(double);
+            PMMH_CUDA(cudaMemcpy2DAsync(dst, (size_t)kUChunk * sizeof(double), src, (size_t)n_obs * sizeof(double),
+                                        (size_t)wsteps * sizeof(double), (size_t)n_particles,
+                                        cudaMemcpyHostToDevice, s2.copy_stream));
+            PMMH_CUDA(cudaEventRecord(s2.ev_chunk[c], s2.copy_stream));
+        }
+        PMMH_CUDA(cudaMemsetAsync(d_hess1, 0, 16 * sizeof(double), st2));
+        PMMH_CUDA(cudaMemsetAsync(d_hess2, 0, 16 * sizeof(double), st2));
+        return pmmh::sv_split_path_run(d_obs, d_params, d_rvr, (const double*)d_stage, n_obs, n_particles, lag,
+                                       d_filt, d_smo, d_log_like, d_gradient, d_traj, d_diag, d_workspace,
+                                       workspace_bytes, st2, kUChunk, s2.ev_chunk.data());
+    }
     SvPlan p;
     int rc = sv_make_plan(n_obs, n_particles, lag, 1, 0, pmmh::kSvFlps, 0, ctas_per_problem, &p, true);
     if (rc != PMMH_OK) return rc;

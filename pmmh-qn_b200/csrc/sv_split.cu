@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(256, 4) split_children_kernel(
     const double* __restrict__ tlast, double* __restrict__ xc, int* __restrict__ pa, unsigned short* __restrict__ cb,
     int* __restrict__ hist_out, double* __restrict__ shift_out, double* __restrict__ xmin_out,
     const int* __restrict__ perm, int* __restrict__ par_out, int fuse_plan, int* __restrict__ nfc,
-    int* __restrict__ fstart, int* __restrict__ cstart) {
+    int* __restrict__ fstart, int* __restrict__ cstart, int u_pm_chunk) {
     extern __shared__ unsigned char smem_raw[];
     double* s_cum = (double*)smem_raw;                       // [kStage]
     int* s_hist = (int*)(smem_raw + (size_t)kStage * 8);     // [kBins]
@@ -487,8 +487,11 @@ __global__ void __launch_bounds__(256, 4) split_children_kernel(
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
                 const long long k = tile * ctile + tid + 256 * m;
+                // time-major u[t][j], or (host-streamed) particle-major chunks u[j][t % chunk] whose
+                // 32-byte sectors serve four consecutive time steps out of L2
                 uvp[m] = (u && tid + 256 * m < ctile && k < nc)
-                             ? ld_stream_f64(u + (size_t)t * (size_t)N + (size_t)(jlo + k))
+                             ? (u_pm_chunk ? __ldg(u + (size_t)(jlo + k) * u_pm_chunk + (t % u_pm_chunk))
+                                           : ld_stream_f64(u + (size_t)t * (size_t)N + (size_t)(jlo + k)))
                              : 0.0;
             }
             if (staged)
@@ -1173,7 +1176,7 @@ int pmmh_svsplit_children(void*, size_t, long long, long long, int, int, const d
                           const double*, int*, double*, double*, void*);
 static int children_impl(void*, size_t, long long, long long, int, int, const double*, const double*,
                          const double*, const double*, unsigned long long, unsigned long long, const double*,
-                         const double*, int*, double*, double*, void*, double*, const int*, int*, int);
+                         const double*, int*, double*, double*, void*, double*, const int*, int*, int, int);
 static int weights_impl(void*, size_t, long long, long long, int, int, int, int, const double*, const double*,
                         const double*, const int*, const double*, double*, double*, double*, void*, int);
 int pmmh_svsplit_plan(void*, size_t, long long, long long, int, const int*, int*, void*);
@@ -1322,7 +1325,8 @@ size_t sv_split_path_ws_bytes(int nobs, int n, int lag) { return make_path_layou
 
 int sv_split_path_run(const double* d_obs, const double* d_params, const double* d_rvr, const double* d_u,
                       int nobs, int n, int lag, double* d_filt, double* d_smo, double* d_ll, double* d_grad,
-                      double* d_traj, long long* d_diag, void* d_ws, size_t ws_bytes, cudaStream_t st) {
+                      double* d_traj, long long* d_diag, void* d_ws, size_t ws_bytes, cudaStream_t st,
+                      int u_pm_chunk, const cudaEvent_t* chunk_ready) {
     if (!sv_split_single_eligible(nobs, n, lag)) return set_error(PMMH_ERR_INVALID, "split kernels: sizes not eligible");
     const PathLayout P = make_path_layout(nobs, n, lag);
     if (ws_bytes < P.total) return set_error(PMMH_ERR_WORKSPACE, "split kernels: workspace too small");
@@ -1388,8 +1392,15 @@ int sv_split_path_run(const double* d_obs, const double* d_params, const double*
         double* Xt = X + (size_t)(t % R) * n;
         int* J1t = J + (size_t)(t % R) * n;
         PMMH_MARK(0);
-        if ((rc = children_impl(sws, sb, n, n, t, n, d_obs, d_params, d_rvr, d_u, 0, 0, gather, xs, hist, shift,
-                                xmin, st, Xt, perm, J1t, 1)))
+        // host-streamed u: d_u holds particle-major chunks of u_pm_chunk time steps that the copy
+        // engine is still filling; wait for the chunk of this step when it is entered
+        const double* ut = d_u;
+        if (u_pm_chunk) {
+            if (t == 1 || t % u_pm_chunk == 0) SPLIT_CUDA(cudaStreamWaitEvent(st, chunk_ready[t / u_pm_chunk], 0));
+            ut = d_u + (size_t)(t / u_pm_chunk) * (size_t)n * (size_t)u_pm_chunk;
+        }
+        if ((rc = children_impl(sws, sb, n, n, t, n, d_obs, d_params, d_rvr, ut, 0, 0, gather, xs, hist, shift,
+                                xmin, st, Xt, perm, J1t, 1, u_pm_chunk)))
             return rc;
         PMMH_MARK(1);
         // jump tables + fixed-lag sums (birth order) on the second stream.  They depend only on the
@@ -1563,7 +1574,8 @@ static int children_impl(void* d_ws, size_t ws_bytes, long long cap_particles, l
                          const double* d_rvr, const double* d_u, unsigned long long seed,
                          unsigned long long philox_offset, const double* d_gather, const double* d_xs,
                          int* d_hist_send, double* d_shift, double* d_xmin, void* stream,
-                         double* xc_override, const int* perm, int* par_out, int fuse_plan = 0) {
+                         double* xc_override, const int* perm, int* par_out, int fuse_plan = 0,
+                         int u_pm_chunk = 0) {
     Layout L = Layout();
     if (int rc = check_ws(d_ws, ws_bytes, cap_particles, cap_children, &L)) return rc;
     if (t < 1 || n_local < 0) return set_error(PMMH_ERR_INVALID, "svsplit_children: bad sizes");
@@ -1585,7 +1597,7 @@ static int children_impl(void* d_ws, size_t ws_bytes, long long cap_particles, l
         (const double*)(ws + L.cumblk), (const double*)(ws + L.boff), (const double*)(ws + L.tlast),
         xc_override ? xc_override : (double*)(ws + L.xc),
         (int*)(ws + L.pa), (unsigned short*)(ws + L.cb), d_hist_send, d_shift, d_xmin, perm, par_out,
-        fuse_plan, (int*)(ws + L.nfc), (int*)(ws + L.fstart), (int*)(ws + L.cstart));
+        fuse_plan, (int*)(ws + L.nfc), (int*)(ws + L.fstart), (int*)(ws + L.cstart), u_pm_chunk);
     SPLIT_CUDA(cudaGetLastError());
     return PMMH_OK;
 }

@@ -219,3 +219,36 @@ def test_streaming_kernels_agree_with_the_general_kernel_over_parameter_sets(cud
         assert relerr(b["filt"][0].cpu().numpy(), a["filt"][0].cpu().numpy()) <= 1e-10
         assert relerr(b["smo"][0].cpu().numpy(), a["smo"][0].cpu().numpy()) <= 1e-10
         assert relerr(b["traj"][0].cpu().numpy(), a["traj"][0].cpu().numpy()) <= 1e-12
+
+
+def test_host_streamed_rvs_on_the_streaming_kernels(cuda_dev):
+    """pmmh_flps_sv_corr_streamed beyond the exchange kernel's size (N = 1.5 M): the copy engine fills
+    particle-major chunks of 64 time steps while the step loop of the streaming kernels is already running (it waits for a chunk's
+    event when it enters it).  Bit-identical to the device-resident evaluation; the staging buffer
+    can be reused by back-to-back calls."""
+    import torch
+    from pmmh_qn_b200 import kernels as K
+    n, nobs, lag = 1500000, 130, 10
+    dev = cuda_dev
+    host = torch.empty((nobs, n + 1), dtype=torch.float64, pin_memory=True)
+    g = torch.Generator()
+    g.manual_seed(5)
+    host.copy_(torch.randn((nobs, n + 1), dtype=torch.float64, generator=g))
+    rvs = host.numpy()
+    assert K.sv_streamed_eligible(nobs, n, lag)
+    obs = torch.from_numpy(gi.sv_obs(nobs)).to(dev)
+    params = torch.tensor([[0.2, 0.9, 0.4, -0.5]], dtype=torch.float64, device=dev)
+    rvr_h, rvp = gi.split_particle(rvs, nobs)      # (Phi of the first n_obs flat entries, rvp)
+    rvr = torch.from_numpy(rvr_h).to(dev)
+    ws, st = K.Workspace(), K.Workspace()
+    a = K.flps_sv_corr_streamed(rvs, obs, params, rvr, nobs, n, lag=lag, workspace=ws, stage=st)
+    a2 = K.flps_sv_corr_streamed(rvs, obs, params, rvr, nobs, n, lag=lag, workspace=ws, stage=st)
+    torch.cuda.synchronize()
+    assert int(a["diag"][0, 6]) == 4 and int(a["diag"][0, 2]) == 0
+    u = torch.from_numpy(to_time_major(rvp, n, nobs)).to(dev)
+    b = K.flps_sv_corr(obs, params, rvr, u, lag=lag, compute_hessian=False)
+    torch.cuda.synchronize()
+    assert int(b["diag"][0, 6]) == 4
+    for k in ("log_like", "filt", "smo", "gradient", "traj"):
+        assert torch.equal(a[k], b[k]), k
+        assert torch.equal(a2[k], b[k]), k
