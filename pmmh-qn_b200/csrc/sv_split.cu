@@ -213,8 +213,14 @@ __global__ void __launch_bounds__(kTileThreads) split_weights_kernel(
         for (int w = 0; w < kTileThreads / 32; ++w) tot = tot + s_wtot[w];
         btot[blockIdx.x] = tot;
     }
-    block_sum<7>(acc, red);
-    if (tid < 7) bpart[(size_t)blockIdx.x * 8 + tid] = acc[tid];
+    if (GRAD) {
+        block_sum<7>(acc, red);
+        if (tid < 7) bpart[(size_t)blockIdx.x * 8 + tid] = acc[tid];
+    } else {   // only sum sh x is non-zero
+        double a1[1] = {acc[0]};
+        block_sum<1>(a1, red);
+        if (tid == 0) bpart[(size_t)blockIdx.x * 8] = a1[0];
+    }
 }
 
 // one block: sequential-in-chunks exclusive scan of the tile totals, fixed-order sums of the
@@ -223,7 +229,7 @@ __global__ void __launch_bounds__(1024) split_weights_finalize_kernel(
     SplitState* __restrict__ st, const double* __restrict__ xs, int n, int ntiles,
     const double* __restrict__ btot, const double* __restrict__ bpart, const double* __restrict__ gpart,
     double* __restrict__ sums_prev, double* __restrict__ boff, double* __restrict__ sums_t,
-    double* __restrict__ gather_send) {
+    double* __restrict__ gather_send, int nval) {
     __shared__ double red[7 * 32];
     __shared__ double s_lane[33];
     __shared__ double s_part[1024], s_off[1024];
@@ -266,11 +272,20 @@ __global__ void __launch_bounds__(1024) split_weights_finalize_kernel(
         }
         if (tid == 0) boff[ntiles] = s_lane[32];
     }
+    // (the two ends of the sorted generation, needed at the very end: loads issued early)
+    const double x_first = (tid == 0 && n > 0) ? xs[0] : 0.0, x_last = (tid == 0 && n > 0) ? xs[n - 1] : 0.0;
     double acc[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    for (int q = tid; q < ntiles; q += blockDim.x)
+    if (nval == 1) {   // no gather variant: only sum sh x is live
+        double a1[1] = {0.0};
+        for (int q = tid; q < ntiles; q += blockDim.x) a1[0] += bpart[(size_t)q * 8];
+        block_sum<1>(a1, red);
+        acc[0] = a1[0];
+    } else {
+        for (int q = tid; q < ntiles; q += blockDim.x)
 #pragma unroll
-        for (int k = 0; k < 7; ++k) acc[k] += bpart[(size_t)q * 8 + k];
-    block_sum<7>(acc, red);
+            for (int k = 0; k < 7; ++k) acc[k] += bpart[(size_t)q * 8 + k];
+        block_sum<7>(acc, red);
+    }
     // path storage: sum sh curr, sum sh g_0..3 of the PREVIOUS generation come from the lineage
     // kernel, which runs one step behind on the second stream (these sums only feed outputs)
     double late[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
@@ -289,8 +304,8 @@ __global__ void __launch_bounds__(1024) split_weights_finalize_kernel(
         for (int k = 0; k < 7; ++k) sums_t[1 + k] = acc[k];
         gather_send[0] = tot;
         gather_send[1] = (double)n;
-        gather_send[2] = n > 0 ? xs[0] : INFINITY;
-        gather_send[3] = n > 0 ? xs[n - 1] : -INFINITY;
+        gather_send[2] = n > 0 ? x_first : INFINITY;
+        gather_send[3] = n > 0 ? x_last : -INFINITY;
     }
 }
 
@@ -1554,7 +1569,8 @@ static int weights_impl(void* d_ws, size_t ws_bytes, long long cap_particles, lo
     split_weights_finalize_kernel<<<1, 1024, 0, st>>>(
         state, d_xs, n_local, ntiles, btot, bpart,
         late ? (const double*)(ws + L.gpart + (size_t)((t - 1) & 1) * gstride) : nullptr,
-        late ? d_sums + (size_t)(t - 1) * 8 : nullptr, boff, d_sums + (size_t)t * 8, d_gather_send);
+        late ? d_sums + (size_t)(t - 1) * 8 : nullptr, boff, d_sums + (size_t)t * 8, d_gather_send,
+        grad ? 7 : 1);
     (void)grad_t;
     SPLIT_CUDA(cudaGetLastError());
     return PMMH_OK;
