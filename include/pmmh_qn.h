@@ -141,6 +141,18 @@ int pmmh_flps_sv_corr_streamed(const double* h_rvs, const double* d_obs, const d
                                long long* d_diag, void* d_workspace, size_t workspace_bytes,
                                int ctas_per_problem, void* stream);
 
+/* The same evaluation (log-likelihood + gradient, one problem, any N) with the auxiliary variables
+ * defined by a Philox4x32-10 stream instead of an array: u[t][j] = standard normal number t*N + j of
+ * stream (seed, philox_offset), exactly what pmmh_crank_nicolson draws with d_xi == NULL.  At
+ * N = 2^26, T = 1000 the array of flps_sv_corr's rvp argument would be 537 GB.  d_rvr as above.
+ * Runs on the streaming kernels with path storage. */
+int pmmh_flps_sv_corr_philox_workspace_bytes(int n_obs, int n_particles, int lag, size_t* bytes);
+int pmmh_flps_sv_corr_philox(const double* d_obs, const double* d_params, const double* d_rvr,
+                             unsigned long long seed, unsigned long long philox_offset, int n_obs,
+                             int n_particles, int lag, double* d_filt, double* d_smo, double* d_log_like,
+                             double* d_gradient, double* d_traj, long long* d_diag, void* d_workspace,
+                             size_t workspace_bytes, void* stream);
+
 /* Bootstrap particle filter (filter only).  read_mode: PMMH_BPF_PARITY / PMMH_BPF_INTENDED. */
 int pmmh_bpf_sv_corr(const double* d_obs, long long obs_stride, const double* d_params,
                      const double* d_rvr, const double* d_u, int n_obs, int n_particles, int batch,

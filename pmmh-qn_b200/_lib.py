@@ -37,6 +37,9 @@ SIGNATURES = {
     "pmmh_flps_sv_corr_streamed": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_size,
                                            c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_size,
                                            c_int, c_vp]),
+    "pmmh_flps_sv_corr_philox_workspace_bytes": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_size)]),
+    "pmmh_flps_sv_corr_philox": (c_int, [c_vp, c_vp, c_vp, c_ull, c_ull, c_int, c_int, c_int, c_vp, c_vp, c_vp,
+                                         c_vp, c_vp, c_vp, c_vp, c_size, c_vp]),
     "pmmh_bpf_sv_corr": (c_int, [c_vp, c_ll, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int,
                                  c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_size, c_int, c_vp]),
     "pmmh_split_rvs": (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp]),

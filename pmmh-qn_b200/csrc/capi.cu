@@ -338,6 +338,35 @@ int pmmh_flps_sv_corr(const double* d_obs, long long obs_stride, const double* d
                   stream);
 }
 
+// ---- auxiliary variables defined by a Philox stream (never stored) --------------------------
+int pmmh_flps_sv_corr_philox(const double* d_obs, const double* d_params, const double* d_rvr,
+                             unsigned long long seed, unsigned long long philox_offset, int n_obs,
+                             int n_particles, int lag, double* d_filt, double* d_smo, double* d_log_like,
+                             double* d_gradient, double* d_traj, long long* d_diag, void* d_workspace,
+                             size_t workspace_bytes, void* stream) {
+    if (!d_obs || !d_params || !d_rvr || !d_filt || !d_smo || !d_log_like || !d_gradient || !d_traj || !d_diag ||
+        !d_workspace)
+        return fail(PMMH_ERR_INVALID, "pmmh_flps_sv_corr_philox: null pointer argument");
+    DeviceInfo di;
+    int rc = get_device_info(&di);
+    if (rc != PMMH_OK) return rc;
+    if (di.major < 10) return fail(PMMH_ERR_NO_DEVICE, "an sm_100 (B200) device is required");
+    if (!pmmh::sv_split_single_eligible(n_obs, n_particles, lag))
+        return fail(PMMH_ERR_INVALID, "pmmh_flps_sv_corr_philox: needs lag in [2, 63] and n_obs >= 2 * lag");
+    if (workspace_bytes < pmmh::sv_split_path_ws_bytes(n_obs, n_particles, lag))
+        return fail(PMMH_ERR_WORKSPACE, "workspace too small");
+    return pmmh::sv_split_path_run(d_obs, d_params, d_rvr, nullptr, n_obs, n_particles, lag, d_filt, d_smo,
+                                   d_log_like, d_gradient, d_traj, d_diag, d_workspace, workspace_bytes,
+                                   (cudaStream_t)stream, 0, nullptr, seed, philox_offset);
+}
+
+int pmmh_flps_sv_corr_philox_workspace_bytes(int n_obs, int n_particles, int lag, size_t* bytes) {
+    if (!bytes || !pmmh::sv_split_single_eligible(n_obs, n_particles, lag))
+        return fail(PMMH_ERR_INVALID, "pmmh_flps_sv_corr_philox_workspace_bytes: bad arguments");
+    *bytes = pmmh::sv_split_path_ws_bytes(n_obs, n_particles, lag);
+    return PMMH_OK;
+}
+
 // ---- host-resident auxiliary variables, copied while the kernel runs ----------------------
 namespace {
 constexpr int kUChunk = 64;   // time steps per copy chunk (512-byte rows for the copy engine)

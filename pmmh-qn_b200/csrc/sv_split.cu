@@ -1341,7 +1341,8 @@ size_t sv_split_path_ws_bytes(int nobs, int n, int lag) { return make_path_layou
 int sv_split_path_run(const double* d_obs, const double* d_params, const double* d_rvr, const double* d_u,
                       int nobs, int n, int lag, double* d_filt, double* d_smo, double* d_ll, double* d_grad,
                       double* d_traj, long long* d_diag, void* d_ws, size_t ws_bytes, cudaStream_t st,
-                      int u_pm_chunk, const cudaEvent_t* chunk_ready) {
+                      int u_pm_chunk, const cudaEvent_t* chunk_ready, unsigned long long seed,
+                      unsigned long long philox_offset) {
     if (!sv_split_single_eligible(nobs, n, lag)) return set_error(PMMH_ERR_INVALID, "split kernels: sizes not eligible");
     const PathLayout P = make_path_layout(nobs, n, lag);
     if (ws_bytes < P.total) return set_error(PMMH_ERR_WORKSPACE, "split kernels: workspace too small");
@@ -1414,7 +1415,7 @@ int sv_split_path_run(const double* d_obs, const double* d_params, const double*
             if (t == 1 || t % u_pm_chunk == 0) SPLIT_CUDA(cudaStreamWaitEvent(st, chunk_ready[t / u_pm_chunk], 0));
             ut = d_u + (size_t)(t / u_pm_chunk) * (size_t)n * (size_t)u_pm_chunk;
         }
-        if ((rc = children_impl(sws, sb, n, n, t, n, d_obs, d_params, d_rvr, ut, 0, 0, gather, xs, hist, shift,
+        if ((rc = children_impl(sws, sb, n, n, t, n, d_obs, d_params, d_rvr, ut, seed, philox_offset, gather, xs, hist, shift,
                                 xmin, st, Xt, perm, J1t, 1, u_pm_chunk)))
             return rc;
         PMMH_MARK(1);

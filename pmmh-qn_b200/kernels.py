@@ -122,6 +122,34 @@ def flps_sv_corr(obs, params, rvr, u, lag=10, compute_hessian=False, store_histo
     return out
 
 
+def flps_sv_corr_philox(obs, params, rvr, seed, philox_offset, n_particles, lag=10, workspace=None):
+    """Log-likelihood + gradient of one problem whose auxiliary variables are a Philox stream
+    (pmmh_flps_sv_corr_philox): any N on one device without ever storing u."""
+    lib = _lib.load()
+    _need_cuda(obs, params, rvr)
+    dev = obs.device
+    n_obs = obs.shape[0]
+    out = {
+        "filt": torch.empty((1, n_obs), dtype=_F64, device=dev),
+        "smo": torch.empty((1, n_obs), dtype=_F64, device=dev),
+        "log_like": torch.empty((1,), dtype=_F64, device=dev),
+        "gradient": torch.empty((1, 4, n_obs), dtype=_F64, device=dev),
+        "traj": torch.empty((1, n_obs), dtype=_F64, device=dev),
+        "diag": torch.zeros((1, _lib.DIAG_COUNT), dtype=torch.int64, device=dev),
+    }
+    nb = ctypes.c_size_t()
+    _lib.check(lib.pmmh_flps_sv_corr_philox_workspace_bytes(n_obs, int(n_particles), int(lag), ctypes.byref(nb)),
+               "pmmh_flps_sv_corr_philox_workspace_bytes")
+    ws = (workspace or Workspace()).get(nb.value, dev)
+    _lib.check(lib.pmmh_flps_sv_corr_philox(
+        _ptr(obs), _ptr(params.reshape(-1)), _ptr(rvr.reshape(-1)), int(seed), int(philox_offset), n_obs,
+        int(n_particles), int(lag), _ptr(out["filt"]), _ptr(out["smo"]), _ptr(out["log_like"]),
+        _ptr(out["gradient"]), _ptr(out["traj"]), _ptr(out["diag"]), _ptr(ws), ws.numel(), _stream()),
+        "pmmh_flps_sv_corr_philox")
+    out["_workspace"] = ws
+    return out
+
+
 def sv_streamed_eligible(n_obs, n_particles, lag=10, ctas_per_problem=0):
     """True if pmmh_flps_sv_corr_streamed takes these sizes (the exchange kernel is eligible)."""
     return bool(_lib.load().pmmh_sv_streamed_eligible(int(n_obs), int(n_particles), int(lag),

@@ -22,7 +22,10 @@ def test_header_declares_the_expected_entry_points():
                  "pmmh_crank_nicolson", "pmmh_subsample_indices", "pmmh_logistic_loglike",
                  "pmmh_split_rvs", "pmmh_norm_cdf", "pmmh_sv_workspace_bytes",
                  "pmmh_flps_sv_corr_host", "pmmh_bpf_sv_corr_host",
-                 "pmmh_importance_discrete_host", "pmmh_stratified_host"):
+                 "pmmh_importance_discrete_host", "pmmh_stratified_host",
+                 "pmmh_svsplit_init", "pmmh_svsplit_weights", "pmmh_svsplit_children", "pmmh_svsplit_plan",
+                 "pmmh_svsplit_pack", "pmmh_svsplit_sort", "pmmh_svsplit_tail", "pmmh_svsplit_finish",
+                 "pmmh_flps_sv_corr_philox", "pmmh_flps_sv_corr_streamed"):
         assert must in syms
 
 

@@ -252,3 +252,31 @@ def test_host_streamed_rvs_on_the_streaming_kernels(cuda_dev):
     for k in ("log_like", "filt", "smo", "gradient", "traj"):
         assert torch.equal(a[k], b[k]), k
         assert torch.equal(a2[k], b[k]), k
+
+
+def test_philox_entry_point_on_one_device(cuda_dev):
+    """pmmh_flps_sv_corr_philox (path storage, u regenerated from the stream) == the same stream
+    materialised and passed to pmmh_flps_sv_corr, and == the split filter's Philox mode."""
+    import torch
+    from pmmh_qn_b200 import kernels as K
+    from pmmh_qn_b200.state.particle_methods import split as SP
+    n, nobs, lag = 40000, 70, 10
+    obs = torch.from_numpy(gi.sv_obs(nobs)).to(cuda_dev)
+    params = torch.tensor([gi.SV_PARAM_SETS[0]], dtype=torch.float64, device=cuda_dev)
+    ph = SP.PhiloxRVS(seed=77, offset=5)
+    rvr = K.norm_cdf(ph.resampling_normals(nobs, n, cuda_dev))
+    a = K.flps_sv_corr_philox(obs, params, rvr, ph.seed, ph.offset, n, lag=lag)
+    u = ph.materialise(nobs, n, cuda_dev)
+    K.set_sv_algorithm(5)
+    try:
+        b = K.flps_sv_corr(obs, params, rvr, u, lag=lag)
+        torch.cuda.synchronize()
+    finally:
+        K.set_sv_algorithm(0)
+    assert int(a["diag"][0, 6]) == 4 and int(a["diag"][0, 2]) == 0
+    for k in ("log_like", "filt", "smo", "gradient", "traj"):
+        assert torch.equal(a[k], b[k]), k
+    c = SP.run_split_smoother(SP.LocalComm(2), gi.sv_obs(nobs), np.array(gi.SV_PARAM_SETS[0]), n, lag, rvr,
+                              philox=(ph.seed, ph.offset), device=cuda_dev)
+    la, lc = float(a["log_like"][0]), float(c["log_like"].item())
+    assert abs(la - lc) <= 1e-10 * abs(la)
