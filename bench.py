@@ -217,15 +217,7 @@ def run_split_pf(args, rank, world, dev, dist):
                 dist.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            if dist is None:
-                # one rank: the same Philox-defined problem on the streaming kernels with path storage
-                o1 = K.flps_sv_corr_philox(torch.from_numpy(obs).to(dev),
-                                           torch.tensor([PARAMS], dtype=torch.float64, device=dev), rvr, 5, 0, n,
-                                           lag=LAG)
-                out = {"log_like": o1["log_like"], "diag": o1["diag"][0].tolist(),
-                       "counts": np.array([[n]], dtype=np.int64)}
-            else:
-                out = SP.run_split_smoother(comm, obs, np.array(PARAMS), n, LAG, rvr, philox=(5, 0), device=dev)
+            out = SP.run_split_smoother(comm, obs, np.array(PARAMS), n, LAG, rvr, philox=(5, 0), device=dev)
             e1.record()
             torch.cuda.synchronize()
             ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -239,7 +231,7 @@ def run_split_pf(args, rank, world, dev, dist):
             "n_gpus": world, "log_like": float(out["log_like"].item()),
             "near_ties_rank0": int(out["diag"][0]), "status": int(out["diag"][2]),
             "max_particles_per_rank": int(out["counts"].max()),
-            "exchange": "none (one rank: pmmh_flps_sv_corr_philox, path storage)" if world == 1 else
+            "exchange": "none (one rank, record variant: faster than path storage from N = 2^23 on)" if world == 1 else
                         "per step: all_gather 32 B + all_gather 16 KB + all_to_all of 80-byte records (NCCL)"}
 
 

@@ -79,9 +79,9 @@ int pmmh_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* Kernel selection for pmmh_flps_sv_corr (process-wide; default 0).
  *   0  automatic, for log-likelihood + gradient (compute_hessian == 0): the "chain" kernel (one
  *      CTA per problem, everything in shared memory) when n_particles <= 4096 and lag <= 10, the
- *      two-exchange "exchange" kernel for teams of CTAs; the streaming kernels (see 5) for one
- *      problem with N >= 2^20 particles (as fast as the exchange kernel there and without its
- *      size limit of ~1.16 M particles); the general kernel for everything else and as the
+ *      two-exchange "exchange" kernel for teams of CTAs; the streaming kernels for one problem
+ *      with N >= 2^20 particles (faster than the exchange kernel there and without its size
+ *      limit of ~1.16 M particles; variant 5 below N = 2^23, variant 4 from there on); the general kernel for everything else and as the
  *      fallback for problems those abandon (degenerate clouds)
  *   1  general kernel only
  *   2  diagnostics: exchange kernel where eligible, without the fallback pass

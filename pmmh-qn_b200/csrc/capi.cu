@@ -75,6 +75,7 @@ struct SvPlan {
     size_t chain_stride, chain_total;
     int skip_fast;           // the exchange kernel is eligible but the streaming kernels are preferred
     int use_split;           // streaming kernels (sv_split.cu), one problem, log-likelihood + gradient
+    int split_path;          // ... with path storage (1) or with records (0)
     size_t split_total;
     size_t fast_sync_bytes, fast_team_stride, fast_total, general_total;
 };
@@ -85,6 +86,7 @@ struct SvPlan {
 // 3 = chain kernel where eligible WITHOUT the fallback pass (diagnostics)
 int g_sv_algorithm = 0;
 int g_split_min_particles = 1 << 20;   // automatic selection of the streaming kernels from this N on
+int g_split_path_max_particles = 1 << 23;   // ... with path storage below this N, with records from it on
 long long* g_sv_prof = nullptr;   // development: per-CTA phase clocks of the exchange kernel
 constexpr int kMaxDynSmem = 227 * 1024;
 
@@ -141,6 +143,7 @@ int sv_make_plan(int nobs, int n, int lag, int batch, int hess, int mode, int ha
         if (p->chain_total > p->total) p->total = p->chain_total;
     }
     p->use_split = 0;
+    p->split_path = 0;
     p->split_total = 0;
     p->use_fast = 0;
     p->NSUB = 0;
@@ -176,8 +179,11 @@ int sv_make_plan(int nobs, int n, int lag, int batch, int hess, int mode, int ha
         pmmh::sv_split_single_eligible(nobs, n, lag)) {
         p->use_split = 1;
         p->skip_fast = 1;
-        // automatic selection takes the path-storage variant (measured faster: 6.9e9 vs 6.4e9 at 2^22)
-        p->split_total = (g_sv_algorithm != 4) ? pmmh::sv_split_path_ws_bytes(nobs, n, lag)
+        // automatic selection: path storage while its jump tables stay (mostly) L2 resident
+        // (7.2e9 vs 6.4e9 particle-steps/s at N = 2^22), the record variant from N = 2^23 on
+        // (6.45e9 vs 6.24e9 at 2^23, 5.8e9 vs 4.9e9 at 2^24: random 4-byte reads from HBM)
+        p->split_path = (g_sv_algorithm == 5 || (g_sv_algorithm == 0 && n < g_split_path_max_particles)) ? 1 : 0;
+        p->split_total = p->split_path ? pmmh::sv_split_path_ws_bytes(nobs, n, lag)
                                                : pmmh::sv_split_single_ws_bytes(nobs, n, lag);
         // the general kernel (fallback pass) reuses the head of the same workspace
         if (p->split_total > p->total) p->total = p->split_total;
@@ -243,7 +249,7 @@ int sv_run(int mode, const double* d_obs, long long obs_stride, const double* d_
     if (p.use_split) {
         // streaming kernels first; an abandoned evaluation (diag status 1) is re-run by the general
         // kernel in the same stream
-        rc = (g_sv_algorithm != 4)
+        rc = p.split_path
                  ? pmmh::sv_split_path_run(d_obs, d_params, d_rvr, d_u, nobs, n, lag, d_filt, d_smo, d_ll,
                                            d_grad, d_traj, d_diag, d_ws, ws_bytes, st)
                  : pmmh::sv_split_single_run(d_obs, d_params, d_rvr, d_u, nobs, n, lag, d_filt, d_smo, d_ll,
