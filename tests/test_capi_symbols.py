@@ -56,6 +56,12 @@ def test_no_cpu_fallback():
     from pmmh_qn_b200 import ParticleMethodsCUDA
     with pytest.raises(RuntimeError):
         ParticleMethodsCUDA(ToySVModel(gi.sv_obs(20), gi.SV_PARAM_SETS[0]))
+    from pmmh_qn_b200.state.particle_methods.split import SplitParticleMethodsCUDA
+    with pytest.raises(RuntimeError):
+        SplitParticleMethodsCUDA(ToySVModel(gi.sv_obs(40), gi.SV_PARAM_SETS[0]), 1000, local_world=2)
+    with pytest.raises(_lib.PmmhError):
+        K.flps_sv_corr_philox(torch.zeros(40, dtype=torch.float64), torch.zeros(4, dtype=torch.float64),
+                              torch.zeros(40, dtype=torch.float64), 1, 0, 1000)
     # the C ABI itself reports the missing device instead of computing anything
     nbytes = ctypes.c_size_t()
     rc = _lib.load().pmmh_sv_workspace_bytes(361, 75, 10, 1, 0, 0, 0, 0, ctypes.byref(nbytes))
