@@ -11,6 +11,7 @@
 #include "../../include/pmmh_qn.h"
 #include "aux_kernels.cuh"
 #include "sv_filter.cuh"
+#include "sv_grid.cuh"
 #include "sv_split.cuh"
 
 namespace {
@@ -78,6 +79,8 @@ struct SvPlan {
     int split_path;          // ... with path storage (1) or with records (0)
     size_t split_total;
     size_t fast_sync_bytes, fast_team_stride, fast_total, general_total;
+    int use_grid, grid_G;    // grid kernel (sv_grid.cu): one problem, log-likelihood + gradient, one tile per CTA
+    size_t grid_total;
 };
 
 // 0 = automatic (chain kernel for problems that fit one CTA, exchange kernel for teams of CTAs,
@@ -87,6 +90,7 @@ struct SvPlan {
 int g_sv_algorithm = 0;
 int g_split_min_particles = 1 << 20;   // automatic selection of the streaming kernels from this N on
 int g_split_path_max_particles = 1 << 23;   // ... with path storage below this N, with records from it on
+int g_grid_min_particles = 1 << 16;         // automatic selection of the grid kernel from this N on (while a tile fits one CTA)
 long long* g_sv_prof = nullptr;   // development: per-CTA phase clocks of the exchange kernel
 constexpr int kMaxDynSmem = 227 * 1024;
 
@@ -151,7 +155,7 @@ int sv_make_plan(int nobs, int n, int lag, int batch, int hess, int mode, int ha
     p->CP = 0;
     // one CTA per problem (batches of small problems) has no exchange to save: the general kernel
     // is the faster one there (measured: 8.8e9 vs 7.0e9 particle-steps/s at 1024 x N=4096)
-    const bool want_fast = !p->use_chain && g_sv_algorithm != 4 && g_sv_algorithm != 5 && ((g_sv_algorithm == 2) || (g_sv_algorithm == 0 && G > 1));
+    const bool want_fast = !p->use_chain && g_sv_algorithm != 4 && g_sv_algorithm != 5 && g_sv_algorithm != 6 && ((g_sv_algorithm == 2) || (g_sv_algorithm == 0 && G > 1));
     if (mode == pmmh::kSvFlps && !hess && want_fast && pmmh::sv_fast_eligible(n, G)) {
         const int S = pmmh::sv_fast_nsub(n, G);
         const int CP = pmmh::sv_fast_pair_cap(n, G);
@@ -167,13 +171,29 @@ int sv_make_plan(int nobs, int n, int lag, int batch, int hess, int mode, int ha
             if (p->fast_total > p->total) p->total = p->fast_total;
         }
     }
+    // one problem, log-likelihood + gradient: the grid kernel (one persistent launch, one tile of the
+    // sorted generation per CTA) while N / #SMs fits the shared memory of one CTA
+    p->use_grid = 0;
+    p->grid_G = 0;
+    p->grid_total = 0;
+    if (mode == pmmh::kSvFlps && !hess && batch == 1 && !p->use_chain &&
+        (g_sv_algorithm == 6 || (g_sv_algorithm == 0 && ctas == 0 && !for_host_streamed && n >= g_grid_min_particles))) {
+        const int GG = pmmh::sv_grid_ctas(n, di.sm, ctas);
+        if (pmmh::sv_grid_eligible(nobs, n, lag, GG)) {
+            p->use_grid = 1;
+            p->grid_G = GG;
+            p->grid_total = pmmh::sv_grid_ws_bytes(nobs, n, lag, GG, have_hist);
+            // (the general kernel's fallback pass uses the head of the same workspace)
+            if (p->grid_total > p->total) p->total = p->grid_total;
+        }
+    }
     // one large problem, log-likelihood + gradient, no history dump: the streaming kernels -- on
     // request (algorithm 4 / 5), or automatically from N = 2^20 on: there they are as fast as the
     // exchange kernel or faster (174.7 vs 181.0 ms at N = 2^20, T = 1000) and they have no size
     // limit (the exchange kernel stops at ~1.16 M particles; the general kernel is ~4x slower).
     // The host-streamed entry point (pmmh_flps_sv_corr_streamed) stays on the exchange kernel.
     p->skip_fast = 0;
-    if (mode == pmmh::kSvFlps && !hess && batch == 1 && !have_hist && ctas == 0 && !p->use_chain &&
+    if (mode == pmmh::kSvFlps && !hess && batch == 1 && !have_hist && ctas == 0 && !p->use_chain && !p->use_grid &&
         (g_sv_algorithm == 4 || g_sv_algorithm == 5 ||
          (g_sv_algorithm == 0 && !for_host_streamed && n >= g_split_min_particles)) &&
         pmmh::sv_split_single_eligible(nobs, n, lag)) {
@@ -246,6 +266,16 @@ int sv_run(int mode, const double* d_obs, long long obs_stride, const double* d_
         if (g_sv_algorithm == 3) return PMMH_OK;   // diagnostics: no fallback pass
         a.only_failed = 1;
     }
+    if (p.use_grid) {
+        // grid kernel first; an abandoned evaluation (diag status 1) is re-run by the general kernel
+        rc = pmmh::sv_grid_run(d_obs, d_params, d_rvr, d_u, nobs, n, lag, p.grid_G, d_filt, d_smo, d_ll, d_grad,
+                               d_traj, d_diag, d_xh, d_ah, d_ws, ws_bytes, g_sv_prof, st);
+        if (rc != PMMH_OK) return rc;
+        PMMH_CUDA(cudaMemsetAsync(d_h1, 0, 16 * sizeof(double), st));
+        PMMH_CUDA(cudaMemsetAsync(d_h2, 0, 16 * sizeof(double), st));
+        if (g_sv_algorithm == 6) return PMMH_OK;   // diagnostics: no fallback pass
+        a.only_failed = 1;
+    }
     if (p.use_split) {
         // streaming kernels first; an abandoned evaluation (diag status 1) is re-run by the general
         // kernel in the same stream
@@ -260,7 +290,7 @@ int sv_run(int mode, const double* d_obs, long long obs_stride, const double* d_
         if (g_sv_algorithm == 4 || g_sv_algorithm == 5) return PMMH_OK;   // no fallback pass
         a.only_failed = 1;
     }
-    if (p.use_fast && !p.skip_fast) {
+    if (p.use_fast && !p.skip_fast && !p.use_grid) {
         // exchange kernel first; problems it abandons (diag status 1) are re-run by the general
         // kernel in the same stream, reusing the workspace
         a.NSUB = p.NSUB;
@@ -310,7 +340,7 @@ int pmmh_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 }
 
 int pmmh_sv_set_algorithm(int algorithm) {
-    if (algorithm < 0 || algorithm > 5) return fail(PMMH_ERR_INVALID, "algorithm must be 0 .. 5");
+    if (algorithm < 0 || algorithm > 6) return fail(PMMH_ERR_INVALID, "algorithm must be 0 .. 6");
     g_sv_algorithm = algorithm;
     return PMMH_OK;
 }
