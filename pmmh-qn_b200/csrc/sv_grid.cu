@@ -40,6 +40,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/pmmh_qn.h"
@@ -54,9 +55,7 @@ int set_cuda_error(cudaError_t err, const char* where);
 
 namespace {
 
-constexpr int kGT = 1024;          // threads per CTA
 constexpr int kCap = 8192;         // entries of one tile (shared-memory capacity)
-constexpr int kKpt = kCap / kGT;   // entries per thread (strided assignment)
 constexpr int kNF = 8192;          // bins of the global value histogram
 constexpr int kNSB = 8192;         // sub-bins of the in-tile counting sort
 constexpr int kMaxSub = 1024;      // a sub-bin larger than this abandons the evaluation
@@ -65,12 +64,12 @@ constexpr double kZ = 6.5;         // histogram range: predicted mean +- 6.5 pre
 constexpr int kDynSmem = 192 * 1024;
 constexpr int kProf = 16;
 
-struct __align__(16) MailEntry {
+struct __align__(16) MailEntry {   // aliases one (x, exp(-x/2)) pair of the sorted generation
     double x;
     int j, a;
 };
-struct __align__(32) PEntry {
-    double n, c, e, pad;   // value, parent value, exp(-parent value / 2)
+struct __align__(16) PEntry {
+    double n, c;           // value, parent value
 };
 struct __align__(32) REntry {
     int a[8];              // birth rows of the ancestors 1 .. 8 steps back
@@ -87,6 +86,7 @@ struct GridCtrl {
 
 struct GridArgs {
     int N, NOBS, LAG, G, Wc, RP, hist;
+    int dbg;   // development (timing only, results wrong): 1 skip R records, 2 skip P store, 4 skip score gather
     const double *obs, *params, *rvr, *U;
     GridCtrl* ctrl;
     int* ghist;        // [2][kNF]
@@ -94,9 +94,8 @@ struct GridArgs {
     double* tinfo;     // [kMaxTiles][4]  tot, n, sum sh m, sum sh m^2
     int* H;            // [N] head markers (-1 = none)
     int* Hcarry;       // [kMaxTiles]
-    double *xs, *es;   // [N] sorted generation, exp(-x/2)
+    double2* XE;       // [N] sorted generation: (x, exp(-x/2)); the mailbox of the next generation aliases it
     int* perm;         // [N] sorted position -> birth row
-    MailEntry* mail;   // [N]
     REntry* R;         // [2][N]
     PEntry* P;         // [RP][N]
     double* psum;      // [NOBS][G][8]
@@ -125,12 +124,46 @@ __device__ __forceinline__ double dec_f64(unsigned long long k) {
     const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
     return __longlong_as_double((long long)b);
 }
-__device__ __forceinline__ void prefetch_l2(const void* p, unsigned bytes) {
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ int odd_chunk(int n) {
-    const int c = (n + kGT - 1) / kGT;
-    return c < 1 ? 1 : (c | 1);
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+__device__ __forceinline__ void prefetch_l2_keep(const void* p) {
+    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(p));
+}
+__device__ __forceinline__ unsigned long long policy_evict_last() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ unsigned long long policy_evict_first() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// 32-byte genealogy records: one 256-bit access, kept in L2 (evict_last)
+__device__ __forceinline__ void ld_rec(const REntry* p, unsigned long long pol, int (&r)[8]) {
+    asm volatile("ld.global.cg.L2::cache_hint.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p), "l"(pol));
+}
+__device__ __forceinline__ void st_rec(REntry* p, unsigned long long pol, int a0, int a1, int a2, int a3, int a4,
+                                       int a5, int a6, int a7) {
+    asm volatile("st.global.cg.L2::cache_hint.v8.s32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}, %9;" ::"l"(p), "r"(a0),
+                 "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5), "r"(a6), "r"(a7), "l"(pol)
+                 : "memory");
+}
+// streaming 16-byte store that should leave L2 first (written once, read 8 steps later or never)
+__device__ __forceinline__ void st_stream_f64x2(void* p, unsigned long long pol, double a, double b) {
+    asm volatile("st.global.cs.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" ::"l"(p), "d"(a), "d"(b), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ double ld_stream_hint_f64(const double* p, unsigned long long pol) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
 }
 __device__ __forceinline__ int warp_incl_max(int v, int lane) {
 #pragma unroll
@@ -140,16 +173,16 @@ __device__ __forceinline__ int warp_incl_max(int v, int lane) {
     }
     return v;
 }
-__device__ __forceinline__ int pick8(const int4 lo, const int4 hi, int idx) {
+__device__ __forceinline__ int pick8(const int (&r)[8], int idx) {
     switch (idx) {
-        case 0: return lo.x;
-        case 1: return lo.y;
-        case 2: return lo.z;
-        case 3: return lo.w;
-        case 4: return hi.x;
-        case 5: return hi.y;
-        case 6: return hi.z;
-        default: return hi.w;
+        case 0: return r[0];
+        case 1: return r[1];
+        case 2: return r[2];
+        case 3: return r[3];
+        case 4: return r[4];
+        case 5: return r[5];
+        case 6: return r[6];
+        default: return r[7];
     }
 }
 
@@ -162,8 +195,7 @@ __device__ __forceinline__ int count_le(double c, double u, int N, double dn, do
     if (!(e >= 0.0)) est = 0;
     else if (e >= dn) est = N;
     else est = (int)e + 1;
-    const double fl = floor(e);
-    const double fr = e - fl;
+    const double fr = e - floor(e);
     frac_out = fmin(fr, 1.0 - fr);
     if (pow2) {
         while (est > 0 && (u + (double)(est - 1)) * inv_n > c) --est;
@@ -188,52 +220,64 @@ __device__ __forceinline__ int sub_bin(double x, double lo, double scale) {
     return (int)t;
 }
 
-// Block-wide exclusive scans over one value per thread (1024 threads).  s_w: shared [32].
-// Two barriers each; s_w may be reused right after the call.
+// Block-wide exclusive scans over one value per thread.  s_w: shared [32].  Every warp scans the
+// warp totals itself (shuffles), so there are two barriers and no serial loop; the order of the
+// additions is fixed (deterministic).  s_w may be reused right after the call.
+template <int GT>
 __device__ __forceinline__ int block_excl_scan_int(int v, int* s_w, int& total, int lane, int warp) {
+    constexpr int NW = GT / 32;
     const int incl = warp_incl_scan(v, lane);
     __syncthreads();
     if (lane == 31) s_w[warp] = incl;
     __syncthreads();
-    int off = 0, tot = 0;
-#pragma unroll
-    for (int w = 0; w < kGT / 32; ++w) {
-        const int s = s_w[w];
-        if (w < warp) off += s;
-        tot += s;
-    }
-    total = tot;
-    return off + incl - v;
+    const int wt = (lane < NW) ? s_w[lane] : 0;
+    const int wincl = warp_incl_scan(wt, lane);
+    total = __shfl_sync(kFullMask, wincl, 31);
+    const int woff = __shfl_sync(kFullMask, wincl - wt, warp);
+    return woff + incl - v;
 }
+template <int GT>
 __device__ __forceinline__ int block_excl_max_int(int v, int init, int* s_w, int lane, int warp) {
+    constexpr int NW = GT / 32;
     const int incl = warp_incl_max(v, lane);
     __syncthreads();
     if (lane == 31) s_w[warp] = incl;
     __syncthreads();
-    int off = init;
-#pragma unroll
-    for (int w = 0; w < kGT / 32; ++w)
-        if (w < warp) off = max(off, s_w[w]);
+    const int wt = (lane < NW) ? s_w[lane] : init;
+    const int wincl = warp_incl_max(wt, lane);
+    int wex = __shfl_up_sync(kFullMask, wincl, 1);
+    if (lane == 0) wex = init;
+    const int woff = max(init, __shfl_sync(kFullMask, wex, warp));
     int ex = __shfl_up_sync(kFullMask, incl, 1);
     if (lane == 0) ex = init;
-    return max(off, ex);
+    return max(woff, ex);
 }
+template <int GT>
 __device__ __forceinline__ double block_excl_scan_f64(double v, double* s_w, int lane, int warp) {
+    constexpr int NW = GT / 32;
     const double incl = warp_incl_scan(v, lane);
     __syncthreads();
     if (lane == 31) s_w[warp] = incl;
     __syncthreads();
-    double off = 0.0;
-    for (int w = 0; w < warp; ++w) off = off + s_w[w];
+    const double wt = (lane < NW) ? s_w[lane] : 0.0;
+    const double wincl = warp_incl_scan(wt, lane);
+    double wex = __shfl_up_sync(kFullMask, wincl, 1);
+    if (lane == 0) wex = 0.0;
+    const double woff = __shfl_sync(kFullMask, wex, warp);
     double ex = __shfl_up_sync(kFullMask, incl, 1);
     if (lane == 0) ex = 0.0;
-    return off + ex;
+    return woff + ex;
 }
 
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
+template <int GT>
+__global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
+    constexpr int KPT = kCap / GT;          // entries per thread (strided assignment)
+    constexpr int KCH = KPT | 1;            // longest chunk of the thread-contiguous passes (odd)
+    constexpr int BPT = kNF / GT;           // histogram bins per thread
+    static_assert(kNF == kNSB, "one scan shape for both histograms");
     extern __shared__ __align__(16) unsigned char smem[];
     // phase B / C view
     double* s_x = (double*)smem;                       // [kCap] sorted values, later exp(-x/2)
@@ -260,6 +304,7 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
     GridCtrl* ctrl = a.ctrl;
     const double dn = (double)N, inv_n = 1.0 / dn;
     const bool pow2 = (N & (N - 1)) == 0;
+    const unsigned long long pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
     unsigned epoch = 0;                 // arrives done so far
     unsigned cnt_near = 0, cnt_soft = 0, cnt_key = 0;
     int my_max_bin = 0;
@@ -302,7 +347,7 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
         s_sc.abort_now = 0;
         for (int i = 0; i < kProf; ++i) s_prof[i] = 0;
     }
-    for (int i = tid; i < kMaxTiles; i += kGT) s_tcnt[i] = 0;
+    for (int i = tid; i < kMaxTiles; i += GT) s_tcnt[i] = 0;
     __syncthreads();
 
     // ------------------------------------------------------------------------------------------
@@ -316,20 +361,17 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
         const double e0 = exp(-0.5 * mu);
         double m0 = s_k.mu + s_k.phi * (mu - s_k.mu);
         m0 += (s_k.sr * e0) * a.obs[0];
-        for (int q = tid; q < n; q += kGT) {
-            __stcg(&a.xs[pstart + q], mu);
-            __stcg(&a.es[pstart + q], e0);
+        for (int q = tid; q < n; q += GT) {
+            __stcg(&a.XE[pstart + q], make_double2(mu, e0));
             __stcg(&a.perm[pstart + q], pstart + q);
             s_sh[q] = 1.0;
-            int4 z = make_int4(0, 0, 0, 0);
-            __stcg((int4*)&a.R[pstart + q].a[0], z);
-            __stcg((int4*)&a.R[pstart + q].a[4], z);
+            st_rec(&a.R[pstart + q], pol_keep, 0, 0, 0, 0, 0, 0, 0, 0);
             if (a.hist) {
                 a.Xhist[pstart + q] = mu;
                 a.Ahist[pstart + q] = pstart + q;
             }
         }
-        const int Lc = odd_chunk(n);
+        const int Lc = ((n + GT - 1) / GT) | 1;
         toff = (double)min(tid * Lc, n);
         if (tid == 0) {
             const double dnk = (double)n;
@@ -364,6 +406,7 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
             s_m2[tid] = t1.y;
         }
         __syncthreads();
+        const double ur = a.rvr[t];
         if (warp == 0) {
             constexpr int kPer = kMaxTiles / 32;
             double loc = 0.0, l1 = 0.0, l2 = 0.0;
@@ -389,6 +432,7 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
             }
             const double S = __shfl_sync(kFullMask, incl, 31);
             const double M1 = warp_sum(l1), M2 = warp_sum(l2);
+            __syncwarp();
             if (lane == 0) {
                 s_off[G] = S;
                 const double invS = 1.0 / S;
@@ -402,28 +446,25 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
                 s_sc.mhat = mhat;
                 s_sc.inv_shat = 1.0 / shat;
                 if (!(S > 0.0) || !isfinite(S) || !isfinite(mhat) || !(shat > 0.0) || !isfinite(shat)) GRID_FLAG(2);
+                // child range end of the tiles in front of this one (running maximum, see below)
+                int carry = 0;
+                double fr;
+                for (int k = max(0, c - 2); k < c; ++k)
+                    carry = max(carry, count_le((s_off[k] + s_tot[k]) * invS, ur, N, dn, inv_n, pow2, fr));
+                s_sc.carry = carry;
             }
         }
         __syncthreads();
-        const double ur = a.rvr[t];
-        if (warp == 0 && lane == 0) {
-            // child range end of the tiles in front of this one (running maximum, see below)
-            int carry = 0;
-            double fr;
-            for (int k = max(0, c - 2); k < c; ++k)
-                carry = max(carry, count_le((s_off[k] + s_tot[k]) * s_sc.invS, ur, N, dn, inv_n, pow2, fr));
-            s_sc.carry = carry;
-        }
         {
             const double invS = s_sc.invS, offk = s_off[c];
-            const int Lc = odd_chunk(n), q0 = tid * Lc;
-            const double tol_near = 64.0 * 2.220446049250313e-16 * dn;
+            const int Lc = ((n + GT - 1) / GT) | 1, q0 = tid * Lc;
             const double tol_soft = 2.220446049250313e-16 * dn * (4.0 + 2.0 * sqrt(dn));
-            int ubv[9];
+            const double tol_near = 64.0 * 2.220446049250313e-16 * dn;
+            int ubv[KCH];
             int rmax = 0;
             double run = 0.0;
 #pragma unroll
-            for (int kk = 0; kk < 9; ++kk) {
+            for (int kk = 0; kk < KCH; ++kk) {
                 const int q = q0 + kk;
                 ubv[kk] = 0;
                 if (kk < Lc && q < n) {
@@ -446,20 +487,27 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
             }
             // parallel scans are monotone only up to an ulp: a running maximum over all parents
             // (and over the tiles in front) keeps the child ranges disjoint
-            __syncthreads();   // s_sc.carry
-            int prev = block_excl_max_int(rmax, s_sc.carry, s_wi, lane, warp);
+            int prev = block_excl_max_int<GT>(rmax, s_sc.carry, s_wi, lane, warp);
+            const float inv_wc = 1.0f / (float)Wc;
 #pragma unroll
-            for (int kk = 0; kk < 9; ++kk) {
+            for (int kk = 0; kk < KCH; ++kk) {
                 const int q = q0 + kk;
                 if (kk < Lc && q < n) {
                     const int ub = max(ubv[kk], prev);
                     if (ub > prev) {
                         const int P = pstart + q;
                         __stcg(&a.H[prev], P);
-                        int m = prev / Wc + 1;              // first child-tile boundary behind prev
-                        while (m < G && m * Wc < ub) {
-                            __stcg(&a.Hcarry[m], P);
+                        if (ub - prev > 1) {
+                            // child-tile boundaries m * Wc strictly inside (prev, ub): the tile's
+                            // first child has no marker of its own
+                            int m = (int)((float)prev * inv_wc);
+                            while (m * Wc > prev) --m;
+                            while ((m + 1) * Wc <= prev) ++m;
                             ++m;
+                            while (m < G && m * Wc < ub) {
+                                __stcg(&a.Hcarry[m], P);
+                                ++m;
+                            }
                         }
                     }
                     prev = ub;
@@ -468,7 +516,7 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
         }
         PROF_MARK(0);
         GRID_ARRIVE();   // ---- barrier 4: head markers complete
-        for (int b = tid; b < kNF; b += kGT) s_fhist[b] = 0;
+        for (int b = tid; b < kNF; b += GT) s_fhist[b] = 0;
         PROF_MARK(1);
         GRID_WAIT();
         PROF_MARK(2);
@@ -477,27 +525,38 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
         // --------------------------------------------------------------------------------------
         // phase A: ancestors of this CTA's children, propagation (:354-358), value histogram
         // --------------------------------------------------------------------------------------
-        for (int i = tid; i < nc; i += kGT) {
-            s_par[i] = __ldcg(&a.H[jb + i]);
-            __stcg(&a.H[jb + i], -1);
-        }
-        if (tid == 0) {
-            s_sc.hc = __ldcg(&a.Hcarry[c]);
-            __stcg(&a.Hcarry[c], -1);
+        {
+            int hv[KPT];
+#pragma unroll
+            for (int kk = 0; kk < KPT; ++kk) {
+                const int i = kk * GT + tid;
+                hv[kk] = -1;
+                if (i < nc) hv[kk] = __ldcg(&a.H[jb + i]);
+            }
+            if (tid == 0) s_sc.hc = __ldcg(&a.Hcarry[c]);
+#pragma unroll
+            for (int kk = 0; kk < KPT; ++kk) {
+                const int i = kk * GT + tid;
+                if (i < nc) {
+                    s_par[i] = hv[kk];
+                    if (hv[kk] >= 0) __stcg(&a.H[jb + i], -1);
+                }
+            }
+            if (tid == 0) __stcg(&a.Hcarry[c], -1);
         }
         __syncthreads();
         {
-            const int Lc2 = odd_chunk(nc), i0 = tid * Lc2;
+            const int Lc2 = ((nc + GT - 1) / GT) | 1, i0 = tid * Lc2;
             int mx = -1;
 #pragma unroll
-            for (int kk = 0; kk < 9; ++kk) {
+            for (int kk = 0; kk < KCH; ++kk) {
                 const int i = i0 + kk;
                 if (kk < Lc2 && i < nc) mx = max(mx, s_par[i]);
             }
-            int run = block_excl_max_int(mx, s_sc.hc, s_wi, lane, warp);
+            int run = block_excl_max_int<GT>(mx, s_sc.hc, s_wi, lane, warp);
             bool orphan = false;
 #pragma unroll
-            for (int kk = 0; kk < 9; ++kk) {
+            for (int kk = 0; kk < KCH; ++kk) {
                 const int i = i0 + kk;
                 if (kk < Lc2 && i < nc) {
                     run = max(run, s_par[i]);
@@ -511,39 +570,52 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
             if (orphan) GRID_FLAG(4);
         }
         __syncthreads();
-        double xn[kKpt];
-        int bp[kKpt];
+        double xn[KPT];
+        int bp[KPT];
         {
             const double y1 = a.obs[t - 1];
             const double mhat = s_sc.mhat, inv_shat = s_sc.inv_shat;
+            const double mu = s_k.mu, phi = s_k.phi, sr = s_k.sr, sd = s_k.sd;
             const double* Ut = a.U + (size_t)t * N;
             PEntry* Pt = a.P + (size_t)(t % RP) * N;
+            const REntry* Rp = a.R + (size_t)((t - 1) & 1) * N;
             double vmin = INFINITY, vmax = -INFINITY;
             bool bad = false;
 #pragma unroll
-            for (int kk = 0; kk < kKpt; ++kk) {
-                const int i = kk * kGT + tid;
-                xn[kk] = 0.0;
-                bp[kk] = 0;
-                if (i < nc) {
-                    const int j = jb + i;
-                    const int p = s_par[i];
-                    const double xp = __ldcg(&a.xs[p]);
-                    const double ep = __ldcg(&a.es[p]);
-                    const int b = __ldcg(&a.perm[p]);
-                    const double uu = ld_stream_f64(Ut + j);
-                    double mean = s_k.mu + s_k.phi * (xp - s_k.mu);     // :355
-                    mean += (s_k.sr * ep) * y1;                         // :356
-                    const double x = mean + s_k.sd * uu;                // :357-358
-                    if (!isfinite(x)) bad = true;
-                    xn[kk] = x;
-                    bp[kk] = b;
-                    atomicAdd(&s_fhist[fine_bin(x, mhat, inv_shat)], 1);
-                    vmin = fmin(vmin, x);
-                    vmax = fmax(vmax, x);
-                    __stcs((double2*)&Pt[j], make_double2(x, xp));
-                    __stcs((double2*)&Pt[j] + 1, make_double2(ep, 0.0));
-                    if (a.hist) a.parentpos[j] = p;
+            for (int k0 = 0; k0 < KPT; k0 += 4) {
+                // all loads of four children are in flight before the first one is used
+                double2 xe[4];
+                double uu[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = (k0 + u) * GT + tid;
+                    xe[u] = make_double2(0.0, 0.0);
+                    uu[u] = 0.0;
+                    bp[k0 + u] = 0;
+                    if (i < nc) {
+                        const int p = s_par[i];
+                        xe[u] = __ldcg(&a.XE[p]);
+                        bp[k0 + u] = __ldcg(&a.perm[p]);
+                        uu[u] = ld_stream_hint_f64(Ut + jb + i, pol_stream);
+                        if (a.hist) a.parentpos[jb + i] = p;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = (k0 + u) * GT + tid;
+                    xn[k0 + u] = 0.0;
+                    if (i < nc) {
+                        double mean = mu + phi * (xe[u].x - mu);     // :355
+                        mean += (sr * xe[u].y) * y1;                  // :356
+                        const double x = mean + sd * uu[u];           // :357-358
+                        if (!isfinite(x)) bad = true;
+                        xn[k0 + u] = x;
+                        if (!(a.dbg & 1)) prefetch_l2_keep(&Rp[bp[k0 + u]]);
+                        atomicAdd(&s_fhist[fine_bin(x, mhat, inv_shat)], 1);
+                        vmin = fmin(vmin, x);
+                        vmax = fmax(vmax, x);
+                        if (!(a.dbg & 2)) st_stream_f64x2(&Pt[jb + i], pol_stream, x, xe[u].x);
+                    }
                 }
             }
             if (bad) GRID_FLAG(2);
@@ -557,12 +629,15 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
         __syncthreads();
         {
             int* gh = a.ghist + par * kNF;
-            for (int b = tid; b < kNF; b += kGT) {
+#pragma unroll
+            for (int kk = 0; kk < BPT; ++kk) {
+                const int b = kk * GT + tid;
                 const int cnt = s_fhist[b];
                 if (cnt) atomicAdd(&gh[b], cnt);
             }
             if (warp == 0) {
-                const double vmin = warp_min(s_red[lane]), vmax = warp_max(s_red[32 + lane]);
+                const double vmin = warp_min(lane < GT / 32 ? s_red[lane] : INFINITY);
+                const double vmax = warp_max(lane < GT / 32 ? s_red[32 + lane] : -INFINITY);
                 if (lane == 0 && nc > 0) {
                     atomicMin(&ctrl->mn[par], enc_f64(vmin));
                     atomicMax(&ctrl->mx[par], enc_f64(vmax));
@@ -571,29 +646,43 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
         }
         PROF_MARK(3);
         GRID_ARRIVE();   // ---- barrier 1: global histogram complete
-        {
+        if (!(a.dbg & 1)) {
             // genealogy records (only feed outputs): child = (parent row, parent's ancestors 1..7)
             const REntry* Rp = a.R + (size_t)((t - 1) & 1) * N;
             REntry* Rc = a.R + (size_t)(t & 1) * N;
+            const PEntry* Pnow = a.P + (size_t)((t - (L - 2) + RP) % RP) * N;
 #pragma unroll
-            for (int kk = 0; kk < kKpt; ++kk) {
-                const int i = kk * kGT + tid;
-                if (i < nc) {
-                    const int j = jb + i;
-                    const int b = bp[kk];
-                    const int4 r0 = __ldcg((const int4*)&Rp[b].a[0]);
-                    const int4 r1 = __ldcg((const int4*)&Rp[b].a[4]);
-                    const int4 n0 = make_int4(b, r0.x, r0.y, r0.z);
-                    const int4 n1 = make_int4(r0.w, r1.x, r1.y, r1.z);
-                    __stcg((int4*)&Rc[j].a[0], n0);
-                    __stcg((int4*)&Rc[j].a[4], n1);
-                    bp[kk] = (L == 2) ? j : pick8(n0, n1, L - 3);   // row of the ancestor L-2 steps back
+            for (int k0 = 0; k0 < KPT; k0 += 2) {
+                int r[2][8];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int i = (k0 + u) * GT + tid;
+#pragma unroll
+                    for (int z = 0; z < 8; ++z) r[u][z] = 0;
+                    if (i < nc) ld_rec(&Rp[bp[k0 + u]], pol_keep, r[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int i = (k0 + u) * GT + tid;
+                    if (i < nc) {
+                        const int j = jb + i;
+                        const int b = bp[k0 + u];
+                        st_rec(&Rc[j], pol_keep, b, r[u][0], r[u][1], r[u][2], r[u][3], r[u][4], r[u][5], r[u][6]);
+                        // row of the ancestor L-2 steps back (new record = (b, r[0..6]))
+                        int anc = j;
+                        if (L == 3) anc = b;
+                        else if (L > 3) anc = pick8(r[u], L - 4);
+                        bp[k0 + u] = anc;
+                        if (t >= L && !(a.dbg & 4)) prefetch_l2(&Pnow[min(max(anc, 0), N - 1)]);
+                    }
                 }
             }
+        }
+        {
             // housekeeping for the next step
             const int zper = (kNF + G - 1) / G;
             int* ghn = a.ghist + (par ^ 1) * kNF;
-            for (int b = c * zper + tid; b < min(kNF, (c + 1) * zper); b += kGT) __stcg(&ghn[b], 0);
+            for (int b = c * zper + tid; b < min(kNF, (c + 1) * zper); b += GT) __stcg(&ghn[b], 0);
             if (tid == 0) {
                 __stcg(&a.tilecnt[(par ^ 1) * kMaxTiles + c], 0);
                 if (c == 0) {
@@ -610,30 +699,36 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
         // scan of the global histogram: tile boundaries on bin edges, tile of every bin
         {
             const int* gh = a.ghist + par * kNF;
-            const int4 v0 = __ldcg((const int4*)(gh + 8 * tid));
-            const int4 v1 = __ldcg((const int4*)(gh + 8 * tid + 4));
-            const int prevcnt = tid > 0 ? __ldcg(gh + 8 * tid - 1) : 0;
-            const int cnt[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            int cnt[BPT];
+#pragma unroll
+            for (int i = 0; i < BPT; i += 4) {
+                const int4 v = __ldcg((const int4*)(gh + BPT * tid + i));
+                cnt[i] = v.x;
+                cnt[i + 1] = v.y;
+                cnt[i + 2] = v.z;
+                cnt[i + 3] = v.w;
+            }
+            const int prevcnt = tid > 0 ? __ldcg(gh + BPT * tid - 1) : 0;
             int loc = 0, mxb = 0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < BPT; ++i) {
                 loc += cnt[i];
                 mxb = max(mxb, cnt[i]);
             }
             my_max_bin = max(my_max_bin, mxb);
             int total;
-            int start = block_excl_scan_int(loc, s_wi, total, lane, warp);
+            int start = block_excl_scan_int<GT>(loc, s_wi, total, lane, warp);
             int tprev = (tid == 0) ? -1 : min(G - 1, (start - prevcnt) / Wc);
             int tl = min(G - 1, start / Wc);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < BPT; ++i) {
                 while (tl < G - 1 && start >= (tl + 1) * Wc) ++tl;
-                s_tileof[8 * tid + i] = (unsigned short)tl;
+                s_tileof[BPT * tid + i] = (unsigned short)tl;
                 for (int k = tprev + 1; k <= tl; ++k) s_tstart[k] = start;
                 tprev = tl;
                 start += cnt[i];
             }
-            if (tid == kGT - 1) {
+            if (tid == GT - 1) {
                 for (int k = tprev + 1; k <= G; ++k) s_tstart[k] = N;
                 if (total != N) GRID_FLAG(5);
             }
@@ -643,12 +738,12 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
             }
         }
         __syncthreads();
-        int kr[kKpt];
+        int kr[KPT];
         {
             const double mhat = s_sc.mhat, inv_shat = s_sc.inv_shat;
 #pragma unroll
-            for (int kk = 0; kk < kKpt; ++kk) {
-                const int i = kk * kGT + tid;
+            for (int kk = 0; kk < KPT; ++kk) {
+                const int i = kk * GT + tid;
                 kr[kk] = 0;
                 if (i < nc) {
                     const int tl = s_tileof[fine_bin(xn[kk], mhat, inv_shat)];
@@ -666,14 +761,17 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
             s_tcnt[tid] = 0;
         }
         __syncthreads();
+        {
+            MailEntry* mail = (MailEntry*)a.XE;
 #pragma unroll
-        for (int kk = 0; kk < kKpt; ++kk) {
-            const int i = kk * kGT + tid;
-            if (i < nc) {
-                const int pos = s_tbase[kr[kk] >> 16] + (kr[kk] & 0xffff);
-                const long long xb = __double_as_longlong(xn[kk]);
-                const int4 ent = make_int4((int)(xb & 0xffffffffll), (int)(xb >> 32), jb + i, bp[kk]);
-                if (pos >= 0 && pos < N) __stcg((int4*)&a.mail[pos], ent);
+            for (int kk = 0; kk < KPT; ++kk) {
+                const int i = kk * GT + tid;
+                if (i < nc) {
+                    const int pos = s_tbase[kr[kk] >> 16] + (kr[kk] & 0xffff);
+                    const long long xb = __double_as_longlong(xn[kk]);
+                    const int4 ent = make_int4((int)(xb & 0xffffffffll), (int)(xb >> 32), jb + i, bp[kk]);
+                    if (pos >= 0 && pos < N) __stcg((int4*)&mail[pos], ent);
+                }
             }
         }
         pstart = s_tstart[c];
@@ -684,7 +782,7 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
         }
         PROF_MARK(6);
         GRID_ARRIVE();   // ---- barrier 2: mailboxes complete
-        for (int b = tid; b < kNSB; b += kGT) s_sub[b] = 0;
+        for (int b = tid; b < kNSB; b += GT) s_sub[b] = 0;
         if (tid == 0) {
             // shift = largest log-weight over [xmin, xmax] (any shift cancels, Q4)
             const double y = a.obs[t];
@@ -704,7 +802,7 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
                 const char* q0 = (const char*)(((uintptr_t)p0 + 15) & ~(uintptr_t)15);
                 const char* q1 = (const char*)((uintptr_t)p1 & ~(uintptr_t)15);
                 for (const char* q = q0; q < q1; q += 16384)
-                    prefetch_l2(q, (unsigned)min((long long)16384, (long long)(q1 - q)));
+                    prefetch_l2_bulk(q, (unsigned)min((long long)16384, (long long)(q1 - q)));
             }
         }
         PROF_MARK(7);
@@ -716,13 +814,13 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
         // phase B: sort this tile (:392-424 / :23-52), weights (:427-442), block scan
         // --------------------------------------------------------------------------------------
         {
-            const MailEntry* mb = a.mail + pstart;
-            double ex[kKpt];
-            int ej[kKpt], ea[kKpt], er[kKpt];
+            const MailEntry* mb = (const MailEntry*)a.XE + pstart;
+            double ex[KPT];
+            int ej[KPT], ea[KPT], er[KPT];
             double lmin = INFINITY, lmax = -INFINITY;
 #pragma unroll
-            for (int kk = 0; kk < kKpt; ++kk) {
-                const int e = kk * kGT + tid;
+            for (int kk = 0; kk < KPT; ++kk) {
+                const int e = kk * GT + tid;
                 ex[kk] = 0.0;
                 ej[kk] = ea[kk] = 0;
                 if (e < n) {
@@ -730,6 +828,12 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
                     ex[kk] = __longlong_as_double(((long long)raw.y << 32) | (long long)(unsigned)raw.x);
                     ej[kk] = raw.z;
                     ea[kk] = raw.w;
+                }
+            }
+#pragma unroll
+            for (int kk = 0; kk < KPT; ++kk) {
+                const int e = kk * GT + tid;
+                if (e < n) {
                     lmin = fmin(lmin, ex[kk]);
                     lmax = fmax(lmax, ex[kk]);
                 }
@@ -742,7 +846,8 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
             }
             __syncthreads();
             if (warp == 0) {
-                const double lo = warp_min(s_red[lane]), hi = warp_max(s_red[32 + lane]);
+                const double lo = warp_min(lane < GT / 32 ? s_red[lane] : INFINITY);
+                const double hi = warp_max(lane < GT / 32 ? s_red[32 + lane] : -INFINITY);
                 if (lane == 0) {
                     s_sc.lo = lo;
                     s_sc.hi = hi;
@@ -752,38 +857,46 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
             const double lo = s_sc.lo;
             const double scale = (s_sc.hi > lo) ? (double)kNSB / (s_sc.hi - lo) : 0.0;
 #pragma unroll
-            for (int kk = 0; kk < kKpt; ++kk) {
-                const int e = kk * kGT + tid;
+            for (int kk = 0; kk < KPT; ++kk) {
+                const int e = kk * GT + tid;
                 er[kk] = 0;
                 if (e < n) er[kk] = atomicAdd(&s_sub[sub_bin(ex[kk], lo, scale)], 1);
             }
             __syncthreads();
             {
-                // exclusive scan of the sub-bin counters in place (8 consecutive bins per thread)
-                int4 v0 = *(int4*)(s_sub + 8 * tid), v1 = *(int4*)(s_sub + 8 * tid + 4);
-                int cnt[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                // exclusive scan of the sub-bin counters in place (BPT consecutive bins per thread)
+                int cnt[BPT];
+#pragma unroll
+                for (int i = 0; i < BPT; i += 4) {
+                    const int4 v = *(const int4*)(s_sub + BPT * tid + i);
+                    cnt[i] = v.x;
+                    cnt[i + 1] = v.y;
+                    cnt[i + 2] = v.z;
+                    cnt[i + 3] = v.w;
+                }
                 int loc = 0, mxb = 0;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < BPT; ++i) {
                     loc += cnt[i];
                     mxb = max(mxb, cnt[i]);
                 }
                 if (mxb > kMaxSub) GRID_FLAG(3);
                 int total;
-                int start = block_excl_scan_int(loc, s_wi, total, lane, warp);
+                int start = block_excl_scan_int<GT>(loc, s_wi, total, lane, warp);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < BPT; ++i) {
                     const int cn = cnt[i];
                     cnt[i] = start;
                     start += cn;
                 }
-                *(int4*)(s_sub + 8 * tid) = make_int4(cnt[0], cnt[1], cnt[2], cnt[3]);
-                *(int4*)(s_sub + 8 * tid + 4) = make_int4(cnt[4], cnt[5], cnt[6], cnt[7]);
+#pragma unroll
+                for (int i = 0; i < BPT; i += 4)
+                    *(int4*)(s_sub + BPT * tid + i) = make_int4(cnt[i], cnt[i + 1], cnt[i + 2], cnt[i + 3]);
             }
             __syncthreads();
 #pragma unroll
-            for (int kk = 0; kk < kKpt; ++kk) {
-                const int e = kk * kGT + tid;
+            for (int kk = 0; kk < KPT; ++kk) {
+                const int e = kk * GT + tid;
                 if (e < n) {
                     const int pos = s_sub[sub_bin(ex[kk], lo, scale)] + er[kk];
                     s_x[pos] = ex[kk];
@@ -793,13 +906,15 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
             }
             __syncthreads();
             // exact order inside a sub-bin: by value, then by birth row (:32-35 never returns 0)
-            int np[kKpt];
+            int np[KPT];
 #pragma unroll
-            for (int kk = 0; kk < kKpt; ++kk) {
-                const int q = kk * kGT + tid;
+            for (int kk = 0; kk < KPT; ++kk) {
+                const int q = kk * GT + tid;
                 np[kk] = q;
+                ex[kk] = 0.0;
                 if (q < n) {
                     const double x = s_x[q];
+                    ex[kk] = x;
                     const int kb = sub_bin(x, lo, scale);
                     const int b0 = s_sub[kb];
                     const int b1 = (kb + 1 < kNSB) ? s_sub[kb + 1] : n;
@@ -819,15 +934,10 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
                 }
             }
             // in-place permutation, one array at a time (keeps the register footprint small)
-#pragma unroll
-            for (int kk = 0; kk < kKpt; ++kk) {
-                const int q = kk * kGT + tid;
-                if (q < n) ex[kk] = s_x[q];
-            }
             __syncthreads();
 #pragma unroll
-            for (int kk = 0; kk < kKpt; ++kk) {
-                const int q = kk * kGT + tid;
+            for (int kk = 0; kk < KPT; ++kk) {
+                const int q = kk * GT + tid;
                 if (q < n) {
                     s_x[np[kk]] = ex[kk];
                     ej[kk] = s_j[q];
@@ -835,8 +945,8 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
             }
             __syncthreads();
 #pragma unroll
-            for (int kk = 0; kk < kKpt; ++kk) {
-                const int q = kk * kGT + tid;
+            for (int kk = 0; kk < KPT; ++kk) {
+                const int q = kk * GT + tid;
                 if (q < n) {
                     s_j[np[kk]] = ej[kk];
                     ea[kk] = s_a[q];
@@ -844,39 +954,37 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
             }
             __syncthreads();
 #pragma unroll
-            for (int kk = 0; kk < kKpt; ++kk) {
-                const int q = kk * kGT + tid;
+            for (int kk = 0; kk < KPT; ++kk) {
+                const int q = kk * GT + tid;
                 if (q < n) s_a[np[kk]] = ea[kk];
             }
             __syncthreads();
         }
         PROF_MARK(9);
-        // the new sorted generation (values, birth rows)
+        // birth rows of the new sorted generation (the values follow with exp(-x/2), below)
 #pragma unroll
-        for (int kk = 0; kk < kKpt; ++kk) {
-            const int q = kk * kGT + tid;
+        for (int kk = 0; kk < KPT; ++kk) {
+            const int q = kk * GT + tid;
             if (q < n) {
-                const double x = s_x[q];
                 const int j = s_j[q];
-                __stcg(&a.xs[pstart + q], x);
                 __stcg(&a.perm[pstart + q], j);
                 if (a.hist) {
-                    a.Xhist[(size_t)t * N + pstart + q] = x;
+                    a.Xhist[(size_t)t * N + pstart + q] = s_x[q];
                     a.Ahist[(size_t)t * N + pstart + q] = __ldcg(&a.parentpos[j]);
                 }
             }
         }
-        __syncthreads();
         {
             // weights (:427-437): lw = -0.9189 - x/2 - y^2 exp(-x) / 2, sh = exp(lw - shift);
             // thread = Lc consecutive sorted particles, sequential running sum
             const double y = a.obs[t], hy2 = 0.5 * y * y, shift = s_sc.shift;
-            const int Lc = odd_chunk(n), q0 = tid * Lc;
+            const double mu = s_k.mu, phi = s_k.phi, sr = s_k.sr;
+            const int Lc = ((n + GT - 1) / GT) | 1, q0 = tid * Lc;
             double run = 0.0;
             double acc[3] = {0.0, 0.0, 0.0};
             bool bad = false;
 #pragma unroll
-            for (int kk = 0; kk < 9; ++kk) {
+            for (int kk = 0; kk < KCH; ++kk) {
                 const int q = q0 + kk;
                 if (kk < Lc && q < n) {
                     const double x = s_x[q];
@@ -887,18 +995,19 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
                         bad = true;
                         sh = 0.0;
                     }
-                    s_x[q] = e;
+                    // (x, e) of the new generation: this thread's chunk is contiguous in memory
+                    __stcg(&a.XE[pstart + q], make_double2(x, e));
                     s_sh[q] = sh;
                     run = run + sh;
                     acc[0] += sh * x;
-                    double m = s_k.mu + s_k.phi * (x - s_k.mu);
-                    m += (s_k.sr * e) * y;
+                    double m = mu + phi * (x - mu);
+                    m += (sr * e) * y;
                     acc[1] += sh * m;
                     acc[2] += sh * (m * m);
                 }
             }
             if (bad) GRID_FLAG(2);
-            toff = block_excl_scan_f64(run, s_wd, lane, warp);
+            toff = block_excl_scan_f64<GT>(run, s_wd, lane, warp);
             if (n > 0 && tid == (n - 1) / Lc) s_sc.tot = toff + run;   // cumulative weight of the tile's last particle
             if (n == 0 && tid == 0) s_sc.tot = 0.0;
             block_sum<3>(acc, s_red);
@@ -914,26 +1023,35 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
         PROF_MARK(10);
         GRID_ARRIVE();   // ---- barrier 3: tile totals published
         {
-            // fixed-lag score terms (:445-470): ancestor pair (time t-L+1, t-L+2) from one sector
-            const int Lc = odd_chunk(n), q0 = tid * Lc;
+            // fixed-lag score terms (:445-470): ancestor pair (time t-L+1, t-L+2) from one half sector
+            const int Lc = ((n + GT - 1) / GT) | 1, q0 = tid * Lc;
             double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-            if (t >= L) {
+            if (t >= L && !(a.dbg & 4)) {
                 const double ylag = a.obs[t - L];   // Q5: obs[i - LAG]
                 const PEntry* Pg = a.P + (size_t)((t - (L - 2)) % RP) * N;
 #pragma unroll
-                for (int kk = 0; kk < 9; ++kk) {
-                    const int q = q0 + kk;
-                    if (kk < Lc && q < n) {
-                        int an = s_a[q];
-                        an = min(max(an, 0), N - 1);
-                        const double sh = s_sh[q];
-                        const double2 p0 = __ldcg((const double2*)&Pg[an]);
-                        const double ec = __ldcg(&Pg[an].e);
-                        double sq, g[4];
-                        sv_score_main_e(s_k, p0.y, ec, p0.x, ylag, sq, g);
-                        acc[0] += sh * p0.y;
+                for (int k0 = 0; k0 < KCH; k0 += 3) {
+                    double2 pe[3];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) acc[1 + i] += g[i] * sh;
+                    for (int u = 0; u < 3; ++u) {
+                        const int kk = k0 + u, q = q0 + kk;
+                        pe[u] = make_double2(0.0, 0.0);
+                        if (kk < KCH && kk < Lc && q < n) {
+                            const int an = min(max(s_a[q], 0), N - 1);
+                            pe[u] = __ldcg((const double2*)&Pg[an]);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        const int kk = k0 + u, q = q0 + kk;
+                        if (kk < KCH && kk < Lc && q < n) {
+                            const double sh = s_sh[q];
+                            double sq, g[4];
+                            sv_score_main_e(s_k, pe[u].y, exp(-0.5 * pe[u].y), pe[u].x, ylag, sq, g);
+                            acc[0] += sh * pe[u].y;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) acc[1 + i] += g[i] * sh;
+                        }
                     }
                 }
             }
@@ -944,13 +1062,11 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
                 for (int i = 0; i < 5; ++i) ps[2 + i] = acc[i];
                 ps[7] = 0.0;
             }
-            const bool keep = t >= NOBS - L;
+            if (t >= NOBS - L) {
 #pragma unroll
-            for (int kk = 0; kk < kKpt; ++kk) {
-                const int q = kk * kGT + tid;
-                if (q < n) {
-                    __stcg(&a.es[pstart + q], s_x[q]);
-                    if (keep) a.shring[(size_t)(t % L) * N + pstart + q] = s_sh[q];
+                for (int kk = 0; kk < KPT; ++kk) {
+                    const int q = kk * GT + tid;
+                    if (q < n) a.shring[(size_t)(t % L) * N + pstart + q] = s_sh[q];
                 }
             }
         }
@@ -1014,7 +1130,7 @@ __global__ void __launch_bounds__(256) grid_tail_kernel(GridArgs a, const double
         const double wT = shT[p] / ST;
         double curr;
         if (idx == 0) {
-            curr = a.xs[p];
+            curr = a.XE[p].x;
             acc[0] += wT * curr;
         } else {
             // entry of the ancestor idx-1 steps back holds (next = its value, curr = its parent's value)
@@ -1025,7 +1141,7 @@ __global__ void __launch_bounds__(256) grid_tail_kernel(GridArgs a, const double
             acc[0] += wT * curr;
             const double wi = shi[p] / Si;
             double sq, g[4];
-            sv_score_tail_e(k, curr, pe.e, pe.n, y1, sq, g);
+            sv_score_tail_e(k, curr, exp(-0.5 * curr), pe.n, y1, sq, g);
 #pragma unroll
             for (int q = 0; q < 4; ++q) acc[1 + q] += g[q] * wi;
         }
@@ -1093,7 +1209,7 @@ __global__ void grid_finish_kernel(const GridCtrl* __restrict__ ctrl, const doub
 }
 
 struct GridLayout {
-    size_t ctrl, ghist, tilecnt, tinfo, H, Hcarry, xs, es, perm, mail, R, P, psum, shiftv, xminv, shring, parentpos,
+    size_t ctrl, ghist, tilecnt, tinfo, H, Hcarry, XE, perm, R, P, psum, shiftv, xminv, shring, parentpos,
         sums, tailpart, tail, info, total;
     int RP, nblk;
 };
@@ -1112,12 +1228,10 @@ GridLayout grid_layout(int nobs, int n, int lag, int G, int hist) {
     L.tinfo = o;     o += al256((size_t)kMaxTiles * 4 * 8);
     L.Hcarry = o;    o += al256((size_t)kMaxTiles * 4);
     L.H = o;         o += al256(N * 4);
-    L.xs = o;        o += al256(N * 8);
-    L.es = o;        o += al256(N * 8);
+    L.XE = o;        o += al256(N * 16);
     L.perm = o;      o += al256(N * 4);
-    L.mail = o;      o += al256(N * 16);
     L.R = o;         o += al256(2 * N * 32);
-    L.P = o;         o += al256((size_t)L.RP * N * 32);
+    L.P = o;         o += al256((size_t)L.RP * N * 16);
     L.psum = o;      o += al256((size_t)nobs * G * 8 * 8);
     L.shiftv = o;    o += al256((size_t)nobs * 8);
     L.xminv = o;     o += al256((size_t)nobs * 8);
@@ -1188,10 +1302,8 @@ int sv_grid_run(const double* d_obs, const double* d_params, const double* d_rvr
     a.tinfo = (double*)(ws + L.tinfo);
     a.H = (int*)(ws + L.H);
     a.Hcarry = (int*)(ws + L.Hcarry);
-    a.xs = (double*)(ws + L.xs);
-    a.es = (double*)(ws + L.es);
+    a.XE = (double2*)(ws + L.XE);
     a.perm = (int*)(ws + L.perm);
-    a.mail = (MailEntry*)(ws + L.mail);
     a.R = (REntry*)(ws + L.R);
     a.P = (PEntry*)(ws + L.P);
     a.psum = (double*)(ws + L.psum);
@@ -1202,18 +1314,31 @@ int sv_grid_run(const double* d_obs, const double* d_params, const double* d_rvr
     a.Xhist = d_xh;
     a.Ahist = d_ah;
     a.prof = d_prof;
+    {
+        const char* e = getenv("PMMH_GRID_DEBUG");
+        a.dbg = e ? atoi(e) : 0;
+    }
     // control block, histograms, reservation counters, tile info: zero; head markers: -1
     GRID_CUDA(cudaMemsetAsync(ws + L.ctrl, 0, L.Hcarry - L.ctrl, st));
-    GRID_CUDA(cudaMemsetAsync(ws + L.Hcarry, 0xff, (L.xs - L.Hcarry), st));
+    GRID_CUDA(cudaMemsetAsync(ws + L.Hcarry, 0xff, (L.XE - L.Hcarry), st));
     static thread_local bool attr_set[64] = {false};
+    static int threads = 0;
+    if (!threads) {
+        const char* e = getenv("PMMH_GRID_THREADS");
+        threads = (e && atoi(e) == 1024) ? 1024 : 512;
+    }
     int dev = 0;
     GRID_CUDA(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        GRID_CUDA(cudaFuncSetAttribute(sv_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem));
+        GRID_CUDA(cudaFuncSetAttribute(sv_grid_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem));
+        GRID_CUDA(cudaFuncSetAttribute(sv_grid_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem));
         attr_set[dev] = true;
     }
     void* kargs[] = {(void*)&a};
-    GRID_CUDA(cudaLaunchCooperativeKernel((void*)sv_grid_kernel, dim3(G), dim3(kGT), kargs, kDynSmem, st));
+    if (threads == 1024)
+        GRID_CUDA(cudaLaunchCooperativeKernel((void*)sv_grid_kernel<1024>, dim3(G), dim3(1024), kargs, kDynSmem, st));
+    else
+        GRID_CUDA(cudaLaunchCooperativeKernel((void*)sv_grid_kernel<512>, dim3(G), dim3(512), kargs, kDynSmem, st));
     double* sums = (double*)(ws + L.sums);
     double* tailpart = (double*)(ws + L.tailpart);
     double* tail = (double*)(ws + L.tail);

@@ -124,7 +124,7 @@ def test_grid_is_bit_reproducible(cuda_dev, grid_only):
 def test_grid_history_invariants_large(cuda_dev, grid_only):
     """N = 2^19: every stored generation is sorted and the composed ancestors are valid sorted
     positions whose multiset is the resampling outcome (monotone before the sort)."""
-    n, nobs = 1 << 19, 14
+    n, nobs = 1 << 19, 24
     obs, params, rvr, rvp, u = _inputs(n, nobs, 2)
     res = _run(grid_only, cuda_dev, obs, params, rvr, u, 10, True)
     assert int(res["diag"][0, DIAG_KERNEL]) == GRID and int(res["diag"][0, DIAG_STATUS]) == 0
