@@ -4,32 +4,36 @@
 // Restates flps_sv_corr (/root/reference/python/state/particle_methods/stochastic_volatility.pyx
 // :205-655: correlated systematic resampling :694-715, propagation :354-358, argsort :392-424 /
 // :23-52, weights :427-442, fixed-lag score terms :445-470, tail :540-562, log-likelihood :537,
-// trajectory :630-633 with quirks Q10/Q11).  B200 design, 148 CTAs x 1024 threads, one CTA per SM:
+// trajectory :630-633 with quirks Q10/Q11).  B200 design, 148 CTAs, one CTA per SM:
 //
 //   * the sorted generation is cut into G TILES of ~N/G particles (7 085 at N = 2^20, G = 148);
-//     CTA c owns tile c while it is sorted and weighted (everything in shared memory) and owns
-//     the CHILDREN [c*Wc, (c+1)*Wc) while they are generated (equal work for every CTA whatever
-//     the weights look like);
+//     CTA c owns tile c while it is sorted and weighted (shared memory) and owns the CHILDREN
+//     [c*Wc, (c+1)*Wc) while they are generated (equal work for every CTA whatever the weights
+//     look like);
 //   * four grid barriers per time step (one atomic counter, arrive / wait split so that work that
 //     only feeds outputs sits between the two):
 //       C  owner of a tile: cumulative weights -> PARENT-side child ranges in closed form
-//          ub(p) = #{j : (u + j)/N <= cum(p)} (exact predicate re-checked), head markers H[first
-//          child] = parent                                                         | barrier 4
-//       A  owner of a child range: max-scan of the head markers = ancestor of every child,
-//          propagation, 8192-bin value histogram (shared-memory atomics, merged into a global
-//          one)                                                                    | barrier 1
-//          scan of the global histogram -> tile boundaries on bin edges (every tile gets N/G
-//          particles +- one bin), slot reservation per (CTA, tile), scatter of 16-byte entries
-//          (value, birth row, lagged ancestor row) into the tile's mailbox        | barrier 2
-//       B  owner of a tile: counting sort over 8192 sub-bins + exact in-bin ranking by (value,
-//          birth row) = the reference's argsort; weights, block scan, moments     | barrier 3
-//          (after the arrive: fixed-lag score terms, copy-out)
-//   * genealogy: a generation is stored ONCE in birth order as P[t][j] = (value, parent value,
-//     exp(-parent value / 2)) and R[t][j] = birth rows of the ancestors 1..8 steps back (one
-//     32-byte sector each).  The fixed-lag terms of step t need one random sector of P[t-lag+2];
-//     a child copies its parent's R with one random sector read.  No history is ever moved.
-//   * one exp per weight, one exp per particle shared by the weight, the propagation mean of the
-//     children and the score terms (exp(-x/2) is stored next to x).
+//          ub(p) = #{j : (u + j)/N <= cum(p)} (exact predicate re-checked), ancestor of every
+//          child written to H (coalesced fill)                                     | barrier 4
+//       A1 owner of a child range: parent (x, exp(-x/2), birth row), propagation, 8192-bin value
+//          histogram (shared-memory atomics, merged into striped global copies)    | barrier 1
+//          (after the arrive: genealogy records)
+//       A2 scan of the global histogram -> tile boundaries on bin edges (every tile gets N/G
+//          particles +- one bin), slot reservation per (CTA, tile), entries ordered by tile in
+//          shared memory and copied out in runs (value, birth row, lagged ancestor row)
+//                                                                                  | barrier 2
+//       B  owner of a tile: counting sort over 4096 sub-bins of the tile's value range + exact
+//          in-bin ranking by (value, birth row) = the reference's argsort; weights, fixed-lag
+//          score terms (one gather from a generation that was bulk-prefetched into L2), sorted
+//          generation written out, block scan of the weights, moments             | barrier 3
+//   * genealogy: a generation is stored ONCE in birth order as P[t][j] = (value, parent value)
+//     and R[t][j] = birth rows of the ancestors 1..8 steps back (one 32-byte sector each).  The
+//     fixed-lag terms of step t need one random sector of P[t-lag+2]; a child copies its parent's
+//     R with one random sector read.  No history is ever moved.  Both tables are older than the
+//     L2 working set when they are needed again, so they are brought back with sequential bulk
+//     prefetches (cp.async.bulk.prefetch.L2) a phase ahead of the random reads.
+//   * one exp per weight, one exp per particle shared by the weight and the propagation mean of
+//     the children (exp(-x/2) is stored next to x), one exp per score term.
 //
 // Deviations from the reference's operation order: parallel sums / scans, log(exp(x/2)) = x/2 and
 // 1/exp(x/2)^2 = exp(-x/2)^2 in the log-weight, cumulative weights multiplied by 1/S; any
@@ -57,20 +61,25 @@ namespace {
 
 constexpr int kCap = 8192;         // entries of one tile (shared-memory capacity)
 constexpr int kNF = 8192;          // bins of the global value histogram
-constexpr int kNSB = 8192;         // sub-bins of the in-tile counting sort
+constexpr int kNCopy = 1;          // striped copies of the global histogram (CTA c adds into copy c % kNCopy)
+constexpr int kNSB = 4096;         // sub-bins of the in-tile counting sort
 constexpr int kMaxSub = 1024;      // a sub-bin larger than this abandons the evaluation
 constexpr int kMaxTiles = 160;     // >= SM count
+constexpr int kCntStride = 32;     // ints between two slot counters (one 128-byte line each)
 constexpr double kZ = 6.5;         // histogram range: predicted mean +- 6.5 predicted sd
-constexpr int kDynSmem = 192 * 1024;
+constexpr int kDynSmem = 208 * 1024;
 constexpr int kProf = 16;
 
 struct __align__(16) MailEntry {   // aliases one (x, exp(-x/2)) pair of the sorted generation
     double x;
     int j, a;
 };
-struct __align__(16) PEntry {
-    double n, c;           // value, parent value
-};
+// Payload of a particle for the fixed-lag terms, four planes of [RP][N] doubles in birth order:
+// parent value c, residual sq (:452-453), ey = exp(-c/2) * obs[i - LAG], own value n (tail only)
+constexpr int kPlaneC = 0, kPlaneSq = 1, kPlaneEy = 2, kPlaneN = 3;
+constexpr double kWScale = 68719476736.0;        // 2^36: fixed-point scale of the descendant weights
+constexpr double kWInv = 1.0 / 68719476736.0;
+constexpr double kWMax = 60.0;                   // weights above this abandon the evaluation (64 * 2^21 * 2^36 = 2^63)
 struct __align__(32) REntry {
     int a[8];              // birth rows of the ancestors 1 .. 8 steps back
 };
@@ -81,7 +90,6 @@ struct GridCtrl {
     int max_bin;
     int pad0;
     unsigned long long near_ties, soft_ties, key_ties;
-    unsigned long long mn[2], mx[2];   // ordered encodings of min / max child value, by step parity
 };
 
 struct GridArgs {
@@ -89,15 +97,15 @@ struct GridArgs {
     int dbg;   // development (timing only, results wrong): 1 skip R records, 2 skip P store, 4 skip score gather
     const double *obs, *params, *rvr, *U;
     GridCtrl* ctrl;
-    int* ghist;        // [2][kNF]
-    int* tilecnt;      // [2][kMaxTiles]
+    int* ghist;        // [2][kNCopy][kNF]
+    int* tilecnt;      // [2][kMaxTiles * kCntStride]
     double* tinfo;     // [kMaxTiles][4]  tot, n, sum sh m, sum sh m^2
-    int* H;            // [N] head markers (-1 = none)
-    int* Hcarry;       // [kMaxTiles]
+    int* H;            // [N] ancestor (sorted position) of every child
     double2* XE;       // [N] sorted generation: (x, exp(-x/2)); the mailbox of the next generation aliases it
     int* perm;         // [N] sorted position -> birth row
     REntry* R;         // [2][N]
-    PEntry* P;         // [RP][N]
+    double* P;         // [4][RP][N] payload planes
+    unsigned long long* W;   // [2][N] fixed-point weight of the step-t descendants of a lagged ancestor, by step parity
     double* psum;      // [NOBS][G][8]
     double *shiftv, *xminv;   // [NOBS]
     double* shring;    // [LAG][N] sh of the last LAG generations (sorted order)
@@ -108,42 +116,40 @@ struct GridArgs {
 };
 
 struct StepScalars {
-    double S, invS, mhat, inv_shat, xmin, xmax, shift, lo, hi, tot;
-    int carry, hc, total, abort_now;
+    double S, invS, mhat, shat, inv_shat, shift, lo, scale, tot, offk;
+    int carry, abort_now, binlo, binhi;
 };
 
 // ---- small device helpers ---------------------------------------------------------------------
 __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ unsigned long long enc_f64(double x) {
-    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
-    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
-}
-__device__ __forceinline__ double dec_f64(unsigned long long k) {
-    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
-    return __longlong_as_double((long long)b);
-}
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-__device__ __forceinline__ void prefetch_l2_keep(const void* p) {
-    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(p));
-}
-__device__ __forceinline__ unsigned long long policy_evict_last() {
-    unsigned long long pol;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
+// [p0, p1) -> L2 in 16 KB pieces (sequential HBM reads issued by the copy unit, no SM cycles);
+// the pieces are dealt to the callers round-robin: piece k goes to caller k % nlanes == lane
+__device__ __forceinline__ void prefetch_range(const void* b0, const void* b1, int lane, int nlanes) {
+    const char* q0 = (const char*)(((uintptr_t)b0 + 15) & ~(uintptr_t)15);
+    const char* q1 = (const char*)((uintptr_t)b1 & ~(uintptr_t)15);
+    for (const char* q = q0 + (size_t)lane * 16384; q < q1; q += (size_t)nlanes * 16384)
+        prefetch_l2_bulk(q, (unsigned)min((long long)16384, (long long)(q1 - q)));
 }
 __device__ __forceinline__ unsigned long long policy_evict_first() {
     unsigned long long pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
-// 32-byte genealogy records: one 256-bit access, kept in L2 (evict_last)
+__device__ __forceinline__ unsigned long long policy_evict_last() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+// 32-byte genealogy records: one 256-bit access, kept in the persisting part of L2 (evict_last; the
+// host sets cudaLimitPersistingL2CacheSize to the size of the two record tables)
 __device__ __forceinline__ void ld_rec(const REntry* p, unsigned long long pol, int (&r)[8]) {
     asm volatile("ld.global.cg.L2::cache_hint.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -155,10 +161,18 @@ __device__ __forceinline__ void st_rec(REntry* p, unsigned long long pol, int a0
                  "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5), "r"(a6), "r"(a7), "l"(pol)
                  : "memory");
 }
-// streaming 16-byte store that should leave L2 first (written once, read 8 steps later or never)
+// streaming 16-byte store that should leave L2 first (written once, read lag - 2 steps later)
 __device__ __forceinline__ void st_stream_f64x2(void* p, unsigned long long pol, double a, double b) {
     asm volatile("st.global.cs.L2::cache_hint.v2.f64 [%0], {%1,%2}, %3;" ::"l"(p), "d"(a), "d"(b), "l"(pol)
                  : "memory");
+}
+__device__ __forceinline__ void st_stream_f64x4(void* p, unsigned long long pol, double a, double b, double c, double d) {
+    asm volatile("st.global.cs.L2::cache_hint.v4.f64 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d),
+                 "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void st_stream_f64(double* p, unsigned long long pol, double a) {
+    asm volatile("st.global.cs.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(a), "l"(pol) : "memory");
 }
 __device__ __forceinline__ double ld_stream_hint_f64(const double* p, unsigned long long pol) {
     double v;
@@ -186,25 +200,32 @@ __device__ __forceinline__ int pick8(const int (&r)[8], int idx) {
     }
 }
 
-// #{ j in [0, N) : (u + j) / N <= c }: closed form, then the exact predicate of :703-711.
-// frac_out = distance of c*N - u to the nearest integer (how close the decision is to a tie).
+// the resampling point of child j, (u + j) / N as the reference computes it (:703)
+__device__ __forceinline__ double cpoint(double u, int j, double dn, double inv_n, bool pow2) {
+    const double s = u + (double)j;
+    return pow2 ? s * inv_n : s / dn;
+}
+__device__ __noinline__ int count_le_slow(int est, double c, double u, int N, double dn, double inv_n, bool pow2) {
+    while (est > 0 && cpoint(u, est - 1, dn, inv_n, pow2) > c) --est;
+    while (est < N && cpoint(u, est, dn, inv_n, pow2) <= c) ++est;
+    return est;
+}
+// #{ j in [0, N) : (u + j) / N <= c }: closed form, then the exact predicate of :703-711 on both
+// neighbours.  frac_out = distance of c*N - u to the nearest integer (how close to a tie).
 __device__ __forceinline__ int count_le(double c, double u, int N, double dn, double inv_n, bool pow2,
                                         double& frac_out) {
     const double e = c * dn - u;
-    int est;
-    if (!(e >= 0.0)) est = 0;
-    else if (e >= dn) est = N;
-    else est = (int)e + 1;
-    const double fr = e - floor(e);
-    frac_out = fmin(fr, 1.0 - fr);
-    if (pow2) {
-        while (est > 0 && (u + (double)(est - 1)) * inv_n > c) --est;
-        while (est < N && (u + (double)est) * inv_n <= c) ++est;
-    } else {
-        while (est > 0 && (u + (double)(est - 1)) / dn > c) --est;
-        while (est < N && (u + (double)est) / dn <= c) ++est;
+    if (!(e >= 0.0) || e >= dn - 1.0) {   // the ends of the range: rare, exact search
+        frac_out = 1.0;
+        return count_le_slow(e >= 0.0 ? N : 0, c, u, N, dn, inv_n, pow2);
     }
-    return est;
+    const int fi = (int)e;               // floor(e), 0 <= fi <= N - 2
+    const double fl = (double)fi;
+    const double fr = e - fl;
+    frac_out = fmin(fr, 1.0 - fr);
+    const double slo = u + fl, shi = u + (fl + 1.0);   // u + j for j = fi, fi + 1 (both exact conversions)
+    const bool ok = pow2 ? (slo * inv_n <= c && !(shi * inv_n <= c)) : (slo / dn <= c && !(shi / dn <= c));
+    return ok ? fi + 1 : count_le_slow(fi + 1, c, u, N, dn, inv_n, pow2);
 }
 
 __device__ __forceinline__ int fine_bin(double x, double mhat, double inv_shat) {
@@ -252,21 +273,54 @@ __device__ __forceinline__ int block_excl_max_int(int v, int init, int* s_w, int
     if (lane == 0) ex = init;
     return max(woff, ex);
 }
+
+// Fixed-lag score terms of step `tstep` (:445-470), this CTA's slice [jb, jb + nc) of the lagged
+// generation: sum over rows of (weight of the row's step-tstep descendants) x (monomials of the
+// row's payload).  Sequential reads, fixed summation order; the weights are cleared for their next
+// use.  grid_finish_kernel assembles the gradient terms from the five sums.
 template <int GT>
-__device__ __forceinline__ double block_excl_scan_f64(double v, double* s_w, int lane, int warp) {
+__device__ __forceinline__ void payload_pass(const GridArgs& a, int tstep, int jb, int nc, int c, double* s_red,
+                                             unsigned long long pol_stream) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = GT / 32;
-    const double incl = warp_incl_scan(v, lane);
+    const int N = a.N, RP = a.RP;
+    const size_t pplane = (size_t)RP * N;
+    const double* Pg = a.P + (size_t)((tstep - (a.LAG - 2)) % RP) * N + jb;
+    unsigned long long* Wt = a.W + (size_t)(tstep & 1) * N + jb;
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int i = tid; i < nc; i += GT) {
+        const unsigned long long w = __ldcg(&Wt[i]);
+        if (w) {
+            const double cc = ld_stream_hint_f64(&Pg[kPlaneC * pplane + i], pol_stream);
+            const double sq = ld_stream_hint_f64(&Pg[kPlaneSq * pplane + i], pol_stream);
+            const double ey = ld_stream_hint_f64(&Pg[kPlaneEy * pplane + i], pol_stream);
+            const double wd = (double)w * kWInv;
+            const double ws = wd * sq;
+            acc[0] = fma(wd, cc, acc[0]);
+            acc[1] += ws;
+            acc[2] = fma(ws, cc, acc[2]);
+            acc[3] = fma(ws, sq, acc[3]);
+            acc[4] = fma(ws, ey, acc[4]);
+            __stcg(&Wt[i], 0ull);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) acc[i] = warp_sum(acc[i]);
     __syncthreads();
-    if (lane == 31) s_w[warp] = incl;
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) s_red[32 * i + warp] = acc[i];
+    }
     __syncthreads();
-    const double wt = (lane < NW) ? s_w[lane] : 0.0;
-    const double wincl = warp_incl_scan(wt, lane);
-    double wex = __shfl_up_sync(kFullMask, wincl, 1);
-    if (lane == 0) wex = 0.0;
-    const double woff = __shfl_sync(kFullMask, wex, warp);
-    double ex = __shfl_up_sync(kFullMask, incl, 1);
-    if (lane == 0) ex = 0.0;
-    return woff + ex;
+    if (warp == 0) {
+        double* ps = a.psum + ((size_t)tstep * a.G + c) * 8;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const double v = warp_sum((lane < NW) ? s_red[32 * i + lane] : 0.0);
+            if (lane == 0) ps[2 + i] = v;
+        }
+    }
+    __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -277,25 +331,30 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
     constexpr int KPT = kCap / GT;          // entries per thread (strided assignment)
     constexpr int KCH = KPT | 1;            // longest chunk of the thread-contiguous passes (odd)
     constexpr int BPT = kNF / GT;           // histogram bins per thread
-    static_assert(kNF == kNSB, "one scan shape for both histograms");
+    constexpr int SPT = kNSB / GT;          // sub-bins per thread
+    constexpr int NW = GT / 32;
+    constexpr int CH = KPT >= 16 ? 8 : 4;   // independent loads in flight per thread in the gather loops
+    constexpr int RB = KPT >= 16 ? 4 : 2;   // genealogy records in flight per thread
+    static_assert(SPT % 4 == 0 && BPT % 4 == 0, "vector loads of the counters");
     extern __shared__ __align__(16) unsigned char smem[];
     // phase B / C view
-    double* s_x = (double*)smem;                       // [kCap] sorted values, later exp(-x/2)
-    double* s_sh = (double*)(smem + 65536);            // [kCap] unnormalised weights
-    int* s_j = (int*)(smem + 131072);                  // [kCap] birth rows
-    int* s_a = (int*)(smem + 163840);                  // [kCap] lagged ancestor rows
-    int* s_sub = (int*)s_sh;                           // [kNSB] sub-bin counters (during the sort only)
+    double* s_xb = (double*)smem;                      // [kCap] values in sub-bin order
+    int* s_jb = (int*)(smem + 65536);                  // [kCap] birth rows in sub-bin order
+    int* s_ab = (int*)(smem + 98304);                  // [kCap] lagged ancestor rows in sub-bin order
+    double* s_sh = (double*)(smem + 131072);           // [kCap] unnormalised weights, sorted order
+    int* s_sub = (int*)(smem + 196608);                // [kNSB] sub-bin counters, then first positions
+    int* s_ub = s_jb;                                  // [kCap] child range ends (phase C)
     // phase A view
     int* s_fhist = (int*)smem;                         // [kNF] histogram of this CTA's children
-    int* s_par = (int*)smem + kNF;                     // [kCap] ancestor (sorted position) of every child
-    unsigned short* s_tileof = (unsigned short*)s_j;   // [kNF] tile of a histogram bin
+    unsigned short* s_tileof = (unsigned short*)(smem + 32768);   // [kNF] tile of a histogram bin
+    int4* s_stage = (int4*)(smem + 49152);             // [kCap] entries ordered by destination tile
 
     __shared__ SvConst s_k;
     __shared__ StepScalars s_sc;
-    __shared__ double s_tot[kMaxTiles], s_m1[kMaxTiles], s_m2[kMaxTiles], s_off[kMaxTiles + 1];
-    __shared__ int s_tstart[kMaxTiles + 1], s_tcnt[kMaxTiles], s_tbase[kMaxTiles];
-    __shared__ double s_red[8 * 32];
-    __shared__ double s_wd[32];
+    __shared__ double s_tot[kMaxTiles], s_off[kMaxTiles + 1];
+    __shared__ int s_tstart[kMaxTiles + 1], s_tbin[kMaxTiles + 1], s_tcnt[kMaxTiles], s_tbase[kMaxTiles],
+        s_loff[kMaxTiles];
+    __shared__ double s_red[9 * 32];
     __shared__ int s_wi[32];
     __shared__ long long s_prof[kProf];
 
@@ -304,7 +363,8 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
     GridCtrl* ctrl = a.ctrl;
     const double dn = (double)N, inv_n = 1.0 / dn;
     const bool pow2 = (N & (N - 1)) == 0;
-    const unsigned long long pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
+    const unsigned long long pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
+    constexpr double kBinW = 2.0 * kZ / (double)kNF;    // width of a histogram bin in predicted sd
     unsigned epoch = 0;                 // arrives done so far
     unsigned cnt_near = 0, cnt_soft = 0, cnt_key = 0;
     int my_max_bin = 0;
@@ -384,8 +444,6 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
             if (c == 0) {
                 a.shiftv[0] = 0.0;
                 a.xminv[0] = mu;
-                ctrl->mn[0] = ctrl->mn[1] = ~0ull;
-                ctrl->mx[0] = ctrl->mx[1] = 0ull;
             }
         }
     }
@@ -398,26 +456,29 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
         // --------------------------------------------------------------------------------------
         // phase C: totals of all tiles -> offsets; child ranges of this tile's parents (:694-715)
         // --------------------------------------------------------------------------------------
-        if (tid < G) {
-            const double2 t0 = __ldcg((const double2*)&a.tinfo[tid * 4]);
-            const double2 t1 = __ldcg((const double2*)&a.tinfo[tid * 4 + 2]);
-            s_tot[tid] = t0.x;
-            s_m1[tid] = t1.x;
-            s_m2[tid] = t1.y;
-        }
-        __syncthreads();
         const double ur = a.rvr[t];
+        double mom1 = 0.0, mom2 = 0.0;   // warp 0: weighted moments of the propagation mean
         if (warp == 0) {
             constexpr int kPer = kMaxTiles / 32;
-            double loc = 0.0, l1 = 0.0, l2 = 0.0;
+            double tv[kPer], m1v[kPer], m2v[kPer];
 #pragma unroll
             for (int i = 0; i < kPer; ++i) {
                 const int k = lane * kPer + i;
+                tv[i] = m1v[i] = m2v[i] = 0.0;
                 if (k < G) {
-                    loc = loc + s_tot[k];
-                    l1 = l1 + s_m1[k];
-                    l2 = l2 + s_m2[k];
+                    const double2 t0 = __ldcg((const double2*)&a.tinfo[k * 4]);
+                    const double2 t1 = __ldcg((const double2*)&a.tinfo[k * 4 + 2]);
+                    tv[i] = t0.x;
+                    m1v[i] = t1.x;
+                    m2v[i] = t1.y;
                 }
+            }
+            double loc = 0.0, l1 = 0.0, l2 = 0.0;
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) {
+                loc = loc + tv[i];
+                l1 = l1 + m1v[i];
+                l2 = l2 + m2v[i];
             }
             const double incl = warp_incl_scan(loc, lane);
             double run = __shfl_up_sync(kFullMask, incl, 1);
@@ -427,36 +488,36 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
                 const int k = lane * kPer + i;
                 if (k < G) {
                     s_off[k] = run;
-                    run = run + s_tot[k];
+                    s_tot[k] = tv[i];
+                    run = run + tv[i];
                 }
             }
             const double S = __shfl_sync(kFullMask, incl, 31);
-            const double M1 = warp_sum(l1), M2 = warp_sum(l2);
+            const double invS = 1.0 / S;
             __syncwarp();
             if (lane == 0) {
-                s_off[G] = S;
-                const double invS = 1.0 / S;
-                const double mhat = M1 / S;
-                double var = M2 / S - mhat * mhat;
-                if (!(var > 0.0)) var = 0.0;
-                var = var + s_k.sd * s_k.sd;
-                const double shat = sqrt(var);
                 s_sc.S = S;
                 s_sc.invS = invS;
-                s_sc.mhat = mhat;
-                s_sc.inv_shat = 1.0 / shat;
-                if (!(S > 0.0) || !isfinite(S) || !isfinite(mhat) || !(shat > 0.0) || !isfinite(shat)) GRID_FLAG(2);
-                // child range end of the tiles in front of this one (running maximum, see below)
-                int carry = 0;
-                double fr;
-                for (int k = max(0, c - 2); k < c; ++k)
-                    carry = max(carry, count_le((s_off[k] + s_tot[k]) * invS, ur, N, dn, inv_n, pow2, fr));
-                s_sc.carry = carry;
+                s_sc.offk = s_off[c];
+                if (!(S > 0.0) || !isfinite(S)) GRID_FLAG(2);
             }
+            // child range end of the tiles in front of this one (running maximum, see below)
+            {
+                int carry = 0;
+                const int k = c - 1 - lane;
+                if (lane < 2 && k >= 0) {
+                    double fr;
+                    carry = count_le((s_off[k] + s_tot[k]) * invS, ur, N, dn, inv_n, pow2, fr);
+                }
+                carry = max(carry, __shfl_down_sync(kFullMask, carry, 1));
+                if (lane == 0) s_sc.carry = carry;
+            }
+            mom1 = warp_sum(l1);
+            mom2 = warp_sum(l2);
         }
         __syncthreads();
         {
-            const double invS = s_sc.invS, offk = s_off[c];
+            const double invS = s_sc.invS, offk = s_sc.offk;
             const int Lc = ((n + GT - 1) / GT) | 1, q0 = tid * Lc;
             const double tol_soft = 2.220446049250313e-16 * dn * (4.0 + 2.0 * sqrt(dn));
             const double tol_near = 64.0 * 2.220446049250313e-16 * dn;
@@ -488,112 +549,101 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
             // parallel scans are monotone only up to an ulp: a running maximum over all parents
             // (and over the tiles in front) keeps the child ranges disjoint
             int prev = block_excl_max_int<GT>(rmax, s_sc.carry, s_wi, lane, warp);
-            const float inv_wc = 1.0f / (float)Wc;
 #pragma unroll
             for (int kk = 0; kk < KCH; ++kk) {
                 const int q = q0 + kk;
                 if (kk < Lc && q < n) {
-                    const int ub = max(ubv[kk], prev);
-                    if (ub > prev) {
-                        const int P = pstart + q;
-                        __stcg(&a.H[prev], P);
-                        if (ub - prev > 1) {
-                            // child-tile boundaries m * Wc strictly inside (prev, ub): the tile's
-                            // first child has no marker of its own
-                            int m = (int)((float)prev * inv_wc);
-                            while (m * Wc > prev) --m;
-                            while ((m + 1) * Wc <= prev) ++m;
-                            ++m;
-                            while (m < G && m * Wc < ub) {
-                                __stcg(&a.Hcarry[m], P);
-                                ++m;
-                            }
-                        }
-                    }
-                    prev = ub;
+                    prev = max(ubv[kk], prev);
+                    s_ub[q] = prev;
                 }
             }
         }
-        PROF_MARK(0);
-        GRID_ARRIVE();   // ---- barrier 4: head markers complete
+        __syncthreads();
+        {
+            // ancestor of every child: parent q owns the children [ub(q-1), ub(q)); consecutive
+            // lanes hold consecutive parents, so the stores of a warp fall into a few lines
+            const int carry = s_sc.carry;
+#pragma unroll 1
+            for (int kk = 0; kk < KPT; ++kk) {
+                const int q = kk * GT + tid;
+                if (kk * GT >= n) break;
+                int lo = 0, hi = 0;
+                if (q < n) {
+                    hi = s_ub[q];
+                    lo = q ? s_ub[q - 1] : carry;
+                }
+                const int P = pstart + q;
+                const bool longr = hi - lo > 8;
+                if (!longr)
+                    for (int k = lo; k < hi; ++k) __stcg(&a.H[k], P);
+                unsigned m = __ballot_sync(kFullMask, longr);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int l0 = __shfl_sync(kFullMask, lo, src), h0 = __shfl_sync(kFullMask, hi, src);
+                    const int P0 = __shfl_sync(kFullMask, P, src);
+                    for (int k = l0 + lane; k < h0; k += 32) __stcg(&a.H[k], P0);
+                }
+            }
+        }
+        if (tid == 0) {
+            // predicted mean / sd of the children: histogram range of phase A
+            const double S = s_sc.S;
+            const double mhat = mom1 / S;
+            double var = mom2 / S - mhat * mhat;
+            if (!(var > 0.0)) var = 0.0;
+            var = var + s_k.sd * s_k.sd;
+            const double shat = sqrt(var);
+            s_sc.mhat = mhat;
+            s_sc.shat = shat;
+            s_sc.inv_shat = 1.0 / shat;
+            if (!isfinite(mhat) || !(shat > 0.0) || !isfinite(shat)) GRID_FLAG(2);
+        }
+        PROF_MARK(0);   // C ranges+fill
+        GRID_ARRIVE();   // ---- barrier 4: ancestors complete
         for (int b = tid; b < kNF; b += GT) s_fhist[b] = 0;
-        PROF_MARK(1);
+        PROF_MARK(1);   // zero hist
         GRID_WAIT();
-        PROF_MARK(2);
+        PROF_MARK(2);   // wait 4
         if (s_sc.abort_now) break;
 
         // --------------------------------------------------------------------------------------
-        // phase A: ancestors of this CTA's children, propagation (:354-358), value histogram
+        // phase A1: parents of this CTA's children, propagation (:354-358), value histogram
         // --------------------------------------------------------------------------------------
-        {
-            int hv[KPT];
-#pragma unroll
-            for (int kk = 0; kk < KPT; ++kk) {
-                const int i = kk * GT + tid;
-                hv[kk] = -1;
-                if (i < nc) hv[kk] = __ldcg(&a.H[jb + i]);
-            }
-            if (tid == 0) s_sc.hc = __ldcg(&a.Hcarry[c]);
-#pragma unroll
-            for (int kk = 0; kk < KPT; ++kk) {
-                const int i = kk * GT + tid;
-                if (i < nc) {
-                    s_par[i] = hv[kk];
-                    if (hv[kk] >= 0) __stcg(&a.H[jb + i], -1);
-                }
-            }
-            if (tid == 0) __stcg(&a.Hcarry[c], -1);
-        }
-        __syncthreads();
-        {
-            const int Lc2 = ((nc + GT - 1) / GT) | 1, i0 = tid * Lc2;
-            int mx = -1;
-#pragma unroll
-            for (int kk = 0; kk < KCH; ++kk) {
-                const int i = i0 + kk;
-                if (kk < Lc2 && i < nc) mx = max(mx, s_par[i]);
-            }
-            int run = block_excl_max_int<GT>(mx, s_sc.hc, s_wi, lane, warp);
-            bool orphan = false;
-#pragma unroll
-            for (int kk = 0; kk < KCH; ++kk) {
-                const int i = i0 + kk;
-                if (kk < Lc2 && i < nc) {
-                    run = max(run, s_par[i]);
-                    if (run < 0 || run >= N) {
-                        orphan = true;
-                        run = 0;
-                    }
-                    s_par[i] = run;
-                }
-            }
-            if (orphan) GRID_FLAG(4);
-        }
-        __syncthreads();
         double xn[KPT];
         int bp[KPT];
         {
+#pragma unroll
+            for (int kk = 0; kk < KPT; ++kk) {
+                const int i = kk * GT + tid;
+                bp[kk] = 0;
+                if (i < nc) bp[kk] = __ldcg(&a.H[jb + i]);
+            }
             const double y1 = a.obs[t - 1];
+            const double ylag = a.obs[t >= 2 ? t - 2 : 0];   // Q5: the score terms of step i use obs[i - LAG]; i = t + LAG - 2
             const double mhat = s_sc.mhat, inv_shat = s_sc.inv_shat;
             const double mu = s_k.mu, phi = s_k.phi, sr = s_k.sr, sd = s_k.sd;
             const double* Ut = a.U + (size_t)t * N;
-            PEntry* Pt = a.P + (size_t)(t % RP) * N;
-            const REntry* Rp = a.R + (size_t)((t - 1) & 1) * N;
-            double vmin = INFINITY, vmax = -INFINITY;
-            bool bad = false;
+            const size_t pplane = (size_t)RP * N;
+            double* Pt = a.P + (size_t)(t % RP) * N;
+            const bool keep_n = t >= NOBS - L - 1;   // the tail (:540-562) reads the values of the last generations
+            bool bad = false, orphan = false;
 #pragma unroll
-            for (int k0 = 0; k0 < KPT; k0 += 4) {
-                // all loads of four children are in flight before the first one is used
-                double2 xe[4];
-                double uu[4];
+            for (int k0 = 0; k0 < KPT; k0 += CH) {
+                // all loads of CH children are in flight before the first one is used
+                double2 xe[CH];
+                double uu[CH];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < CH; ++u) {
                     const int i = (k0 + u) * GT + tid;
                     xe[u] = make_double2(0.0, 0.0);
                     uu[u] = 0.0;
-                    bp[k0 + u] = 0;
                     if (i < nc) {
-                        const int p = s_par[i];
+                        int p = bp[k0 + u];
+                        if ((unsigned)p >= (unsigned)N) {
+                            orphan = true;
+                            p = 0;
+                        }
                         xe[u] = __ldcg(&a.XE[p]);
                         bp[k0 + u] = __ldcg(&a.perm[p]);
                         uu[u] = ld_stream_hint_f64(Ut + jb + i, pol_stream);
@@ -601,7 +651,7 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < CH; ++u) {
                     const int i = (k0 + u) * GT + tid;
                     xn[k0 + u] = 0.0;
                     if (i < nc) {
@@ -610,59 +660,50 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
                         const double x = mean + sd * uu[u];           // :357-358
                         if (!isfinite(x)) bad = true;
                         xn[k0 + u] = x;
-                        if (!(a.dbg & 1)) prefetch_l2_keep(&Rp[bp[k0 + u]]);
                         atomicAdd(&s_fhist[fine_bin(x, mhat, inv_shat)], 1);
-                        vmin = fmin(vmin, x);
-                        vmax = fmax(vmax, x);
-                        if (!(a.dbg & 2)) st_stream_f64x2(&Pt[jb + i], pol_stream, x, xe[u].x);
+                        if (!(a.dbg & 2)) {
+                            // residual of the transition parent -> child as the score terms use it (:452-453)
+                            double sq = x - mu - phi * (xe[u].x - mu);
+                            sq -= sr * xe[u].y * ylag;
+                            st_stream_f64(&Pt[kPlaneC * pplane + jb + i], pol_stream, xe[u].x);
+                            st_stream_f64(&Pt[kPlaneSq * pplane + jb + i], pol_stream, sq);
+                            st_stream_f64(&Pt[kPlaneEy * pplane + jb + i], pol_stream, xe[u].y * ylag);
+                            if (keep_n) Pt[kPlaneN * pplane + jb + i] = x;
+                        }
                     }
                 }
             }
             if (bad) GRID_FLAG(2);
-            vmin = warp_min(vmin);
-            vmax = warp_max(vmax);
-            if (lane == 0) {
-                s_red[warp] = vmin;
-                s_red[32 + warp] = vmax;
-            }
+            if (orphan) GRID_FLAG(4);
         }
         __syncthreads();
         {
-            int* gh = a.ghist + par * kNF;
+            int* gh = a.ghist + ((size_t)par * kNCopy + (c % kNCopy)) * kNF;
 #pragma unroll
             for (int kk = 0; kk < BPT; ++kk) {
                 const int b = kk * GT + tid;
                 const int cnt = s_fhist[b];
                 if (cnt) atomicAdd(&gh[b], cnt);
             }
-            if (warp == 0) {
-                const double vmin = warp_min(lane < GT / 32 ? s_red[lane] : INFINITY);
-                const double vmax = warp_max(lane < GT / 32 ? s_red[32 + lane] : -INFINITY);
-                if (lane == 0 && nc > 0) {
-                    atomicMin(&ctrl->mn[par], enc_f64(vmin));
-                    atomicMax(&ctrl->mx[par], enc_f64(vmax));
-                }
-            }
         }
-        PROF_MARK(3);
+        PROF_MARK(3);   // A1 children+hist
         GRID_ARRIVE();   // ---- barrier 1: global histogram complete
         if (!(a.dbg & 1)) {
             // genealogy records (only feed outputs): child = (parent row, parent's ancestors 1..7)
             const REntry* Rp = a.R + (size_t)((t - 1) & 1) * N;
             REntry* Rc = a.R + (size_t)(t & 1) * N;
-            const PEntry* Pnow = a.P + (size_t)((t - (L - 2) + RP) % RP) * N;
 #pragma unroll
-            for (int k0 = 0; k0 < KPT; k0 += 2) {
-                int r[2][8];
+            for (int k0 = 0; k0 < KPT; k0 += RB) {
+                int r[RB][8];
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
+                for (int u = 0; u < RB; ++u) {
                     const int i = (k0 + u) * GT + tid;
 #pragma unroll
                     for (int z = 0; z < 8; ++z) r[u][z] = 0;
-                    if (i < nc) ld_rec(&Rp[bp[k0 + u]], pol_keep, r[u]);
+                    if (i < nc) ld_rec(&Rp[(a.dbg & 8) ? jb + i : bp[k0 + u]], pol_keep, r[u]);
                 }
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
+                for (int u = 0; u < RB; ++u) {
                     const int i = (k0 + u) * GT + tid;
                     if (i < nc) {
                         const int j = jb + i;
@@ -673,42 +714,46 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
                         if (L == 3) anc = b;
                         else if (L > 3) anc = pick8(r[u], L - 4);
                         bp[k0 + u] = anc;
-                        if (t >= L && !(a.dbg & 4)) prefetch_l2(&Pnow[min(max(anc, 0), N - 1)]);
                     }
                 }
             }
         }
+        if (t - 1 >= L && !(a.dbg & 4)) payload_pass<GT>(a, t - 1, jb, nc, c, s_red, pol_stream);
         {
             // housekeeping for the next step
-            const int zper = (kNF + G - 1) / G;
-            int* ghn = a.ghist + (par ^ 1) * kNF;
-            for (int b = c * zper + tid; b < min(kNF, (c + 1) * zper); b += GT) __stcg(&ghn[b], 0);
-            if (tid == 0) {
-                __stcg(&a.tilecnt[(par ^ 1) * kMaxTiles + c], 0);
-                if (c == 0) {
-                    ctrl->mn[par ^ 1] = ~0ull;
-                    ctrl->mx[par ^ 1] = 0ull;
-                }
-            }
+            constexpr int kZero = kNCopy * kNF;
+            const int zper = (kZero + G - 1) / G;
+            int* ghn = a.ghist + (size_t)(par ^ 1) * kZero;
+            for (int b = c * zper + tid; b < min(kZero, (c + 1) * zper); b += GT) __stcg(&ghn[b], 0);
+            if (tid == 0) __stcg(&a.tilecnt[((par ^ 1) * kMaxTiles + c) * kCntStride], 0);
         }
-        PROF_MARK(4);
+        PROF_MARK(4);   // A1 records
         GRID_WAIT();
-        PROF_MARK(5);
+        PROF_MARK(5);   // wait 1
         if (s_sc.abort_now) break;
 
-        // scan of the global histogram: tile boundaries on bin edges, tile of every bin
+        // --------------------------------------------------------------------------------------
+        // phase A2: scan of the global histogram: tile boundaries on bin edges, tile of every bin;
+        // entries ordered by tile in shared memory, copied to the mailboxes in runs
+        // --------------------------------------------------------------------------------------
         {
-            const int* gh = a.ghist + par * kNF;
+            const int* gh = a.ghist + (size_t)par * kNCopy * kNF;
             int cnt[BPT];
 #pragma unroll
-            for (int i = 0; i < BPT; i += 4) {
-                const int4 v = __ldcg((const int4*)(gh + BPT * tid + i));
-                cnt[i] = v.x;
-                cnt[i + 1] = v.y;
-                cnt[i + 2] = v.z;
-                cnt[i + 3] = v.w;
+            for (int i = 0; i < BPT; ++i) cnt[i] = 0;
+            int prevcnt = 0;
+#pragma unroll
+            for (int cp = 0; cp < kNCopy; ++cp) {
+#pragma unroll
+                for (int i = 0; i < BPT; i += 4) {
+                    const int4 v = __ldcg((const int4*)(gh + cp * kNF + BPT * tid + i));
+                    cnt[i] += v.x;
+                    cnt[i + 1] += v.y;
+                    cnt[i + 2] += v.z;
+                    cnt[i + 3] += v.w;
+                }
+                if (tid > 0) prevcnt += __ldcg(gh + cp * kNF + BPT * tid - 1);
             }
-            const int prevcnt = tid > 0 ? __ldcg(gh + BPT * tid - 1) : 0;
             int loc = 0, mxb = 0;
 #pragma unroll
             for (int i = 0; i < BPT; ++i) {
@@ -724,17 +769,23 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
             for (int i = 0; i < BPT; ++i) {
                 while (tl < G - 1 && start >= (tl + 1) * Wc) ++tl;
                 s_tileof[BPT * tid + i] = (unsigned short)tl;
-                for (int k = tprev + 1; k <= tl; ++k) s_tstart[k] = start;
+                for (int k = tprev + 1; k <= tl; ++k) {
+                    s_tstart[k] = start;
+                    s_tbin[k] = BPT * tid + i;
+                }
                 tprev = tl;
+                if (cnt[i] > 0) {
+                    if (start == 0) s_sc.binlo = BPT * tid + i;
+                    if (start + cnt[i] == total) s_sc.binhi = BPT * tid + i;
+                }
                 start += cnt[i];
             }
             if (tid == GT - 1) {
-                for (int k = tprev + 1; k <= G; ++k) s_tstart[k] = N;
+                for (int k = tprev + 1; k <= G; ++k) {
+                    s_tstart[k] = N;
+                    s_tbin[k] = kNF;
+                }
                 if (total != N) GRID_FLAG(5);
-            }
-            if (tid == 0) {
-                s_sc.xmin = dec_f64(*(volatile unsigned long long*)&ctrl->mn[par]);
-                s_sc.xmax = dec_f64(*(volatile unsigned long long*)&ctrl->mx[par]);
             }
         }
         __syncthreads();
@@ -754,9 +805,10 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
         }
         __syncthreads();
         if (tid < G) {
+            // slots of this CTA's run in every mailbox
             const int cnt = s_tcnt[tid];
             int base = s_tstart[tid];
-            if (cnt) base += atomicAdd(&a.tilecnt[par * kMaxTiles + tid], cnt);
+            if (cnt) base += atomicAdd(&a.tilecnt[(par * kMaxTiles + tid) * kCntStride], cnt);
             s_tbase[tid] = base;
             s_tcnt[tid] = 0;
         }
@@ -780,95 +832,77 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
             if (tid == 0) GRID_FLAG(1);
             n = n < 0 ? 0 : kCap;
         }
-        PROF_MARK(6);
-        GRID_ARRIVE();   // ---- barrier 2: mailboxes complete
-        for (int b = tid; b < kNSB; b += GT) s_sub[b] = 0;
         if (tid == 0) {
-            // shift = largest log-weight over [xmin, xmax] (any shift cancels, Q4)
+            // sub-bins of this tile: its histogram bins cover [lo, hi)
+            const double mhat = s_sc.mhat, shat = s_sc.shat;
+            const double lo = mhat + shat * ((double)s_tbin[c] * kBinW - kZ);
+            const double hi = mhat + shat * ((double)s_tbin[c + 1] * kBinW - kZ);
+            s_sc.lo = lo;
+            s_sc.scale = (hi > lo) ? (double)kNSB / (hi - lo) : 0.0;
+            // shift = largest log-weight over the occupied bins (any shift cancels, Q4)
             const double y = a.obs[t];
-            const double xmin = s_sc.xmin, xmax = s_sc.xmax;
+            const double xmin = mhat + shat * ((double)s_sc.binlo * kBinW - kZ);
+            const double xmax = mhat + shat * ((double)(s_sc.binhi + 1) * kBinW - kZ);
             double xs_ = (y != 0.0) ? 2.0 * log(fabs(y)) : xmin;
             xs_ = fmin(fmax(xs_, xmin), xmax);
             const double es_ = exp(-0.5 * xs_);
             s_sc.shift = (-0.91893853320467267 - 0.5 * xs_) - (0.5 * y * y) * (es_ * es_);
-            if (c == 0) {
-                a.shiftv[t] = s_sc.shift;
-                a.xminv[t] = xmin;
-            }
-            if (t + 1 < NOBS && nc > 0) {
-                // next step's slice of u -> L2 (TMA-class bulk prefetch, no SM cycles)
-                const char* p0 = (const char*)(a.U + (size_t)(t + 1) * N + jb);
-                const char* p1 = (const char*)(a.U + (size_t)(t + 1) * N + je);
-                const char* q0 = (const char*)(((uintptr_t)p0 + 15) & ~(uintptr_t)15);
-                const char* q1 = (const char*)((uintptr_t)p1 & ~(uintptr_t)15);
-                for (const char* q = q0; q < q1; q += 16384)
-                    prefetch_l2_bulk(q, (unsigned)min((long long)16384, (long long)(q1 - q)));
+            if (c == 0) a.shiftv[t] = s_sc.shift;
+        }
+        PROF_MARK(6);   // A2 scan+scatter
+        GRID_ARRIVE();   // ---- barrier 2: mailboxes complete
+        for (int b = tid; b < kNSB; b += GT) s_sub[b] = 0;
+        if (warp == 0 && nc > 0) {
+            // the generation the fixed-lag terms of this step gather from, and the next step's slice of u -> L2
+            if (t + 1 < NOBS) {
+                const double* Un = a.U + (size_t)(t + 1) * N;
+                prefetch_range(Un + jb, Un + je, lane, 32);
             }
         }
-        PROF_MARK(7);
+        PROF_MARK(7);   // zero+prefetch
         GRID_WAIT();
-        PROF_MARK(8);
+        PROF_MARK(8);   // wait 2
         if (s_sc.abort_now) break;
 
         // --------------------------------------------------------------------------------------
-        // phase B: sort this tile (:392-424 / :23-52), weights (:427-442), block scan
+        // phase B: sort this tile (:392-424 / :23-52), weights (:427-442), fixed-lag score terms
+        // (:445-470), block scan
         // --------------------------------------------------------------------------------------
+        double acc[3] = {0.0, 0.0, 0.0};   // sh * {x, m, m^2}
         {
             const MailEntry* mb = (const MailEntry*)a.XE + pstart;
-            double ex[KPT];
-            int ej[KPT], ea[KPT], er[KPT];
-            double lmin = INFINITY, lmax = -INFINITY;
+            const double lo = s_sc.lo, scale = s_sc.scale;
+            double bx[KPT];
+            int bj[KPT], bae[KPT];
 #pragma unroll
-            for (int kk = 0; kk < KPT; ++kk) {
-                const int e = kk * GT + tid;
-                ex[kk] = 0.0;
-                ej[kk] = ea[kk] = 0;
-                if (e < n) {
-                    const int4 raw = __ldcg((const int4*)(mb + e));
-                    ex[kk] = __longlong_as_double(((long long)raw.y << 32) | (long long)(unsigned)raw.x);
-                    ej[kk] = raw.z;
-                    ea[kk] = raw.w;
-                }
-            }
+            for (int k0 = 0; k0 < KPT; k0 += CH) {
+                int4 raw[CH];
 #pragma unroll
-            for (int kk = 0; kk < KPT; ++kk) {
-                const int e = kk * GT + tid;
-                if (e < n) {
-                    lmin = fmin(lmin, ex[kk]);
-                    lmax = fmax(lmax, ex[kk]);
+                for (int u = 0; u < CH; ++u) {
+                    const int e = (k0 + u) * GT + tid;
+                    raw[u] = make_int4(0, 0, 0, 0);
+                    if (e < n) raw[u] = __ldcg((const int4*)(mb + e));
                 }
-            }
-            lmin = warp_min(lmin);
-            lmax = warp_max(lmax);
-            if (lane == 0) {
-                s_red[warp] = lmin;
-                s_red[32 + warp] = lmax;
-            }
-            __syncthreads();
-            if (warp == 0) {
-                const double lo = warp_min(lane < GT / 32 ? s_red[lane] : INFINITY);
-                const double hi = warp_max(lane < GT / 32 ? s_red[32 + lane] : -INFINITY);
-                if (lane == 0) {
-                    s_sc.lo = lo;
-                    s_sc.hi = hi;
-                }
-            }
-            __syncthreads();
-            const double lo = s_sc.lo;
-            const double scale = (s_sc.hi > lo) ? (double)kNSB / (s_sc.hi - lo) : 0.0;
 #pragma unroll
-            for (int kk = 0; kk < KPT; ++kk) {
-                const int e = kk * GT + tid;
-                er[kk] = 0;
-                if (e < n) er[kk] = atomicAdd(&s_sub[sub_bin(ex[kk], lo, scale)], 1);
+                for (int u = 0; u < CH; ++u) {
+                    const int e = (k0 + u) * GT + tid;
+                    const double x = __longlong_as_double(((long long)raw[u].y << 32) | (long long)(unsigned)raw[u].x);
+                    bx[k0 + u] = x;
+                    bj[k0 + u] = raw[u].z;
+                    bae[k0 + u] = raw[u].w & 0x1fffff;
+                    if (e < n) {
+                        const int er = atomicAdd(&s_sub[sub_bin(x, lo, scale)], 1);
+                        bae[k0 + u] |= min(er, 2047) << 21;
+                    }
+                }
             }
             __syncthreads();
             {
-                // exclusive scan of the sub-bin counters in place (BPT consecutive bins per thread)
-                int cnt[BPT];
+                // exclusive scan of the sub-bin counters in place (SPT consecutive bins per thread)
+                int cnt[SPT];
 #pragma unroll
-                for (int i = 0; i < BPT; i += 4) {
-                    const int4 v = *(const int4*)(s_sub + BPT * tid + i);
+                for (int i = 0; i < SPT; i += 4) {
+                    const int4 v = *(const int4*)(s_sub + SPT * tid + i);
                     cnt[i] = v.x;
                     cnt[i + 1] = v.y;
                     cnt[i + 2] = v.z;
@@ -876,7 +910,7 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
                 }
                 int loc = 0, mxb = 0;
 #pragma unroll
-                for (int i = 0; i < BPT; ++i) {
+                for (int i = 0; i < SPT; ++i) {
                     loc += cnt[i];
                     mxb = max(mxb, cnt[i]);
                 }
@@ -884,183 +918,167 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
                 int total;
                 int start = block_excl_scan_int<GT>(loc, s_wi, total, lane, warp);
 #pragma unroll
-                for (int i = 0; i < BPT; ++i) {
+                for (int i = 0; i < SPT; ++i) {
                     const int cn = cnt[i];
                     cnt[i] = start;
                     start += cn;
                 }
 #pragma unroll
-                for (int i = 0; i < BPT; i += 4)
-                    *(int4*)(s_sub + BPT * tid + i) = make_int4(cnt[i], cnt[i + 1], cnt[i + 2], cnt[i + 3]);
+                for (int i = 0; i < SPT; i += 4)
+                    *(int4*)(s_sub + SPT * tid + i) = make_int4(cnt[i], cnt[i + 1], cnt[i + 2], cnt[i + 3]);
             }
             __syncthreads();
 #pragma unroll
             for (int kk = 0; kk < KPT; ++kk) {
                 const int e = kk * GT + tid;
                 if (e < n) {
-                    const int pos = s_sub[sub_bin(ex[kk], lo, scale)] + er[kk];
-                    s_x[pos] = ex[kk];
-                    s_j[pos] = ej[kk];
-                    s_a[pos] = ea[kk];
+                    const int pos = min(s_sub[sub_bin(bx[kk], lo, scale)] + (int)((unsigned)bae[kk] >> 21), kCap - 1);
+                    s_xb[pos] = bx[kk];
+                    s_jb[pos] = bj[kk];
+                    s_ab[pos] = bae[kk] & 0x1fffff;
                 }
             }
             __syncthreads();
-            // exact order inside a sub-bin: by value, then by birth row (:32-35 never returns 0)
-            int np[KPT];
+        }
+        PROF_MARK(9);   // B bin sort
+        {
+            // sub-bin order -> exact order (by value, then by birth row: :32-35 never returns 0), in place
+            const double lo = s_sc.lo, scale = s_sc.scale;
+            double bx[KPT];
+            int bj[KPT], ba[KPT], np[KPT];
 #pragma unroll
             for (int kk = 0; kk < KPT; ++kk) {
                 const int q = kk * GT + tid;
+                bx[kk] = 0.0;
+                bj[kk] = ba[kk] = 0;
                 np[kk] = q;
-                ex[kk] = 0.0;
                 if (q < n) {
-                    const double x = s_x[q];
-                    ex[kk] = x;
+                    const double x = s_xb[q];
+                    const int j = s_jb[q];
+                    bx[kk] = x;
+                    bj[kk] = j;
+                    ba[kk] = s_ab[q];
                     const int kb = sub_bin(x, lo, scale);
                     const int b0 = s_sub[kb];
                     const int b1 = (kb + 1 < kNSB) ? s_sub[kb + 1] : n;
                     if (b1 - b0 > 1 && b1 - b0 <= kMaxSub) {
-                        const int j = s_j[q];
                         int rank = 0;
                         for (int m = b0; m < b1; ++m) {
-                            const double xm = s_x[m];
+                            const double xm = s_xb[m];
                             if (xm < x) ++rank;
                             else if (xm == x && m != q) {
                                 ++cnt_key;
-                                if (s_j[m] < j) ++rank;
+                                if (s_jb[m] < j) ++rank;
                             }
                         }
                         np[kk] = b0 + rank;
                     }
                 }
             }
-            // in-place permutation, one array at a time (keeps the register footprint small)
             __syncthreads();
 #pragma unroll
             for (int kk = 0; kk < KPT; ++kk) {
                 const int q = kk * GT + tid;
-                if (q < n) {
-                    s_x[np[kk]] = ex[kk];
-                    ej[kk] = s_j[q];
+                if (q < n && np[kk] != q) {
+                    s_xb[np[kk]] = bx[kk];
+                    s_jb[np[kk]] = bj[kk];
+                    s_ab[np[kk]] = ba[kk];
                 }
             }
             __syncthreads();
-#pragma unroll
-            for (int kk = 0; kk < KPT; ++kk) {
-                const int q = kk * GT + tid;
-                if (q < n) {
-                    s_j[np[kk]] = ej[kk];
-                    ea[kk] = s_a[q];
-                }
-            }
-            __syncthreads();
-#pragma unroll
-            for (int kk = 0; kk < KPT; ++kk) {
-                const int q = kk * GT + tid;
-                if (q < n) s_a[np[kk]] = ea[kk];
-            }
-            __syncthreads();
-        }
-        PROF_MARK(9);
-        // birth rows of the new sorted generation (the values follow with exp(-x/2), below)
-#pragma unroll
-        for (int kk = 0; kk < KPT; ++kk) {
-            const int q = kk * GT + tid;
-            if (q < n) {
-                const int j = s_j[q];
-                __stcg(&a.perm[pstart + q], j);
-                if (a.hist) {
-                    a.Xhist[(size_t)t * N + pstart + q] = s_x[q];
-                    a.Ahist[(size_t)t * N + pstart + q] = __ldcg(&a.parentpos[j]);
-                }
-            }
         }
         {
             // weights (:427-437): lw = -0.9189 - x/2 - y^2 exp(-x) / 2, sh = exp(lw - shift);
-            // thread = Lc consecutive sorted particles, sequential running sum
+            // fixed-lag score terms (:445-470): ancestor pair (time t-L+1, t-L+2) from one half sector
             const double y = a.obs[t], hy2 = 0.5 * y * y, shift = s_sc.shift;
             const double mu = s_k.mu, phi = s_k.phi, sr = s_k.sr;
-            const int Lc = ((n + GT - 1) / GT) | 1, q0 = tid * Lc;
-            double run = 0.0;
-            double acc[3] = {0.0, 0.0, 0.0};
+            const bool score = t >= L && !(a.dbg & 4);
+            unsigned long long* Wt = a.W + (size_t)par * N;
             bool bad = false;
 #pragma unroll
-            for (int kk = 0; kk < KCH; ++kk) {
-                const int q = q0 + kk;
-                if (kk < Lc && q < n) {
-                    const double x = s_x[q];
+            for (int kk = 0; kk < KPT; ++kk) {
+                const int q = kk * GT + tid;
+                if (q < n) {
+                    const double x = s_xb[q];
+                    const int j = s_jb[q];
                     const double e = exp(-0.5 * x);
                     const double lw = (-0.91893853320467267 - 0.5 * x) - hy2 * (e * e);
                     double sh = exp(lw - shift);
-                    if (!isfinite(sh)) {
+                    if (!isfinite(sh) || sh > kWMax) {
                         bad = true;
                         sh = 0.0;
                     }
-                    // (x, e) of the new generation: this thread's chunk is contiguous in memory
                     __stcg(&a.XE[pstart + q], make_double2(x, e));
+                    __stcg(&a.perm[pstart + q], j);
                     s_sh[q] = sh;
-                    run = run + sh;
-                    acc[0] += sh * x;
+                    // fixed-lag terms (:445-470): the weight goes to the lagged ancestor (integer
+                    // additions: exact and order independent); payload_pass() multiplies it with the
+                    // ancestor's payload
+                    if (score) atomicAdd(&Wt[min(s_ab[q], N - 1)], (unsigned long long)(sh * kWScale + 0.5));
+                    if (pstart + q == 0) a.xminv[t] = x;   // Q10/Q11: traj[t] = X_t[0]
+                    if (a.hist) {
+                        a.Xhist[(size_t)t * N + pstart + q] = x;
+                        a.Ahist[(size_t)t * N + pstart + q] = __ldcg(&a.parentpos[j]);
+                    }
+                    acc[0] = fma(sh, x, acc[0]);
                     double m = mu + phi * (x - mu);
                     m += (sr * e) * y;
-                    acc[1] += sh * m;
-                    acc[2] += sh * (m * m);
+                    const double shm = sh * m;
+                    acc[1] += shm;
+                    acc[2] = fma(shm, m, acc[2]);
                 }
             }
             if (bad) GRID_FLAG(2);
-            toff = block_excl_scan_f64<GT>(run, s_wd, lane, warp);
-            if (n > 0 && tid == (n - 1) / Lc) s_sc.tot = toff + run;   // cumulative weight of the tile's last particle
-            if (n == 0 && tid == 0) s_sc.tot = 0.0;
-            block_sum<3>(acc, s_red);
-            if (tid == 0) {
-                const double tot = s_sc.tot;
-                __stcg((double2*)&a.tinfo[c * 4], make_double2(tot, (double)n));
-                __stcg((double2*)&a.tinfo[c * 4 + 2], make_double2(acc[1], acc[2]));
-                double* ps = a.psum + ((size_t)t * G + c) * 8;
-                ps[0] = tot;
-                ps[1] = acc[0];
-            }
         }
-        PROF_MARK(10);
-        GRID_ARRIVE();   // ---- barrier 3: tile totals published
+        __syncthreads();
+        PROF_MARK(10);   // B rank+weights+score
         {
-            // fixed-lag score terms (:445-470): ancestor pair (time t-L+1, t-L+2) from one half sector
+            // cumulative weights: thread = Lc consecutive sorted particles, sequential running sum;
+            // one block-wide pass gives the offsets of the chunks and the eight weighted sums
             const int Lc = ((n + GT - 1) / GT) | 1, q0 = tid * Lc;
-            double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-            if (t >= L && !(a.dbg & 4)) {
-                const double ylag = a.obs[t - L];   // Q5: obs[i - LAG]
-                const PEntry* Pg = a.P + (size_t)((t - (L - 2)) % RP) * N;
+            double run = 0.0;
 #pragma unroll
-                for (int k0 = 0; k0 < KCH; k0 += 3) {
-                    double2 pe[3];
+            for (int kk = 0; kk < KCH; ++kk) {
+                const int q = q0 + kk;
+                if (kk < Lc && q < n) run = run + s_sh[q];
+            }
+            const double incl = warp_incl_scan(run, lane);
 #pragma unroll
-                    for (int u = 0; u < 3; ++u) {
-                        const int kk = k0 + u, q = q0 + kk;
-                        pe[u] = make_double2(0.0, 0.0);
-                        if (kk < KCH && kk < Lc && q < n) {
-                            const int an = min(max(s_a[q], 0), N - 1);
-                            pe[u] = __ldcg((const double2*)&Pg[an]);
-                        }
-                    }
+            for (int i = 0; i < 3; ++i) acc[i] = warp_sum(acc[i]);
+            if (lane == 31) s_red[warp] = incl;
+            if (lane == 0) {
 #pragma unroll
-                    for (int u = 0; u < 3; ++u) {
-                        const int kk = k0 + u, q = q0 + kk;
-                        if (kk < KCH && kk < Lc && q < n) {
-                            const double sh = s_sh[q];
-                            double sq, g[4];
-                            sv_score_main_e(s_k, pe[u].y, exp(-0.5 * pe[u].y), pe[u].x, ylag, sq, g);
-                            acc[0] += sh * pe[u].y;
+                for (int i = 0; i < 3; ++i) s_red[32 * (1 + i) + warp] = acc[i];
+            }
+            __syncthreads();
+            const double wt = (lane < NW) ? s_red[lane] : 0.0;
+            const double wincl = warp_incl_scan(wt, lane);
+            double wex = __shfl_up_sync(kFullMask, wincl, 1);
+            if (lane == 0) wex = 0.0;
+            const double woff = __shfl_sync(kFullMask, wex, warp);
+            double ex = __shfl_up_sync(kFullMask, incl, 1);
+            if (lane == 0) ex = 0.0;
+            toff = woff + ex;
+            double* ps = a.psum + ((size_t)t * G + c) * 8;
+            if ((n > 0 && tid == (n - 1) / Lc) || (n == 0 && tid == 0)) {
+                const double tot = (n > 0) ? toff + run : 0.0;   // cumulative weight of the tile's last particle
+                __stcg(&a.tinfo[c * 4], tot);
+                ps[0] = tot;
+            }
+            if (warp == 0) {
+                double v[3];
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) acc[1 + i] += g[i] * sh;
-                        }
+                for (int i = 0; i < 3; ++i) v[i] = warp_sum((lane < NW) ? s_red[32 * (1 + i) + lane] : 0.0);
+                if (lane == 0) {
+                    __stcg(&a.tinfo[c * 4 + 1], (double)n);
+                    __stcg((double2*)&a.tinfo[c * 4 + 2], make_double2(v[1], v[2]));
+                    ps[1] = v[0];
+                    ps[7] = 0.0;
+                    if (t < L || (a.dbg & 4)) {   // later steps: payload_pass() writes ps[2..6]
+#pragma unroll
+                        for (int i = 2; i < 7; ++i) ps[i] = 0.0;
                     }
                 }
-            }
-            block_sum<5>(acc, s_red);
-            if (tid == 0) {
-                double* ps = a.psum + ((size_t)t * G + c) * 8;
-#pragma unroll
-                for (int i = 0; i < 5; ++i) ps[2 + i] = acc[i];
-                ps[7] = 0.0;
             }
             if (t >= NOBS - L) {
 #pragma unroll
@@ -1070,11 +1088,20 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
                 }
             }
         }
-        PROF_MARK(11);
+        PROF_MARK(11);   // B scan+publish
+        GRID_ARRIVE();   // ---- barrier 3: tile totals published
+        if (warp == 0 && t >= L && nc > 0 && !(a.dbg & 4)) {
+            // payload planes of the lagged generation -> L2 for payload_pass() (sequential HBM reads)
+            const size_t pplane = (size_t)RP * N;
+            const double* Pg = a.P + (size_t)((t - (L - 2)) % RP) * N;
+            for (int pl = 0; pl < 3; ++pl) prefetch_range(Pg + pl * pplane + jb, Pg + pl * pplane + je, lane, 32);
+        }
         GRID_WAIT();
-        PROF_MARK(12);
+        PROF_MARK(12);   // wait 3
         if (s_sc.abort_now) break;
     }
+
+    if (!s_sc.abort_now && NOBS - 1 >= L && !(a.dbg & 4)) payload_pass<GT>(a, NOBS - 1, jb, nc, c, s_red, pol_stream);
 
     // diagnostics
     cnt_near = __reduce_add_sync(kFullMask, cnt_near);
@@ -1136,12 +1163,13 @@ __global__ void __launch_bounds__(256) grid_tail_kernel(GridArgs a, const double
             // entry of the ancestor idx-1 steps back holds (next = its value, curr = its parent's value)
             const int m = idx - 1;
             const int row = (m == 0) ? b : min(max(Rt[b].a[m - 1], 0), N - 1);
-            const PEntry pe = a.P[(size_t)((T - m) % RP) * N + row];
-            curr = pe.c;
+            const size_t prow = (size_t)((T - m) % RP) * N + row, pplane = (size_t)RP * N;
+            curr = a.P[kPlaneC * pplane + prow];
+            const double pe_n = a.P[kPlaneN * pplane + prow];
             acc[0] += wT * curr;
             const double wi = shi[p] / Si;
             double sq, g[4];
-            sv_score_tail_e(k, curr, exp(-0.5 * curr), pe.n, y1, sq, g);
+            sv_score_tail_e(k, curr, exp(-0.5 * curr), pe_n, y1, sq, g);   // the tail uses obs[i - 1] (Q6)
 #pragma unroll
             for (int q = 0; q < 4; ++q) acc[1 + q] += g[q] * wi;
         }
@@ -1162,7 +1190,8 @@ __global__ void __launch_bounds__(256) grid_tail_reduce_kernel(const double* __r
     if (tid < 5) out[irel * 8 + tid] = acc[tid];
 }
 
-// sums[t][0] = sum sh, [1] = sum sh x, [2] = sum sh curr, [3..6] = sum sh g;  tail[irel][0..4]
+// sums[t][0] = sum sh, [1] = sum sh x, [2] = sum sh c, [3] = sum sh sq, [4] = sum sh sq c, [5] = sum sh sq^2,
+// [6] = sum sh sq ey (c = lagged ancestor value, sq / ey as stored in P);  tail[irel][0..4]
 __global__ void grid_finish_kernel(const GridCtrl* __restrict__ ctrl, const double* __restrict__ sums,
                                    const double* __restrict__ shift, const double* __restrict__ xmin,
                                    const double* __restrict__ tail, const double* __restrict__ params,
@@ -1194,9 +1223,16 @@ __global__ void grid_finish_kernel(const GridCtrl* __restrict__ ctrl, const doub
         double s = 0.0, g[4] = {0.0, 0.0, 0.0, 0.0};
         const int src = t + L - 1;   // main-loop terms land at tt = i - L + 1 (:445-470)
         if (t >= 1 && src < nobs) {
-            const double S = sums[(size_t)src * 8];
-            s = sums[(size_t)src * 8 + 2] / S;
-            for (int q = 0; q < 4; ++q) g[q] = sums[(size_t)src * 8 + 3 + q] / S;
+            const double* sm = sums + (size_t)src * 8;
+            const double S = sm[0];
+            SvConst k;
+            sv_const_init(k, params);
+            s = sm[2] / S;
+            // weighted means of g[0..3] of :454-465 written in the monomials sq, sq c, sq^2, sq ey
+            g[0] = k.q * k.one_m_phi * sm[3] / S;
+            g[1] = k.q * k.one_m_phi2 * (sm[4] - k.mu * sm[3]) / S;
+            g[2] = (k.q * sm[5] + k.q * k.sr * sm[6] - S) / S;
+            g[3] = (k.rho * S - k.q * k.rho * sm[5] + k.inv_sv * sm[6]) / S;
         }
         const int irel_s = t - (nobs - L);   // tail: i = nobs-L+irel adds smo[i], gradient[.][i-L+1]
         if (irel_s >= 0 && irel_s < L) s += tail[irel_s * 8];
@@ -1209,8 +1245,8 @@ __global__ void grid_finish_kernel(const GridCtrl* __restrict__ ctrl, const doub
 }
 
 struct GridLayout {
-    size_t ctrl, ghist, tilecnt, tinfo, H, Hcarry, XE, perm, R, P, psum, shiftv, xminv, shring, parentpos,
-        sums, tailpart, tail, info, total;
+    size_t ctrl, ghist, tilecnt, tinfo, H, XE, perm, R, P, W, psum, shiftv, xminv, shring, parentpos, sums,
+        tailpart, tail, info, total;
     int RP, nblk;
 };
 
@@ -1218,20 +1254,22 @@ size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 GridLayout grid_layout(int nobs, int n, int lag, int G, int hist) {
     GridLayout L = GridLayout();
-    L.RP = lag - 1 < 2 ? 2 : lag - 1;
+    // ring depth of the payload planes: the terms of step t-1 are summed after phase A1 of step t has
+    // written generation t, and read generation t-1-(lag-2) = t-(lag-1): lag slots keep the two apart
+    L.RP = lag < 2 ? 2 : lag;
     L.nblk = 296;
     size_t o = 0;
     const size_t N = (size_t)n;
     L.ctrl = o;      o += al256(sizeof(GridCtrl));
-    L.ghist = o;     o += al256((size_t)2 * kNF * 4);
-    L.tilecnt = o;   o += al256((size_t)2 * kMaxTiles * 4);
+    L.ghist = o;     o += al256((size_t)2 * kNCopy * kNF * 4);
+    L.tilecnt = o;   o += al256((size_t)2 * kMaxTiles * kCntStride * 4);
     L.tinfo = o;     o += al256((size_t)kMaxTiles * 4 * 8);
-    L.Hcarry = o;    o += al256((size_t)kMaxTiles * 4);
     L.H = o;         o += al256(N * 4);
     L.XE = o;        o += al256(N * 16);
     L.perm = o;      o += al256(N * 4);
     L.R = o;         o += al256(2 * N * 32);
-    L.P = o;         o += al256((size_t)L.RP * N * 16);
+    L.P = o;         o += al256((size_t)4 * L.RP * N * 8);
+    L.W = o;         o += al256((size_t)2 * N * 8);
     L.psum = o;      o += al256((size_t)nobs * G * 8 * 8);
     L.shiftv = o;    o += al256((size_t)nobs * 8);
     L.xminv = o;     o += al256((size_t)nobs * 8);
@@ -1265,7 +1303,7 @@ int sv_grid_ctas(int n, int sm_count, int ctas) {
 // a tile holds N/G particles +- one histogram bin; 12 % head room below the shared-memory capacity
 bool sv_grid_eligible(int nobs, int n, int lag, int G) {
     if (G < 1 || G > kMaxTiles) return false;
-    if (lag < 2 || lag > 10 || nobs < 2 * lag || n < 32) return false;
+    if (lag < 2 || lag > 10 || nobs < 2 * lag || n < 32 || n > (1 << 21)) return false;
     const int Wc = (n + G - 1) / G;
     return Wc <= kCap - kCap / 8;
 }
@@ -1301,11 +1339,11 @@ int sv_grid_run(const double* d_obs, const double* d_params, const double* d_rvr
     a.tilecnt = (int*)(ws + L.tilecnt);
     a.tinfo = (double*)(ws + L.tinfo);
     a.H = (int*)(ws + L.H);
-    a.Hcarry = (int*)(ws + L.Hcarry);
     a.XE = (double2*)(ws + L.XE);
     a.perm = (int*)(ws + L.perm);
     a.R = (REntry*)(ws + L.R);
-    a.P = (PEntry*)(ws + L.P);
+    a.P = (double*)(ws + L.P);
+    a.W = (unsigned long long*)(ws + L.W);
     a.psum = (double*)(ws + L.psum);
     a.shiftv = (double*)(ws + L.shiftv);
     a.xminv = (double*)(ws + L.xminv);
@@ -1318,17 +1356,32 @@ int sv_grid_run(const double* d_obs, const double* d_params, const double* d_rvr
         const char* e = getenv("PMMH_GRID_DEBUG");
         a.dbg = e ? atoi(e) : 0;
     }
-    // control block, histograms, reservation counters, tile info: zero; head markers: -1
-    GRID_CUDA(cudaMemsetAsync(ws + L.ctrl, 0, L.Hcarry - L.ctrl, st));
-    GRID_CUDA(cudaMemsetAsync(ws + L.Hcarry, 0xff, (L.XE - L.Hcarry), st));
+    // control block, histograms, reservation counters, tile info: zero
+    GRID_CUDA(cudaMemsetAsync(ws + L.ctrl, 0, L.H - L.ctrl, st));
+    GRID_CUDA(cudaMemsetAsync(ws + L.W, 0, (size_t)2 * n * 8, st));
     static thread_local bool attr_set[64] = {false};
     static int threads = 0;
     if (!threads) {
         const char* e = getenv("PMMH_GRID_THREADS");
-        threads = (e && atoi(e) == 1024) ? 1024 : 512;
+        threads = (e && atoi(e) == 512) ? 512 : 1024;
     }
     int dev = 0;
     GRID_CUDA(cudaGetDevice(&dev));
+    {
+        // the two genealogy record tables live in the persisting part of L2 (their reuse distance is a
+        // whole time step); the limit is a device-wide setting, set once per device and size
+        static size_t persist_set[64] = {0};
+        size_t want = 0;
+        const char* e = getenv("PMMH_GRID_L2_PERSIST_MB");
+        if (e) want = (size_t)atoi(e) << 20;
+        int maxp = 0;
+        GRID_CUDA(cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, dev));
+        if (want > (size_t)maxp) want = (size_t)maxp;
+        if (dev >= 0 && dev < 64 && persist_set[dev] != want + 1) {
+            GRID_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+            persist_set[dev] = want + 1;
+        }
+    }
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
         GRID_CUDA(cudaFuncSetAttribute(sv_grid_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem));
         GRID_CUDA(cudaFuncSetAttribute(sv_grid_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem));
