@@ -73,13 +73,6 @@ struct __align__(16) MailEntry {   // aliases one (x, exp(-x/2)) pair of the sor
     double x;
     int j, pad;
 };
-constexpr double kWScale = 68719476736.0;        // 2^36: fixed-point scale of the descendant weights
-constexpr double kWInv = 1.0 / 68719476736.0;
-constexpr double kWMax = 60.0;                   // weights above this abandon the evaluation (64 * 2^21 * 2^36 = 2^63)
-struct __align__(32) REntry {
-    int a[8];              // birth rows of the ancestors 1 .. 8 steps back
-};
-
 struct GridCtrl {
     unsigned bar;                  // arrival counter of the grid barrier of the main warps (monotone)
     int status;                    // 0, or (reason << 24) | first barrier index at which everybody stops
@@ -90,7 +83,7 @@ struct GridCtrl {
 
 struct GridArgs {
     int N, NOBS, LAG, G, Wc, RP, hist;
-    int dbg;   // development (timing only, results wrong): 1 skip the genealogy records, 4 skip the score terms
+    int dbg;   // development (timing only, results wrong): 1 skip the helper's work, 4 skip the score terms
     const double *obs, *params, *rvr, *U;
     GridCtrl* ctrl;
     int* ghist;        // [2][kNFMax]
@@ -99,10 +92,10 @@ struct GridArgs {
     int* H;            // [N] ancestor (sorted position) of every child
     double2* XE;       // [N] sorted generation: (x, exp(-x/2)); the mailbox of the next generation aliases it
     int* perm;         // [N] sorted position -> birth row
-    int* BP;           // [2][N] birth row of the parent of child j (main warps -> helper warps), by step parity
-    REntry* R;         // [2][N]
+    int* BP;           // [kRingBP][N] birth row of the parent of row j of generation t % kRingBP (main -> helper warps)
+    int *J2, *J4;      // [kRingJ][N] birth rows of the ancestors 2 / 4 generations back
+    double2* Q;        // [2][N] lagged pair of row j of generation t (helper -> main warps), by step parity
     double2* P;        // [RP][N] (parent value, own value) of generation t % RP in birth order
-    unsigned long long* W;   // [2][N] fixed-point weight of the step-t descendants of a lagged ancestor, by step parity
     double* psum;      // [NOBS][G][8]
     double *shiftv, *xminv;   // [NOBS]
     double* shring;    // [LAG][N] sh of the last LAG generations (sorted order)
@@ -140,23 +133,6 @@ __device__ __forceinline__ unsigned long long policy_evict_first() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
-__device__ __forceinline__ unsigned long long policy_evict_last() {
-    unsigned long long pol;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-// 32-byte genealogy records: one 256-bit access
-__device__ __forceinline__ void ld_rec(const REntry* p, unsigned long long pol, int (&r)[8]) {
-    asm volatile("ld.global.cg.L2::cache_hint.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "l"(p), "l"(pol));
-}
-__device__ __forceinline__ void st_rec(REntry* p, unsigned long long pol, int a0, int a1, int a2, int a3, int a4,
-                                       int a5, int a6, int a7) {
-    asm volatile("st.global.cg.L2::cache_hint.v8.s32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}, %9;" ::"l"(p), "r"(a0),
-                 "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5), "r"(a6), "r"(a7), "l"(pol)
-                 : "memory");
-}
 __device__ __forceinline__ double ld_stream_hint_f64(const double* p, unsigned long long pol) {
     double v;
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
@@ -170,19 +146,6 @@ __device__ __forceinline__ int warp_incl_max(int v, int lane) {
     }
     return v;
 }
-__device__ __forceinline__ int pick8(const int (&r)[8], int idx) {
-    switch (idx) {
-        case 0: return r[0];
-        case 1: return r[1];
-        case 2: return r[2];
-        case 3: return r[3];
-        case 4: return r[4];
-        case 5: return r[5];
-        case 6: return r[6];
-        default: return r[7];
-    }
-}
-
 // the resampling point of child j, (u + j) / N as the reference computes it (:703)
 __device__ __forceinline__ double cpoint(double u, int j, double dn, double inv_n, bool pow2) {
     const double s = u + (double)j;
@@ -262,121 +225,158 @@ __device__ __forceinline__ int block_excl_max_int(int v, int init, int* s_w, int
 // ---------------------------------------------------------------------------------------------
 // helper warps: what only feeds outputs (genealogy, fixed-lag score terms)
 // ---------------------------------------------------------------------------------------------
-// Step t, children [jb, jb + nc) of this CTA in birth order: the record of child j = (birth row of
-// its parent, the parent's ancestors 1..7); the child's weight (same formula and shift as the main
-// warps) is added, as a fixed-point integer (exact, order independent), to the slot of its ancestor
-// LAG-2 generations back.
+// Genealogy by pointer jumping.  BP[t][j] = birth row (generation t-1) of the parent of row j of
+// generation t (written by the main warps), J2[t] = BP[t-1] o BP[t] (2 generations back), J4[t] =
+// J2[t-2] o J2[t] (4 back).  Every random read goes to a table of an OLDER step, so one helper
+// barrier per step orders everything; the tables are 4 bytes per particle and the hot ones stay in
+// L2.  The ancestor LAG-2 generations back follows from at most three more hops; its (parent
+// value, value) pair and the particle's own weight (same formula and shift as the main warps) give
+// the fixed-lag score terms of step t (:445-470) directly: no atomics, fixed summation order.
+// grid_finish_kernel assembles the gradient terms from the six sums.
+constexpr int kRingBP = 12, kRingJ = 8;
+
+// Helper warps, step t, rows [jb, jb + nc) of generation t: jump tables, then the (parent value,
+// value) pair of the ancestor LAG-2 generations back is copied to Q[t & 1][j] (birth order), where
+// the main warps read it sequentially one step later (score_pass).  No arithmetic here: the
+// helper warps are few, all they have is memory-level parallelism (IT independent chains each).
 template <int GTH>
-__device__ __forceinline__ void helper_records(const GridArgs& a, const SvConst& k, int t, int jb, int nc, int htid,
-                                               double shift, unsigned long long pol_keep) {
-    constexpr int RB = 4;   // records in flight per thread
-    const int N = a.N, L = a.LAG;
-    const REntry* Rp = a.R + (size_t)((t - 1) & 1) * N;
-    REntry* Rc = a.R + (size_t)(t & 1) * N + jb;
-    const int* BPt = a.BP + (size_t)(t & 1) * N + jb;
-    const double2* Pt = a.P + (size_t)(t % a.RP) * N + jb;
-    unsigned long long* Wt = a.W + (size_t)(t & 1) * N;
-    const bool score = t >= L && !(a.dbg & 4), recs = !(a.dbg & 1);
-    const double y = a.obs[t], hy2 = 0.5 * y * y;
-    (void)k;
-    int bn[RB];
-    double xn[RB];
+__device__ __forceinline__ void helper_lineage(const GridArgs& a, int t, int jb, int nc, int htid) {
+    constexpr int IT = 16;   // independent chains in flight per thread
+    const int N = a.N, L = a.LAG, RP = a.RP;
+    const int* BPt = a.BP + (size_t)(t % kRingBP) * N + jb;
+    const int* BPm1 = a.BP + (size_t)((t - 1) % kRingBP) * N;
+    int* J2t = a.J2 + (size_t)(t % kRingJ) * N + jb;
+    const int* J2m2 = a.J2 + (size_t)((t + kRingJ - 2) % kRingJ) * N;
+    int* J4t = a.J4 + (size_t)(t % kRingJ) * N + jb;
+    const bool do2 = t >= 2, do4 = t >= 4, score = t >= L && !(a.dbg & 4);
+    const int g = t - (L - 2);                               // generation of the lagged pair
+    const double2* Pg = a.P + (size_t)((g > 0 ? g : 0) % RP) * N;
+    double2* Qt = a.Q + (size_t)(t & 1) * N + jb;
+    for (int i0 = 0; i0 < nc; i0 += IT * GTH) {
+        int cur[IT], b1[IT];
 #pragma unroll
-    for (int u = 0; u < RB; ++u) {
-        const int i = u * GTH + htid;
-        bn[u] = 0;
-        xn[u] = 0.0;
-        if (i < nc) {
-            bn[u] = __ldcg(&BPt[i]);
-            xn[u] = __ldcg(&Pt[i].y);
-        }
-    }
-    for (int i0 = 0; i0 < nc; i0 += RB * GTH) {
-        int b[RB], r[RB][8];
-        double x[RB];
-#pragma unroll
-        for (int u = 0; u < RB; ++u) {
+        for (int u = 0; u < IT; ++u) {
             const int i = i0 + u * GTH + htid;
-            b[u] = bn[u];
-            x[u] = xn[u];
-#pragma unroll
-            for (int z = 0; z < 8; ++z) r[u][z] = 0;
-            if (i < nc && recs) ld_rec(&Rp[min(max(b[u], 0), N - 1)], pol_keep, r[u]);
+            b1[u] = (i < nc) ? __ldcg(&BPt[i]) : 0;
         }
 #pragma unroll
-        for (int u = 0; u < RB; ++u) {   // the next batch's inputs travel while this one is consumed
-            const int i = i0 + (RB + u) * GTH + htid;
-            if (i < nc) {
-                bn[u] = __ldcg(&BPt[i]);
-                xn[u] = __ldcg(&Pt[i].y);
+        for (int u = 0; u < IT; ++u) cur[u] = do2 ? __ldcg(&BPm1[min(max(b1[u], 0), N - 1)]) : 0;
+        if (do2) {
+#pragma unroll
+            for (int u = 0; u < IT; ++u) {
+                const int i = i0 + u * GTH + htid;
+                if (i < nc) __stcg(&J2t[i], cur[u]);
             }
         }
+        int gen = t, rem = L - 2;
+        if (rem >= 4 || !score) {
+            // 4 generations back (the table is needed by later steps whatever the lag is)
+            if (do4) {
 #pragma unroll
-        for (int u = 0; u < RB; ++u) {
-            const int i = i0 + u * GTH + htid;
-            if (i < nc) {
-                if (recs) st_rec(&Rc[i], pol_keep, b[u], r[u][0], r[u][1], r[u][2], r[u][3], r[u][4], r[u][5], r[u][6]);
-                if (score) {
-                    // row of the ancestor L-2 steps back (new record = (b, r[0..6]))
-                    int anc = jb + i;
-                    if (L == 3) anc = b[u];
-                    else if (L > 3) anc = pick8(r[u], L - 4);
-                    const double e = exp(-0.5 * x[u]);
-                    const double lw = (-0.91893853320467267 - 0.5 * x[u]) - hy2 * (e * e);
-                    double sh = exp(lw - shift);
-                    if (!isfinite(sh) || sh > kWMax) sh = 0.0;   // the main warps abandon the evaluation
-                    atomicAdd(&Wt[min(max(anc, 0), N - 1)], (unsigned long long)(sh * kWScale + 0.5));
+                for (int u = 0; u < IT; ++u) cur[u] = __ldcg(&J2m2[min(max(cur[u], 0), N - 1)]);
+#pragma unroll
+                for (int u = 0; u < IT; ++u) {
+                    const int i = i0 + u * GTH + htid;
+                    if (i < nc) __stcg(&J4t[i], cur[u]);
+                }
+            }
+            gen -= 4;
+            rem -= 4;
+        } else {
+            if (do4) {
+#pragma unroll
+                for (int u = 0; u < IT; ++u) {
+                    const int i = i0 + u * GTH + htid;
+                    const int b4 = __ldcg(&J2m2[min(max(cur[u], 0), N - 1)]);
+                    if (i < nc) __stcg(&J4t[i], b4);
+                }
+            }
+            if (rem >= 2) {
+                gen -= 2;
+                rem -= 2;
+            } else if (rem == 1) {
+#pragma unroll
+                for (int u = 0; u < IT; ++u) cur[u] = b1[u];
+                gen -= 1;
+                rem -= 1;
+            } else {
+#pragma unroll
+                for (int u = 0; u < IT; ++u) cur[u] = jb + i0 + u * GTH + htid;
+            }
+        }
+        if (score) {
+            // the remaining hops to generation g (uniform over the threads)
+            while (rem > 0) {
+                const int h = rem >= 4 ? 4 : (rem >= 2 ? 2 : 1);
+                const int* tab = (h == 4 ? a.J4 + (size_t)(gen % kRingJ) * N
+                                         : (h == 2 ? a.J2 + (size_t)(gen % kRingJ) * N : a.BP + (size_t)(gen % kRingBP) * N));
+#pragma unroll
+                for (int u = 0; u < IT; ++u) cur[u] = __ldcg(&tab[min(max(cur[u], 0), N - 1)]);
+                gen -= h;
+                rem -= h;
+            }
+#pragma unroll
+            for (int u0 = 0; u0 < IT; u0 += 8) {
+                double2 pe[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) pe[u] = __ldcg(&Pg[min(max(cur[u0 + u], 0), N - 1)]);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = i0 + (u0 + u) * GTH + htid;
+                    if (i < nc) __stcg(&Qt[i], pe[u]);
                 }
             }
         }
     }
 }
 
-// Fixed-lag score terms of step ts (:445-470), this CTA's slice [jb, jb + nc) of the lagged
-// generation: sum over rows of (weight of the row's step-ts descendants) x (monomials of the
-// row's payload).  Sequential reads, fixed summation order; the weights are cleared for their next
-// use.  grid_finish_kernel assembles the gradient terms from the six sums.
-template <int GTH>
-__device__ __forceinline__ void helper_payload(const GridArgs& a, const SvConst& k, int ts, int jb, int nc, int c,
-                                               int htid, double* s_hred) {
-    constexpr int NWH = GTH / 32, PB = 4;
-    const int hlane = htid & 31, hwarp = htid >> 5;
+// Main warps: fixed-lag score terms of step ts (:445-470) over the rows [jb, jb + nc) of generation
+// ts (birth order): the row's weight (same formula and shift as phase B) times the monomials of the
+// lagged pair Q[ts & 1][j] the helper warps left behind.  Sequential reads, fixed summation order.
+// grid_finish_kernel assembles the gradient terms from the six sums.
+template <int GT, int KPT>
+__device__ __forceinline__ void score_pass(const GridArgs& a, const SvConst& k, int ts, int jb, int nc, int c, int tid,
+                                           double shift, double* s_red) {
+    constexpr int NW = GT / 32;
+    const int lane = tid & 31, warp = tid >> 5;
     const int N = a.N, L = a.LAG, g = ts - (L - 2);
-    const double2* Pg = a.P + (size_t)(g % a.RP) * N + jb;
-    unsigned long long* Ws = a.W + (size_t)(ts & 1) * N + jb;
+    const double2* Pt = a.P + (size_t)(ts % a.RP) * N + jb;
+    const double2* Qt = a.Q + (size_t)(ts & 1) * N + jb;
+    const double y = a.obs[ts], hy2 = 0.5 * y * y;
     const double ylag = a.obs[g >= 2 ? g - 2 : 0];   // Q5: the score terms of step i use obs[i - LAG]
     const double mu = k.mu, phi = k.phi, sr = k.sr;
     double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    for (int i0 = 0; i0 < nc; i0 += PB * GTH) {
-        unsigned long long w[PB];
-        double2 pe[PB];
 #pragma unroll
-        for (int u = 0; u < PB; ++u) {
-            const int i = i0 + u * GTH + htid;
-            w[u] = (i < nc) ? __ldcg(&Ws[i]) : 0ull;
-        }
+    for (int k0 = 0; k0 < KPT; k0 += 2) {
+        double xv[2];
+        double2 pe[2];
 #pragma unroll
-        for (int u = 0; u < PB; ++u) {
-            const int i = i0 + u * GTH + htid;
+        for (int u = 0; u < 2; ++u) {
+            const int i = (k0 + u) * GT + tid;
+            xv[u] = 0.0;
             pe[u] = make_double2(0.0, 0.0);
-            if (w[u]) {
-                pe[u] = __ldcg(&Pg[i]);
-                __stcg(&Ws[i], 0ull);
+            if (k0 + u < KPT && i < nc) {
+                xv[u] = __ldcg(&Pt[i].y);
+                pe[u] = __ldcg(&Qt[i]);
             }
         }
 #pragma unroll
-        for (int u = 0; u < PB; ++u) {
-            if (w[u]) {
-                const double cc = pe[u].x, x = pe[u].y;
+        for (int u = 0; u < 2; ++u) {
+            const int i = (k0 + u) * GT + tid;
+            if (k0 + u < KPT && i < nc) {
+                const double e = exp(-0.5 * xv[u]);
+                const double lw = (-0.91893853320467267 - 0.5 * xv[u]) - hy2 * (e * e);
+                double sh = exp(lw - shift);
+                if (!isfinite(sh)) sh = 0.0;   // phase B has abandoned the evaluation
+                const double cc = pe[u].x, xa = pe[u].y;
                 const double ec = exp(-0.5 * cc);
-                // residual of the transition parent -> child as the score terms use it (:452-453)
-                double sq = x - mu - phi * (cc - mu);
+                // residual of the transition (value at g-1) -> (value at g) as the score terms use it (:452-453)
+                double sq = xa - mu - phi * (cc - mu);
                 sq -= sr * ec * ylag;
                 const double ey = ec * ylag;
-                const double wd = (double)w[u] * kWInv;
-                const double ws = wd * sq;
-                acc[0] += wd;
-                acc[1] = fma(wd, cc, acc[1]);
+                const double ws = sh * sq;
+                acc[0] += sh;
+                acc[1] = fma(sh, cc, acc[1]);
                 acc[2] += ws;
                 acc[3] = fma(ws, cc, acc[3]);
                 acc[4] = fma(ws, sq, acc[4]);
@@ -386,18 +386,18 @@ __device__ __forceinline__ void helper_payload(const GridArgs& a, const SvConst&
     }
 #pragma unroll
     for (int i = 0; i < 6; ++i) acc[i] = warp_sum(acc[i]);
-    bar_sync(2, GTH);
-    if (hlane == 0) {
+    bar_sync(1, GT);
+    if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) s_hred[32 * i + hwarp] = acc[i];
+        for (int i = 0; i < 6; ++i) s_red[32 * i + warp] = acc[i];
     }
-    bar_sync(2, GTH);
-    if (hwarp == 0) {
+    bar_sync(1, GT);
+    if (warp == 0) {
         double* ps = a.psum + ((size_t)ts * a.G + c) * 8;
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
-            const double v = warp_sum((hlane < NWH) ? s_hred[32 * i + hlane] : 0.0);
-            if (hlane == 0) ps[i == 0 ? 7 : 1 + i] = v;   // [7] = sum w, [2..6] = the monomial sums
+            const double v = warp_sum((lane < NW) ? s_red[32 * i + lane] : 0.0);
+            if (lane == 0) ps[i == 0 ? 7 : 1 + i] = v;   // [7] = sum sh, [2..6] = the monomial sums
         }
     }
 }
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
     __shared__ StepScalars s_sc;
     __shared__ double s_tot[kMaxTiles], s_off[kMaxTiles + 1];
     __shared__ int s_tstart[kMaxTiles + 1], s_tbin[kMaxTiles + 1], s_tcnt[kMaxTiles], s_tbase[kMaxTiles];
-    __shared__ double s_red[4 * 32], s_hred[6 * 32];
+    __shared__ double s_red[6 * 32];
     __shared__ int s_wi[32];
     __shared__ long long s_prof[kProf];
     // main warps -> helper warps: s_main_step = last step whose BP / P slices and shift are complete;
@@ -462,17 +462,16 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
         // helper warps
         // ======================================================================================
         const int htid = tid - GT;
-        const unsigned long long pol_keep = policy_evict_last();
         long long hclk = 0, hbusy = 0, hwait = 0;
         if (prof && htid == 0) hclk = clock64();
         bool stopped = false;
-        for (int t = 1; t <= NOBS; ++t) {
-            // step t < NOBS: records and weights of step t, then the sums of step t-1;
-            // t == NOBS: the sums of the last step.  Both need every helper's step t-1.
+        for (int t = 1; t < NOBS; ++t) {
+            // step t needs the BP / P slices and the shift of step t from the main warps of this CTA
+            // and the tables of every helper's step t-1
             if (htid == 0) {
                 const unsigned tgt = (unsigned)(t - 1) * (unsigned)G;
                 int ab = 0;
-                while (!(ab = s_abort) && ((t < NOBS && s_main_step < t) || ld_acquire_u32(&ctrl->hbar) < tgt)) {
+                while (!(ab = s_abort) && (s_main_step < t || ld_acquire_u32(&ctrl->hbar) < tgt)) {
                 }
                 __threadfence();
                 s_habort[t & 1] = ab;
@@ -487,33 +486,28 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
                 stopped = true;
                 break;
             }
-            if (t < NOBS) {
-                if (htid < 32 && t >= 2 && t + 1 >= L && nc > 0 && !(a.dbg & 4)) {
-                    // the payload slice the NEXT step's sums read -> L2 (sequential HBM reads)
-                    const double2* Pg = a.P + (size_t)((t - (L - 2)) % RP) * N;
-                    prefetch_range(Pg + jb, Pg + je, htid, 32);
-                }
-                helper_records<GTH>(a, s_k, t, jb, nc, htid, s_shiftring[t & 3], pol_keep);
+            if (htid < 32 && t + 1 >= L && t + 1 < NOBS && nc > 0 && !(a.dbg & 4)) {
+                // the generation the NEXT step's score terms gather from -> L2 (sequential HBM reads)
+                const double2* Pg = a.P + (size_t)((t + 1 - (L - 2)) % RP) * N;
+                prefetch_range(Pg + jb, Pg + je, htid, 32);
             }
-            if (t - 1 >= L && !(a.dbg & 4)) helper_payload<GTH>(a, s_k, t - 1, jb, nc, c, htid, s_hred);
-            if (t < NOBS) {
-                __threadfence();
-                bar_sync(2, GTH);
-                if (htid == 0) {
-                    red_release_add(&ctrl->hbar, 1u);
-                    s_help_step = t;
-                    if (prof) {
-                        const long long now = clock64();
-                        hbusy += now - hclk;
-                        hclk = now;
-                    }
+            if (!(a.dbg & 1)) helper_lineage<GTH>(a, t, jb, nc, htid);
+            __threadfence();
+            bar_sync(2, GTH);
+            if (htid == 0) {
+                red_release_add(&ctrl->hbar, 1u);
+                s_help_step = t;
+                if (prof) {
+                    const long long now = clock64();
+                    hbusy += now - hclk;
+                    hclk = now;
                 }
             }
         }
         (void)stopped;
         if (prof && htid == 0) {
-            s_prof[13] = hbusy;
-            s_prof[14] = hwait;
+            s_prof[14] = hbusy;
+            s_prof[15] = hwait;
         }
     } else {
         // ======================================================================================
@@ -567,7 +561,6 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
         int pstart = jb, n = nc;                                             // this CTA's tile
         double toff;                                                          // cumulative weight in front of this thread's chunk
         {
-            const unsigned long long pol_keep = policy_evict_last();
             const double mu = s_k.mu;
             const double e0 = exp(-0.5 * mu);
             double m0 = s_k.mu + s_k.phi * (mu - s_k.mu);
@@ -576,7 +569,6 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
                 __stcg(&a.XE[pstart + q], make_double2(mu, e0));
                 __stcg(&a.perm[pstart + q], pstart + q);
                 s_sh[q] = 1.0;
-                st_rec(&a.R[pstart + q], pol_keep, 0, 0, 0, 0, 0, 0, 0, 0);
                 if (a.hist) {
                     a.Xhist[pstart + q] = mu;
                     a.Ahist[pstart + q] = pstart + q;
@@ -776,7 +768,7 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
                 const double mu = s_k.mu, phi = s_k.phi, sr = s_k.sr, sd = s_k.sd;
                 const double* Ut = a.U + (size_t)t * N;
                 double2* Pt = a.P + (size_t)(t % RP) * N;
-                int* BPt = a.BP + (size_t)par * N;
+                int* BPt = a.BP + (size_t)(t % kRingBP) * N;
                 bool bad = false, orphan = false;
 #pragma unroll
                 for (int k0 = 0; k0 < KPT; k0 += CH) {
@@ -1104,7 +1096,7 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
                         const double e = exp(-0.5 * x);
                         const double lw = (-0.91893853320467267 - 0.5 * x) - hy2 * (e * e);
                         double sh = exp(lw - shift);
-                        if (!isfinite(sh) || sh > kWMax) {
+                        if (!isfinite(sh)) {
                             bad = true;
                             sh = 0.0;
                         }
@@ -1185,11 +1177,27 @@ __global__ void __launch_bounds__(kGT, 1) sv_grid_kernel(const GridArgs a) {
             }
             PROF_MARK(11);   // B scan+publish
             GRID_ARRIVE();   // ---- barrier 3: tile totals published
+            if (t - 1 >= L && !(a.dbg & 4)) {
+                // score terms of the previous step (its lagged pairs come from the helper warps)
+                if (tid == 0)
+                    while (s_help_step < t - 1) {
+                    }
+                MSYNC();
+                score_pass<GT, KPT>(a, s_k, t - 1, jb, nc, c, tid, s_shiftring[(t - 1) & 3], s_red);
+            }
+            PROF_MARK(13);   // score terms
             GRID_WAIT((void)0);
             PROF_MARK(12);   // wait 3
             if (s_sc.abort_now) break;
         }
         if (tid == 0 && s_sc.abort_now) s_abort = 1;
+        if (!s_sc.abort_now && NOBS - 1 >= L && !(a.dbg & 4)) {
+            if (tid == 0)
+                while (s_help_step < NOBS - 1) {
+                }
+            MSYNC();
+            score_pass<GT, KPT>(a, s_k, NOBS - 1, jb, nc, c, tid, s_shiftring[(NOBS - 1) & 3], s_red);
+        }
 
         // diagnostics
         cnt_near = __reduce_add_sync(kFullMask, cnt_near);
@@ -1240,7 +1248,6 @@ __global__ void __launch_bounds__(256) grid_tail_kernel(GridArgs a, const double
     const double ST = sums[(size_t)T * 8], Si = sums[(size_t)i * 8];
     const double* shT = a.shring + (size_t)(T % L) * N;
     const double* shi = a.shring + (size_t)(i % L) * N;
-    const REntry* Rt = a.R + (size_t)(T & 1) * N;
     double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     const bool live = a.ctrl->status == 0;   // an abandoned evaluation leaves stale rows behind
     for (int p = blockIdx.x * 256 + tid; live && p < N; p += nblk * 256) {
@@ -1253,7 +1260,8 @@ __global__ void __launch_bounds__(256) grid_tail_kernel(GridArgs a, const double
         } else {
             // entry of the ancestor idx-1 steps back holds (next = its value, curr = its parent's value)
             const int m = idx - 1;
-            const int row = (m == 0) ? b : min(max(Rt[b].a[m - 1], 0), N - 1);
+            int row = b;   // birth row of the ancestor m generations back: m hops through the parent tables
+            for (int h = 0; h < m; ++h) row = min(max(a.BP[(size_t)((T - h) % kRingBP) * N + row], 0), N - 1);
             const double2 pe = a.P[(size_t)((T - m) % RP) * N + row];
             curr = pe.x;
             const double pe_n = pe.y;
@@ -1339,7 +1347,7 @@ __global__ void grid_finish_kernel(const GridCtrl* __restrict__ ctrl, const doub
 }
 
 struct GridLayout {
-    size_t ctrl, ghist, tilecnt, tinfo, H, XE, perm, BP, R, P, W, psum, shiftv, xminv, shring, parentpos, sums,
+    size_t ctrl, ghist, tilecnt, tinfo, H, XE, perm, BP, J2, J4, Q, P, psum, shiftv, xminv, shring, parentpos, sums,
         tailpart, tail, info, total;
     int RP, nblk;
 };
@@ -1362,10 +1370,11 @@ GridLayout grid_layout(int nobs, int n, int lag, int G, int hist) {
     L.H = o;         o += al256(N * 4);
     L.XE = o;        o += al256(N * 16);
     L.perm = o;      o += al256(N * 4);
-    L.BP = o;        o += al256(2 * N * 4);
-    L.R = o;         o += al256(2 * N * 32);
+    L.BP = o;        o += al256((size_t)kRingBP * N * 4);
+    L.J2 = o;        o += al256((size_t)kRingJ * N * 4);
+    L.J4 = o;        o += al256((size_t)kRingJ * N * 4);
+    L.Q = o;         o += al256((size_t)2 * N * 16);
     L.P = o;         o += al256((size_t)L.RP * N * 16);
-    L.W = o;         o += al256((size_t)2 * N * 8);
     L.psum = o;      o += al256((size_t)nobs * G * 8 * 8);
     L.shiftv = o;    o += al256((size_t)nobs * 8);
     L.xminv = o;     o += al256((size_t)nobs * 8);
@@ -1438,9 +1447,10 @@ int sv_grid_run(const double* d_obs, const double* d_params, const double* d_rvr
     a.XE = (double2*)(ws + L.XE);
     a.perm = (int*)(ws + L.perm);
     a.BP = (int*)(ws + L.BP);
-    a.R = (REntry*)(ws + L.R);
+    a.J2 = (int*)(ws + L.J2);
+    a.J4 = (int*)(ws + L.J4);
+    a.Q = (double2*)(ws + L.Q);
     a.P = (double2*)(ws + L.P);
-    a.W = (unsigned long long*)(ws + L.W);
     a.psum = (double*)(ws + L.psum);
     a.shiftv = (double*)(ws + L.shiftv);
     a.xminv = (double*)(ws + L.xminv);
@@ -1455,7 +1465,6 @@ int sv_grid_run(const double* d_obs, const double* d_params, const double* d_rvr
     }
     // control block, histograms, reservation counters, tile info: zero
     GRID_CUDA(cudaMemsetAsync(ws + L.ctrl, 0, L.H - L.ctrl, st));
-    GRID_CUDA(cudaMemsetAsync(ws + L.W, 0, (size_t)2 * n * 8, st));
     static thread_local bool attr_set[64] = {false};
     static int main_threads = 0;
     if (!main_threads) {
