@@ -41,10 +41,9 @@ ms = e0.elapsed_time(e1)
 d = out["diag"][0].cpu().numpy()
 c = buf.cpu().numpy().astype(np.float64)
 c = c[c.sum(axis=1) > 0]
-names = ["C:ranges+fill", "zero hist", "wait 4", "A1:children+hist", "housekeeping", "wait 1", "A2:scan+scatter",
-         "zero+prefetch", "wait 2", "B:bin sort", "B:rank+weights", "B:scan+publish", "wait 3", "score terms",
-         "helper busy", "helper wait"]
-clk = c[:, :14].sum(axis=1).mean() / (ms * 1e-3) / 1e6   # MHz seen by clock64 (main warps: slots 0..12)
+names = ["C:ranges+fill", "zero hist", "wait 4", "A1:children+hist", "A1:records", "wait 1", "A2:scan+scatter",
+         "zero+prefetch", "wait 2", "B:bin sort", "B:rank+wts+score", "B:scan+publish", "wait 3", "score terms"]
+clk = c.sum(axis=1).mean() / (ms * 1e-3) / 1e6   # MHz seen by clock64
 print(json.dumps({"N": n, "T": T, "ms": ms, "us_per_step": ms * 1e3 / T, "particle_steps_per_s": n * T / ms * 1e3,
                   "kernel": int(d[6]), "status": int(d[2]), "info": int(d[7]), "near_ties": int(d[0]),
                   "max_bin": int(d[1]), "ctas": int(c.shape[0]), "clock_mhz": clk,
