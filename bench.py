@@ -34,7 +34,9 @@ PARAMS = (0.2, 0.9, 0.4, -0.5)
 BYTES_PER_PARTICLE_STEP = 96          # 7s + 40 at s = 8 (filter + fixed-lag gradient)
 KERNEL_NAMES = {1: "sv_pf_kernel<false> (general kernel)", 2: "sv_fast_kernel (exchange kernel)",
                 3: "sv_chain_kernel", 4: "streaming kernels with path storage (sv_split.cu: children, "
-                                         "lineage, fine histogram, offsets, scatter, rank, weights, finalize per time step)"}
+                                         "lineage, fine histogram, offsets, scatter, rank, weights, finalize per time step)",
+                5: "sv_grid_kernel (grid kernel: one persistent cooperative launch, one tile of the sorted "
+                   "generation per SM, four grid barriers per time step)"}
 METRIC = "particle_timesteps_per_sec"
 UNIT = "particle-timesteps/s"
 
@@ -121,6 +123,38 @@ def _port_worker(args):
     return time.perf_counter() - t0, out["log_like"]
 
 
+def _port_sample_worker(args):
+    """The O(T N) oracle port at the headline N for a short series (same-config CPU number)."""
+    seed, n, tsteps = args
+    import oracle
+    import golden_inputs as gi
+    nobs = tsteps + 1
+    rng = np.random.default_rng(seed)
+    obs = gi.sv_obs(nobs)
+    rvr = rng.random(nobs)
+    rvp = rng.standard_normal(n * nobs)
+    t0 = time.perf_counter()
+    out = oracle.flps_sv_corr(obs, np.array(PARAMS), rvr, rvp, n, LAG, 0)
+    return time.perf_counter() - t0, out["log_like"]
+
+
+def cpu_port_same_config(n, tsteps=12):
+    """All host cores, one independent N-particle evaluation per core over `tsteps` time steps."""
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cores = min(cores, 32)            # 92 MB of u per worker at N = 2^20; bounded fan-out
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_port_sample_worker, [(77 + w, n, tsteps) for w in range(cores)])
+    wall = time.perf_counter() - t0
+    inner = max(r[0] for r in res)
+    return {"value": cores * n * tsteps / inner, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "oracle port (O(T N) restatement, oracle/pmmh_oracle.c) flps_sv_corr hess=0, N=%d, first %d time "
+                      "steps, one independent evaluation per core; time = slowest worker (%.1f s, %.1f s with "
+                      "process start-up and input generation)" % (n, tsteps, inner, wall)}
+
+
 def cpu_reference_throughput(steps, warmup):
     """Times the reference's CPU path on all host cores (one process per core, independent
     chains, because the reference itself is single-threaded).  Returns (value, info dict)."""
@@ -193,6 +227,204 @@ class BenchSVModel(object):
 
     def log_prior_hessian(self):
         return {k: 0.0 for k in self.params}
+
+
+def parity_at_shape(obs_h, params_t, rvr, u, n, psteps, dev):
+    """The CUDA path against the oracle on the bench inputs themselves: the first `psteps` time steps
+    of the headline problem (same N, same u).  Ancestors / sorted generations are compared at every
+    step, the estimates to fp64 tolerances.  Also ties the full-length run to the prefix (filtered
+    means are causal)."""
+    import torch
+    import oracle
+    from pmmh_qn_b200 import kernels as K
+    nobs = psteps + 1
+    u_p = u[0, :nobs].contiguous()
+    rvr_p = rvr[0, :nobs].contiguous()
+    obs_p = torch.from_numpy(obs_h[:nobs].copy()).to(dev)
+    out = K.flps_sv_corr(obs_p, params_t, rvr_p.reshape(1, nobs), u_p.reshape(1, nobs, n), lag=LAG,
+                         compute_hessian=False, store_history=True)
+    torch.cuda.synchronize()
+    u_host = u_p.cpu().numpy()
+    rvp = np.ascontiguousarray(u_host.T).reshape(-1)          # rvp[i + j * nobs]
+    del u_host
+    t0 = time.perf_counter()
+    ref = oracle.flps_sv_corr(obs_h[:nobs].copy(), np.array(PARAMS), rvr_p.cpu().numpy(), rvp, n, LAG, 0, dumps=True)
+    oracle_s = time.perf_counter() - t0
+    A = out["A"][0].cpu().numpy()
+    X = out["X"][0].cpu().numpy()
+    mism = int(np.sum(np.any(A[1:] != ref["A"][1:], axis=1)))
+    first = None
+    if mism:
+        first = int(np.argmax(np.any(A[1:] != ref["A"][1:], axis=1))) + 1
+    ll = float(out["log_like"][0])
+    g = out["gradient"][0].cpu().numpy()
+    gref = np.asarray(ref["gradient"])
+    d = out["diag"][0].tolist()
+    return {"against": "oracle/pmmh_oracle.c (restates stochastic_volatility.pyx:205-655), same inputs as the timed run",
+            "N": n, "time_steps": psteps, "kernel": KERNEL_NAMES.get(int(d[6]), "?"),
+            "generations_mismatched": mism, "first_mismatch_step": first,
+            "x_max_rel": float(np.max(np.abs(X - ref["X"])) / max(1e-300, np.max(np.abs(ref["X"])))),
+            "ll_rel": abs(ll - ref["log_like"]) / abs(ref["log_like"]),
+            "grad_rel": float(np.max(np.abs(g - gref)) / max(1e-300, np.max(np.abs(gref)))),
+            "filt_rel": float(np.max(np.abs(out["filt"][0].cpu().numpy() - ref["filt"])) /
+                              max(1e-300, np.max(np.abs(ref["filt"])))),
+            "near_ties": int(d[0]), "status": int(d[2]), "oracle_seconds": oracle_s,
+            "tolerances": {"ancestors": "bit-exact", "ll_rel": 1e-10, "grad_rel": 1e-9, "filt_rel": 1e-10}}
+
+
+def count_launches(fn):
+    """Kernel launches of one call of fn(), counted from a CUPTI activity trace (torch.profiler)."""
+    import torch
+    try:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn()
+            torch.cuda.synchronize()
+        names = {}
+        for ev in prof.events():
+            if str(getattr(ev, "device_type", "")).endswith("CUDA"):
+                nm = ev.name
+                if nm.startswith("Memcpy") or nm.startswith("Memset"):
+                    continue
+                names[nm] = names.get(nm, 0) + 1
+        total = sum(names.values())
+        top = sorted(names.items(), key=lambda kv: -kv[1])[:6]
+        return total, [{"kernel": k[:80], "launches": v} for k, v in top]
+    except Exception as e:   # reported
+        return None, [{"error": str(e)[:160]}]
+
+
+def timed_events(fn, reps, warm):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e-3)
+    return float(np.median(ts))
+
+
+def max_over_ranks(seconds, dev, dist):
+    import torch
+    if dist is None:
+        return seconds
+    tt = torch.tensor([seconds], dtype=torch.float64, device=dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    return float(tt.item())
+
+
+def run_config4_chains(rank, world, dev, dist, peak):
+    """BASELINE configs[3]: 1024 independent SV chains x N = 4096 particles, T = 1000, one chain batch
+    per GPU (1024 / world chains on every rank, no collective) => strong scaling."""
+    import torch
+    import golden_inputs as gi
+    from pmmh_qn_b200 import kernels as K
+    n, nobs, btot = 4096, NOBS, 1024
+    b = btot // world
+    g = torch.Generator(device=dev)
+    g.manual_seed(400 + rank)
+    obs = torch.from_numpy(gi.sv_obs(nobs)).to(dev)
+    base = torch.tensor(PARAMS, dtype=torch.float64, device=dev)
+    params = (base + 0.01 * torch.randn((b, 4), dtype=torch.float64, device=dev, generator=g)).contiguous()
+    u = torch.randn((b, nobs, n), dtype=torch.float64, device=dev, generator=g)
+    rvr = torch.rand((b, nobs), dtype=torch.float64, device=dev, generator=g)
+    ws = K.Workspace()
+    out = {}
+    for hess in (False, True):
+        fn = lambda: K.flps_sv_corr(obs, params, rvr, u, lag=LAG, compute_hessian=hess, workspace=ws)  # noqa: E731
+        if dist is not None:
+            dist.barrier()
+        t = max_over_ranks(timed_events(fn, 2, 1), dev, dist)
+        steps = btot * n * (nobs - 1)
+        byt = (192 if hess else 96)
+        o = fn()
+        out["hessian" if hess else "gradient"] = {
+            "seconds": t, "value": steps / t, "unit": UNIT, "loglik_evals_per_sec": btot / t,
+            "kernel": KERNEL_NAMES.get(int(o["diag"][0, 6]), "?"), "status_max": int(o["diag"][:, 2].max()),
+            "roofline": {"bound": "hbm", "achieved": steps * byt / t / 1e9 / world, "peak": peak, "unit": "GB/s",
+                         "frac": steps * byt / t / 1e9 / world / peak, "traffic": None,
+                         "algorithmic_bytes_per_particle_step": byt, "note": "per GPU"}}
+    del u
+    torch.cuda.empty_cache()
+    return {"workload": "sv_flps_1024chains_N4096_T1000", "chains": btot, "chains_per_gpu": b, "N": n, "T": nobs - 1,
+            "scaling": "strong", "n_gpus": world, **out}
+
+
+def run_config1_re(dev, peak):
+    """BASELINE configs[0]: random-effects importance sampler, 100 individuals x 100 samples; one
+    evaluation and batches of independent evaluations (proposals) per launch."""
+    import torch
+    import golden_inputs as gi
+    from pmmh_qn_b200 import kernels as K
+    nobs = n = 100
+    obs_r, par_r, rvr_r, rvp_r = gi.re_inputs(n, nobs, 0)
+    obs = torch.from_numpy(obs_r).to(dev)
+    rows = []
+    for B in (1, 1024, 65536):
+        g = torch.Generator(device=dev)
+        g.manual_seed(B)
+        params = torch.tensor(par_r, dtype=torch.float64, device=dev).repeat(B, 1).contiguous()
+        rvr = torch.rand((B,), dtype=torch.float64, device=dev, generator=g)
+        rvp = torch.randn((B, nobs * n), dtype=torch.float64, device=dev, generator=g)
+        t = timed_events(lambda: K.importance_discrete(obs, params, rvr, rvp, nobs, n), 5, 2)
+        byt = B * nobs * n * 8
+        rows.append({"batch": B, "seconds": t, "evals_per_sec": B / t,
+                     "roofline": {"bound": "hbm", "achieved": byt / t / 1e9, "peak": peak, "unit": "GB/s",
+                                  "frac": byt / t / 1e9 / peak, "traffic": None,
+                                  "algorithmic_bytes_per_eval": nobs * n * 8}})
+    return {"workload": "re_importance_100x100", "kernel": "importance_discrete_kernel (aux_kernels.cu)", "rows": rows}
+
+
+def run_config3_subsampling(rank, world, dev, dist, peak):
+    """BASELINE configs[2]: correlated data-subsampling estimator, n = 11 M x 28 regressors row-sharded
+    over the ranks, m = 550 000 (5 %): Crank-Nicolson + Phi + sort + stratified indices (redundant on
+    every rank) + gather-reduce of the owned rows + ONE all-reduce of 1 + d + d^2 doubles."""
+    import torch
+    from pmmh_qn_b200 import kernels as K
+    n, d, m = 11_000_000, 28, 550_000
+    per = (n + world - 1) // world
+    r0, r1 = min(n, rank * per), min(n, (rank + 1) * per)
+    g = torch.Generator(device=dev)
+    g.manual_seed(30 + rank)
+    x = torch.randn((r1 - r0, d), dtype=torch.float64, device=dev, generator=g)
+    g0 = torch.Generator(device=dev)
+    g0.manual_seed(31)
+    beta = 0.1 * torch.randn((d,), dtype=torch.float64, device=dev, generator=g0)
+    y = (torch.rand((r1 - r0,), dtype=torch.float64, device=dev, generator=g) < torch.sigmoid(x @ beta)).to(torch.float64)
+    u = torch.randn((m,), dtype=torch.float64, device=dev, generator=g0)     # same u on every rank
+    ws1, ws2 = K.Workspace(), K.Workspace()
+    res = {}
+    for hess in (False, True):
+        def fn():
+            un = K.crank_nicolson(u, 0.05, seed=1)
+            idx = K.subsample_indices(un, n, workspace=ws1)
+            o = K.logistic_loglike(x, y, idx, beta, compute_hessian=hess, row_begin=r0, row_end=r1, workspace=ws2)
+            if dist is not None:
+                dist.all_reduce(o, op=dist.ReduceOp.SUM)
+            return o
+        if dist is not None:
+            dist.barrier()
+        t = max_over_ranks(timed_events(fn, 5, 2), dev, dist)
+        idx = K.subsample_indices(K.crank_nicolson(u, 0.05, seed=1), n, workspace=ws1)
+        t_red = timed_events(lambda: K.logistic_loglike(x, y, idx, beta, compute_hessian=hess, row_begin=r0,
+                                                        row_end=r1, workspace=ws2), 5, 2)
+        byt = m * (8 * d + 12) / world
+        res["hessian" if hess else "gradient"] = {
+            "seconds": t, "rows_per_sec": m / t, "evals_per_sec": 1.0 / t, "gather_reduce_seconds_this_rank": t_red,
+            "roofline": {"bound": "hbm", "achieved": byt / t_red / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": byt / t_red / 1e9 / peak, "traffic": None, "kernel": "logistic gather-reduce",
+                         "algorithmic_bytes_per_row": 8 * d + 12}}
+    del x, y
+    torch.cuda.empty_cache()
+    return {"workload": "logistic_subsampling_n11M_d28_m550000", "n_gpus": world, "scaling": "strong",
+            "collective": "none (one rank)" if world == 1 else "one all_reduce(SUM) of %d doubles per evaluation (NCCL)" % (1 + d + d * d),
+            **res}
 
 
 def run_split_pf(args, rank, world, dev, dist):
@@ -301,7 +533,7 @@ def run_ours(args, rank, world, local_rank):
     # persistent exchange kernel (pmmh_sv_set_algorithm(2)) when the headline ran on the streaming
     # kernels, and the other way round
     alt = None
-    alt_alg = 2 if int(diag[6]) == 4 else 5
+    alt_alg = 5 if int(diag[6]) == 5 else (2 if int(diag[6]) == 4 else 6)
     try:
         K.set_sv_algorithm(alt_alg)
         ws5 = K.Workspace()
@@ -325,8 +557,26 @@ def run_ours(args, rank, world, local_rank):
     finally:
         K.set_sv_algorithm(0)
 
+    # ---- launches of one step, counted (CUPTI activity trace of one extra, untimed step)
+    launches_per_step, launch_top = count_launches(step)
+
+    # ---- parity at the benchmarked shape: the oracle on the first time steps of the bench inputs
+    parity = None
+    if rank == 0 and world == 1 and args.parity_steps > 0:
+        try:
+            parity = parity_at_shape(obs_h, params, rvr, u, n, min(args.parity_steps, T_STEPS), dev)
+            full_filt = out["filt"][0, :parity["time_steps"] + 1].cpu().numpy()
+            pre = K.flps_sv_corr(torch.from_numpy(obs_h[:parity["time_steps"] + 1].copy()).to(dev), params,
+                                 rvr[:, :parity["time_steps"] + 1].contiguous(),
+                                 u[:, :parity["time_steps"] + 1].contiguous(), lag=LAG, compute_hessian=False)
+            parity["full_run_filt_vs_prefix_rel"] = float(
+                np.max(np.abs(full_filt - pre["filt"][0].cpu().numpy())) / max(1e-300, np.max(np.abs(full_filt))))
+            del pre
+        except Exception as e:   # reported, never hidden
+            parity = {"error": str(e)[:300]}
+
     # ---- end to end through the public estimator API with HOST (pinned) buffers
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    e2e_steps = max(1, args.e2e_steps)
     model = BenchSVModel(obs_h, PARAMS)
     est = ParticleMethodsCUDA(model, no_particles=n, fixed_lag=LAG, device=dev)
     rvs_pinned = torch.empty((NOBS, n + 1), dtype=torch.float64, pin_memory=True)
@@ -349,6 +599,27 @@ def run_ours(args, rank, world, local_rank):
     h2d = rvs_np.nbytes + (NOBS + 4 + NOBS) * 8
     d2h = (NOBS * 3 + 4 * NOBS + 1 + 32 + 8) * 8
 
+    del rvs_pinned, rvs_np, est
+    torch.cuda.empty_cache()
+    peak, peak_src = measured_hbm_peak()
+
+    # ---- the other BASELINE configs (secondary blocks, each with its own roofline)
+    cfg1 = cfg3 = cfg4 = None
+    if not args.no_configs:
+        try:
+            cfg4 = run_config4_chains(rank, world, dev, dist, peak)
+        except Exception as e:
+            cfg4 = {"error": str(e)[:200]}
+        try:
+            cfg3 = run_config3_subsampling(rank, world, dev, dist, peak)
+        except Exception as e:
+            cfg3 = {"error": str(e)[:200]}
+        if rank == 0:
+            try:
+                cfg1 = run_config1_re(dev, peak)
+            except Exception as e:
+                cfg1 = {"error": str(e)[:200]}
+
     # ---- BASELINE configs[4]: ONE particle filter split over the ranks (strong scaling, fixed N)
     split_line = None
     if not args.no_split:
@@ -361,7 +632,6 @@ def run_ours(args, rank, world, local_rank):
             args.traffic_bytes = float(tj["by_kernel"][str(int(diag[6]))]["dram_bytes_per_launch"])
         except Exception:
             pass
-        peak, peak_src = measured_hbm_peak()
         achieved = n * T_STEPS * BYTES_PER_PARTICLE_STEP / (kern_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -380,18 +650,26 @@ def run_ours(args, rank, world, local_rank):
                          "algorithmic_bytes_per_launch": n * T_STEPS * BYTES_PER_PARTICLE_STEP,
                          "kernel": KERNEL_NAMES.get(int(diag[6]), "sv_pf_kernel<false>"),
                          "kernel_ms": kern_ms,
+                         "traffic_source": "ncu --set full capture of this kernel committed under profiles/ "
+                                           "(profiles/traffic.json); not re-measured in this run",
                          "note": "kernel_ms = CUDA events around one pmmh_flps_sv_corr call on the launching "
-                                 "stream (all its launches plus the empty general-kernel fallback pass); for the "
-                                 "streaming kernels one call is 8 launches per time step, and achieved = algorithmic "
-                                 "bytes of the evaluation / that time"},
+                                 "stream (the persistent kernel plus its four small reduction / tail launches and "
+                                 "the empty fallback pass); achieved = algorithmic bytes of the evaluation / that time"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                     "api": "ParticleMethodsCUDA.smoother(model, rvs={'rvs': pinned ndarray})",
                     "note": "host rvs -> pmmh_flps_sv_corr_streamed: the copy engine feeds the running kernel "
                             "in chunks of 64 time steps (no layout kernel); results read back to the host"},
-            "gpu_launches": args.steps * (8 * T_STEPS + 21 if int(diag[6]) == 4 else 2),
+            "gpu_launches": (launches_per_step * args.steps) if launches_per_step is not None else None,
+            "gpu_launches_per_step": launches_per_step, "gpu_launches_top": launch_top,
+            "gpu_launches_source": "CUPTI activity trace (torch.profiler) of one extra untimed step x steps",
         }
+        if parity is not None:
+            line["parity"] = parity
+        for key, blk in (("config1_re", cfg1), ("config3_subsampling", cfg3), ("config4_chains", cfg4)):
+            if blk is not None:
+                line[key] = blk
         if alt is not None:
             line["alt_kernel_same_workload"] = alt
         if split_line is not None:
@@ -399,6 +677,10 @@ def run_ours(args, rank, world, local_rank):
         if world == 1 and not args.no_cpu_baseline:
             _, _, info = cpu_reference_throughput(1, 0)
             line["cpu_baseline"] = info
+            try:
+                line["cpu_baseline_same_config"] = cpu_port_same_config(n, args.port_steps)
+            except Exception as e:
+                line["cpu_baseline_same_config"] = {"error": str(e)[:200]}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
@@ -412,11 +694,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--particles", type=int, default=1 << 20)
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--parity-steps", type=int, default=40,
+                    help="time steps of the bench inputs re-run on the CPU oracle (0 = skip)")
+    ap.add_argument("--port-steps", type=int, default=12,
+                    help="time steps of the same-config CPU port sample (N = --particles on every core)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the config 1 / 3 / 4 blocks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-split", action="store_true", help="skip the config-5 split particle filter block")
     ap.add_argument("--split-particles", type=int, default=1 << 24)
-    ap.add_argument("--split-steps", type=int, default=100)
+    ap.add_argument("--split-steps", type=int, default=1000)
     ap.add_argument("--traffic-bytes", type=float, default=None,
                     help="dram bytes per launch from the committed ncu capture (profiles/)")
     args = ap.parse_args()

@@ -123,15 +123,19 @@ int pmmh_flps_sv_corr(const double* d_obs, long long obs_stride, const double* d
  * in HOST memory -- what the samplers hand to estimator.smoother(model, rvs={'rvs': ndarray})
  * (mh_quasi_newton.py:333, state/particle_methods/cython.py:89-91).  h_rvs is the reference's
  * (n_obs, N+1) row-major array (pinned memory makes the copies asynchronous).  The copy engine
- * moves it in chunks of 64 time steps on an internal stream into d_stage (particle-major chunks,
- * no layout kernel) while the persistent kernel is already running; the kernel waits for a
- * chunk only when it reaches it.  d_rvr = Phi of the first n_obs flat entries (computed by the
- * caller as in cython.py:90).  Sizes the exchange kernel takes run on it; larger N (>= 2^20) runs
- * on the streaming kernels, whose host-driven step loop waits for a chunk's event when it enters
- * it (pmmh_sv_streamed_eligible tells whether a size is taken at all);
- * there is no fallback inside: if d_diag[PMMH_DIAG_STATUS] == 1 afterwards, upload the array and
- * call pmmh_flps_sv_corr.  d_stage needs pmmh_sv_stage_bytes() bytes and must stay untouched
- * until the kernel has finished; the workspace size is that of pmmh_sv_workspace_bytes(batch 1). */
+ * moves it in chunks of time steps on an internal stream into d_stage (particle-major chunks, no
+ * layout kernel) while the persistent kernel is already running; the kernel waits for a chunk only
+ * when it reaches it, and the caller's stream ends after the last copy.  d_rvr = Phi of the first
+ * n_obs flat entries (computed by the caller as in cython.py:90).  Kernel by size: the grid kernel
+ * where a tile fits one SM (2^16 <= N <= ~1.06 M, chunks of 256 time steps), else the exchange
+ * kernel where it is eligible (chunks of 64), else the streaming kernels, whose host-driven step
+ * loop waits for a chunk's event when it enters it (pmmh_sv_streamed_eligible tells whether a size
+ * is taken at all).  There is no fallback inside: if d_diag[PMMH_DIAG_STATUS] == 1 afterwards,
+ * upload the array and call pmmh_flps_sv_corr.  d_stage needs pmmh_sv_stage_bytes() bytes and must
+ * stay untouched until the stream has been synchronised; the workspace needs
+ * pmmh_sv_streamed_workspace_bytes() bytes.  Not re-entrant per device and host thread: the internal
+ * copy stream and its events are per (thread, device) state. */
+int pmmh_sv_streamed_workspace_bytes(int n_obs, int n_particles, int lag, int ctas_per_problem, size_t* bytes);
 int pmmh_sv_stage_bytes(int n_obs, int n_particles, size_t* bytes);
 int pmmh_sv_streamed_eligible(int n_obs, int n_particles, int lag, int ctas_per_problem);
 int pmmh_flps_sv_corr_streamed(const double* h_rvs, const double* d_obs, const double* d_params,

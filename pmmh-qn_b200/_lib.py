@@ -33,6 +33,7 @@ SIGNATURES = {
                                   c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
                                   c_vp, c_size, c_int, c_vp]),
     "pmmh_sv_stage_bytes": (c_int, [c_int, c_int, ctypes.POINTER(c_size)]),
+    "pmmh_sv_streamed_workspace_bytes": (c_int, [c_int, c_int, c_int, c_int, ctypes.POINTER(c_size)]),
     "pmmh_sv_streamed_eligible": (c_int, [c_int, c_int, c_int, c_int]),
     "pmmh_flps_sv_corr_streamed": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_size,
                                            c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_size,

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -87,7 +88,10 @@ struct SvPlan {
 //     general kernel otherwise and as their fallback),
 // 1 = general kernel only, 2 = exchange kernel where eligible WITHOUT the fallback pass (diagnostics),
 // 3 = chain kernel where eligible WITHOUT the fallback pass (diagnostics)
-int g_sv_algorithm = 0;
+// The selection is per host thread (thread_local): a thread that calls pmmh_sv_set_algorithm changes the
+// sizing and the kernel choice of its own later calls only, so a toggle on one thread cannot land between
+// another thread's workspace query and its run call.
+thread_local int g_sv_algorithm = 0;
 int g_split_min_particles = 1 << 20;   // automatic selection of the streaming kernels from this N on
 int g_split_path_max_particles = 1 << 23;   // ... with path storage below this N, with records from it on
 int g_grid_min_particles = 1 << 16;         // automatic selection of the grid kernel from this N on (while a tile fits one CTA)
@@ -409,7 +413,7 @@ constexpr int kUChunk = 64;   // time steps per copy chunk (512-byte rows for th
 struct StreamedState {
     std::vector<cudaEvent_t> ev_chunk;   // streaming kernels: one event per landed chunk
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_start = nullptr, ev_reset = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_reset = nullptr, ev_done = nullptr;
     int* h_vals = nullptr;   // pinned: h_vals[c] = time steps available after chunk c
     int h_cap = 0;
 };
@@ -421,9 +425,75 @@ size_t streamed_data_bytes(int n_obs, int n) {
 }
 }  // namespace
 
+namespace {
+// grid kernel with host-resident u: chunks of g_grid_u_chunk time steps (2 KB rows for the copy engine)
+int grid_u_chunk() {
+    static int v = 0;
+    if (!v) {
+        const char* e = getenv("PMMH_GRID_U_CHUNK");
+        v = e ? atoi(e) : 256;
+        if (v < 16 || v > 4096) v = 256;
+    }
+    return v;
+}
+size_t streamed_grid_data_bytes(int n_obs, int n) {
+    const int ch = grid_u_chunk();
+    return (size_t)((n_obs + ch - 1) / ch) * (size_t)n * ch * sizeof(double);
+}
+// immutable pinned table tab[i] = i: the copy engine writes &tab[rows landed] to the device flag, so
+// no call ever rewrites a host value that a queued copy may still read
+const int* step_table(int need) {
+    static std::mutex mu;
+    static int* tab = nullptr;
+    static int cap = 0;
+    std::lock_guard<std::mutex> lk(mu);
+    if (cap < need + 1) {
+        int ncap = need + 1 > 65536 ? need + 1 : 65536;
+        int* t = nullptr;
+        if (cudaHostAlloc((void**)&t, (size_t)ncap * sizeof(int), cudaHostAllocPortable) != cudaSuccess) return nullptr;
+        for (int i = 0; i < ncap; ++i) t[i] = i;
+        tab = t;   // an older, smaller table stays allocated: copies queued earlier may still read it
+        cap = ncap;
+    }
+    return tab;
+}
+bool streamed_grid_ok(int n_obs, int n, int lag, int ctas, int* G_out) {
+    if (!(g_sv_algorithm == 0 || g_sv_algorithm == 6) || ctas != 0) return false;
+    if (g_sv_algorithm == 0 && n < g_grid_min_particles) return false;
+    DeviceInfo di;
+    if (get_device_info(&di) != PMMH_OK || di.major < 10 || !di.coop) return false;
+    const int GG = pmmh::sv_grid_ctas(n, di.sm, 0);
+    if (!pmmh::sv_grid_eligible(n_obs, n, lag, GG)) return false;
+    if (G_out) *G_out = GG;
+    return true;
+}
+}  // namespace
+
 int pmmh_sv_stage_bytes(int n_obs, int n_particles, size_t* bytes) {
     if (!bytes || n_obs < 2 || n_particles < 1) return fail(PMMH_ERR_INVALID, "pmmh_sv_stage_bytes: bad arguments");
-    *bytes = streamed_data_bytes(n_obs, n_particles) + 256;
+    size_t b = streamed_data_bytes(n_obs, n_particles);
+    const size_t bg = streamed_grid_data_bytes(n_obs, n_particles);
+    if (bg > b) b = bg;
+    *bytes = b + 256;
+    return PMMH_OK;
+}
+
+int pmmh_sv_streamed_workspace_bytes(int n_obs, int n_particles, int lag, int ctas_per_problem, size_t* bytes) {
+    if (!bytes) return fail(PMMH_ERR_INVALID, "bytes is null");
+    SvPlan p;
+    int rc = sv_make_plan(n_obs, n_particles, lag, 1, 0, pmmh::kSvFlps, 0, ctas_per_problem, &p, true);
+    if (rc != PMMH_OK) return rc;
+    size_t b = p.total;
+    int GG = 0;
+    if (streamed_grid_ok(n_obs, n_particles, lag, ctas_per_problem, &GG)) {
+        const size_t g = pmmh::sv_grid_ws_bytes(n_obs, n_particles, lag, GG, 0);
+        if (g > b) b = g;
+    }
+    if (pmmh::sv_split_single_eligible(n_obs, n_particles, lag)) {
+        const size_t sp = pmmh::sv_split_path_ws_bytes(n_obs, n_particles, lag);
+        if (sp > b) b = sp;
+    }
+    *bytes = b;
     return PMMH_OK;
 }
 
@@ -438,7 +508,8 @@ bool streamed_prefers_split(int n_obs, int n, int lag, int ctas) {
 int pmmh_sv_streamed_eligible(int n_obs, int n_particles, int lag, int ctas_per_problem) {
     SvPlan p;
     if (sv_make_plan(n_obs, n_particles, lag, 1, 0, pmmh::kSvFlps, 0, ctas_per_problem, &p, true) != PMMH_OK) return 0;
-    return (p.use_fast || streamed_prefers_split(n_obs, n_particles, lag, ctas_per_problem)) ? 1 : 0;
+    return (p.use_fast || streamed_prefers_split(n_obs, n_particles, lag, ctas_per_problem) ||
+            streamed_grid_ok(n_obs, n_particles, lag, ctas_per_problem, nullptr)) ? 1 : 0;
 }
 
 int pmmh_flps_sv_corr_streamed(const double* h_rvs, const double* d_obs, const double* d_params,
@@ -450,6 +521,58 @@ int pmmh_flps_sv_corr_streamed(const double* h_rvs, const double* d_obs, const d
     if (!h_rvs || !d_obs || !d_params || !d_rvr || !d_stage || !d_filt || !d_smo || !d_log_like || !d_gradient ||
         !d_traj || !d_hess1 || !d_hess2 || !d_diag || !d_workspace)
         return fail(PMMH_ERR_INVALID, "pmmh_flps_sv_corr_streamed: null pointer argument");
+    // The grid kernel where it takes the size: the copy engine lays the reference's particle-major host
+    // array down in chunks of 256 time steps (2 KB rows), the kernel reads its column of the chunk with a
+    // stride and polls one flag per time step; the call is bound by the host link, not by the kernel.
+    int GGs = 0;
+    if (streamed_grid_ok(n_obs, n_particles, lag, ctas_per_problem, &GGs)) {
+        const int ch = grid_u_chunk();
+        const size_t gws = pmmh::sv_grid_ws_bytes(n_obs, n_particles, lag, GGs, 0);
+        if (workspace_bytes < gws) return fail(PMMH_ERR_WORKSPACE, "workspace too small (pmmh_sv_streamed_workspace_bytes)");
+        const size_t gdata = streamed_grid_data_bytes(n_obs, n_particles);
+        if (stage_bytes < gdata + 256) return fail(PMMH_ERR_WORKSPACE, "staging buffer too small");
+        int devg = 0;
+        PMMH_CUDA(cudaGetDevice(&devg));
+        if (devg < 0 || devg >= 64) return fail(PMMH_ERR_NO_DEVICE, "device ordinal out of range");
+        StreamedState& sg = g_streamed[devg];
+        if (!sg.copy_stream) {
+            PMMH_CUDA(cudaStreamCreateWithFlags(&sg.copy_stream, cudaStreamNonBlocking));
+            PMMH_CUDA(cudaEventCreateWithFlags(&sg.ev_start, cudaEventDisableTiming));
+            PMMH_CUDA(cudaEventCreateWithFlags(&sg.ev_reset, cudaEventDisableTiming));
+        }
+        if (!sg.ev_done) PMMH_CUDA(cudaEventCreateWithFlags(&sg.ev_done, cudaEventDisableTiming));
+        const int* tab = step_table(n_obs + ch);
+        if (!tab) return fail(PMMH_ERR_CUDA, "pinned step table allocation failed");
+        cudaStream_t stg = (cudaStream_t)stream;
+        char* stageg = (char*)d_stage;
+        int* d_flagg = (int*)(stageg + gdata);
+        PMMH_CUDA(cudaEventRecord(sg.ev_start, stg));
+        PMMH_CUDA(cudaStreamWaitEvent(sg.copy_stream, sg.ev_start, 0));
+        PMMH_CUDA(cudaMemsetAsync(d_flagg, 0, sizeof(int), sg.copy_stream));
+        PMMH_CUDA(cudaEventRecord(sg.ev_reset, sg.copy_stream));
+        const int chunksg = (n_obs + ch - 1) / ch;
+        for (int c = 0; c < chunksg; ++c) {
+            const int t0 = c * ch;
+            const int wsteps = (n_obs - t0 < ch) ? (n_obs - t0) : ch;
+            const double* src = h_rvs + (size_t)n_obs + (size_t)t0;   // rvp[i + j * n_obs], cython.py:89-91
+            char* dst = stageg + (size_t)c * (size_t)n_particles * ch * sizeof(double);
+            PMMH_CUDA(cudaMemcpy2DAsync(dst, (size_t)ch * sizeof(double), src, (size_t)n_obs * sizeof(double),
+                                        (size_t)wsteps * sizeof(double), (size_t)n_particles, cudaMemcpyHostToDevice,
+                                        sg.copy_stream));
+            PMMH_CUDA(cudaMemcpyAsync(d_flagg, &tab[t0 + wsteps], sizeof(int), cudaMemcpyHostToDevice, sg.copy_stream));
+        }
+        PMMH_CUDA(cudaEventRecord(sg.ev_done, sg.copy_stream));
+        PMMH_CUDA(cudaStreamWaitEvent(stg, sg.ev_reset, 0));   // the kernel must not start before the flag is reset
+        int rcg = pmmh::sv_grid_run(d_obs, d_params, d_rvr, (const double*)d_stage, n_obs, n_particles, lag, GGs, d_filt,
+                                    d_smo, d_log_like, d_gradient, d_traj, d_diag, nullptr, nullptr, d_workspace,
+                                    workspace_bytes, g_sv_prof, stg, ch, d_flagg);
+        if (rcg != PMMH_OK) return rcg;
+        PMMH_CUDA(cudaMemsetAsync(d_hess1, 0, 16 * sizeof(double), stg));
+        PMMH_CUDA(cudaMemsetAsync(d_hess2, 0, 16 * sizeof(double), stg));
+        // an evaluation that is abandoned early leaves copies behind: the caller's stream ends after them
+        PMMH_CUDA(cudaStreamWaitEvent(stg, sg.ev_done, 0));
+        return PMMH_OK;
+    }
     // Host-resident u runs on the exchange kernel where it takes the size (measured at N = 2^20:
     // 206 ms per call against 242 ms on the streaming kernels, whose strided reads of the
     // particle-major chunks cost more than they save) and on the streaming kernels beyond it.

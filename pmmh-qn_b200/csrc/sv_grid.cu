@@ -98,6 +98,12 @@ struct GridArgs {
     int N, NOBS, LAG, G, Wc, RP, hist;
     int dbg;   // development (timing only, results wrong): 1 skip R records, 2 skip P store, 4 skip score gather, 8 bulk prefetch of the lagged generation
     const double *obs, *params, *rvr, *U;
+    // U[t][j] = U[(t / u_cs) * u_cstride + (t % u_cs) * u_tstride + j * u_jstride]: time-major resident array
+    // (u_cs = 2^30, u_tstride = N, u_jstride = 1) or particle-major chunks of u_cs time steps as the copy
+    // engine lays them down from the reference's host array (u_tstride = 1, u_jstride = u_cs)
+    long long u_cstride, u_tstride, u_jstride;
+    int u_cs;
+    const int* u_flag;   // host-streamed u: number of time rows that have landed (written by the copy engine)
     GridCtrl* ctrl;
     int* ghist;        // [2][kNCopy][kNF]
     int* tilecnt;      // [2][kMaxTiles * kCntStride]
@@ -553,6 +559,11 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
         GRID_ARRIVE();   // ---- barrier 4: ancestors complete
         for (int b = tid; b < kNF; b += GT) s_fhist[b] = 0;
         PROF_MARK(1);   // zero hist
+        if (a.u_flag && tid == 0) {
+            // host-streamed u: row t has to have landed (the flag is written by the copy engine)
+            while (ld_acquire_sys_s32(a.u_flag) <= t) {
+            }
+        }
         GRID_WAIT();
         PROF_MARK(2);   // wait 4
         if (s_sc.abort_now) break;
@@ -573,7 +584,8 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
             const double ylag = a.obs[t >= 2 ? t - 2 : 0];   // Q5: the score terms of step i use obs[i - LAG]; i = t + LAG - 2
             const double mhat = s_sc.mhat, inv_shat = s_sc.inv_shat;
             const double mu = s_k.mu, phi = s_k.phi, sr = s_k.sr, sd = s_k.sd;
-            const double* Ut = a.U + (size_t)t * N;
+            const double* Ut = a.U + (size_t)(t / a.u_cs) * a.u_cstride + (size_t)(t % a.u_cs) * a.u_tstride;
+            const long long ujs = a.u_jstride;
             PEntry* Pt = a.P + (size_t)(t % RP) * N;
             bool bad = false, orphan = false;
 #pragma unroll
@@ -594,7 +606,7 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
                         }
                         xe[u] = __ldcg(&a.XE[p]);
                         bp[k0 + u] = __ldcg(&a.perm[p]);
-                        uu[u] = ld_stream_hint_f64(Ut + jb + i, pol_stream);
+                        uu[u] = ld_stream_hint_f64(Ut + (size_t)(jb + i) * ujs, pol_stream);
                         if (a.hist) a.parentpos[jb + i] = p;
                     }
                 }
@@ -798,7 +810,7 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
         for (int b = tid; b < kNSB; b += GT) s_sub[b] = 0;
         if (warp == 0 && nc > 0) {
             // the generation the fixed-lag terms of this step gather from, and the next step's slice of u -> L2
-            if (t + 1 < NOBS) {
+            if (t + 1 < NOBS && !a.u_flag) {
                 const double* Un = a.U + (size_t)(t + 1) * N;
                 prefetch_range(Un + jb, Un + je, lane, 32);
             }
@@ -1299,7 +1311,7 @@ size_t sv_grid_ws_bytes(int nobs, int n, int lag, int G, int hist) {
 int sv_grid_run(const double* d_obs, const double* d_params, const double* d_rvr, const double* d_u, int nobs,
                 int n, int lag, int G, double* d_filt, double* d_smo, double* d_ll, double* d_grad, double* d_traj,
                 long long* d_diag, double* d_xh, int* d_ah, void* d_ws, size_t ws_bytes, long long* d_prof,
-                cudaStream_t st) {
+                cudaStream_t st, int u_chunk_steps, const int* d_u_flag) {
     if (!sv_grid_eligible(nobs, n, lag, G)) return set_error(PMMH_ERR_INVALID, "grid kernel: sizes not eligible");
     const int hist = d_xh != nullptr;
     const GridLayout L = grid_layout(nobs, n, lag, G, hist);
@@ -1318,6 +1330,19 @@ int sv_grid_run(const double* d_obs, const double* d_params, const double* d_rvr
     a.params = d_params;
     a.rvr = d_rvr;
     a.U = d_u;
+    if (u_chunk_steps > 0) {   // particle-major chunks of u_chunk_steps time steps (host-streamed)
+        a.u_cs = u_chunk_steps;
+        a.u_cstride = (long long)n * u_chunk_steps;
+        a.u_tstride = 1;
+        a.u_jstride = u_chunk_steps;
+        a.u_flag = d_u_flag;
+    } else {
+        a.u_cs = 1 << 30;
+        a.u_cstride = 0;
+        a.u_tstride = n;
+        a.u_jstride = 1;
+        a.u_flag = nullptr;
+    }
     a.ctrl = (GridCtrl*)(ws + L.ctrl);
     a.ghist = (int*)(ws + L.ghist);
     a.tilecnt = (int*)(ws + L.tilecnt);

@@ -11,6 +11,6 @@ size_t sv_grid_ws_bytes(int nobs, int n, int lag, int G, int hist);
 int sv_grid_run(const double* d_obs, const double* d_params, const double* d_rvr, const double* d_u, int nobs,
                 int n, int lag, int G, double* d_filt, double* d_smo, double* d_ll, double* d_grad, double* d_traj,
                 long long* d_diag, double* d_xh, int* d_ah, void* d_ws, size_t ws_bytes, long long* d_prof,
-                cudaStream_t st);
+                cudaStream_t st, int u_chunk_steps = 0, const int* d_u_flag = nullptr);
 int sv_grid_read_info(const void* d_ws, int nobs, int n, int lag, int G, int hist, long long* h_info);
 }  // namespace pmmh

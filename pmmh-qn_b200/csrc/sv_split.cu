@@ -86,6 +86,8 @@ struct SplitState {
     unsigned int ticket_c;   // last-block-done counter of the children kernel (fused plan)
 };
 
+__global__ void split_set_state_kernel(SplitState* dst, const SplitState h) { *dst = h; }
+
 struct Layout {
     size_t state, cumblk, boff, btot, tlast, bpart, gpart, cstart, xc, pa, cb, dest, nfc, fstart, counts, fcnt, fst,
         rnk, fb, tkey, tidx, tfb, total;
@@ -1524,9 +1526,10 @@ int pmmh_svsplit_init(void* d_ws, size_t ws_bytes, long long n_total, int n_obs,
     h.nobs = n_obs;
     h.cap = cap_particles;
     h.capc = cap_children;
-    SPLIT_CUDA(cudaMemcpyAsync((char*)d_ws + L.state, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+    // the state travels as a kernel argument (copied at launch): no host buffer to keep alive, no
+    // synchronisation -- the call is asynchronous on the stream like every other entry point
+    split_set_state_kernel<<<1, 1, 0, st>>>((SplitState*)((char*)d_ws + L.state), h);
     SPLIT_CUDA(cudaMemsetAsync((char*)d_ws + L.fcnt, 0, (size_t)(L.nf_max + 1) * 4, st));
-    SPLIT_CUDA(cudaStreamSynchronize(st));   // h lives on this stack frame
     if (n_local > 0)
         split_init_kernel<<<grid_for(n_local, 256), 256, 0, st>>>(d_xs, d_perm, d_rec, n_local, h.LR,
                                                                    d_params);

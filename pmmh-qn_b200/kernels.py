@@ -179,8 +179,10 @@ def flps_sv_corr_streamed(rvs_host, obs, params, rvr, n_obs, n_particles, lag=10
         "hess2": torch.empty((1, 4, 4), dtype=_F64, device=dev),
         "diag": torch.zeros((1, _lib.DIAG_COUNT), dtype=torch.int64, device=dev),
     }
-    nbytes = sv_workspace_bytes(n_obs, n_particles, lag, 1, 0, 0, False, ctas_per_problem)
-    ws = (workspace or Workspace()).get(nbytes, dev)
+    wb = ctypes.c_size_t()
+    _lib.check(lib.pmmh_sv_streamed_workspace_bytes(n_obs, n_particles, lag, ctas_per_problem, ctypes.byref(wb)),
+               "pmmh_sv_streamed_workspace_bytes")
+    ws = (workspace or Workspace()).get(wb.value, dev)
     sb = ctypes.c_size_t()
     _lib.check(lib.pmmh_sv_stage_bytes(n_obs, n_particles, ctypes.byref(sb)), "pmmh_sv_stage_bytes")
     st = (stage or Workspace()).get(sb.value, dev)

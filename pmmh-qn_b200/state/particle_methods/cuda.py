@@ -16,7 +16,7 @@ import torch
 from scipy.stats import norm
 
 from ... import kernels as K
-from ..._lib import BPF_INTENDED, BPF_PARITY, DIAG_NEAR_TIES, DIAG_STATUS
+from ..._lib import BPF_INTENDED, BPF_PARITY, DIAG_NEAR_TIES, DIAG_STATUS, PmmhError
 from ...parameter.rvs import DeviceRVS
 from ..base_state_inference import BaseStateInference
 
@@ -85,9 +85,12 @@ class ParticleMethodsCUDA(BaseStateInference):
         flat = rvs.reshape(-1)
         rv_r = norm.cdf(flat[0:n_obs]).flatten()   # bit-identical to cython.py:90
         rvr = torch.from_numpy(rv_r).to(self.device, non_blocking=True)
-        out = K.flps_sv_corr_streamed(rvs, obs_d, torch.from_numpy(params).to(self.device), rvr, n_obs, n,
-                                      lag=lag, ctas_per_problem=self.ctas_per_problem,
-                                      workspace=self._workspace, stage=self._stage)
+        try:
+            out = K.flps_sv_corr_streamed(rvs, obs_d, torch.from_numpy(params).to(self.device), rvr, n_obs, n,
+                                          lag=lag, ctas_per_problem=self.ctas_per_problem,
+                                          workspace=self._workspace, stage=self._stage)
+        except PmmhError:      # a size / workspace the streamed entry point refuses: upload instead
+            return None
         if int(out['diag'][0, DIAG_STATUS].item()) != 0:   # synchronises; abandoned: use the general path
             return None
         return out

@@ -223,6 +223,10 @@ class LocalComm(object):
         for t in tensors:
             t.copy_(tot)
 
+    def agree_status(self, status, device):
+        """The largest status word over all ranks (every rank acts on the same value)."""
+        return int(status)
+
 
 class DistComm(object):
     """One rank per process: torch.distributed (NCCL on GPUs; gloo works for the host logic)."""
@@ -251,6 +255,13 @@ class DistComm(object):
 
     def all_reduce_sum(self, tensors):
         self.dist.all_reduce(tensors[0], op=self.dist.ReduceOp.SUM, group=self.group)
+
+    def agree_status(self, status, device):
+        """The largest status word over all ranks: cap overflows (status 4 / 8) are rank-local, and a
+        rank that raised alone would leave the others blocked in the next collective."""
+        t = torch.tensor([int(status)], dtype=torch.int64, device=device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+        return int(t.item())
 
 
 def run_split_smoother(comm, obs, params, n_total, lag, rvr_d, u_d=None, philox=None, device=None,
@@ -292,11 +303,13 @@ def run_split_smoother(comm, obs, params, n_total, lag, rvr_d, u_d=None, philox=
         torch.cuda.current_stream(device).synchronize()      # the counts are on the host now
         cnt = [rk.counts() for rk in ranks]
         nc_hist.append([c[3] for c in cnt])
-        for rk, c in zip(ranks, cnt):
-            if c[5] != 0:
-                raise FloatingPointError("split particle filter abandoned at t=%d on rank %d (status %d: "
-                                         "1/2 non-finite weights, 4 children > cap_children, 8 arrivals > "
-                                         "cap_particles)" % (t, rk.rank, c[5]))
+        status = max(int(c[5]) for c in cnt)
+        if G > 1:
+            status = comm.agree_status(status, device)     # the same decision on every rank
+        if status != 0:
+            raise FloatingPointError("split particle filter abandoned at t=%d (largest status over the ranks %d; "
+                                     "local %s: 1/2 non-finite weights, 4 children > cap_children, 8 arrivals > "
+                                     "cap_particles)" % (t, status, [int(c[5]) for c in cnt]))
         if G == 1:
             rk = ranks[0]
             rk.rec_next, rk.send = rk.send, rk.rec_next       # the exchange is the identity

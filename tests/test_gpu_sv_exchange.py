@@ -180,11 +180,11 @@ def test_streamed_host_rvs_equals_resident(cuda_dev, pinned):
     params = torch.tensor([[0.2, 0.9, 0.4, -0.5]], dtype=torch.float64, device=dev)
     rvr_h, rvp = gi.split_particle(rvs, nobs)
     rvr = torch.from_numpy(rvr_h).to(dev)
-    a = K.flps_sv_corr_streamed(rvs, obs, params, rvr, nobs, n, lag=lag)
-    torch.cuda.synchronize()
-    assert int(a["diag"][0, DIAG_KERNEL]) == 2 and int(a["diag"][0, DIAG_STATUS]) == 0
-    K.set_sv_algorithm(2)
+    K.set_sv_algorithm(2)      # (automatic selection would take the grid kernel at this size)
     try:
+        a = K.flps_sv_corr_streamed(rvs, obs, params, rvr, nobs, n, lag=lag)
+        torch.cuda.synchronize()
+        assert int(a["diag"][0, DIAG_KERNEL]) == 2 and int(a["diag"][0, DIAG_STATUS]) == 0
         u = torch.from_numpy(to_time_major(rvp, n, nobs)).to(dev)
         b = K.flps_sv_corr(obs, params, rvr, u, lag=lag, compute_hessian=False)
         torch.cuda.synchronize()
@@ -194,9 +194,13 @@ def test_streamed_host_rvs_equals_resident(cuda_dev, pinned):
         assert torch.equal(a[k], b[k]), k
     # twice in a row on the same staging buffer (the second call must wait for the first)
     ws, st = K.Workspace(), K.Workspace()
-    c1 = K.flps_sv_corr_streamed(rvs, obs, params, rvr, nobs, n, lag=lag, workspace=ws, stage=st)
-    c2 = K.flps_sv_corr_streamed(rvs, obs, params, rvr, nobs, n, lag=lag, workspace=ws, stage=st)
-    torch.cuda.synchronize()
+    K.set_sv_algorithm(2)
+    try:
+        c1 = K.flps_sv_corr_streamed(rvs, obs, params, rvr, nobs, n, lag=lag, workspace=ws, stage=st)
+        c2 = K.flps_sv_corr_streamed(rvs, obs, params, rvr, nobs, n, lag=lag, workspace=ws, stage=st)
+        torch.cuda.synchronize()
+    finally:
+        K.set_sv_algorithm(0)
     for k in ("log_like", "gradient"):
         assert torch.equal(c1[k], a[k]) and torch.equal(c2[k], a[k]), k
 

@@ -150,3 +150,39 @@ def test_grid_automatic_selection_and_fallback(cuda_dev):
     u0 = np.zeros_like(u)
     res0 = _run(K, cuda_dev, obs, params, rvr, u0, 10, False)
     assert int(res0["diag"][0, DIAG_KERNEL]) == 1, res0["diag"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pinned,n,nobs", [(True, 65536, 300), (False, 100000, 70), (True, 1 << 20, 30)])
+def test_grid_host_streamed_rvs_equals_resident(cuda_dev, pinned, n, nobs):
+    """pmmh_flps_sv_corr_streamed on the grid kernel: the copy engine lays the reference's (NOBS, N+1)
+    host array down in particle-major chunks of 256 time steps while the kernel runs and polls one flag
+    per step; bit-identical to upload -> time-major array -> pmmh_flps_sv_corr."""
+    import torch
+    from helpers import to_time_major
+    from pmmh_qn_b200 import kernels as K
+    lag, dev = 10, cuda_dev
+    rs = np.random.RandomState(33)
+    if pinned:
+        host = torch.empty((nobs, n + 1), dtype=torch.float64, pin_memory=True)
+        rvs = host.numpy()
+        rvs[...] = rs.normal(size=(nobs, n + 1))
+    else:
+        rvs = rs.normal(size=(nobs, n + 1))
+    assert K.sv_streamed_eligible(nobs, n, lag)
+    obs = torch.from_numpy(gi.sv_obs(nobs)).to(dev)
+    params = torch.tensor([[0.2, 0.9, 0.4, -0.5]], dtype=torch.float64, device=dev)
+    rvr_h, rvp = gi.split_particle(rvs, nobs)
+    rvr = torch.from_numpy(rvr_h).to(dev)
+    ws, st = K.Workspace(), K.Workspace()
+    a = K.flps_sv_corr_streamed(rvs, obs, params, rvr, nobs, n, lag=lag, workspace=ws, stage=st)
+    a2 = K.flps_sv_corr_streamed(rvs, obs, params, rvr, nobs, n, lag=lag, workspace=ws, stage=st)   # back to back
+    torch.cuda.synchronize()
+    assert int(a["diag"][0, DIAG_KERNEL]) == GRID and int(a["diag"][0, DIAG_STATUS]) == 0
+    u = torch.from_numpy(to_time_major(rvp, n, nobs)).to(dev)
+    b = K.flps_sv_corr(obs, params, rvr, u, lag=lag, compute_hessian=False)
+    torch.cuda.synchronize()
+    assert int(b["diag"][0, DIAG_KERNEL]) == GRID
+    for k in ("log_like", "filt", "smo", "gradient", "traj"):
+        assert torch.equal(a[k], b[k]), k
+        assert torch.equal(a2[k], b[k]), k
