@@ -63,6 +63,9 @@ extern "C" {
 #define PMMH_DIAG_STATUS 2      /* 0 ok, 1 degenerate particle cloud (evaluation abandoned) */
 #define PMMH_DIAG_KEY_TIES 3    /* equal keys met while sorting */
 #define PMMH_DIAG_WAVEFRONT 4   /* bpf parity mode: deepest dependency chain */
+#define PMMH_DIAG_SOFT_TIES 4   /* flps, grid kernel: ancestor decisions whose margin is below the bound on the
+                                   difference between the reference's sequential cumulative sums and parallel ones
+                                   (eps N (4 + 2 sqrt N) child-index units): only these can differ from the reference */
 #define PMMH_DIAG_TRAJ_IDX 5    /* bpf: sampled trajectory index */
 #define PMMH_DIAG_KERNEL 6      /* kernel that produced the outputs: 1 general, 2 exchange, 3 chain, 4 split */
 #define PMMH_DIAG_FAST_INFO 7   /* exchange kernel: abandon reason (1 run / 2 chunk overflow) |

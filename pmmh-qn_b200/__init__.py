@@ -19,6 +19,7 @@ _LAZY = {
     "DirectComputationCUDA": ("state.direct.cuda", "DirectComputationCUDA"),
     "DeviceRVS": ("parameter.rvs", "DeviceRVS"),
     "propose_rvs": ("parameter.rvs", "propose_rvs"),
+    "CorrelatedRVSState": ("parameter.rvs", "CorrelatedRVSState"),
 }
 
 

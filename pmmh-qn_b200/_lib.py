@@ -18,6 +18,7 @@ c_vp = ctypes.c_void_p
 c_dbl = ctypes.c_double
 
 DIAG_NEAR_TIES, DIAG_MAX_BIN, DIAG_STATUS, DIAG_KEY_TIES, DIAG_WAVEFRONT, DIAG_TRAJ_IDX, DIAG_KERNEL = range(7)
+DIAG_SOFT_TIES = 4   # flps on the grid kernel (same slot as the bpf wave-front depth)
 DIAG_COUNT = 8
 BPF_PARITY, BPF_INTENDED = 0, 1
 

@@ -1208,6 +1208,7 @@ __global__ void grid_finish_kernel(const GridCtrl* __restrict__ ctrl, const doub
         diag[PMMH_DIAG_MAX_BIN] = ctrl->max_bin;
         diag[PMMH_DIAG_STATUS] = ctrl->status ? 1 : 0;
         diag[PMMH_DIAG_KEY_TIES] = (long long)ctrl->key_ties;
+        diag[PMMH_DIAG_SOFT_TIES] = (long long)ctrl->soft_ties;
         diag[PMMH_DIAG_KERNEL] = 5;
         diag[PMMH_DIAG_FAST_INFO] = ctrl->status;
         if (info) {

@@ -44,11 +44,11 @@ class ParticleMethodsCUDA(BaseStateInference):
 
     # ------------------------------------------------------------------ helpers
     def _obs_device(self, model):
+        # (the comparison reads n_obs doubles per call: the observations may be replaced on the model
+        # between calls, and n_obs is ~1e3)
         obs = np.array(model.obs.flatten()).astype(float)
-        key = (obs.ctypes.data, obs.shape[0])
         if self._obs_cache is None or not np.array_equal(self._obs_cache[0], obs):
             self._obs_cache = (obs, torch.from_numpy(obs).to(self.device))
-        del key
         return obs, self._obs_cache[1]
 
     def _rvs_device(self, kwargs):

@@ -71,6 +71,49 @@ def test_device_rvs_handle_equals_numpy_path(cuda_dev):
     assert prop2.tensors['u'].shape == h.tensors['u'].shape and prop2 is not h
 
 
+def test_correlated_rvs_state_two_slots_and_stale_handles(cuda_dev):
+    """Device-resident CPMH state: the proposal is written into the spare slot (no allocation), accept
+    swaps the slots, reject keeps the current one; a history handle whose slot has been written again
+    is stale and refuses to be read (base_class.py:221-241, :269-300; mh_quasi_newton.py:226-233)."""
+    import oracle
+    from pmmh_qn_b200 import CorrelatedRVSState, DeviceRVS, ParticleMethodsCUDA
+    n, nobs, sigma_u = 400, 120, 0.3
+    model = ToySVModel(gi.sv_obs(nobs), gi.SV_PARAM_SETS[0])
+    est = ParticleMethodsCUDA(model, no_particles=n)
+    rvs0 = gi.sv_rvs(n, nobs, 5)
+    st = CorrelatedRVSState.from_numpy_particle(rvs0, cuda_dev, sigma_u, seed=3)
+    cur0 = st.current
+    hist = copy.deepcopy({'rvs': cur0})                      # what the sampler's history does
+    assert hist['rvs'] is cur0 and not cur0.stale
+    ptrs = sorted(t.data_ptr() for slot in st._slots for t in slot.values())
+    # proposal with supplied noise = the reference's formula bit for bit; reject keeps the current state
+    xi = gi.sv_rvs(n, nobs, 6)
+    prop = st.propose(xi=DeviceRVS.from_numpy_particle(xi, cuda_dev))
+    want = oracle.crank_nicolson(rvs0, xi, sigma_u)
+    assert np.array_equal(prop.to_numpy_particle(), want)
+    st.reject()
+    assert np.array_equal(st.current.to_numpy_particle(), rvs0) and not cur0.stale
+    # accept swaps; the estimator sees the accepted u
+    prop = st.propose(xi=DeviceRVS.from_numpy_particle(xi, cuda_dev))
+    assert est.smoother(model, rvs={'rvs': prop})
+    ll_prop = est.results['log_like']
+    st.accept()
+    assert np.array_equal(st.current.to_numpy_particle(), want) and not cur0.stale   # old slot still intact
+    assert est.smoother(model, rvs={'rvs': want})
+    assert abs(est.results['log_like'] - ll_prop) <= 1e-10 * abs(ll_prop)
+    # the next proposal reuses the slot cur0 views: that handle is stale from now on
+    p2 = st.propose()                                        # Philox normals on the device
+    assert cur0.stale
+    with pytest.raises(RuntimeError):
+        cur0.tensors
+    assert not p2.stale and not st.current.stale
+    assert sorted(t.data_ptr() for slot in st._slots for t in slot.values()) == ptrs   # never reallocated
+    u_cur, u_new = st.current.tensors['u'], p2.tensors['u']
+    resid = (u_new - np.sqrt(1.0 - sigma_u ** 2) * u_cur) / sigma_u         # = the Philox normals
+    assert abs(float(resid.mean())) < 0.02 and abs(float(resid.std()) - 1.0) < 0.02
+    assert st.proposals == 3 and st.accepted == 1
+
+
 def test_importance_sampling_cuda_vs_reference_estimator(cuda_dev, golden):
     from pmmh_qn_b200 import ImportanceSamplingCUDA
     g = golden["estimators"]
@@ -137,3 +180,23 @@ def test_calls_recorded_from_reference_qn_sampler(cuda_dev, golden):
         assert abs(est.results['log_like'] - want_ll) <= 1e-10 * abs(want_ll)
         checked += 1
     assert checked >= 4
+
+
+def test_host_rvs_beyond_the_record_threshold(cuda_dev):
+    """N = 2^23 with a host (NumPy) rvs array: the host-streamed entry point runs the streaming kernels
+    with path storage and sizes its own workspace (pmmh_sv_streamed_workspace_bytes); same estimate as
+    the device-resident handle of the same numbers."""
+    from pmmh_qn_b200 import DeviceRVS, ParticleMethodsCUDA
+    n, nobs = 1 << 23, 24
+    model = ToySVModel(gi.sv_obs(nobs), gi.SV_PARAM_SETS[0])
+    est = ParticleMethodsCUDA(model, no_particles=n)
+    rs = np.random.RandomState(8)
+    rvs = rs.normal(size=(nobs, n + 1))
+    assert est.smoother(model, rvs={'rvs': rvs})
+    ll_np, g_np = est.results['log_like'], est.results['gradient_internal'].copy()
+    assert est.diagnostics['status'] == 0
+    h = DeviceRVS.from_numpy_particle(rvs, cuda_dev)
+    del rvs
+    assert est.smoother(model, rvs={'rvs': h})
+    assert abs(est.results['log_like'] - ll_np) <= 1e-10 * abs(ll_np)
+    assert np.max(np.abs(est.results['gradient_internal'] - g_np)) <= 1e-9 * np.max(np.abs(g_np))

@@ -44,13 +44,18 @@ t0 = time.perf_counter()
 ref = oracle.flps_sv_corr(obs_h, params_h, rvr[0].cpu().numpy(), rvp, n, lag, 0, dumps=True)
 secs = time.perf_counter() - t0
 neq = np.any(A[1:] != ref["A"][1:], axis=1)
+per_step = np.sum(A[1:] != ref["A"][1:], axis=1)
+xdiff = np.sum(X[1:] != ref["X"][1:], axis=1)
 rel = lambda a, b: float(np.max(np.abs(a - b)) / max(1e-300, np.max(np.abs(b))))
 print(json.dumps({
     "what": "CUDA path vs oracle at the headline shape", "N": n, "T": T, "lag": lag, "kernel": int(d[6]),
-    "status": int(d[2]), "near_ties": int(d[0]), "generations_mismatched": int(neq.sum()),
+    "status": int(d[2]), "near_ties": int(d[0]), "soft_ties": int(d[4]), "generations_mismatched": int(neq.sum()),
     "first_mismatch_step": (int(np.argmax(neq)) + 1) if neq.any() else None,
     "x_max_rel": rel(X, ref["X"]), "ll": ll, "ll_oracle": ref["log_like"],
     "ll_rel": abs(ll - ref["log_like"]) / abs(ref["log_like"]),
     "grad_rel": rel(res["gradient"], np.asarray(ref["gradient"])), "filt_rel": rel(res["filt"], ref["filt"]),
     "smo_rel": rel(res["smo"], ref["smo"]), "traj_rel": rel(res["traj"], ref["traj"]),
+    "ancestor_entries_differing_max_per_step": int(per_step.max()), "ancestor_entries_differing_total": int(per_step.sum()),
+    "particle_values_differing_max_per_step": int(xdiff.max()), "steps_with_differing_values": int((xdiff > 0).sum()),
+    "episodes": int(np.sum((xdiff[1:] > 0) & (xdiff[:-1] == 0)) + (xdiff[0] > 0)),
     "oracle_seconds": secs}))

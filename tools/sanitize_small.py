@@ -28,3 +28,18 @@ for alg in algs:
     d = out["diag"][0].cpu().numpy()
     print("alg %d: log_like %.12f kernel %d status %d" % (alg, float(out["log_like"][0]), int(d[6]), int(d[2])), flush=True)
 K.set_sv_algorithm(0)
+if "streamed" in os.environ.get("PMMH_SANITIZE_EXTRA", "streamed"):
+    # host-resident rvs: the copy engine feeds the running kernel (flag polled per time step)
+    for alg, n, nobs in ((6, 6000, 40), (2, 6000, 40)):
+        rvs = gi.sv_rvs(n, nobs, 2)
+        rvr_h, rvp = gi.split_particle(rvs, nobs)
+        obs = gi.sv_obs(nobs)
+        K.set_sv_algorithm(alg)
+        out = K.flps_sv_corr_streamed(np.ascontiguousarray(rvs), torch.from_numpy(obs).to(dev),
+                                      torch.tensor([gi.SV_PARAM_SETS[0]], dtype=torch.float64, device=dev),
+                                      torch.from_numpy(rvr_h).to(dev), nobs, n, lag=10,
+                                      ctas_per_problem=(0 if alg == 6 else 4))
+        torch.cuda.synchronize()
+        d = out["diag"][0].cpu().numpy()
+        print("streamed alg %d: log_like %.12f kernel %d status %d" % (alg, float(out["log_like"][0]), int(d[6]), int(d[2])), flush=True)
+    K.set_sv_algorithm(0)
