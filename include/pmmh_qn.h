@@ -160,6 +160,23 @@ int pmmh_flps_sv_corr_philox(const double* d_obs, const double* d_params, const 
                              double* d_gradient, double* d_traj, long long* d_diag, void* d_workspace,
                              size_t workspace_bytes, void* stream);
 
+/* Model-generic fixed-lag smoother (log-likelihood + gradient): the same algorithm as pmmh_flps_sv_corr
+ * (sorted correlated systematic resampling, fixed-lag score terms, tail, quirks Q1 / Q5 / Q6) with the
+ * model's propagation, log-weight and score formulas plugged in through the device-function interface
+ * of csrc/pf_model.cuh -- the three things python/README.md:73-76 tells a user to change in the Cython
+ * smoother for another scalar-state model.  One CTA per problem (chain kernel): 2 <= n_particles <= 4096,
+ * 2 <= lag <= 10, any batch.  d_params [batch][4] (unused slots ignored), gradient [4][n_obs] (unused rows 0).
+ * PMMH_MODEL_SV_LEVERAGE gives bit-identical results to pmmh_flps_sv_corr at these sizes.  No fallback
+ * inside: d_diag[PMMH_DIAG_STATUS] == 1 reports an abandoned problem (log-likelihood NaN). */
+#define PMMH_MODEL_SV_LEVERAGE 0      /* mu, phi, sigma_v, rho   (models/stochastic_volatility.py) */
+#define PMMH_MODEL_LINEAR_GAUSSIAN 1  /* phi, sigma_v, sigma_e: x' = phi x + sigma_v v, y = x + sigma_e e */
+int pmmh_flps_model_workspace_bytes(int n_obs, int n_particles, int lag, int batch, size_t* bytes);
+int pmmh_flps_model_corr(int model_id, const double* d_obs, long long obs_stride, const double* d_params,
+                         const double* d_rvr, const double* d_u, int n_obs, int n_particles, int lag, int batch,
+                         double* d_filt, double* d_smo, double* d_log_like, double* d_gradient, double* d_traj,
+                         long long* d_diag, double* d_x_hist, int* d_a_hist, void* d_workspace,
+                         size_t workspace_bytes, void* stream);
+
 /* Bootstrap particle filter (filter only).  read_mode: PMMH_BPF_PARITY / PMMH_BPF_INTENDED. */
 int pmmh_bpf_sv_corr(const double* d_obs, long long obs_stride, const double* d_params,
                      const double* d_rvr, const double* d_u, int n_obs, int n_particles, int batch,

@@ -20,6 +20,7 @@ c_dbl = ctypes.c_double
 DIAG_NEAR_TIES, DIAG_MAX_BIN, DIAG_STATUS, DIAG_KEY_TIES, DIAG_WAVEFRONT, DIAG_TRAJ_IDX, DIAG_KERNEL = range(7)
 DIAG_SOFT_TIES = 4   # flps on the grid kernel (same slot as the bpf wave-front depth)
 DIAG_COUNT = 8
+MODEL_SV_LEVERAGE, MODEL_LINEAR_GAUSSIAN = 0, 1
 BPF_PARITY, BPF_INTENDED = 0, 1
 
 # name -> (restype, argtypes); mirrors include/pmmh_qn.h one to one
@@ -33,6 +34,9 @@ SIGNATURES = {
     "pmmh_flps_sv_corr": (c_int, [c_vp, c_ll, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int,
                                   c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
                                   c_vp, c_size, c_int, c_vp]),
+    "pmmh_flps_model_workspace_bytes": (c_int, [c_int, c_int, c_int, c_int, ctypes.POINTER(c_size)]),
+    "pmmh_flps_model_corr": (c_int, [c_int, c_vp, c_ll, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int,
+                                     c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_size, c_vp]),
     "pmmh_sv_stage_bytes": (c_int, [c_int, c_int, ctypes.POINTER(c_size)]),
     "pmmh_sv_streamed_workspace_bytes": (c_int, [c_int, c_int, c_int, c_int, ctypes.POINTER(c_size)]),
     "pmmh_sv_streamed_eligible": (c_int, [c_int, c_int, c_int, c_int]),

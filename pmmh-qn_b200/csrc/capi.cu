@@ -709,6 +709,73 @@ int pmmh_flps_sv_corr_streamed(const double* h_rvs, const double* d_obs, const d
     return PMMH_OK;
 }
 
+// ---- model-generic entry point: the chain kernel instantiated for a model of pf_model.cuh ----------
+int pmmh_flps_model_workspace_bytes(int n_obs, int n_particles, int lag, int batch, size_t* bytes) {
+    if (!bytes || n_obs < 2 || batch < 1) return fail(PMMH_ERR_INVALID, "pmmh_flps_model_workspace_bytes: bad arguments");
+    if (!pmmh::sv_chain_eligible(n_particles, lag) || pmmh::sv_chain_smem_bytes(n_particles) > kMaxDynSmem)
+        return fail(PMMH_ERR_INVALID, "pmmh_flps_model_corr: 2 <= n_particles <= 4096 and 2 <= lag <= 10");
+    DeviceInfo di;
+    int rc = get_device_info(&di);
+    if (rc != PMMH_OK) return rc;
+    const int grid = batch < di.sm ? batch : di.sm;
+    *bytes = (size_t)grid * pmmh::sv_chain_ws_bytes(n_particles, lag);
+    return PMMH_OK;
+}
+
+int pmmh_flps_model_corr(int model_id, const double* d_obs, long long obs_stride, const double* d_params,
+                         const double* d_rvr, const double* d_u, int n_obs, int n_particles, int lag, int batch,
+                         double* d_filt, double* d_smo, double* d_log_like, double* d_gradient, double* d_traj,
+                         long long* d_diag, double* d_x_hist, int* d_a_hist, void* d_workspace,
+                         size_t workspace_bytes, void* stream) {
+    if (!d_obs || !d_params || !d_rvr || !d_u || !d_filt || !d_smo || !d_log_like || !d_gradient || !d_traj ||
+        !d_diag || !d_workspace)
+        return fail(PMMH_ERR_INVALID, "pmmh_flps_model_corr: null pointer argument");
+    if (model_id != PMMH_MODEL_SV_LEVERAGE && model_id != PMMH_MODEL_LINEAR_GAUSSIAN)
+        return fail(PMMH_ERR_INVALID, "pmmh_flps_model_corr: unknown model id");
+    if ((d_x_hist == nullptr) != (d_a_hist == nullptr))
+        return fail(PMMH_ERR_INVALID, "d_x_hist and d_a_hist must be given together");
+    if (n_obs < lag + 1) return fail(PMMH_ERR_INVALID, "n_obs must be at least lag + 1");
+    size_t need = 0;
+    int rc = pmmh_flps_model_workspace_bytes(n_obs, n_particles, lag, batch, &need);
+    if (rc != PMMH_OK) return rc;
+    if (workspace_bytes < need) return fail(PMMH_ERR_WORKSPACE, "workspace too small");
+    DeviceInfo di;
+    rc = get_device_info(&di);
+    if (rc != PMMH_OK) return rc;
+    if (di.major < 10) return fail(PMMH_ERR_NO_DEVICE, "an sm_100 (B200) device is required");
+    pmmh::SvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.N = n_particles;
+    a.NOBS = n_obs;
+    a.LAG = lag;
+    a.B = batch;
+    a.G = 1;
+    a.n_teams = batch < di.sm ? batch : di.sm;
+    a.mode = pmmh::kSvFlps;
+    a.model_id = model_id;
+    a.obs = d_obs;
+    a.obs_stride = obs_stride;
+    a.params = d_params;
+    a.rvr = d_rvr;
+    a.U = d_u;
+    a.filt = d_filt;
+    a.smo = d_smo;
+    a.loglike = d_log_like;
+    a.grad = d_gradient;
+    a.traj = d_traj;
+    a.hess1 = nullptr;
+    a.hess2 = nullptr;
+    a.diag = d_diag;
+    a.Xhist = d_x_hist;
+    a.Ahist = d_a_hist;
+    a.prof = nullptr;
+    a.ws = (char*)d_workspace;
+    a.ws_sync_bytes = 0;
+    a.ws_team_stride = pmmh::sv_chain_ws_bytes(n_particles, lag);
+    PMMH_CUDA(pmmh::sv_chain_launch(a, a.n_teams, (cudaStream_t)stream));
+    return PMMH_OK;
+}
+
 int pmmh_bpf_sv_corr(const double* d_obs, long long obs_stride, const double* d_params,
                      const double* d_rvr, const double* d_u, int n_obs, int n_particles, int batch,
                      int read_mode, double* d_filt, double* d_log_like, double* d_traj,

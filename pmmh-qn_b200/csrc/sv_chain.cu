@@ -26,6 +26,7 @@
 
 #include "common.cuh"
 #include "sv_filter.cuh"
+#include "pf_model.cuh"
 #include "sv_math.cuh"
 
 namespace pmmh {
@@ -101,10 +102,6 @@ __device__ __forceinline__ int chain_scan_i(int v, int* s_w, int* total) {
     return r;
 }
 
-__device__ __forceinline__ double chain_logw(double x, double e, double half_y2) {
-    return (-0.91893853320467267 - 0.5 * x) - half_y2 * (e * e);
-}
-
 // development instrumentation: cycles per phase, accumulated by thread 0 of every CTA
 #define CPROF(slot)                                                              \
     do {                                                                         \
@@ -115,6 +112,8 @@ __device__ __forceinline__ double chain_logw(double x, double e, double half_y2)
         }                                                                        \
     } while (0)
 
+// M = the model (pf_model.cuh): propagation, log-weight, score terms
+template <class M>
 __global__ void __launch_bounds__(kCT, 1) sv_chain_kernel(SvArgs a) {
     long long prof_t = clock64();
     extern __shared__ __align__(16) unsigned char dsm_raw[];
@@ -158,13 +157,12 @@ __global__ void __launch_bounds__(kCT, 1) sv_chain_kernel(SvArgs a) {
         double* Xh = a.Xhist ? a.Xhist + (size_t)prob * NOBS * N : nullptr;
         int* Ah = a.Ahist ? a.Ahist + (size_t)prob * NOBS * N : nullptr;
 
-        SvConst c;
-        sv_const_init(c, a.params + (size_t)prob * 4);
+        typename M::Const c;
+        M::init(c, a.params + (size_t)prob * 4);
         const double logN = log((double)N);
 
-        // ---------------- time 0 (:306-323, Q1): every particle equals mu + stDev * 0.0
-        const double stdev0 = c.sigmav / sqrt(1.0 - (c.phi * c.phi));
-        const double x0 = c.mu + stdev0 * 0.0;
+        // ---------------- time 0 (:306-323, Q1): every particle starts at the same point
+        const double x0 = M::initial_state(c);
         __syncthreads();
         for (int p = tid; p < N; p += kCT) {
             s_x[p] = x0;
@@ -206,7 +204,6 @@ __global__ void __launch_bounds__(kCT, 1) sv_chain_kernel(SvArgs a) {
         }
         for (int inext = 1; inext < NOBS; ++inext) {
             const double y1 = obs[inext - 1], yi = obs[inext];
-            const double half_y2 = 0.5 * (yi * yi);
             const double u = rvr[inext];
             double un[kP];
 #pragma unroll
@@ -219,7 +216,7 @@ __global__ void __launch_bounds__(kCT, 1) sv_chain_kernel(SvArgs a) {
             // over [x_min, x_max], widened by 6.5 sd (outliers clamp into the end bins)
             if (tid == 0) {
                 double lo, hi;
-                sv_child_range(c, s_x[0], s_x[N - 1], y1, 6.5, lo, hi);
+                M::child_range(c, s_x[0], s_x[N - 1], y1, 6.5, lo, hi);
                 double scale = (double)N / (hi - lo);
                 if (!(hi > lo) || !isfinite(scale) || !isfinite(lo)) scale = 0.0;
                 s_bin[0] = isfinite(lo) ? lo : 0.0;
@@ -230,14 +227,7 @@ __global__ void __launch_bounds__(kCT, 1) sv_chain_kernel(SvArgs a) {
             const double bin_lo = s_bin[0], bin_scale = s_bin[1], bin_hi = s_bin[2];
             // shift: maximum of the (concave) log-weight over the predicted range (the
             // reference's my_max, Q4, picks another element; the shift cancels analytically)
-            double shift;
-            {
-                double xs = log(yi * yi);
-                if (!(xs >= bin_lo)) xs = bin_lo;
-                if (xs > bin_hi) xs = bin_hi;
-                if (!isfinite(xs)) xs = 0.0;
-                shift = chain_logw(xs, exp(-0.5 * xs), half_y2);
-            }
+            const double shift = M::logw_max(c, bin_lo, bin_hi, yi);
 
             // =========== resample (:694-715) + propagate (:354-358) + bin histogram
             double xn[kP];
@@ -274,10 +264,7 @@ __global__ void __launch_bounds__(kCT, 1) sv_chain_kernel(SvArgs a) {
                         const double tol = 64.0 * 2.220446049250313e-16 * cp;
                         if (fabs(cv_hi - cp) <= tol || (cv_lo >= 0.0 && fabs(cp - cv_lo) <= tol)) near_ties++;
                     }
-                    const double xpv = s_x[l];
-                    double mean = c.mu + c.phi * (xpv - c.mu);
-                    mean += c.sr * exp(-0.5 * xpv) * y1;
-                    xn[m] = mean + c.sd * un[m];
+                    xn[m] = M::propagate(c, s_x[l], y1, un[m]);
                     an[m] = l;
                     bn[m] = sv_bin(xn[m], bin_lo, bin_scale, N);
                     rk[m] = atomicAdd(&s_hist[bn[m]], 1);
@@ -375,8 +362,7 @@ __global__ void __launch_bounds__(kCT, 1) sv_chain_kernel(SvArgs a) {
                         s_b[2 * NP + p] = (unsigned short)ib2[m];
                         s_b[3 * NP + p] = (unsigned short)ib3[m];
                         b4n[p] = (unsigned short)ib3[m];
-                        const double e = exp(-0.5 * xs[m]);
-                        double sh = exp(chain_logw(xs[m], e, half_y2) - shift);
+                        double sh = exp(M::logw(c, xs[m], yi) - shift);
                         if (!isfinite(sh)) sh = 0.0;
                         s_cum[p] = sh;
                         xpn[p] = make_double2(xs[m], xpar[m]);
@@ -438,8 +424,8 @@ __global__ void __launch_bounds__(kCT, 1) sv_chain_kernel(SvArgs a) {
                         const double sx = v[q] * s_x[p];
                         if (isfinite(sx)) acc[0] += sx;
                         if (lagged) {
-                            double sq, g[4];
-                            sv_score_main(c, pv[q].y, pv[q].x, yl, sq, g);
+                            double g[4];
+                            M::score_main(c, pv[q].y, pv[q].x, yl, g);
                             acc[1] += v[q] * pv[q].y;
                             acc[2] += g[0] * v[q];
                             acc[3] += g[1] * v[q];
@@ -496,8 +482,8 @@ __global__ void __launch_bounds__(kCT, 1) sv_chain_kernel(SvArgs a) {
                     tacc[0] += (sT / S_T) * curr;
                     if (k >= 1) {
                         const double next = __ldcg(&XPG(ip + 1)[bprev]).x;
-                        double sq, g[4];
-                        sv_score_tail(c, curr, next, y1, sq, g);
+                        double g[4];
+                        M::score_tail(c, curr, next, y1, g);
                         double si = __ldcg(&shI[j]);
                         if (!isfinite(si)) si = 0.0;
                         const double wi = si / S_ip;
@@ -543,7 +529,7 @@ __global__ void __launch_bounds__(kCT, 1) sv_chain_kernel(SvArgs a) {
                 o_diag[kDiagKernel] = 3;
                 o_diag[kDiagFastInfo] = 0;
             }
-            if (tid < 16 && status == 0) {
+            if (tid < 16 && status == 0 && a.hess1) {
                 a.hess1[(size_t)prob * 16 + tid] = 0.0;
                 a.hess2[(size_t)prob * 16 + tid] = 0.0;
             }
@@ -568,9 +554,21 @@ int sv_chain_smem_bytes(int N) {
 
 cudaError_t sv_chain_launch(const SvArgs& a, int grid, cudaStream_t stream) {
     const int smem = sv_chain_smem_bytes(a.N);
-    cudaError_t err = cudaFuncSetAttribute(sv_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (err != cudaSuccess) return err;
-    sv_chain_kernel<<<grid, kCT, smem, stream>>>(a);
+    cudaError_t err;
+    switch (a.model_id) {
+        case 0:
+            err = cudaFuncSetAttribute(sv_chain_kernel<SvLeverageModel>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (err != cudaSuccess) return err;
+            sv_chain_kernel<SvLeverageModel><<<grid, kCT, smem, stream>>>(a);
+            break;
+        case 1:
+            err = cudaFuncSetAttribute(sv_chain_kernel<LinearGaussianModel>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (err != cudaSuccess) return err;
+            sv_chain_kernel<LinearGaussianModel><<<grid, kCT, smem, stream>>>(a);
+            break;
+        default:
+            return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 

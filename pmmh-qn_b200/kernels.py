@@ -122,6 +122,39 @@ def flps_sv_corr(obs, params, rvr, u, lag=10, compute_hessian=False, store_histo
     return out
 
 
+def flps_model_corr(model_id, obs, params, rvr, u, lag=10, store_history=False, workspace=None):
+    """Model-generic fixed-lag smoother (pmmh_flps_model_corr, csrc/pf_model.cuh): log-likelihood +
+    gradient of [B] problems with N <= 4096 particles each, one CTA per problem.  ``model_id``:
+    _lib.MODEL_SV_LEVERAGE or _lib.MODEL_LINEAR_GAUSSIAN; params [B, 4] (unused slots ignored)."""
+    lib = _lib.load()
+    obs, obs_stride, params, rvr, u, batch, n_obs, n = _sv_common(obs, params, rvr, u)
+    dev = u.device
+    out = {
+        "filt": torch.empty((batch, n_obs), dtype=_F64, device=dev),
+        "smo": torch.empty((batch, n_obs), dtype=_F64, device=dev),
+        "log_like": torch.empty((batch,), dtype=_F64, device=dev),
+        "gradient": torch.empty((batch, 4, n_obs), dtype=_F64, device=dev),
+        "traj": torch.empty((batch, n_obs), dtype=_F64, device=dev),
+        "diag": torch.zeros((batch, _lib.DIAG_COUNT), dtype=torch.int64, device=dev),
+    }
+    xh = ah = None
+    if store_history:
+        xh = torch.empty((batch, n_obs, n), dtype=_F64, device=dev)
+        ah = torch.empty((batch, n_obs, n), dtype=torch.int32, device=dev)
+        out["X"] = xh
+        out["A"] = ah
+    wb = ctypes.c_size_t()
+    _lib.check(lib.pmmh_flps_model_workspace_bytes(n_obs, n, lag, batch, ctypes.byref(wb)),
+               "pmmh_flps_model_workspace_bytes")
+    ws = (workspace or Workspace()).get(wb.value, dev)
+    _lib.check(lib.pmmh_flps_model_corr(
+        int(model_id), _ptr(obs), obs_stride, _ptr(params), _ptr(rvr), _ptr(u), n_obs, n, lag, batch,
+        _ptr(out["filt"]), _ptr(out["smo"]), _ptr(out["log_like"]), _ptr(out["gradient"]), _ptr(out["traj"]),
+        _ptr(out["diag"]), _ptr(xh), _ptr(ah), _ptr(ws), ws.numel(), _stream()), "pmmh_flps_model_corr")
+    out["_workspace"] = ws
+    return out
+
+
 def flps_sv_corr_philox(obs, params, rvr, seed, philox_offset, n_particles, lag=10, workspace=None):
     """Log-likelihood + gradient of one problem whose auxiliary variables are a Philox stream
     (pmmh_flps_sv_corr_philox): any N on one device without ever storing u."""

@@ -111,3 +111,24 @@ def logit_prior(d):
 
 def logit_u(m, seed):
     return np.random.RandomState(seed).normal(size=m)
+
+
+LG_PARAM_SETS = [(0.8, 0.5, 0.3, 0.0), (0.95, 0.2, 1.0, 0.0), (-0.5, 1.0, 0.5, 0.0)]
+
+
+def lg_obs(nobs, params=(0.8, 0.5, 0.3, 0.0), seed=4711):
+    """Synthetic data from x' = phi x + sigma_v v, y = x + sigma_e e, x_0 = 0 (csrc/pf_model.cuh)."""
+    phi, sv, se = params[:3]
+    rs = np.random.RandomState(seed)
+    x, y = 0.0, np.zeros(int(nobs))
+    for t in range(1, int(nobs)):
+        x = phi * x + sv * rs.normal()
+        y[t] = x + se * rs.normal()
+    return y
+
+
+def lg_inputs(n, nobs, seed):
+    params = np.array(LG_PARAM_SETS[seed % len(LG_PARAM_SETS)], dtype=np.float64)
+    obs = lg_obs(nobs, params)
+    rvr, rvp = split_particle(sv_rvs(n, nobs, 100 + seed), nobs)
+    return obs, params, rvr, rvp

@@ -119,3 +119,19 @@ def test_oracle_vs_compiled_reference_fresh_inputs():
         r = ref.bpf_sv_corr(obs, params, rvr, np.ascontiguousarray(rvp))
         o = oracle.bpf_sv_corr(obs, params, rvr, rvp, n)
         assert _same(o["filt"], r[0]) and _same(o["log_like"], r[1]) and _same(o["traj"], r[2])
+
+
+def test_generic_numpy_restatement_reproduces_the_c_oracle():
+    """oracle/generic_pf.py (the checker of the model-generic device entry point) with the SV callbacks
+    = oracle_flps_sv_corr: ancestors and sorted generations exact, estimates to 1e-12."""
+    import generic_pf as gp
+    import oracle
+    for (n, nobs, lag, seed) in [(75, 361, 10, 0), (200, 120, 10, 1), (64, 40, 4, 0), (37, 50, 10, 1)]:
+        obs, params, rvr, rvp = gi.sv_inputs(n, nobs, seed)
+        ref = oracle.flps_sv_corr(obs, params, rvr, rvp, n, lag, 0, dumps=True)
+        got = gp.flps_generic(gp.SvLeverage(params), obs, rvr, rvp, n, lag, dumps=True)
+        assert np.array_equal(got["A"][1:], ref["A"][1:])
+        for k in ("X", "filt", "smo", "gradient"):
+            assert np.max(np.abs(got[k] - ref[k])) <= 1e-12 * np.max(np.abs(ref[k])), k
+        assert abs(got["log_like"] - ref["log_like"]) <= 1e-12 * abs(ref["log_like"])
+        assert np.max(np.abs(got["traj"][1:] - ref["traj"][1:])) <= 1e-12 * np.max(np.abs(ref["traj"]))
