@@ -115,7 +115,7 @@ int sv_make_plan(int nobs, int n, int lag, int batch, int hess, int mode, int ha
     if (!di.coop) return fail(PMMH_ERR_NO_DEVICE, "device lacks cooperative launch");
     // log-likelihood + gradient of a problem that fits one CTA: the chain kernel (everything in
     // shared memory, no exchanges)
-    const bool chain_ok = (mode == pmmh::kSvFlps) && !hess && pmmh::sv_chain_eligible(n, lag) &&
+    const bool chain_ok = (mode == pmmh::kSvFlps) && pmmh::sv_chain_eligible(n, lag) &&
                           (g_sv_algorithm == 0 || g_sv_algorithm == 3) && (ctas <= 1);
     int G;
     if (ctas > 0) G = ctas;
@@ -146,7 +146,7 @@ int sv_make_plan(int nobs, int n, int lag, int batch, int hess, int mode, int ha
     p->chain_stride = p->chain_total = 0;
     if (chain_ok && G == 1 && pmmh::sv_chain_smem_bytes(n) <= kMaxDynSmem) {
         p->use_chain = 1;
-        p->chain_stride = pmmh::sv_chain_ws_bytes(n, lag);
+        p->chain_stride = pmmh::sv_chain_ws_bytes(n, lag, nobs, hess);
         p->chain_total = (size_t)p->grid * p->chain_stride;
         if (p->chain_total > p->total) p->total = p->chain_total;
     }
@@ -718,7 +718,7 @@ int pmmh_flps_model_workspace_bytes(int n_obs, int n_particles, int lag, int bat
     int rc = get_device_info(&di);
     if (rc != PMMH_OK) return rc;
     const int grid = batch < di.sm ? batch : di.sm;
-    *bytes = (size_t)grid * pmmh::sv_chain_ws_bytes(n_particles, lag);
+    *bytes = (size_t)grid * pmmh::sv_chain_ws_bytes(n_particles, lag, n_obs, 0);
     return PMMH_OK;
 }
 
@@ -771,7 +771,7 @@ int pmmh_flps_model_corr(int model_id, const double* d_obs, long long obs_stride
     a.prof = nullptr;
     a.ws = (char*)d_workspace;
     a.ws_sync_bytes = 0;
-    a.ws_team_stride = pmmh::sv_chain_ws_bytes(n_particles, lag);
+    a.ws_team_stride = pmmh::sv_chain_ws_bytes(n_particles, lag, n_obs, 0);
     PMMH_CUDA(pmmh::sv_chain_launch(a, a.n_teams, (cudaStream_t)stream));
     return PMMH_OK;
 }

@@ -1,9 +1,12 @@
 // sv_chain.cu -- "chain" kernel for the SV fixed-lag particle smoother: one CTA per problem,
 // the whole particle generation in shared memory (N <= 4096).  This is the shape of BASELINE
 // config 4 (1024 independent CPMH-QN chains / proposals x N = 4096, T = 1000) and of small single
-// evaluations: log-likelihood + fixed-lag gradient, flps_sv_corr with compute_hessian = 0
-// (stochastic_volatility.pyx:205-655; mh_quasi_newton.py:333,378 makes this call twice per
-// iteration).
+// evaluations: log-likelihood + fixed-lag gradient (flps_sv_corr with compute_hessian = 0,
+// stochastic_volatility.pyx:205-655; mh_quasi_newton.py:333,378 makes this call twice per
+// iteration) and, as a second instantiation, the Hessian branch (compute_hessian = 1,
+// :361-390 alpha recursion with Q7 / Q8, :472-534, :564-626: what mh_second_order.py asks for).
+// The kernel is a template over the MODEL (pf_model.cuh: propagation, log-weight, score terms);
+// the Hessian branch exists for the reference's SV model only.
 //
 // One persistent launch, CTAs loop over the problems of the batch; nothing is exchanged between
 // CTAs.  Per time step (all in shared memory unless noted):
@@ -20,6 +23,13 @@
 // The tail (:540-562, Q6) chases one-step ancestors through global rings of the last LAG
 // generations.  Quirks reproduced: Q1, Q3 (as in the other kernels: cumulative weights are
 // normalised at look-up), Q5, Q6, Q11.  Sums over particles are fixed-order tree sums.
+// Hessian branch: the cumulative alpha of a particle (4 doubles) lives in a global ring by sorted
+// position next to the (value, parent value) ring; the child adds its own term to its parent's
+// (one 32-byte gather), the score phase gathers the lagged ancestor's; Q7's flat-layout read needs
+// the first few sorted values of every past generation (a [NOBS][SQ] table) and of the unsorted new
+// one; the 20 sums of hessian1 / hessian2 stay thread-local over the whole series (normalised
+// weights, as the reference) and are reduced once.  1024 chains x N = 4096, T = 1000: 0.87 s
+// against 1.50 s on the general kernel (0.27 s without the Hessian).
 // A degenerate cloud (a sort bin with more than 1024 keys) abandons the problem with status 1;
 // the host re-runs the general kernel for it.
 #include <math.h>
@@ -48,9 +58,13 @@ struct ChainWs {
     double2* xp;   // [LAG + 1][N]  (value, parent value) by sorted position, ring over generations
     int* b1;       // [LAG][N]      one-step ancestor position, last LAG generations (tail)
     double* sh;    // [LAG][N]      shifted weights, last LAG generations (tail)
+    // Hessian branch (:361-390, :472-534, :564-626) only:
+    double4* al;   // [LAG + 1][N]  cumulative alpha of a particle (4 parameters) by sorted position, ring
+    double* xlow;  // [NOBS][SQ]    the first SQ sorted values of every generation (Q7 reads them)
+    double* xnf;   // [SQ]          the first SQ UNSORTED values of the generation being built (Q7)
 };
 
-__host__ __device__ inline size_t chain_ws_carve(int N, int LAG, char* base, ChainWs* w) {
+__host__ __device__ inline size_t chain_ws_carve(int N, int LAG, int NOBS, int SQ, int hess, char* base, ChainWs* w) {
     size_t off = 0;
 #define PMMH_CARVE(field, type, count)                   \
     do {                                                 \
@@ -60,6 +74,14 @@ __host__ __device__ inline size_t chain_ws_carve(int N, int LAG, char* base, Cha
     PMMH_CARVE(xp, double2, (size_t)(LAG + 1) * N);
     PMMH_CARVE(b1, int, (size_t)LAG * N);
     PMMH_CARVE(sh, double, (size_t)LAG * N);
+    if (hess) {
+        PMMH_CARVE(al, double4, (size_t)(LAG + 1) * N);
+        PMMH_CARVE(xlow, double, (size_t)NOBS * SQ);
+        PMMH_CARVE(xnf, double, (size_t)SQ);
+    } else if (w) {
+        w->al = nullptr;
+        w->xlow = w->xnf = nullptr;
+    }
 #undef PMMH_CARVE
     return off;
 }
@@ -102,6 +124,11 @@ __device__ __forceinline__ int chain_scan_i(int v, int* s_w, int* total) {
     return r;
 }
 
+__device__ __forceinline__ double4 chain_ld_d4(const double4* p) {
+    const double2 lo = __ldcg((const double2*)p), hi = __ldcg((const double2*)p + 1);
+    return make_double4(lo.x, lo.y, hi.x, hi.y);
+}
+
 // development instrumentation: cycles per phase, accumulated by thread 0 of every CTA
 #define CPROF(slot)                                                              \
     do {                                                                         \
@@ -113,7 +140,8 @@ __device__ __forceinline__ int chain_scan_i(int v, int* s_w, int* total) {
     } while (0)
 
 // M = the model (pf_model.cuh): propagation, log-weight, score terms
-template <class M>
+// HESS (SvLeverageModel only): the Hessian branch of the reference with its quirks Q7 / Q8
+template <class M, bool HESS>
 __global__ void __launch_bounds__(kCT, 1) sv_chain_kernel(SvArgs a) {
     long long prof_t = clock64();
     extern __shared__ __align__(16) unsigned char dsm_raw[];
@@ -132,17 +160,20 @@ __global__ void __launch_bounds__(kCT, 1) sv_chain_kernel(SvArgs a) {
 
     __shared__ double s_w[33];
     __shared__ int s_iw[33];
-    __shared__ double s_red[12 * 32];
+    __shared__ double s_red[20 * 32];
+    __shared__ double s_hacc[20];        // running hessian1 / hessian2 (upper triangles)
     __shared__ double s_S[kMaxLagC];
     __shared__ double s_bin[4];
     __shared__ int s_flag;
 
     char* wsbase = a.ws + (size_t)blockIdx.x * a.ws_team_stride;
     ChainWs w;
-    chain_ws_carve(N, LAG, wsbase, &w);
+    const int SQ = HESS ? a.SQ : 1;
+    chain_ws_carve(N, LAG, NOBS, SQ, HESS ? 1 : 0, wsbase, &w);
 #define XPG(t) (w.xp + (size_t)((t) % RXP) * N)
 #define B1G(t) (w.b1 + (size_t)((t) - (NOBS - LAG)) * N)
 #define SHG(t) (w.sh + (size_t)((t) - (NOBS - LAG)) * N)
+#define ALG(t) (w.al + (size_t)((t) % RXP) * N)
 
     for (int prob = blockIdx.x; prob < a.B; prob += gridDim.x) {
         if (a.only_failed && a.diag[(size_t)prob * kDiagCount + kDiagStatus] != 1) continue;
@@ -171,6 +202,10 @@ __global__ void __launch_bounds__(kCT, 1) sv_chain_kernel(SvArgs a) {
             s_b[p] = s_b[NP + p] = s_b[2 * NP + p] = s_b[3 * NP + p] = 0;
             for (int q = 0; q < kB4Ring; ++q) s_B4[q * (size_t)NP + p] = 0;
             XPG(0)[p] = make_double2(x0, x0);
+            if (HESS) {
+                ALG(0)[p] = make_double4(0.0, 0.0, 0.0, 0.0);
+                if (p < SQ) w.xlow[p] = x0;
+            }
             if (Xh) {
                 Xh[p] = x0;
                 Ah[p] = p;
@@ -189,6 +224,9 @@ __global__ void __launch_bounds__(kCT, 1) sv_chain_kernel(SvArgs a) {
             s_S[0] = (double)N;
             s_flag = 0;
         }
+        double hacc[HESS ? 20 : 1];   // thread-local hessian1 / hessian2 sums (upper triangles)
+#pragma unroll
+        for (int q = 0; q < (HESS ? 20 : 1); ++q) hacc[q] = 0.0;
         double loglike = 0.0;
         double S_prev = (double)N;
         long long near_ties = 0, key_ties2 = 0;
@@ -268,6 +306,7 @@ __global__ void __launch_bounds__(kCT, 1) sv_chain_kernel(SvArgs a) {
                     an[m] = l;
                     bn[m] = sv_bin(xn[m], bin_lo, bin_scale, N);
                     rk[m] = atomicAdd(&s_hist[bn[m]], 1);
+                    if (HESS && j < SQ) w.xnf[j] = xn[m];
                 }
             }
             __syncthreads();
@@ -307,22 +346,32 @@ __global__ void __launch_bounds__(kCT, 1) sv_chain_kernel(SvArgs a) {
                 if (j < N) {
                     const int slot = s_hist[bn[m]] + rk[m];
                     s_key[slot] = xn[m];
-                    s_pay[slot] = (unsigned short)an[m];
+                    int payv = an[m];
+                    if (HESS) {
+                        // Q7 reads xnew[slot'] only when slot' <= j: remember that in the spare bit
+                        const long long qq = (long long)inext - 1 + an[m];
+                        if ((int)(qq / NOBS) <= j) payv |= 0x8000;
+                    }
+                    s_pay[slot] = (unsigned short)payv;
                 }
             }
             __syncthreads();
             // =========== order each bin (all pairs), fetch what the children inherit
             double xs[kP], xpar[kP];
             int pos[kP], anc[kP], ib1[kP], ib2[kP], ib3[kP];
+            bool q7ok[kP];
 #pragma unroll
             for (int m = 0; m < kP; ++m) {
                 const int s = tid + m * kCT;
                 pos[m] = -1;
                 xs[m] = xpar[m] = 0.0;
                 anc[m] = ib1[m] = ib2[m] = ib3[m] = 0;
+                q7ok[m] = false;
                 if (s < N) {
                     const double key = s_key[s];
-                    const int pay = s_pay[s];
+                    const int payf = s_pay[s];
+                    const int pay = payf & 0x7fff;
+                    q7ok[m] = (payf & 0x8000) != 0;
                     const int b = sv_bin(key, bin_lo, bin_scale, N);
                     const int start = s_hist[b], end = s_hist[b + 1];
                     int rank = 0;
@@ -332,7 +381,7 @@ __global__ void __launch_bounds__(kCT, 1) sv_chain_kernel(SvArgs a) {
                         if (k2 < key) rank++;
                         else if (k2 == key) {
                             key_ties2++;
-                            const int p2 = s_pay[q];
+                            const int p2 = s_pay[q] & 0x7fff;
                             if ((p2 < pay) || (p2 == pay && q < s)) rank++;
                         }
                     }
@@ -366,6 +415,31 @@ __global__ void __launch_bounds__(kCT, 1) sv_chain_kernel(SvArgs a) {
                         if (!isfinite(sh)) sh = 0.0;
                         s_cum[p] = sh;
                         xpn[p] = make_double2(xs[m], xpar[m]);
+                        if constexpr (HESS) {
+                            // alpha recursion (:361-390).  Q7: particles[i - 1 + ancestors[j]] read through the flat
+                            // layout = sorted value `sl` of time tq, or the unsorted new value `sl`, or 0
+                            const long long qq = (long long)inext - 1 + anc[m];
+                            const int tq = (int)(qq % NOBS), sl = (int)(qq / NOBS);
+                            double curr;
+                            if (tq < inext) curr = __ldcg(&w.xlow[(size_t)tq * SQ + sl]);
+                            else if (tq == inext) curr = q7ok[m] ? __ldcg(&w.xnf[sl]) : 0.0;
+                            else curr = 0.0;
+                            const double ylag = obs_wrap(obs, inext - LAG, NOBS);   // Q8
+                            double sq = xs[m] - c.mu - c.phi * (curr - c.mu);
+                            const double ec = exp(-0.5 * curr);
+                            sq -= c.sr * ec * ylag;
+                            const double a0 = c.q * sq * c.one_m_phi;
+                            const double a1 = c.q * sq * (curr - c.mu) * c.one_m_phi2;
+                            double a2 = sq;
+                            a2 += c.sr * ec * yi;
+                            a2 *= c.q * sq;
+                            a2 -= 1.0;
+                            double a3 = c.rho - c.q * c.rho * sq * sq;
+                            a3 += c.inv_sv * sq * ec * yi;
+                            const double4 pa = chain_ld_d4(&ALG(inext - 1)[anc[m]]);
+                            ALG(inext)[p] = make_double4(a0 + pa.x, a1 + pa.y, a2 + pa.z, a3 + pa.w);
+                            if (p < SQ) w.xlow[(size_t)inext * SQ + p] = xs[m];
+                        }
                         if (keep_tail) {
                             B1G(inext)[p] = anc[m];
                             SHG(inext)[p] = sh;
@@ -381,7 +455,8 @@ __global__ void __launch_bounds__(kCT, 1) sv_chain_kernel(SvArgs a) {
             __syncthreads();
             CPROF(3);   // new generation: weights, tables
             // =========== position order: cumulative weights, sums, fixed-lag terms (:445-470)
-            double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            constexpr int NACC = 6;
+            double acc[NACC] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
             double S_i;
             {
                 double v[kP], tsum = 0.0;
@@ -425,7 +500,18 @@ __global__ void __launch_bounds__(kCT, 1) sv_chain_kernel(SvArgs a) {
                         if (isfinite(sx)) acc[0] += sx;
                         if (lagged) {
                             double g[4];
-                            M::score_main(c, pv[q].y, pv[q].x, yl, g);
+                            if constexpr (HESS) {
+                                double sq;
+                                const double ec = exp(-0.5 * pv[q].y);
+                                sv_score_main_e(c, pv[q].y, ec, pv[q].x, yl, sq, g);
+                                const double4 a4 = chain_ld_d4(&ALG(inext - K)[idl[q]]);
+                                const double al[4] = {a4.x, a4.y, a4.z, a4.w};
+                                // (normalised weight, as the reference; the 20 sums stay thread-local over the
+                                // whole series and are reduced once at the end)
+                                sv_hessian_terms_e(c, pv[q].y, ec, ec * ec, sq, yl, g, al, v[q] / S_i, hacc);
+                            } else {
+                                M::score_main(c, pv[q].y, pv[q].x, yl, g);
+                            }
                             acc[1] += v[q] * pv[q].y;
                             acc[2] += g[0] * v[q];
                             acc[3] += g[1] * v[q];
@@ -434,7 +520,7 @@ __global__ void __launch_bounds__(kCT, 1) sv_chain_kernel(SvArgs a) {
                         }
                     }
                 }
-                block_sum<6>(acc, s_red);
+                block_sum<NACC>(acc, s_red);
             }
             if (!(S_i > 0.0) || !isfinite(S_i)) {   // uniform
                 status = 1;
@@ -466,7 +552,11 @@ __global__ void __launch_bounds__(kCT, 1) sv_chain_kernel(SvArgs a) {
             const double* shT = SHG(T);
             for (int k = 0; k < LAG; ++k) {
                 const int ip = T - k;
-                double tacc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+                constexpr int NT = 5;
+                double tacc[NT];
+#pragma unroll
+                for (int q = 0; q < NT; ++q) tacc[q] = 0.0;
+                const double ylag = obs_wrap(obs, ip - LAG, NOBS);
                 const double S_ip = s_S[ip % kMaxLagC];
                 const double y1 = obs_wrap(obs, ip - 1, NOBS);
                 const double* shI = SHG(ip);
@@ -483,17 +573,27 @@ __global__ void __launch_bounds__(kCT, 1) sv_chain_kernel(SvArgs a) {
                     if (k >= 1) {
                         const double next = __ldcg(&XPG(ip + 1)[bprev]).x;
                         double g[4];
-                        M::score_tail(c, curr, next, y1, g);
                         double si = __ldcg(&shI[j]);
                         if (!isfinite(si)) si = 0.0;
                         const double wi = si / S_ip;
+                        if constexpr (HESS) {
+                            double sq;
+                            sv_score_tail(c, curr, next, y1, sq, g);
+                            int b_l2 = j;   // index at lag LAG-2 (for alpha)
+                            for (int h = 0; h < LAG - 2; ++h) b_l2 = __ldcg(&B1G(T - h)[b_l2]);
+                            const double4 a4 = chain_ld_d4(&ALG(T - LAG + 2)[b_l2]);
+                            const double al[4] = {a4.x, a4.y, a4.z, a4.w};
+                            sv_hessian_terms(c, curr, sq, ylag, g, al, wi, hacc);
+                        } else {
+                            M::score_tail(c, curr, next, y1, g);
+                        }
                         tacc[1] += g[0] * wi;
                         tacc[2] += g[1] * wi;
                         tacc[3] += g[2] * wi;
                         tacc[4] += g[3] * wi;
                     }
                 }
-                block_sum<5>(tacc, s_red);
+                block_sum<NT>(tacc, s_red);
                 if (tid == 0) {
                     o_smo[ip] += tacc[0];
                     if (k >= 1) {
@@ -511,6 +611,11 @@ __global__ void __launch_bounds__(kCT, 1) sv_chain_kernel(SvArgs a) {
         }
 
         // ---------------- outputs
+        if constexpr (HESS) {
+            block_sum<20>(hacc, s_red);
+            if (tid < 20) s_hacc[tid] = hacc[tid];
+            __syncthreads();
+        }
         {
             double nt[2] = {(double)near_ties, (double)key_ties2};
             block_sum<2>(nt, s_red);
@@ -530,8 +635,12 @@ __global__ void __launch_bounds__(kCT, 1) sv_chain_kernel(SvArgs a) {
                 o_diag[kDiagFastInfo] = 0;
             }
             if (tid < 16 && status == 0 && a.hess1) {
-                a.hess1[(size_t)prob * 16 + tid] = 0.0;
-                a.hess2[(size_t)prob * 16 + tid] = 0.0;
+                // expand the upper triangles into the symmetric 4x4 outputs
+                const int r = tid >> 2, cidx = tid & 3;
+                const int k = min(r, cidx), l = max(r, cidx);
+                const int tri = k * 4 - (k * (k - 1)) / 2 + (l - k);
+                a.hess1[(size_t)prob * 16 + tid] = HESS ? s_hacc[tri] : 0.0;
+                a.hess2[(size_t)prob * 16 + tid] = HESS ? s_hacc[10 + tri] : 0.0;
             }
             __syncthreads();
         }
@@ -539,37 +648,37 @@ __global__ void __launch_bounds__(kCT, 1) sv_chain_kernel(SvArgs a) {
 #undef XPG
 #undef B1G
 #undef SHG
+#undef ALG
 }
 
 }  // namespace
 
 int sv_chain_eligible(int N, int LAG) { return N >= 2 && N <= kChainMaxN && LAG >= 2 && LAG <= 10; }
 
-size_t sv_chain_ws_bytes(int N, int LAG) { return chain_ws_carve(N, LAG, nullptr, nullptr); }
+size_t sv_chain_ws_bytes(int N, int LAG, int NOBS, int hess) {
+    const int SQ = hess ? (NOBS + N - 2) / NOBS + 1 : 1;
+    return chain_ws_carve(N, LAG, NOBS, SQ, hess, nullptr, nullptr);
+}
 
 int sv_chain_smem_bytes(int N) {
     const size_t NP = (size_t)((N + 1) & ~1);
     return (int)(NP * 8 * 3 + (NP + 2) * 4 + NP * 2 * (4 + kB4Ring + 1) + 64);
 }
 
+template <class M, bool HESS>
+static cudaError_t chain_launch_one(const SvArgs& a, int grid, int smem, cudaStream_t stream) {
+    cudaError_t err = cudaFuncSetAttribute(sv_chain_kernel<M, HESS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (err != cudaSuccess) return err;
+    sv_chain_kernel<M, HESS><<<grid, kCT, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
 cudaError_t sv_chain_launch(const SvArgs& a, int grid, cudaStream_t stream) {
     const int smem = sv_chain_smem_bytes(a.N);
-    cudaError_t err;
-    switch (a.model_id) {
-        case 0:
-            err = cudaFuncSetAttribute(sv_chain_kernel<SvLeverageModel>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            if (err != cudaSuccess) return err;
-            sv_chain_kernel<SvLeverageModel><<<grid, kCT, smem, stream>>>(a);
-            break;
-        case 1:
-            err = cudaFuncSetAttribute(sv_chain_kernel<LinearGaussianModel>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            if (err != cudaSuccess) return err;
-            sv_chain_kernel<LinearGaussianModel><<<grid, kCT, smem, stream>>>(a);
-            break;
-        default:
-            return cudaErrorInvalidValue;
-    }
-    return cudaGetLastError();
+    if (a.model_id == 0) return a.hess ? chain_launch_one<SvLeverageModel, true>(a, grid, smem, stream)
+                                       : chain_launch_one<SvLeverageModel, false>(a, grid, smem, stream);
+    if (a.model_id == 1 && !a.hess) return chain_launch_one<LinearGaussianModel, false>(a, grid, smem, stream);
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace pmmh

@@ -125,7 +125,7 @@ int sv_dynamic_smem_bytes(int G);
 
 // chain kernel (sv_chain.cu): one CTA per problem, N <= kChainMaxN
 int sv_chain_eligible(int N, int LAG);
-size_t sv_chain_ws_bytes(int N, int LAG);
+size_t sv_chain_ws_bytes(int N, int LAG, int NOBS, int hess);
 int sv_chain_smem_bytes(int N);
 cudaError_t sv_chain_launch(const SvArgs& a, int grid, cudaStream_t stream);
 

@@ -108,11 +108,19 @@ __device__ __forceinline__ void sv_score_tail(const SvConst& c, double curr, dou
 // Upper-triangular sub_hessian1 / sub_hessian2 terms, stochastic_volatility.pyx:473-519,
 // accumulated with the isfinite guards of :521-534.  Order: (0,0)(0,1)(0,2)(0,3)(1,1)(1,2)
 // (1,3)(2,2)(2,3)(3,3); acc[0..9] = hessian1, acc[10..19] = hessian2.
+// (e = exp(-curr / 2) and e2 = exp(-curr) are passed in: the chain kernel shares e with the score terms and
+// uses e * e for e2)
+__device__ __forceinline__ void sv_hessian_terms_e(const SvConst& c, double curr, double e, double e2, double sq,
+                                                   double yl, const double g[4], const double al[4], double w,
+                                                   double* acc);
 __device__ __forceinline__ void sv_hessian_terms(const SvConst& c, double curr, double sq, double yl,
                                                  const double g[4], const double al[4], double w,
                                                  double* acc) {
-    const double e = exp(-0.5 * curr);
-    const double e2 = exp(-curr);
+    sv_hessian_terms_e(c, curr, exp(-0.5 * curr), exp(-curr), sq, yl, g, al, w, acc);
+}
+__device__ __forceinline__ void sv_hessian_terms_e(const SvConst& c, double curr, double e, double e2, double sq,
+                                                   double yl, const double g[4], const double al[4], double w,
+                                                   double* acc) {
     const double cm = curr - c.mu;
     double h1[10], h2[10];
     // (0,0)

@@ -232,6 +232,69 @@ def test_chain_vs_oracle(cuda_dev, chain_only, n, nobs, lag):
     assert np.max(np.abs(res["gradient"][0] - ref["gradient"])) <= 1e-9 * np.max(np.abs(ref["gradient"]))
 
 
+@pytest.mark.parametrize("n,nobs,lag,seed", [(75, 361, 10, 0), (200, 120, 10, 1), (37, 50, 10, 1), (64, 40, 4, 0),
+                                             (1024, 1001, 10, 0), (4096, 1001, 10, 0), (3000, 90, 10, 2),
+                                             (4096, 60, 10, 1), (2500, 120, 3, 2), (2500, 120, 2, 1)])
+def test_chain_hessian_branch_vs_oracle(cuda_dev, chain_only, n, nobs, lag, seed):
+    """The Hessian branch (:361-390 alpha recursion with Q7 / Q8, :472-534, :564-626) on the chain kernel,
+    no fallback pass: hess1 / hess2 within 1e-8 of the oracle, everything else as without it."""
+    import oracle
+    import torch
+    obs, params, rvr, rvp = gi.sv_inputs(n, nobs, seed)
+    ref = oracle.flps_sv_corr(obs, params, rvr, rvp, n, lag, 1, dumps=True)
+    dev = cuda_dev
+    out = chain_only.flps_sv_corr(torch.from_numpy(obs).to(dev), torch.from_numpy(params).to(dev),
+                                  torch.from_numpy(rvr[:nobs].copy()).to(dev),
+                                  torch.from_numpy(to_time_major(rvp, n, nobs)).to(dev), lag=lag,
+                                  compute_hessian=True, store_history=True)
+    torch.cuda.synchronize()
+    res = {k: v.cpu().numpy() for k, v in out.items() if not k.startswith("_")}
+    assert int(res["diag"][0, DIAG_KERNEL]) == 3 and int(res["diag"][0, DIAG_STATUS]) == 0
+    assert first_mismatch_step(res["A"][0][1:], ref["A"][1:]) is None
+    assert abs(res["log_like"][0] - ref["log_like"]) <= 1e-10 * abs(ref["log_like"])
+    assert np.max(np.abs(res["gradient"][0] - ref["gradient"])) <= 1e-9 * np.max(np.abs(ref["gradient"]))
+    for k in ("hess1", "hess2"):
+        assert np.max(np.abs(res[k][0] - ref[k])) <= 1e-8 * np.max(np.abs(ref[k])), k
+        assert np.array_equal(res[k][0], res[k][0].T)
+
+
+def test_chain_hessian_batch_and_golden(cuda_dev, chain_only, golden):
+    """Batch of chains with the Hessian branch: every problem equals its single launch bit for bit; the
+    shipped size against the compiled reference's own outputs (tests/golden)."""
+    import torch
+    K, dev = chain_only, cuda_dev
+    n, nobs, lag, B = 1500, 80, 10, 160
+    obs = gi.sv_obs(nobs)
+    rs = np.random.RandomState(31)
+    params = np.array(gi.SV_PARAM_SETS[0]) + 0.02 * rs.normal(size=(B, 4))
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    u = torch.randn((B, nobs, n), dtype=torch.float64, device=dev, generator=g)
+    rvr = torch.rand((B, nobs), dtype=torch.float64, device=dev, generator=g)
+    t = lambda x: torch.from_numpy(x).to(dev)   # noqa: E731
+    out = K.flps_sv_corr(t(obs), t(params), rvr, u, lag=lag, compute_hessian=True)
+    torch.cuda.synchronize()
+    assert np.all(out["diag"][:, DIAG_KERNEL].cpu().numpy() == 3) and np.all(out["diag"][:, DIAG_STATUS].cpu().numpy() == 0)
+    for b in (0, 77, 159):
+        single = K.flps_sv_corr(t(obs), t(params[b:b + 1]), rvr[b:b + 1].contiguous(), u[b:b + 1].contiguous(),
+                                lag=lag, compute_hessian=True)
+        torch.cuda.synchronize()
+        for k in ("log_like", "gradient", "hess1", "hess2"):
+            assert torch.equal(out[k][b], single[k][0]), (b, k)
+    gg = golden["sv_kernels"]
+    for (n, nobs, lag, seeds) in gi.SV_KERNEL_CASES:
+        for seed in seeds:
+            obs, params, rvr, rvp = gi.sv_inputs(n, nobs, seed)
+            o = K.flps_sv_corr(t(obs), t(params), t(rvr[:nobs].copy()), t(to_time_major(rvp, n, nobs)), lag=lag,
+                               compute_hessian=True)
+            torch.cuda.synchronize()
+            assert int(o["diag"][0, DIAG_KERNEL]) == 3
+            pre = "flps_n%d_t%d_l%d_s%d_h1_" % (n, nobs, lag, seed)
+            for k in ("hess1", "hess2"):
+                href = gg[pre + k].reshape(4, 4)
+                assert np.max(np.abs(o[k][0].cpu().numpy() - href)) <= 1e-8 * np.max(np.abs(href)), pre + k
+
+
 def test_chain_batch_equals_singles_and_general(cuda_dev, chain_only):
     """A batch of chains (more problems than CTAs) == single launches bit for bit, and agrees with
     the general kernel within the tolerances."""
