@@ -33,10 +33,14 @@
 //     ever moved.
 //   * two exp per particle and step: exp(-x/2) is shared by the weight, the propagation mean of
 //     the children and the payload; the score terms need none.
+//   * L2 eviction hints on every access (createpolicy): data that is dead after its read (previous record
+//     table, mailbox entries, H, the parents' (x, e) / perm entries, lagged payloads, u) is read
+//     evict_first, what the next phase reads is stored evict_last: 114 -> 103 us per step.
 //   * tried and measured slower (git history): descendant weights by integer atomics + sequential
 //     payload pass (132 us per step), genealogy and score terms on dedicated helper warps (122 -
 //     150 us: the helper's traffic slows the main warps as much as it saves them), pointer-jumping
-//     tables instead of records, bulk L2 prefetch of the lagged generation.  This version: 114 us.
+//     tables instead of records, bulk L2 prefetch of the lagged generation, L2 prefetch of the record / payload
+//     sectors a phase ahead, 16-byte payloads with an exp in the score terms.  This version: 103 us.
 //
 // Deviations from the reference's operation order: parallel sums / scans, log(exp(x/2)) = x/2 and
 // 1/exp(x/2)^2 = exp(-x/2)^2 in the log-weight, cumulative weights multiplied by 1/S; any
@@ -96,7 +100,7 @@ struct GridCtrl {
 
 struct GridArgs {
     int N, NOBS, LAG, G, Wc, RP, hist;
-    int dbg;   // development (timing only, results wrong): 1 skip R records, 2 skip P store, 4 skip score gather, 8 bulk prefetch of the lagged generation
+    int dbg;   // development (timing only, results wrong): 1 skip R records, 2 skip P store, 4 skip score gather, 8 bulk prefetch of the lagged generation, 64 no L2 eviction hints
     const double *obs, *params, *rvr, *U;
     // U[t][j] = U[(t / u_cs) * u_cstride + (t % u_cs) * u_tstride + j * u_jstride]: time-major resident array
     // (u_cs = 2^30, u_tstride = N, u_jstride = 1) or particle-major chunks of u_cs time steps as the copy
@@ -147,6 +151,11 @@ __device__ __forceinline__ unsigned long long policy_evict_first() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
+__device__ __forceinline__ unsigned long long policy_evict_normal() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 __device__ __forceinline__ unsigned long long policy_evict_last() {
     unsigned long long pol;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
@@ -184,6 +193,30 @@ __device__ __forceinline__ void st_stream_f64(double* p, unsigned long long pol,
 __device__ __forceinline__ double ld_stream_hint_f64(const double* p, unsigned long long pol) {
     double v;
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
+// L2 residency plan (dbg & 64 switches it off): what the next phase or the next step reads again -- the
+// sorted (x, e) pairs / the mailbox that aliases them, perm, H, the genealogy records being written -- is
+// stored evict_last (56 MB at N = 2^20); what is dead after its read -- the previous record table, the
+// mailbox entries, H, u -- and what is not read for 8 steps -- the payloads -- goes evict_first
+__device__ __forceinline__ void st_hint_b128(void* p, unsigned long long pol, int4 v) {
+    asm volatile("st.global.cg.L2::cache_hint.v4.s32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ int4 ld_hint_b128(const void* p, unsigned long long pol) {
+    int4 v;
+    asm volatile("ld.global.cg.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st_hint_b32(void* p, unsigned long long pol, int v) {
+    asm volatile("st.global.cg.L2::cache_hint.s32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ int ld_hint_b32(const void* p, unsigned long long pol) {
+    int v;
+    asm volatile("ld.global.cg.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
     return v;
 }
 __device__ __forceinline__ int warp_incl_max(int v, int lane) {
@@ -319,7 +352,12 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
     GridCtrl* ctrl = a.ctrl;
     const double dn = (double)N, inv_n = 1.0 / dn;
     const bool pow2 = (N & (N - 1)) == 0;
-    const unsigned long long pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
+    const unsigned long long pol_stream = policy_evict_first();
+    const unsigned long long pol_keep = (a.dbg & 64) ? policy_evict_normal() : policy_evict_last();
+    const unsigned long long pol_dead = (a.dbg & 64) ? policy_evict_normal() : policy_evict_first();
+    // (measured one by one, N = 2^20: the previous record table, the lagged payloads and the parents' (x, e)
+    // / perm entries read as evict_first are worth 8 + 3 us per step; evict_last on the stores alone is not)
+    const unsigned long long pol_rld = pol_dead, pol_pld = pol_dead, pol_xld = pol_dead, pol_rst = pol_keep;
     constexpr double kBinW = 2.0 * kZ / (double)kNF;    // width of a histogram bin in predicted sd
     unsigned epoch = 0;                 // arrives done so far
     unsigned cnt_near = 0, cnt_soft = 0, cnt_key = 0;
@@ -531,14 +569,14 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
                 const int P = pstart + q;
                 const bool longr = hi - lo > 8;
                 if (!longr)
-                    for (int k = lo; k < hi; ++k) __stcg(&a.H[k], P);
+                    for (int k = lo; k < hi; ++k) st_hint_b32(&a.H[k], pol_keep, P);
                 unsigned m = __ballot_sync(kFullMask, longr);
                 while (m) {
                     const int src = __ffs(m) - 1;
                     m &= m - 1;
                     const int l0 = __shfl_sync(kFullMask, lo, src), h0 = __shfl_sync(kFullMask, hi, src);
                     const int P0 = __shfl_sync(kFullMask, P, src);
-                    for (int k = l0 + lane; k < h0; k += 32) __stcg(&a.H[k], P0);
+                    for (int k = l0 + lane; k < h0; k += 32) st_hint_b32(&a.H[k], pol_keep, P0);
                 }
             }
         }
@@ -578,7 +616,7 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
             for (int kk = 0; kk < KPT; ++kk) {
                 const int i = kk * GT + tid;
                 bp[kk] = 0;
-                if (i < nc) bp[kk] = __ldcg(&a.H[jb + i]);
+                if (i < nc) bp[kk] = ld_hint_b32(&a.H[jb + i], pol_dead);
             }
             const double y1 = a.obs[t - 1];
             const double ylag = a.obs[t >= 2 ? t - 2 : 0];   // Q5: the score terms of step i use obs[i - LAG]; i = t + LAG - 2
@@ -604,8 +642,12 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
                             orphan = true;
                             p = 0;
                         }
-                        xe[u] = __ldcg(&a.XE[p]);
-                        bp[k0 + u] = __ldcg(&a.perm[p]);
+                        {
+                            const int4 xr = ld_hint_b128(&a.XE[p], pol_xld);
+                            xe[u].x = __longlong_as_double(((long long)xr.y << 32) | (long long)(unsigned)xr.x);
+                            xe[u].y = __longlong_as_double(((long long)xr.w << 32) | (long long)(unsigned)xr.z);
+                        }
+                        bp[k0 + u] = ld_hint_b32(&a.perm[p], pol_xld);
                         uu[u] = ld_stream_hint_f64(Ut + (size_t)(jb + i) * ujs, pol_stream);
                         if (a.hist) a.parentpos[jb + i] = p;
                     }
@@ -657,7 +699,7 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
                     const int i = (k0 + u) * GT + tid;
 #pragma unroll
                     for (int z = 0; z < 8; ++z) r[u][z] = 0;
-                    if (i < nc) ld_rec(&Rp[(a.dbg & 8) ? jb + i : bp[k0 + u]], pol_keep, r[u]);
+                    if (i < nc) ld_rec(&Rp[(a.dbg & 8) ? jb + i : bp[k0 + u]], pol_rld, r[u]);
                 }
 #pragma unroll
                 for (int u = 0; u < RB; ++u) {
@@ -665,7 +707,7 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
                     if (i < nc) {
                         const int j = jb + i;
                         const int b = bp[k0 + u];
-                        st_rec(&Rc[j], pol_keep, b, r[u][0], r[u][1], r[u][2], r[u][3], r[u][4], r[u][5], r[u][6]);
+                        st_rec(&Rc[j], pol_rst, b, r[u][0], r[u][1], r[u][2], r[u][3], r[u][4], r[u][5], r[u][6]);
                         // row of the ancestor L-2 steps back (new record = (b, r[0..6]))
                         int anc = j;
                         if (L == 3) anc = b;
@@ -778,7 +820,7 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
                     const int pos = s_tbase[kr[kk] >> 16] + (kr[kk] & 0xffff);
                     const long long xb = __double_as_longlong(xn[kk]);
                     const int4 ent = make_int4((int)(xb & 0xffffffffll), (int)(xb >> 32), jb + i, bp[kk]);
-                    if (pos >= 0 && pos < N) __stcg((int4*)&mail[pos], ent);
+                    if (pos >= 0 && pos < N) st_hint_b128(&mail[pos], pol_keep, ent);
                 }
             }
         }
@@ -841,7 +883,7 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
                 for (int u = 0; u < CH; ++u) {
                     const int e = (k0 + u) * GT + tid;
                     raw[u] = make_int4(0, 0, 0, 0);
-                    if (e < n) raw[u] = __ldcg((const int4*)(mb + e));
+                    if (e < n) raw[u] = ld_hint_b128(mb + e, pol_dead);
                 }
 #pragma unroll
                 for (int u = 0; u < CH; ++u) {
@@ -966,8 +1008,12 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
                         bad = true;
                         sh = 0.0;
                     }
-                    __stcg(&a.XE[pstart + q], make_double2(x, e));
-                    __stcg(&a.perm[pstart + q], j);
+                    {
+                        const long long xb = __double_as_longlong(x), eb = __double_as_longlong(e);
+                        st_hint_b128(&a.XE[pstart + q], pol_keep,
+                                     make_int4((int)(xb & 0xffffffffll), (int)(xb >> 32), (int)(eb & 0xffffffffll), (int)(eb >> 32)));
+                    }
+                    st_hint_b32(&a.perm[pstart + q], pol_keep, j);
                     s_sh[q] = sh;
                     if (pstart + q == 0) a.xminv[t] = x;   // Q10/Q11: traj[t] = X_t[0]
                     if (a.hist) {
@@ -1059,9 +1105,9 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
                     if (q < n) {
                         const PEntry* pp = &Pg[min(max(s_ab[q], 0), N - 1)];
                         double d3;
-                        asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];"
+                        asm volatile("ld.global.cg.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
                                      : "=d"(pc[u]), "=d"(psq[u]), "=d"(pey[u]), "=d"(d3)
-                                     : "l"(pp));
+                                     : "l"(pp), "l"(pol_pld));
                     }
                 }
 #pragma unroll
