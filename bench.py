@@ -360,6 +360,54 @@ def run_config4_chains(rank, world, dev, dist, peak):
             "scaling": "strong", "n_gpus": world, **out}
 
 
+def run_config4_lockstep(rank, world, dev, dist, iters=3):
+    """BASELINE configs[3] as an actual sampler run: 1024 / world correlated pseudo-marginal chains per GPU
+    in lock-step (parameter/lockstep.py), N = 4096, T = 1000, u of every chain resident in HBM (two
+    [B, NOBS, N] tensors), Crank-Nicolson proposals on the device, ONE batched smoother launch per MH
+    iteration, accept / reject per chain on the host.  The chains are pmmh_qn_b200.parameter.cpmh
+    .CorrelatedPMMH (the reference's samplers are not available on the GPU box; they run under the same
+    front-end unchanged: tests/test_lockstep_reference.py)."""
+    import torch
+    import golden_inputs as gi
+    from pmmh_qn_b200.parameter.cpmh import BatchedRVSState, CorrelatedPMMH, _ChainRVS
+    from pmmh_qn_b200.parameter.lockstep import LockstepRunner
+    from pmmh_qn_b200.state.particle_methods.batched import BatchedParticleMethodsCUDA
+    n, btot = 4096, 1024
+    b = btot // world
+    obs_h = gi.sv_obs(NOBS)
+    state = BatchedRVSState(b, NOBS, n, dev, sigma_u=0.05, seed=900 + rank)
+    rs = np.random.RandomState(40 + rank)
+    chains = []
+    for k in range(b):
+        model = BenchSVModel(obs_h, PARAMS)
+        model.no_params_to_estimate = 4
+        init = np.array(PARAMS) + np.array([0.02, 0.005, 0.01, 0.01]) * rs.normal(size=4)
+        chains.append(CorrelatedPMMH(model, {'no_iters': iters + 1, 'no_burnin_iters': 0, 'initial_params': init,
+                                             'step_size': 0.01, 'precond': (1.0, 0.01, 0.05, 0.05), 'drift': True,
+                                             'rvs': _ChainRVS(state, k)}))
+    backend = BatchedParticleMethodsCUDA(chains[0].model, no_particles=n)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    runner = LockstepRunner(chains, backend, seeds=[5000 + 1000 * rank + k for k in range(b)]).run()
+    torch.cuda.synchronize()
+    secs = max_over_ranks(time.perf_counter() - t0, dev, dist)
+    evals = iters + 1                                   # the initial evaluation + one per iteration
+    acc = float(np.mean([np.mean([c.state_history[i]['accepted'] for i in range(1, iters + 1)]) for c in chains]))
+    ll = np.array([c.state_history[iters]['log_like'] for c in chains])
+    del state, backend, runner, chains
+    torch.cuda.empty_cache()
+    return {"workload": "cpmh_lockstep_1024chains_N4096_T1000", "chains": btot, "chains_per_gpu": b, "N": n, "T": T_STEPS,
+            "mh_iterations": iters, "seconds": secs, "value": btot * n * T_STEPS * evals / secs, "unit": UNIT,
+            "chain_iterations_per_sec": btot * iters / secs, "batched_launches_per_gpu": evals,
+            "mean_acceptance": acc, "log_like_mean": float(ll.mean()), "all_finite": bool(np.all(np.isfinite(ll))),
+            "n_gpus": world, "scaling": "strong",
+            "note": "end to end through the sampler front-end: per iteration and chain a Crank-Nicolson pass over "
+                    "its u (device), the batched smoother launch, results to the host, accept / reject in Python "
+                    "(one coroutine per chain); the kernel-only figure is config4_chains"}
+
+
 def run_config1_re(dev, peak):
     """BASELINE configs[0]: random-effects importance sampler, 100 individuals x 100 samples; one
     evaluation and batches of independent evaluations (proposals) per launch."""
@@ -646,6 +694,11 @@ def run_ours(args, rank, world, local_rank):
             cfg4 = run_config4_chains(rank, world, dev, dist, peak)
         except Exception as e:
             cfg4 = {"error": str(e)[:200]}
+        try:
+            cfg4["lockstep_cpmh"] = run_config4_lockstep(rank, world, dev, dist)
+        except Exception as e:
+            if isinstance(cfg4, dict):
+                cfg4["lockstep_cpmh"] = {"error": str(e)[:200]}
         try:
             cfg3 = run_config3_subsampling(rank, world, dev, dist, peak)
         except Exception as e:

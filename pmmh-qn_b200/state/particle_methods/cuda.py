@@ -146,37 +146,41 @@ class ParticleMethodsCUDA(BaseStateInference):
             xf, xs, ll, grad, xtraj, hess1, hess2, diag = self._to_host(
                 [out['filt'][0], out['smo'][0], out['log_like'], out['gradient'][0], out['traj'][0],
                  out['hess1'][0], out['hess2'][0], out['diag'][0]])
-            self.diagnostics = {'near_ties': int(diag[DIAG_NEAR_TIES]), 'status': int(diag[DIAG_STATUS])}
-            if int(diag[DIAG_STATUS]) != 0:
-                raise FloatingPointError("degenerate particle cloud")
-
-            # estimate of gradient and Hessian, cython.py:100-114 (Q9: np.inner is a scalar)
-            if model.using_gradients or model.using_hessians:
-                grad = np.array(grad).reshape((model.no_params, model.no_obs + 1))
-                grad[np.isinf(grad)] = 0.0
-                grad[np.isnan(grad)] = 0.0
-                grad_est = np.nansum(grad, axis=1)
-            if model.using_hessians:
-                part1 = np.inner(grad_est, grad_est)
-                part2 = np.array(hess1).reshape((model.no_params, model.no_params))
-                part2 += np.array(hess2).reshape((model.no_params, model.no_params))
-                hessian_est = part1 - part2
-
-            self.results.update({'filt_state_est': np.array(xf).flatten()})
-            self.results.update({'state_trajectory': np.array(xtraj).flatten()})
-            self.results.update({'smo_state_est': np.array(xs).flatten()})
-            self.results.update({'log_like': float(ll[0])})
-            if model.using_gradients or model.using_hessians:
-                self.results.update({'log_joint_gradient_estimate': grad_est})
-            if model.using_hessians:
-                self.results.update({'log_joint_hessian_estimate': -hessian_est})
-            if self._estimate_gradient_and_hessian(model):
-                return True
-            return False
+            return self._publish_smoother(model, xf, xs, ll, grad, xtraj, hess1, hess2, diag)
         except Exception as e:
             print("Error in CUDA code for particle smoother.")
             print(e)
             return False
+
+    def _publish_smoother(self, model, xf, xs, ll, grad, xtraj, hess1, hess2, diag):
+        """Host arrays of one evaluation -> `results` (cython.py:100-126); raises on a degenerate cloud."""
+        self.diagnostics = {'near_ties': int(diag[DIAG_NEAR_TIES]), 'status': int(diag[DIAG_STATUS])}
+        if int(diag[DIAG_STATUS]) != 0:
+            raise FloatingPointError("degenerate particle cloud")
+
+        # estimate of gradient and Hessian, cython.py:100-114 (Q9: np.inner is a scalar)
+        if model.using_gradients or model.using_hessians:
+            grad = np.array(grad).reshape((model.no_params, model.no_obs + 1))
+            grad[np.isinf(grad)] = 0.0
+            grad[np.isnan(grad)] = 0.0
+            grad_est = np.nansum(grad, axis=1)
+        if model.using_hessians:
+            part1 = np.inner(grad_est, grad_est)
+            part2 = np.array(hess1).reshape((model.no_params, model.no_params))
+            part2 += np.array(hess2).reshape((model.no_params, model.no_params))
+            hessian_est = part1 - part2
+
+        self.results.update({'filt_state_est': np.array(xf).flatten()})
+        self.results.update({'state_trajectory': np.array(xtraj).flatten()})
+        self.results.update({'smo_state_est': np.array(xs).flatten()})
+        self.results.update({'log_like': float(np.asarray(ll).reshape(-1)[0])})
+        if model.using_gradients or model.using_hessians:
+            self.results.update({'log_joint_gradient_estimate': grad_est})
+        if model.using_hessians:
+            self.results.update({'log_joint_hessian_estimate': -hessian_est})
+        if self._estimate_gradient_and_hessian(model):
+            return True
+        return False
 
     # -------------------------------------------------------------------- init
     def _init_particle_method(self, model, no_particles, fixed_lag, verbose):
