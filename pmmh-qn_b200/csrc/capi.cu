@@ -414,8 +414,6 @@ struct StreamedState {
     std::vector<cudaEvent_t> ev_chunk;   // streaming kernels: one event per landed chunk
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_reset = nullptr, ev_done = nullptr;
-    int* h_vals = nullptr;   // pinned: h_vals[c] = time steps available after chunk c
-    int h_cap = 0;
 };
 thread_local StreamedState g_streamed[64];
 
@@ -640,12 +638,9 @@ int pmmh_flps_sv_corr_streamed(const double* h_rvs, const double* d_obs, const d
         PMMH_CUDA(cudaEventCreateWithFlags(&ss.ev_start, cudaEventDisableTiming));
         PMMH_CUDA(cudaEventCreateWithFlags(&ss.ev_reset, cudaEventDisableTiming));
     }
-    if (ss.h_cap < chunks) {
-        if (ss.h_vals) cudaFreeHost(ss.h_vals);
-        ss.h_vals = nullptr;
-        PMMH_CUDA(cudaHostAlloc((void**)&ss.h_vals, (size_t)chunks * sizeof(int), cudaHostAllocDefault));
-        ss.h_cap = chunks;
-    }
+    if (!ss.ev_done) PMMH_CUDA(cudaEventCreateWithFlags(&ss.ev_done, cudaEventDisableTiming));
+    const int* tabx = step_table(n_obs + kUChunk);   // immutable pinned table: no host value is ever rewritten
+    if (!tabx) return fail(PMMH_ERR_CUDA, "pinned step table allocation failed");
     cudaStream_t st = (cudaStream_t)stream;
     char* stage = (char*)d_stage;
     int* d_flag = (int*)(stage + data_bytes);
@@ -664,9 +659,9 @@ int pmmh_flps_sv_corr_streamed(const double* h_rvs, const double* d_obs, const d
         PMMH_CUDA(cudaMemcpy2DAsync(dst, (size_t)kUChunk * sizeof(double), src, (size_t)n_obs * sizeof(double),
                                     (size_t)wsteps * sizeof(double), (size_t)n_particles, cudaMemcpyHostToDevice,
                                     ss.copy_stream));
-        ss.h_vals[c] = t0 + wsteps;
-        PMMH_CUDA(cudaMemcpyAsync(d_flag, &ss.h_vals[c], sizeof(int), cudaMemcpyHostToDevice, ss.copy_stream));
+        PMMH_CUDA(cudaMemcpyAsync(d_flag, &tabx[t0 + wsteps], sizeof(int), cudaMemcpyHostToDevice, ss.copy_stream));
     }
+    PMMH_CUDA(cudaEventRecord(ss.ev_done, ss.copy_stream));
     // the kernel must not start before the flag has been reset
     PMMH_CUDA(cudaStreamWaitEvent(st, ss.ev_reset, 0));
     pmmh::SvArgs a;
@@ -706,6 +701,8 @@ int pmmh_flps_sv_corr_streamed(const double* h_rvs, const double* d_obs, const d
     a.ws_team_stride = p.fast_team_stride;
     PMMH_CUDA(cudaMemsetAsync(d_workspace, 0, p.fast_sync_bytes, st));
     PMMH_CUDA(pmmh::sv_fast_launch(a, p.grid, st));
+    // an evaluation that is abandoned early leaves copies behind: the caller's stream ends after them
+    PMMH_CUDA(cudaStreamWaitEvent(st, ss.ev_done, 0));
     return PMMH_OK;
 }
 
