@@ -75,6 +75,10 @@ def _worker(rank, world, port, ret):
     red = torch.full((3, 8), float(rank + 1), dtype=torch.float64)
     comm.all_reduce_sum([red])
     ok3 = ok3 and bool((red == 3.0).all())
+    # a rank-local abandon (capacity overflow on one rank only) is agreed on before anybody acts on it:
+    # every rank sees the largest status word, so all of them leave the time loop in the same step
+    ok3 = ok3 and comm.agree_status(8 if rank == 1 else 0, torch.device("cpu")) == 8
+    ok3 = ok3 and comm.agree_status(0, torch.device("cpu")) == 0
     ret[rank] = bool(ok1 and ok2 and ok3)
     dist.barrier()
     dist.destroy_process_group()
