@@ -170,6 +170,8 @@ int pmmh_flps_sv_corr_philox(const double* d_obs, const double* d_params, const 
  * inside: d_diag[PMMH_DIAG_STATUS] == 1 reports an abandoned problem (log-likelihood NaN). */
 #define PMMH_MODEL_SV_LEVERAGE 0      /* mu, phi, sigma_v, rho   (models/stochastic_volatility.py) */
 #define PMMH_MODEL_LINEAR_GAUSSIAN 1  /* phi, sigma_v, sigma_e: x' = phi x + sigma_v v, y = x + sigma_e e */
+#define PMMH_MODEL_LINEAR_GAUSSIAN_FA 2 /* the same model as a FULLY ADAPTED particle filter: pass the observations shifted by
+                                         one (obs'[t] = obs[t + 1], n_obs - 1 entries); log-likelihood of y_2..y_T given y_1 */
 int pmmh_flps_model_workspace_bytes(int n_obs, int n_particles, int lag, int batch, size_t* bytes);
 int pmmh_flps_model_corr(int model_id, const double* d_obs, long long obs_stride, const double* d_params,
                          const double* d_rvr, const double* d_u, int n_obs, int n_particles, int lag, int batch,

@@ -727,7 +727,8 @@ int pmmh_flps_model_corr(int model_id, const double* d_obs, long long obs_stride
     if (!d_obs || !d_params || !d_rvr || !d_u || !d_filt || !d_smo || !d_log_like || !d_gradient || !d_traj ||
         !d_diag || !d_workspace)
         return fail(PMMH_ERR_INVALID, "pmmh_flps_model_corr: null pointer argument");
-    if (model_id != PMMH_MODEL_SV_LEVERAGE && model_id != PMMH_MODEL_LINEAR_GAUSSIAN)
+    if (model_id != PMMH_MODEL_SV_LEVERAGE && model_id != PMMH_MODEL_LINEAR_GAUSSIAN &&
+        model_id != PMMH_MODEL_LINEAR_GAUSSIAN_FA)
         return fail(PMMH_ERR_INVALID, "pmmh_flps_model_corr: unknown model id");
     if ((d_x_hist == nullptr) != (d_a_hist == nullptr))
         return fail(PMMH_ERR_INVALID, "d_x_hist and d_a_hist must be given together");

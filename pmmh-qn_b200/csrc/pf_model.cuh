@@ -122,4 +122,59 @@ struct LinearGaussianModel {
     }
 };
 
+// ---- 2: the same linear Gaussian model run as a FULLY ADAPTED particle filter (Pitt & Shephard): particles are
+// drawn from p(x_t | x_{t-1}, y_t) and weighted with the predictive density p(y_{t+1} | x_t), both in closed form
+// for this model.  The kernel's algorithm is untouched: the caller hands over the observations shifted by one
+// (obs'[t] = obs[t + 1]), so `propagate` sees y_t where the SV model sees y_{t-1} (leverage) and `logw` sees
+// y_{t+1}.  The reference has no fully adapted filter (SURVEY 8a note): parity is unpinned, the check is the exact
+// Kalman likelihood.  Outputs: log-likelihood of y_2 .. y_T given y_1 (the caller adds log p(y_1)), and
+// E[x_t | y_1 .. y_{t+1}] in `filt`; the score terms are not defined for this variant (gradient rows 0).
+struct LinearGaussianFullyAdapted {
+    struct Const {
+        double phi, sv, se, k, sdp, inv_s2, log_s;   // gain, proposal sd, predictive variance
+    };
+    static __device__ __forceinline__ void init(Const& c, const double* par) {
+        c.phi = par[0];
+        c.sv = par[1];
+        c.se = par[2];
+        const double s2 = c.sv * c.sv + c.se * c.se;
+        c.k = (c.sv * c.sv) / s2;
+        c.sdp = sqrt((c.sv * c.sv) * (c.se * c.se) / s2);
+        c.inv_s2 = 1.0 / s2;
+        c.log_s = 0.5 * log(s2);
+    }
+    static __device__ __forceinline__ double initial_state(const Const&) { return 0.0; }
+    // x_t | x_{t-1}, y_t ~ N(phi x + k (y_t - phi x), sv^2 se^2 / (sv^2 + se^2))
+    static __device__ __forceinline__ double propagate(const Const& c, double xp, double y_now, double u) {
+        const double m = c.phi * xp;
+        return (m + c.k * (y_now - m)) + c.sdp * u;
+    }
+    static __device__ __forceinline__ void child_range(const Const& c, double xmin, double xmax, double y_now, double nsd,
+                                                       double& lo, double& hi) {
+        const double a = c.phi * xmin, b = c.phi * xmax;
+        const double ma = a + c.k * (y_now - a), mb = b + c.k * (y_now - b);
+        lo = fmin(ma, mb) - nsd * c.sdp;
+        hi = fmax(ma, mb) + nsd * c.sdp;
+    }
+    // log p(y_{t+1} | x_t) = log N(y; phi x, sv^2 + se^2)
+    static __device__ __forceinline__ double logw(const Const& c, double x, double y_next) {
+        const double r = y_next - c.phi * x;
+        return (-0.91893853320467267 - c.log_s) - (0.5 * (r * r)) * c.inv_s2;
+    }
+    static __device__ __forceinline__ double logw_max(const Const& c, double lo, double hi, double y_next) {
+        double xs = (c.phi != 0.0) ? y_next / c.phi : lo;
+        const double l2 = fmin(lo, hi), h2 = fmax(lo, hi);
+        if (!(xs >= l2)) xs = l2;
+        if (xs > h2) xs = h2;
+        if (!isfinite(xs)) xs = 0.0;
+        return logw(c, xs, y_next);
+    }
+    static __device__ __forceinline__ void score_main(const Const&, double, double, double, double g[4]) {
+        g[0] = g[1] = g[2] = g[3] = 0.0;
+    }
+    static __device__ __forceinline__ void score_tail(const Const&, double, double, double, double g[4]) {
+        g[0] = g[1] = g[2] = g[3] = 0.0;
+    }
+};
+
 }  // namespace pmmh

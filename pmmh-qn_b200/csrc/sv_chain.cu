@@ -678,6 +678,7 @@ cudaError_t sv_chain_launch(const SvArgs& a, int grid, cudaStream_t stream) {
     if (a.model_id == 0) return a.hess ? chain_launch_one<SvLeverageModel, true>(a, grid, smem, stream)
                                        : chain_launch_one<SvLeverageModel, false>(a, grid, smem, stream);
     if (a.model_id == 1 && !a.hess) return chain_launch_one<LinearGaussianModel, false>(a, grid, smem, stream);
+    if (a.model_id == 2 && !a.hess) return chain_launch_one<LinearGaussianFullyAdapted, false>(a, grid, smem, stream);
     return cudaErrorInvalidValue;
 }
 

@@ -84,6 +84,35 @@ def test_linear_gaussian_likelihood_against_the_kalman_filter(cuda_dev):
     assert abs(ll.mean() - exact) < 4.0 * ll.std(ddof=1) / np.sqrt(B) + 0.25, (ll.mean(), exact, ll.std())
 
 
+def test_fully_adapted_filter_against_the_kalman_filter(cuda_dev):
+    """PMMH_MODEL_LINEAR_GAUSSIAN_FA: optimal proposal + predictive weights through the same kernel (shifted
+    observations).  log p(y_1) + its estimate of log p(y_2..y_T | y_1) is consistent with the exact value and
+    much less variable than the bootstrap filter's estimate on the same data and u."""
+    import generic_pf as gp
+    from pmmh_qn_b200 import _lib, kernels as K
+    n, nobs, B = 4096, 201, 16
+    params = np.array(gi.LG_PARAM_SETS[0])
+    phi, sv, se = params[:3]
+    obs = gi.lg_obs(nobs, params)
+    exact = gp.kalman_loglike(obs, phi, sv, se)
+    s2 = sv * sv + se * se
+    ll_y1 = -0.5 * np.log(2.0 * np.pi * s2) - 0.5 * obs[1] ** 2 / s2          # log p(y_1 | x_0 = 0)
+    rs = np.random.RandomState(12)
+    u = rs.normal(size=(B, nobs, n))
+    rvr = rs.uniform(size=(B, nobs))
+    obs_d, par_d, rvr_d, u_d = _dev(cuda_dev, obs, np.tile(params, (B, 1)), rvr, u)
+    boot = K.flps_model_corr(_lib.MODEL_LINEAR_GAUSSIAN, obs_d, par_d, rvr_d, u_d, lag=10)["log_like"].cpu().numpy()
+    shifted = np.ascontiguousarray(obs[1:])                                    # obs'[t] = obs[t + 1]
+    obs_s, rvr_s, u_s = _dev(cuda_dev, shifted, rvr[:, :nobs - 1], u[:, :nobs - 1])
+    out = K.flps_model_corr(_lib.MODEL_LINEAR_GAUSSIAN_FA, obs_s, par_d, rvr_s, u_s, lag=10)
+    assert int(out["diag"][:, 2].max()) == 0
+    fa = out["log_like"].cpu().numpy() + ll_y1
+    assert np.all(np.abs(fa - exact) < 0.5), (fa, exact)
+    assert abs(fa.mean() - exact) < 4.0 * fa.std(ddof=1) / np.sqrt(B) + 0.05, (fa.mean(), exact, fa.std())
+    assert fa.std(ddof=1) < 0.5 * boot.std(ddof=1), (fa.std(ddof=1), boot.std(ddof=1))
+    assert np.all(out["gradient"].cpu().numpy() == 0.0)
+
+
 def test_generic_entry_rejects_bad_arguments(cuda_dev):
     from pmmh_qn_b200 import _lib, kernels as K
     obs, params, rvr, rvp = gi.lg_inputs(100, 40, 0)
