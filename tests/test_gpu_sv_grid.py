@@ -186,3 +186,43 @@ def test_grid_host_streamed_rvs_equals_resident(cuda_dev, pinned, n, nobs):
     for k in ("log_like", "filt", "smo", "gradient", "traj"):
         assert torch.equal(a[k], b[k]), k
         assert torch.equal(a2[k], b[k]), k
+
+
+@pytest.mark.parametrize("logn,nobs,seed", [(20, 25, 7), (22, 21, 8)])
+def test_large_n_against_the_oracle(cuda_dev, logn, nobs, seed):
+    """The sizes of BASELINE configs[1] (N = 2^20, the headline) and configs[4] (N = 2^22) themselves against
+    the CPU oracle over a short series: automatic kernel selection (grid kernel at 2^20, streaming kernels
+    with path storage at 2^22).  Ancestors are compared exactly; if a generation differs, the first one must
+    come with a counted tie (at this N the reference's sequential cumulative sums and any
+    parallel sum round differently about once per time step)."""
+    import oracle
+    import torch
+    from pmmh_qn_b200 import kernels as K
+    n, lag, dev = 1 << logn, 10, cuda_dev
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    u = torch.randn((nobs, n), dtype=torch.float64, device=dev, generator=g)
+    rvr = torch.rand((nobs,), dtype=torch.float64, device=dev, generator=g)
+    obs = gi.sv_obs(nobs)
+    params = np.array(gi.SV_PARAM_SETS[0])
+    store = logn <= 20
+    out = K.flps_sv_corr(torch.from_numpy(obs).to(dev), torch.from_numpy(params).to(dev), rvr, u, lag=lag,
+                         compute_hessian=False, store_history=store)
+    torch.cuda.synchronize()
+    d = out["diag"][0].cpu().numpy()
+    assert int(d[DIAG_STATUS]) == 0 and int(d[DIAG_KERNEL]) == (GRID if logn <= 20 else 4)
+    rvp = np.ascontiguousarray(u.cpu().numpy().T).reshape(-1)
+    ref = oracle.flps_sv_corr(obs, params, rvr.cpu().numpy(), rvp, n, lag, 0, dumps=store)
+    ties = int(d[4]) if logn <= 20 else int(d[DIAG_NEAR_TIES])
+    exact = True
+    if store:
+        step = first_mismatch_step(out["A"][0].cpu().numpy()[1:], ref["A"][1:])
+        exact = step is None
+        assert exact or ties > 0, "ancestors differ at time %d without a counted tie" % (step + 1)
+    ll = float(out["log_like"][0])
+    assert abs(ll - ref["log_like"]) <= 1e-10 * abs(ref["log_like"])
+    assert relerr(out["filt"][0].cpu().numpy(), ref["filt"]) <= 1e-9
+    gtol = 1e-9 if exact and store else 1e-4          # a flipped neighbour moves the fixed-lag means by O(1/N)
+    gr = out["gradient"][0].cpu().numpy()
+    assert np.max(np.abs(gr - ref["gradient"])) <= gtol * np.max(np.abs(ref["gradient"]))
+    assert relerr(out["smo"][0].cpu().numpy(), ref["smo"]) <= gtol
