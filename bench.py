@@ -138,7 +138,7 @@ def _port_sample_worker(args):
     return time.perf_counter() - t0, out["log_like"]
 
 
-def cpu_port_same_config(n, tsteps=12):
+def cpu_port_same_config(n, tsteps=24):
     """All host cores, one independent N-particle evaluation per core over `tsteps` time steps."""
     import multiprocessing as mp
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
@@ -187,16 +187,45 @@ def cpu_reference_throughput(steps, warmup):
 
 
 def run_reference_arm(args, rank, world):
+    """The CPU arm on the SAME config as ours (N = --particles, hess = 0): the reference's algorithm restated
+    with O(T N) ancestry (oracle/pmmh_oracle.c, bit-exact against the compiled reference where that runs) on all
+    host cores, one independent evaluation per core, each step a bounded sample of `--port-steps` time steps of
+    the T = 1000 series.  The compiled reference itself (oracle/_ref) cannot run this config (O(T^2 N) ancestry
+    copies, stack arrays); its number at N = 1024, its feasible size, is reported beside it."""
     if rank != 0:
         return
-    value, per_step, info = cpu_reference_throughput(args.steps, args.warmup)
+    import multiprocessing as mp
+    n = args.particles
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cores = min(cores, 32)
+    ctx = mp.get_context("fork")
+    times = []
+    with ctx.Pool(cores) as pool:
+        for k in range(args.warmup + args.steps):
+            res = pool.map(_port_sample_worker, [(1000 * k + w, n, args.port_steps) for w in range(cores)])
+            if k >= args.warmup:
+                times.append(max(r[0] for r in res))
+    per_step = float(np.mean(times))
+    value = cores * n * args.port_steps / per_step
+    info = {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "oracle port (O(T N) restatement of flps_sv_corr, hess=0) at N=%d, %d of the %d time steps per "
+                      "step, one independent evaluation per core (time = slowest worker)" % (n, args.port_steps, T_STEPS)}
+    extra = None
+    try:
+        v2, _, info2 = cpu_reference_throughput(1, 0)
+        extra = info2
+    except Exception as e:   # reported
+        extra = {"error": str(e)[:200]}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "sv_flps_T1000_N2^20_grad", "reference_sample": info["sample"]},
+        "config": {"workload": "sv_flps_T1000_N2^20_grad" if n == (1 << 20) else "sv_flps_T1000_N%d_grad" % n,
+                   "T": T_STEPS, "N": n, "lag": LAG, "compute_hessian": 0,
+                   "reference_sample": info["sample"]},
         "cpu_baseline": info,
+        "cpu_baseline_compiled_reference": extra,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -789,7 +818,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--parity-steps", type=int, default=40,
                     help="time steps of the bench inputs re-run on the CPU oracle (0 = skip)")
-    ap.add_argument("--port-steps", type=int, default=12,
+    ap.add_argument("--port-steps", type=int, default=24,
                     help="time steps of the same-config CPU port sample (N = --particles on every core)")
     ap.add_argument("--no-configs", action="store_true", help="skip the config 1 / 3 / 4 blocks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
