@@ -95,6 +95,7 @@ thread_local int g_sv_algorithm = 0;
 int g_split_min_particles = 1 << 20;   // automatic selection of the streaming kernels from this N on
 int g_split_path_max_particles = 1 << 23;   // ... with path storage below this N, with records from it on
 int g_grid_min_particles = 1 << 14;         // automatic selection of the grid kernel from this N on (while a tile fits one CTA)
+int g_grid_hess_min_particles = 1 << 15;    // ... with the Hessian branch
 long long* g_sv_prof = nullptr;   // development: per-CTA phase clocks of the exchange kernel
 constexpr int kMaxDynSmem = 227 * 1024;
 
@@ -180,13 +181,15 @@ int sv_make_plan(int nobs, int n, int lag, int batch, int hess, int mode, int ha
     p->use_grid = 0;
     p->grid_G = 0;
     p->grid_total = 0;
-    if (mode == pmmh::kSvFlps && !hess && batch == 1 && !p->use_chain &&
-        (g_sv_algorithm == 6 || (g_sv_algorithm == 0 && ctas == 0 && !for_host_streamed && n >= g_grid_min_particles))) {
+    // (with compute_hessian: the kernel's second instantiation, automatically from g_grid_hess_min_particles on)
+    if (mode == pmmh::kSvFlps && batch == 1 && !p->use_chain &&
+        (g_sv_algorithm == 6 || (g_sv_algorithm == 0 && ctas == 0 && !for_host_streamed &&
+                                 n >= (hess ? g_grid_hess_min_particles : g_grid_min_particles)))) {
         const int GG = pmmh::sv_grid_ctas(n, di.sm, ctas);
         if (pmmh::sv_grid_eligible(nobs, n, lag, GG)) {
             p->use_grid = 1;
             p->grid_G = GG;
-            p->grid_total = pmmh::sv_grid_ws_bytes(nobs, n, lag, GG, have_hist);
+            p->grid_total = pmmh::sv_grid_ws_bytes(nobs, n, lag, GG, have_hist, hess);
             // (the general kernel's fallback pass uses the head of the same workspace)
             if (p->grid_total > p->total) p->total = p->grid_total;
         }
@@ -273,10 +276,13 @@ int sv_run(int mode, const double* d_obs, long long obs_stride, const double* d_
     if (p.use_grid) {
         // grid kernel first; an abandoned evaluation (diag status 1) is re-run by the general kernel
         rc = pmmh::sv_grid_run(d_obs, d_params, d_rvr, d_u, nobs, n, lag, p.grid_G, d_filt, d_smo, d_ll, d_grad,
-                               d_traj, d_diag, d_xh, d_ah, d_ws, ws_bytes, g_sv_prof, st);
+                               d_traj, d_diag, d_xh, d_ah, d_ws, ws_bytes, g_sv_prof, st, 0, nullptr,
+                               hess ? d_h1 : nullptr, hess ? d_h2 : nullptr);
         if (rc != PMMH_OK) return rc;
-        PMMH_CUDA(cudaMemsetAsync(d_h1, 0, 16 * sizeof(double), st));
-        PMMH_CUDA(cudaMemsetAsync(d_h2, 0, 16 * sizeof(double), st));
+        if (!hess) {
+            PMMH_CUDA(cudaMemsetAsync(d_h1, 0, 16 * sizeof(double), st));
+            PMMH_CUDA(cudaMemsetAsync(d_h2, 0, 16 * sizeof(double), st));
+        }
         if (g_sv_algorithm == 6) return PMMH_OK;   // diagnostics: no fallback pass
         a.only_failed = 1;
     }

@@ -120,6 +120,11 @@ struct GridArgs {
     REntry* R;         // [2][N]
     PEntry* P;         // [RP][N] payloads of generation t % RP
     double* psum;      // [NOBS][G][8]
+    // Hessian branch (:361-390, :472-534, :564-626) only:
+    double4* CA;       // [RPH][N] cumulative alpha of a particle (4 parameters), birth order, ring over generations
+    double* xlow;      // [NOBS][SQ] the first SQ sorted values of every generation (Q7 reads them)
+    double* psumH;     // [NOBS][G][20] per-step sums of the hessian1 / hessian2 terms (upper triangles)
+    int SQ, RPH;
     double *shiftv, *xminv;   // [NOBS]
     double* shring;    // [LAG][N] sh of the last LAG generations (sorted order)
     int* parentpos;    // [N] (history dump only)
@@ -319,7 +324,8 @@ __device__ __forceinline__ int block_excl_max_int(int v, int init, int* s_w, int
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <int GT>
+// HESS: the Hessian branch of the reference with its quirks Q7 / Q8 (second instantiation)
+template <int GT, bool HESS>
 __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
     constexpr int KPT = kCap / GT;          // entries per thread (strided assignment)
     constexpr int KCH = KPT | 1;            // longest chunk of the thread-contiguous passes (odd)
@@ -346,6 +352,7 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
     __shared__ double s_tot[kMaxTiles], s_off[kMaxTiles + 1];
     __shared__ int s_tstart[kMaxTiles + 1], s_tbin[kMaxTiles + 1], s_tcnt[kMaxTiles], s_tbase[kMaxTiles];
     __shared__ double s_red[9 * 32];
+    __shared__ double s_redH[HESS ? 20 * 32 : 1];   // Hessian branch: warp sums of the 20 hessian1 / hessian2 terms
     __shared__ int s_wi[32];
     __shared__ long long s_prof[kProf];
 
@@ -422,6 +429,10 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
             __stcg(&a.perm[pstart + q], pstart + q);
             s_sh[q] = 1.0;
             st_rec(&a.R[pstart + q], pol_keep, 0, 0, 0, 0, 0, 0, 0, 0);
+            if constexpr (HESS) {
+                a.CA[pstart + q] = make_double4(0.0, 0.0, 0.0, 0.0);
+                if (pstart + q < a.SQ) a.xlow[pstart + q] = mu;
+            }
             if (a.hist) {
                 a.Xhist[pstart + q] = mu;
                 a.Ahist[pstart + q] = pstart + q;
@@ -613,6 +624,7 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
         // --------------------------------------------------------------------------------------
         double xn[KPT];
         int bp[KPT];
+        int pb[HESS ? KPT : 1];   // Hessian branch: birth row of the parent (bp becomes the lagged ancestor below)
         {
 #pragma unroll
             for (int kk = 0; kk < KPT; ++kk) {
@@ -687,6 +699,10 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
                 if (cnt) atomicAdd(&gh[b], cnt);
             }
         }
+        if constexpr (HESS) {
+#pragma unroll
+            for (int kk = 0; kk < KPT; ++kk) pb[kk] = bp[kk];
+        }
         PROF_MARK(3);   // A1 children+hist
         GRID_ARRIVE();   // ---- barrier 1: global histogram complete
         if (!(a.dbg & 1)) {
@@ -731,6 +747,60 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
         GRID_WAIT();
         PROF_MARK(5);   // wait 1
         if (s_sc.abort_now) break;
+        if constexpr (HESS) {
+            // alpha recursion (:361-390): cumulative alpha of the child = its own term + its parent's.  Q7: the
+            // "current" state is read through the flat layout: particles[t - 1 + ancestor] = sorted value `sl` of
+            // time tq (a table of the first SQ sorted values of every generation), or the unsorted new value `sl`
+            // (complete since barrier 1), or 0.  Q8: obs[t - LAG] wraps.
+            const double yi = a.obs[t], ylagH = obs_wrap(a.obs, t - L, NOBS);
+            const double4* CAp = a.CA + (size_t)((t - 1) % a.RPH) * N;
+            double4* CAt = a.CA + (size_t)(t % a.RPH) * N;
+            const PEntry* Pnow = a.P + (size_t)(t % RP) * N;
+            const int SQ = a.SQ;
+#pragma unroll
+            for (int k0 = 0; k0 < KPT; k0 += 4) {
+                double2 pa0[4], pa1[4];
+                double cur[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = (k0 + u) * GT + tid;
+                    pa0[u] = pa1[u] = make_double2(0.0, 0.0);
+                    cur[u] = 0.0;
+                    if (i < nc) {
+                        const int j = jb + i;
+                        const int b = min(max(pb[k0 + u], 0), N - 1);
+                        pa0[u] = __ldcg((const double2*)&CAp[b]);
+                        pa1[u] = __ldcg((const double2*)&CAp[b] + 1);
+                        const int ppos = __ldcg(&a.H[j]);
+                        const long long qq = (long long)t - 1 + ppos;
+                        const int tq = (int)(qq % NOBS), sl = (int)(qq / NOBS);
+                        if (tq < t) cur[u] = (sl < SQ) ? __ldcg(&a.xlow[(size_t)tq * SQ + sl]) : 0.0;
+                        else if (tq == t) cur[u] = (sl <= j && sl < N) ? __ldcg(&Pnow[sl].x) : 0.0;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = (k0 + u) * GT + tid;
+                    if (i < nc) {
+                        const double x = xn[k0 + u], curr = cur[u];
+                        double sq = x - s_k.mu - s_k.phi * (curr - s_k.mu);
+                        const double ec = exp(-0.5 * curr);
+                        sq -= s_k.sr * ec * ylagH;
+                        const double a0 = s_k.q * sq * s_k.one_m_phi;
+                        const double a1 = s_k.q * sq * (curr - s_k.mu) * s_k.one_m_phi2;
+                        double a2 = sq;
+                        a2 += s_k.sr * ec * yi;
+                        a2 *= s_k.q * sq;
+                        a2 -= 1.0;
+                        double a3 = s_k.rho - s_k.q * s_k.rho * sq * sq;
+                        a3 += s_k.inv_sv * sq * ec * yi;
+                        double2* dst = (double2*)&CAt[jb + i];
+                        __stcg(dst, make_double2(a0 + pa0[u].x, a1 + pa0[u].y));
+                        __stcg(dst + 1, make_double2(a2 + pa1[u].x, a3 + pa1[u].y));
+                    }
+                }
+            }
+        }
 
         // --------------------------------------------------------------------------------------
         // phase A2: scan of the global histogram: tile boundaries on bin edges, tile of every bin;
@@ -1016,6 +1086,9 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
                                      make_int4((int)(xb & 0xffffffffll), (int)(xb >> 32), (int)(eb & 0xffffffffll), (int)(eb >> 32)));
                     }
                     st_hint_b32(&a.perm[pstart + q], pol_keep, j);
+                    if constexpr (HESS) {
+                        if (pstart + q < a.SQ) a.xlow[(size_t)t * a.SQ + pstart + q] = x;
+                    }
                     s_sh[q] = sh;
                     if (pstart + q == 0) a.xminv[t] = x;   // Q10/Q11: traj[t] = X_t[0]
                     if (a.hist) {
@@ -1097,23 +1170,39 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
             // LAG-2 generations back (one random sector each), fixed summation order
             const PEntry* Pg = a.P + (size_t)((t - (L - 2)) % RP) * N;
             double sc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+            // Hessian branch (:472-534): the cumulative alpha of the same ancestor (one more random sector) and
+            // the 20 hessian1 / hessian2 terms, weighted with the unnormalised weight (divided by S afterwards)
+            constexpr int SB = HESS ? 2 : 4;   // gathers in flight per thread
+            const double4* CAg = HESS ? a.CA + (size_t)((t - (L - 2)) % a.RPH) * N : nullptr;
+            double hacc[HESS ? 20 : 1];
+            if constexpr (HESS) {
 #pragma unroll
-            for (int k0 = 0; k0 < KPT; k0 += 4) {
-                double pc[4], psq[4], pey[4];
+                for (int i = 0; i < 20; ++i) hacc[i] = 0.0;
+            }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+            for (int k0 = 0; k0 < KPT; k0 += SB) {
+                double pc[SB], psq[SB], pey[SB];
+                double2 al0[HESS ? SB : 1], al1[HESS ? SB : 1];
+#pragma unroll
+                for (int u = 0; u < SB; ++u) {
                     const int q = (k0 + u) * GT + tid;
                     pc[u] = psq[u] = pey[u] = 0.0;
+                    if constexpr (HESS) al0[u] = al1[u] = make_double2(0.0, 0.0);
                     if (q < n) {
-                        const PEntry* pp = &Pg[min(max(s_ab[q], 0), N - 1)];
+                        const int row = min(max(s_ab[q], 0), N - 1);
+                        const PEntry* pp = &Pg[row];
                         double d3;
                         asm volatile("ld.global.cg.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
                                      : "=d"(pc[u]), "=d"(psq[u]), "=d"(pey[u]), "=d"(d3)
                                      : "l"(pp), "l"(pol_pld));
+                        if constexpr (HESS) {
+                            al0[u] = __ldcg((const double2*)&CAg[row]);
+                            al1[u] = __ldcg((const double2*)&CAg[row] + 1);
+                        }
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < SB; ++u) {
                     const int q = (k0 + u) * GT + tid;
                     if (q < n) {
                         const double wd = s_sh[q];
@@ -1123,8 +1212,29 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
                         sc[2] = fma(ws, pc[u], sc[2]);
                         sc[3] = fma(ws, psq[u], sc[3]);
                         sc[4] = fma(ws, pey[u], sc[4]);
+                        if constexpr (HESS) {
+                            // g of :454-465 from (curr, sq, ey)
+                            const double sq = psq[u], ey = pey[u];
+                            double g[4];
+                            g[0] = s_k.q * sq * s_k.one_m_phi;
+                            g[1] = s_k.q * sq * (pc[u] - s_k.mu) * s_k.one_m_phi2;
+                            double g2 = sq;
+                            g2 += s_k.sr * ey;
+                            g2 *= s_k.q * sq;
+                            g2 -= 1.0;
+                            g[2] = g2;
+                            double g3 = s_k.rho - s_k.q * s_k.rho * sq * sq;
+                            g3 += s_k.inv_sv * sq * ey;
+                            g[3] = g3;
+                            const double al[4] = {al0[u].x, al0[u].y, al1[u].x, al1[u].y};
+                            sv_hessian_terms_ey(s_k, pc[u], ey, sq, g, al, wd, hacc);
+                        }
                     }
                 }
+            }
+            if constexpr (HESS) {
+#pragma unroll
+                for (int i = 0; i < 20; ++i) hacc[i] = warp_sum(hacc[i]);
             }
 #pragma unroll
             for (int i = 0; i < 5; ++i) sc[i] = warp_sum(sc[i]);
@@ -1132,8 +1242,18 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
             if (lane == 0) {
 #pragma unroll
                 for (int i = 0; i < 5; ++i) s_red[32 * i + warp] = sc[i];
+                if constexpr (HESS) {
+#pragma unroll
+                    for (int i = 0; i < 20; ++i) s_redH[32 * i + warp] = hacc[i];
+                }
             }
             __syncthreads();
+            if constexpr (HESS) {
+                for (int k = warp; k < 20; k += NW) {   // a warp sums component k over the warps (fixed order)
+                    const double v = warp_sum((lane < NW) ? s_redH[32 * k + lane] : 0.0);
+                    if (lane == 0) a.psumH[((size_t)t * G + c) * 20 + k] = v;
+                }
+            }
             if (warp == 0) {
                 double* ps = a.psum + ((size_t)t * G + c) * 8;
 #pragma unroll
@@ -1183,9 +1303,13 @@ __global__ void __launch_bounds__(256) grid_reduce_kernel(const double* __restri
 // part[irel][block][0] = sum_p W_T[p] hist_idx[p];  [1..4] = sum_p W_i[p] g(hist_idx, hist_idx-1)
 // with i = NOBS - L + irel, idx = L - 1 - irel; hist_k[p] = value of the ancestor k steps back of
 // the particle at sorted position p of the final generation.
+// HESS: partH[irel][block][0..19] = the hessian1 / hessian2 terms of :564-626 (alpha of the ancestor LAG-2 steps
+// back of the final particle, weights W_i, obs[i - LAG] with wrap-around, Q8)
+template <bool HESS>
 __global__ void __launch_bounds__(256) grid_tail_kernel(GridArgs a, const double* __restrict__ sums,
-                                                        double* __restrict__ part, int nblk) {
-    __shared__ double red[5 * 32];
+                                                        double* __restrict__ part, double* __restrict__ partH,
+                                                        int nblk) {
+    __shared__ double red[(HESS ? 20 : 5) * 32];
     const int tid = threadIdx.x;
     const int L = a.LAG, N = a.N, T = a.NOBS - 1, RP = a.RP;
     const int irel = blockIdx.y, i = a.NOBS - L + irel, idx = L - 1 - irel;
@@ -1197,6 +1321,12 @@ __global__ void __launch_bounds__(256) grid_tail_kernel(GridArgs a, const double
     const double* shi = a.shring + (size_t)(i % L) * N;
     const REntry* Rt = a.R + (size_t)(T & 1) * N;
     double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    double hacc[HESS ? 20 : 1];
+    if constexpr (HESS) {
+#pragma unroll
+        for (int q = 0; q < 20; ++q) hacc[q] = 0.0;
+    }
+    const double ylagH = obs_wrap(a.obs, i - L, a.NOBS);
     const bool live = a.ctrl->status == 0;   // an abandoned evaluation leaves stale rows behind
     for (int p = blockIdx.x * 256 + tid; live && p < N; p += nblk * 256) {
         const int b = min(max(a.perm[p], 0), N - 1);
@@ -1215,13 +1345,65 @@ __global__ void __launch_bounds__(256) grid_tail_kernel(GridArgs a, const double
             acc[0] += wT * curr;
             const double wi = shi[p] / Si;
             double sq, g[4];
-            sv_score_tail_e(k, curr, exp(-0.5 * curr), pe_n, y1, sq, g);   // the tail uses obs[i - 1] (Q6)
+            const double ec = exp(-0.5 * curr);
+            sv_score_tail_e(k, curr, ec, pe_n, y1, sq, g);   // the tail uses obs[i - 1] (Q6)
 #pragma unroll
             for (int q = 0; q < 4; ++q) acc[1 + q] += g[q] * wi;
+            if constexpr (HESS) {
+                const int m2 = L - 2;
+                const int row2 = (m2 == 0) ? b : min(max(Rt[b].a[m2 - 1], 0), N - 1);
+                const double4 a4 = a.CA[(size_t)((T - m2) % a.RPH) * N + row2];
+                const double al[4] = {a4.x, a4.y, a4.z, a4.w};
+                sv_hessian_terms_e(k, curr, ec, exp(-curr), sq, ylagH, g, al, wi, hacc);
+            }
         }
     }
     block_sum<5>(acc, red);
     if (tid < 5) part[((size_t)irel * nblk + blockIdx.x) * 8 + tid] = acc[tid];
+    if constexpr (HESS) {
+        __syncthreads();
+        block_sum<20>(hacc, red);
+        if (tid < 20) partH[((size_t)irel * nblk + blockIdx.x) * 20 + tid] = hacc[tid];
+    }
+}
+
+// Hessian branch: sumsH[t][k] = sum over the tiles of psumH[t][.][k] (t >= lag; 0 before)
+__global__ void __launch_bounds__(640) grid_reduceH_kernel(const double* __restrict__ psumH, int G, int lag,
+                                                           double* __restrict__ sumsH) {
+    const int t = blockIdx.x, k = threadIdx.x >> 5, lane = threadIdx.x & 31;   // 20 warps = 20 components
+    double s = 0.0;
+    if (t >= lag)
+        for (int c = lane; c < G; c += 32) s = s + psumH[((size_t)t * G + c) * 20 + k];
+    s = warp_sum(s);
+    if (lane == 0) sumsH[(size_t)t * 20 + k] = s;
+}
+
+// hessian1 / hessian2 (:521-534, :613-626): main-loop terms divided by the weight sum of their step + tail terms,
+// upper triangles expanded into the symmetric 4 x 4 outputs
+__global__ void __launch_bounds__(32) grid_hess_finish_kernel(const GridCtrl* __restrict__ ctrl,
+                                                              const double* __restrict__ sums,
+                                                              const double* __restrict__ sumsH,
+                                                              const double* __restrict__ partH, int nblk, int nobs,
+                                                              int lag, double* __restrict__ hess1,
+                                                              double* __restrict__ hess2) {
+    __shared__ double tri[20];
+    const int k = threadIdx.x;
+    if (ctrl->status != 0) return;   // abandoned: the general kernel writes the outputs
+    if (k < 20) {
+        double h = 0.0;
+        for (int t = lag; t < nobs; ++t) h += sumsH[(size_t)t * 20 + k] / sums[(size_t)t * 8];
+        for (int irel = 0; irel < lag - 1; ++irel)
+            for (int q = 0; q < nblk; ++q) h += partH[((size_t)irel * nblk + q) * 20 + k];
+        tri[k] = h;
+    }
+    __syncwarp();
+    if (k < 16) {
+        const int r = k >> 2, cidx = k & 3;
+        const int lo = min(r, cidx), hi = max(r, cidx);
+        const int ti = lo * 4 - (lo * (lo - 1)) / 2 + (hi - lo);
+        hess1[k] = tri[ti];
+        hess2[k] = tri[10 + ti];
+    }
 }
 
 __global__ void __launch_bounds__(256) grid_tail_reduce_kernel(const double* __restrict__ part, int nblk,
@@ -1293,13 +1475,13 @@ __global__ void grid_finish_kernel(const GridCtrl* __restrict__ ctrl, const doub
 
 struct GridLayout {
     size_t ctrl, ghist, tilecnt, tinfo, H, XE, perm, R, P, psum, shiftv, xminv, shring, parentpos, sums,
-        tailpart, tail, info, total;
-    int RP, nblk;
+        tailpart, tail, info, CA, xlow, psumH, sumsH, tailpartH, total;
+    int RP, nblk, SQ;
 };
 
 size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-GridLayout grid_layout(int nobs, int n, int lag, int G, int hist) {
+GridLayout grid_layout(int nobs, int n, int lag, int G, int hist, int hess) {
     GridLayout L = GridLayout();
     // ring depth of the payloads: step t writes generation t and gathers from generation t-(lag-2)
     L.RP = lag < 2 ? 2 : lag;
@@ -1324,8 +1506,15 @@ GridLayout grid_layout(int nobs, int n, int lag, int G, int hist) {
     L.tailpart = o;  o += al256((size_t)lag * L.nblk * 8 * 8);
     L.tail = o;      o += al256((size_t)lag * 8 * 8);
     L.info = o;      o += al256(8 * 8);
+    // Hessian branch: cumulative alpha ring (32 B per particle and generation), the first SQ sorted values of every
+    // generation (Q7: particles[i - 1 + ancestor] read through the flat layout), per-tile / per-step sums
+    L.SQ = hess ? (nobs + n - 2) / nobs + 1 : 1;
+    L.CA = o;        o += al256(hess ? (size_t)L.RP * N * 32 : 0);
+    L.xlow = o;      o += al256(hess ? (size_t)nobs * L.SQ * 8 : 0);
+    L.psumH = o;     o += al256(hess ? (size_t)nobs * G * 20 * 8 : 0);
+    L.sumsH = o;     o += al256(hess ? (size_t)nobs * 20 * 8 : 0);
+    L.tailpartH = o; o += al256(hess ? (size_t)lag * L.nblk * 20 * 8 : 0);
     L.total = o;
-    (void)G;
     return L;
 }
 
@@ -1353,17 +1542,18 @@ bool sv_grid_eligible(int nobs, int n, int lag, int G) {
     return Wc <= kCap - kCap / 8;
 }
 
-size_t sv_grid_ws_bytes(int nobs, int n, int lag, int G, int hist) {
-    return grid_layout(nobs, n, lag, G, hist).total;
+size_t sv_grid_ws_bytes(int nobs, int n, int lag, int G, int hist, int hess) {
+    return grid_layout(nobs, n, lag, G, hist, hess).total;
 }
 
 int sv_grid_run(const double* d_obs, const double* d_params, const double* d_rvr, const double* d_u, int nobs,
                 int n, int lag, int G, double* d_filt, double* d_smo, double* d_ll, double* d_grad, double* d_traj,
                 long long* d_diag, double* d_xh, int* d_ah, void* d_ws, size_t ws_bytes, long long* d_prof,
-                cudaStream_t st, int u_chunk_steps, const int* d_u_flag) {
+                cudaStream_t st, int u_chunk_steps, const int* d_u_flag, double* d_hess1, double* d_hess2) {
     if (!sv_grid_eligible(nobs, n, lag, G)) return set_error(PMMH_ERR_INVALID, "grid kernel: sizes not eligible");
     const int hist = d_xh != nullptr;
-    const GridLayout L = grid_layout(nobs, n, lag, G, hist);
+    const int hess = d_hess1 != nullptr && d_hess2 != nullptr;
+    const GridLayout L = grid_layout(nobs, n, lag, G, hist, hess);
     if (ws_bytes < L.total) return set_error(PMMH_ERR_WORKSPACE, "grid kernel: workspace too small");
     char* ws = (char*)d_ws;
     GridArgs a;
@@ -1406,6 +1596,11 @@ int sv_grid_run(const double* d_obs, const double* d_params, const double* d_rvr
     a.xminv = (double*)(ws + L.xminv);
     a.shring = (double*)(ws + L.shring);
     a.parentpos = (int*)(ws + L.parentpos);
+    a.CA = (double4*)(ws + L.CA);
+    a.xlow = (double*)(ws + L.xlow);
+    a.psumH = (double*)(ws + L.psumH);
+    a.SQ = L.SQ;
+    a.RPH = L.RP;
     a.Xhist = d_xh;
     a.Ahist = d_ah;
     a.prof = d_prof;
@@ -1439,20 +1634,29 @@ int sv_grid_run(const double* d_obs, const double* d_params, const double* d_rvr
         }
     }
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        GRID_CUDA(cudaFuncSetAttribute(sv_grid_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem));
-        GRID_CUDA(cudaFuncSetAttribute(sv_grid_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem));
+        GRID_CUDA(cudaFuncSetAttribute(sv_grid_kernel<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem));
+        GRID_CUDA(cudaFuncSetAttribute(sv_grid_kernel<1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem));
+        GRID_CUDA(cudaFuncSetAttribute(sv_grid_kernel<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem));
+        GRID_CUDA(cudaFuncSetAttribute(sv_grid_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDynSmem));
         attr_set[dev] = true;
     }
     void* kargs[] = {(void*)&a};
-    if (threads == 1024)
-        GRID_CUDA(cudaLaunchCooperativeKernel((void*)sv_grid_kernel<1024>, dim3(G), dim3(1024), kargs, kDynSmem, st));
-    else
-        GRID_CUDA(cudaLaunchCooperativeKernel((void*)sv_grid_kernel<512>, dim3(G), dim3(512), kargs, kDynSmem, st));
+    const void* kern = hess ? (threads == 1024 ? (const void*)sv_grid_kernel<1024, true> : (const void*)sv_grid_kernel<512, true>)
+                            : (threads == 1024 ? (const void*)sv_grid_kernel<1024, false> : (const void*)sv_grid_kernel<512, false>);
+    GRID_CUDA(cudaLaunchCooperativeKernel(kern, dim3(G), dim3(threads), kargs, kDynSmem, st));
     double* sums = (double*)(ws + L.sums);
     double* tailpart = (double*)(ws + L.tailpart);
     double* tail = (double*)(ws + L.tail);
     grid_reduce_kernel<<<nobs, 256, 0, st>>>(a.psum, G, sums);
-    grid_tail_kernel<<<dim3(L.nblk, lag), 256, 0, st>>>(a, sums, tailpart, L.nblk);
+    if (hess) {
+        double* sumsH = (double*)(ws + L.sumsH);
+        double* tailpartH = (double*)(ws + L.tailpartH);
+        grid_reduceH_kernel<<<nobs, 640, 0, st>>>(a.psumH, G, lag, sumsH);
+        grid_tail_kernel<true><<<dim3(L.nblk, lag), 256, 0, st>>>(a, sums, tailpart, tailpartH, L.nblk);
+        grid_hess_finish_kernel<<<1, 32, 0, st>>>(a.ctrl, sums, sumsH, tailpartH, L.nblk, nobs, lag, d_hess1, d_hess2);
+    } else {
+        grid_tail_kernel<false><<<dim3(L.nblk, lag), 256, 0, st>>>(a, sums, tailpart, nullptr, L.nblk);
+    }
     grid_tail_reduce_kernel<<<lag, 256, 0, st>>>(tailpart, L.nblk, tail);
     grid_finish_kernel<<<(nobs + 255) / 256, 256, 0, st>>>(a.ctrl, sums, a.shiftv, a.xminv, tail, d_params, nobs, lag,
                                                            (double)n, d_ll, d_filt, d_smo, d_grad, d_traj, d_diag,
@@ -1463,7 +1667,7 @@ int sv_grid_run(const double* d_obs, const double* d_params, const double* d_rvr
 
 // soft ties / raw status of the last evaluation that used this workspace (after synchronisation)
 int sv_grid_read_info(const void* d_ws, int nobs, int n, int lag, int G, int hist, long long* h_info) {
-    const GridLayout L = grid_layout(nobs, n, lag, G, hist);
+    const GridLayout L = grid_layout(nobs, n, lag, G, hist, 0);   // (the Hessian buffers sit behind `info`)
     GRID_CUDA(cudaMemcpy(h_info, (const char*)d_ws + L.info, 2 * sizeof(long long), cudaMemcpyDeviceToHost));
     return PMMH_OK;
 }

@@ -187,6 +187,77 @@ __device__ __forceinline__ void sv_hessian_terms_e(const SvConst& c, double curr
     }
 }
 
+// the same terms from ey = exp(-curr / 2) * yl (what the grid kernel keeps in its payload): e and yl only ever
+// appear as that product
+__device__ __forceinline__ void sv_hessian_terms_ey(const SvConst& c, double curr, double ey, double sq,
+                                                    const double g[4], const double al[4], double w,
+                                                    double* acc) {
+    const double cm = curr - c.mu;
+    double h1[10], h2[10];
+    // (0,0)
+    h1[0] = -c.q * (c.one_m_phi * c.one_m_phi);
+    // (1,1)
+    double t = 2.0 * c.phi * sq + cm * c.one_m_phi2;
+    t *= -c.q * cm * c.one_m_phi2;
+    h1[4] = t;
+    // (2,2)
+    t = -2.0 * c.q * sq * sq;
+    t -= 2.0 * c.q * sq * c.rho * c.sigmav * ey;
+    {
+        double r = c.rho * c.sigmav * ey;
+        t -= c.q * (r * r);
+    }
+    t += c.q * sq * c.rho * c.sigmav * ey;
+    h1[7] = t;
+    // (3,3)   note the reference's "sigmav*(-2)" typo
+    t = c.rho_term - 2.0 * c.q * (c.rho * c.rho) * (sq * sq) - c.sigmav * (-2.0) * (sq * sq);
+    t += 2.0 * c.inv_sv * c.rho * sq * ey;
+    t -= (ey * ey) * c.rho_term;
+    h1[9] = t;
+    // (0,1)
+    t = -c.q * cm * c.one_m_phi - c.q * sq;
+    t *= c.one_m_phi2;
+    h1[1] = t;
+    // (0,2)
+    t = -2.0 * sq * c.one_m_phi;
+    t -= c.q * c.one_m_phi * c.sigmav * c.rho * sq * ey;
+    h1[2] = t;
+    // (0,3)
+    t = 2.0 * c.q * c.rho * sq * c.one_m_phi;
+    t -= c.inv_sv2 * c.one_m_phi * c.sigmav * ey;
+    h1[3] = t;
+    // (1,2)
+    t = -2.0 * sq - c.rho * c.sigmav * ey;
+    t *= c.q * cm * c.one_m_phi2;
+    h1[5] = t;
+    // (1,3)
+    t = 2.0 * c.rho * sq - c.sigmav * ey * c.rho_term;
+    t *= c.q * cm * c.one_m_phi2;
+    h1[6] = t;
+    // (2,3)
+    t = 2.0 * c.q * (sq * sq) * c.rho;
+    t += 2.0 * (c.rho * c.rho) * c.q * sq * c.sigmav * ey;
+    t -= c.rho * (ey * ey);
+    t += c.inv_sv * sq * ey;
+    h1[8] = t;
+
+    h2[0] = g[0] * g[0] + 2.0 * al[0] * g[0];
+    h2[1] = g[0] * g[1] + al[0] * g[1] + al[1] * g[0];
+    h2[2] = g[0] * g[2] + al[0] * g[2] + al[2] * g[0];
+    h2[3] = g[0] * g[3] + al[0] * g[3] + al[3] * g[0];
+    h2[4] = g[1] * g[1] + 2.0 * al[1] * g[1];
+    h2[5] = g[1] * g[2] + al[1] * g[2] * al[2] * g[1];   // '*' typos of :513,514,517 kept
+    h2[6] = g[1] * g[3] + al[1] * g[3] * al[3] * g[1];
+    h2[7] = g[2] * g[2] + 2.0 * al[2] * g[2];
+    h2[8] = g[2] * g[3] + al[2] * g[3] * al[3] * g[2];
+    h2[9] = g[3] * g[3] + 2.0 * al[3] * g[3];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+        if (isfinite(h1[k])) acc[k] += h1[k] * w;
+        if (isfinite(h2[k])) acc[10 + k] += h2[k] * w;
+    }
+}
+
 __device__ __forceinline__ double obs_wrap(const double* obs, int k, int nobs) {
     return obs[k < 0 ? k + nobs : k];   // Cython memoryview wraparound (Q8)
 }

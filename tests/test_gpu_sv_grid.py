@@ -27,11 +27,11 @@ def grid_only():
     K.set_sv_algorithm(0)
 
 
-def _run(K, dev, obs, params, rvr, u_tm, lag, hist, ctas=0):
+def _run(K, dev, obs, params, rvr, u_tm, lag, hist, ctas=0, hess=False):
     import torch
     out = K.flps_sv_corr(torch.from_numpy(obs).to(dev), torch.from_numpy(params).to(dev),
                          torch.from_numpy(rvr).to(dev), torch.from_numpy(u_tm).to(dev), lag=lag,
-                         compute_hessian=False, store_history=hist, ctas_per_problem=ctas)
+                         compute_hessian=hess, store_history=hist, ctas_per_problem=ctas)
     torch.cuda.synchronize()
     return {k: v.cpu().numpy() for k, v in out.items() if not k.startswith("_")}
 
@@ -76,6 +76,26 @@ def test_grid_other_lags(cuda_dev, grid_only, lag):
     res = _run(grid_only, cuda_dev, obs, params, rvr, u, lag, False, 5)
     assert int(res["diag"][0, DIAG_KERNEL]) == GRID and int(res["diag"][0, DIAG_STATUS]) == 0
     _check_outputs(res, ref)
+
+
+@pytest.mark.parametrize("n,nobs,ctas,lag,seed", [(4096, 300, 4, 10, 3), (20000, 120, 16, 10, 3), (5003, 80, 3, 7, 1),
+                                                  (1000, 150, 7, 10, 2), (5000, 60, 5, 2, 1), (5000, 60, 5, 3, 1),
+                                                  (65536, 45, 148, 10, 5), (300, 400, 2, 10, 4)])
+def test_grid_hessian_vs_oracle(cuda_dev, grid_only, n, nobs, ctas, lag, seed):
+    """Hessian branch (stochastic_volatility.pyx:361-390,472-534,564-626 with Q7 / Q8) on the grid kernel's
+    second instantiation: hessian1 / hessian2 <= 1e-8 * max|H| (the tolerance of the other Hessian tests),
+    everything else as without the Hessian.  n < n_obs makes Q7 read real (sorted / unsorted) values."""
+    import oracle
+    obs, params, rvr, rvp, u = _inputs(n, nobs, seed)
+    ref = oracle.flps_sv_corr(obs, params, rvr, rvp, n, lag, 1, dumps=True)
+    res = _run(grid_only, cuda_dev, obs, params, rvr, u, lag, True, ctas, hess=True)
+    assert int(res["diag"][0, DIAG_KERNEL]) == GRID, res["diag"]
+    assert int(res["diag"][0, DIAG_STATUS]) == 0, "abandoned: info %x" % int(res["diag"][0, DIAG_INFO])
+    assert first_mismatch_step(res["A"][0][1:], ref["A"][1:]) is None
+    _check_outputs(res, ref)
+    for k in ("hess1", "hess2"):
+        h = res[k][0].reshape(4, 4)
+        assert np.max(np.abs(h - ref[k].reshape(4, 4))) <= 1e-8 * np.max(np.abs(ref[k])), (k, h, ref[k])
 
 
 @pytest.mark.parametrize("n", [1 << 20, 1000003])

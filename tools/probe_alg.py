@@ -1,4 +1,4 @@
-"""Time pmmh_flps_sv_corr for one algorithm: python tools/probe_alg.py ALG logN T [reps]"""
+"""Time pmmh_flps_sv_corr for one algorithm: python tools/probe_alg.py ALG logN T [reps]  (PMMH_PROBE_HESS=1: with the Hessian branch)"""
 import json
 import os
 import sys
@@ -31,11 +31,12 @@ for rep in range(reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
-    out = K.flps_sv_corr(obs, params, rvr, u, lag=10, workspace=ws)
+    out = K.flps_sv_corr(obs, params, rvr, u, lag=10, workspace=ws, compute_hessian=bool(os.environ.get("PMMH_PROBE_HESS")))
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     d = out["diag"][0].cpu().numpy()
     print(json.dumps({"alg": alg, "N": n, "T": T, "ms": ms, "particle_steps_per_s": n * T / ms * 1e3,
                       "log_like": float(out["log_like"][0]), "kernel": int(d[6]), "status": int(d[2]),
-                      "near_ties": int(d[0]), "grad0": float(out["gradient"][0].sum(dim=1)[0])}), flush=True)
+                      "near_ties": int(d[0]), "grad0": float(out["gradient"][0].sum(dim=1)[0]),
+                      "hess1_00": float(out["hess1"][0].flatten()[0]), "hess2_23": float(out["hess2"][0].flatten()[11])}), flush=True)
