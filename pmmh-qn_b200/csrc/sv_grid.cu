@@ -120,11 +120,14 @@ struct GridArgs {
     REntry* R;         // [2][N]
     PEntry* P;         // [RP][N] payloads of generation t % RP
     double* psum;      // [NOBS][G][8]
-    // Hessian branch (:361-390, :472-534, :564-626) only:
-    double4* CA;       // [RPH][N] cumulative alpha of a particle (4 parameters), birth order, ring over generations
-    double* xlow;      // [NOBS][SQ] the first SQ sorted values of every generation (Q7 reads them)
-    double* psumH;     // [NOBS][G][20] per-step sums of the hessian1 / hessian2 terms (upper triangles)
-    int SQ, RPH;
+    // Hessian branch (:361-390, :472-534, :564-626) only: the entries of R and P are 64 bytes (RS = 2 sectors), the
+    // second sector is the cumulative alpha (4 parameters) of the particle -- next to its record for the children
+    // (who gather both with one 64-byte access) and next to its payload for the descendants LAG-2 steps later
+    int RS;            // 32-byte sectors per entry of R and P (1, Hessian branch 2)
+    double* xlow;      // [SQ][NOBS] the first SQ sorted values of every generation, slot-major: consecutive parents read
+                       // consecutive times (Q7), so the reads of a warp coalesce
+    double* psumH;     // [NOBS][G][20] per-step sums: [0..3] monomials of hessian1, [10..19] hessian2 (upper triangle)
+    int SQ;
     double *shiftv, *xminv;   // [NOBS]
     double* shring;    // [LAG][N] sh of the last LAG generations (sorted order)
     int* parentpos;    // [N] (history dump only)
@@ -225,6 +228,16 @@ __device__ __forceinline__ int ld_hint_b32(const void* p, unsigned long long pol
     int v;
     asm volatile("ld.global.cg.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
     return v;
+}
+__device__ __forceinline__ void ld_f64x4(const void* p, unsigned long long pol, double& a, double& b, double& c, double& d) {
+    asm volatile("ld.global.cg.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=d"(a), "=d"(b), "=d"(c), "=d"(d)
+                 : "l"(p), "l"(pol));
+}
+__device__ __forceinline__ void st_keep_f64x4(void* p, unsigned long long pol, double a, double b, double c, double d) {
+    asm volatile("st.global.cg.L2::cache_hint.v4.f64 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d),
+                 "l"(pol)
+                 : "memory");
 }
 __device__ __forceinline__ int warp_incl_max(int v, int lane) {
 #pragma unroll
@@ -333,7 +346,14 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
     constexpr int SPT = kNSB / GT;          // sub-bins per thread
     constexpr int NW = GT / 32;
     constexpr int CH = KPT >= 16 ? 8 : 4;   // independent loads in flight per thread in the gather loops
-    constexpr int RB = KPT >= 16 ? 4 : 2;   // genealogy records in flight per thread
+#ifndef PMMH_GRID_HESS_RB
+#define PMMH_GRID_HESS_RB 2
+#endif
+#ifndef PMMH_GRID_HESS_SB
+#define PMMH_GRID_HESS_SB 1
+#endif
+    constexpr int RB = HESS ? (KPT >= 16 ? 2 * PMMH_GRID_HESS_RB : PMMH_GRID_HESS_RB) : (KPT >= 16 ? 4 : 2);   // genealogy records in flight per thread
+    constexpr int RS = HESS ? 2 : 1;        // 32-byte sectors per entry of R and P
     static_assert(SPT % 4 == 0 && BPT % 4 == 0, "vector loads of the counters");
     extern __shared__ __align__(16) unsigned char smem[];
     // phase B / C view
@@ -428,10 +448,10 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
             __stcg(&a.XE[pstart + q], make_double2(mu, e0));
             __stcg(&a.perm[pstart + q], pstart + q);
             s_sh[q] = 1.0;
-            st_rec(&a.R[pstart + q], pol_keep, 0, 0, 0, 0, 0, 0, 0, 0);
+            st_rec(&a.R[(size_t)(pstart + q) * RS], pol_keep, 0, 0, 0, 0, 0, 0, 0, 0);
             if constexpr (HESS) {
-                a.CA[pstart + q] = make_double4(0.0, 0.0, 0.0, 0.0);
-                if (pstart + q < a.SQ) a.xlow[pstart + q] = mu;
+                st_rec(&a.R[(size_t)(pstart + q) * RS + 1], pol_keep, 0, 0, 0, 0, 0, 0, 0, 0);   // alpha = 0
+                if (pstart + q < a.SQ) a.xlow[(size_t)(pstart + q) * NOBS] = mu;
             }
             if (a.hist) {
                 a.Xhist[pstart + q] = mu;
@@ -624,7 +644,6 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
         // --------------------------------------------------------------------------------------
         double xn[KPT];
         int bp[KPT];
-        int pb[HESS ? KPT : 1];   // Hessian branch: birth row of the parent (bp becomes the lagged ancestor below)
         {
 #pragma unroll
             for (int kk = 0; kk < KPT; ++kk) {
@@ -638,7 +657,7 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
             const double mu = s_k.mu, phi = s_k.phi, sr = s_k.sr, sd = s_k.sd;
             const double* Ut = a.U + (size_t)(t / a.u_cs) * a.u_cstride + (size_t)(t % a.u_cs) * a.u_tstride;
             const long long ujs = a.u_jstride;
-            PEntry* Pt = a.P + (size_t)(t % RP) * N;
+            PEntry* Pt = a.P + (size_t)(t % RP) * N * RS;
             bool bad = false, orphan = false;
 #pragma unroll
             for (int k0 = 0; k0 < KPT; k0 += CH) {
@@ -681,7 +700,7 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
                             // residual of the transition parent -> child as the score terms use it (:452-453)
                             double sq = x - mu - phi * (xe[u].x - mu);
                             sq -= sr * xe[u].y * ylag;
-                            st_stream_f64x4(&Pt[jb + i], pol_stream, xe[u].x, sq, xe[u].y * ylag, x);
+                            st_stream_f64x4(&Pt[(size_t)(jb + i) * RS], pol_stream, xe[u].x, sq, xe[u].y * ylag, x);
                         }
                     }
                 }
@@ -699,25 +718,45 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
                 if (cnt) atomicAdd(&gh[b], cnt);
             }
         }
-        if constexpr (HESS) {
-#pragma unroll
-            for (int kk = 0; kk < KPT; ++kk) pb[kk] = bp[kk];
-        }
         PROF_MARK(3);   // A1 children+hist
         GRID_ARRIVE();   // ---- barrier 1: global histogram complete
+        unsigned defer = 0;   // Hessian branch: children whose Q7 read needs generation t complete (bit kk)
         if (!(a.dbg & 1)) {
             // genealogy records (only feed outputs): child = (parent row, parent's ancestors 1..7)
-            const REntry* Rp = a.R + (size_t)((t - 1) & 1) * N;
-            REntry* Rc = a.R + (size_t)(t & 1) * N;
+            const REntry* Rp = a.R + (size_t)((t - 1) & 1) * N * RS;
+            REntry* Rc = a.R + (size_t)(t & 1) * N * RS;
+            // Hessian branch: alpha recursion (:361-390) in the same pass -- the parent's cumulative alpha is the
+            // second sector of its record entry.  cumulative alpha of the child = its own term + its parent's.
+            // Q7: the "current" state is particles[t - 1 + ancestor] read through the flat layout = sorted value
+            // `sl` of time tq (table of the first SQ sorted values of every generation), or the unsorted new value
+            // `sl` of this generation (complete only after barrier 1: deferred), or 0.  Q8: obs[t - LAG] wraps.
+            const double yi = a.obs[t], ylagH = HESS ? obs_wrap(a.obs, t - L, NOBS) : 0.0;
+            REntry* Pc = (REntry*)(a.P + (size_t)(t % RP) * N * RS);
 #pragma unroll
             for (int k0 = 0; k0 < KPT; k0 += RB) {
                 int r[RB][8];
+                double2 pa0[HESS ? RB : 1], pa1[HESS ? RB : 1];
+                double cur[HESS ? RB : 1];
 #pragma unroll
                 for (int u = 0; u < RB; ++u) {
                     const int i = (k0 + u) * GT + tid;
 #pragma unroll
                     for (int z = 0; z < 8; ++z) r[u][z] = 0;
-                    if (i < nc) ld_rec(&Rp[(a.dbg & 8) ? jb + i : bp[k0 + u]], pol_rld, r[u]);
+                    if constexpr (HESS) {
+                        pa0[u] = pa1[u] = make_double2(0.0, 0.0);
+                        cur[u] = 0.0;
+                    }
+                    if (i < nc) {
+                        const REntry* src = &Rp[(size_t)((a.dbg & 8) ? jb + i : bp[k0 + u]) * RS];
+                        ld_rec(src, pol_rld, r[u]);
+                        if constexpr (HESS) {
+                            ld_f64x4(src + 1, pol_rld, pa0[u].x, pa0[u].y, pa1[u].x, pa1[u].y);
+                            const unsigned qq = (unsigned)(t - 1) + (unsigned)__ldcg(&a.H[jb + i]);
+                            const unsigned sl = qq / (unsigned)NOBS, tq = qq - sl * (unsigned)NOBS;
+                            if ((int)tq < t) cur[u] = ((int)sl < a.SQ) ? __ldcg(&a.xlow[(size_t)sl * NOBS + tq]) : 0.0;
+                            else if ((int)tq == t) defer |= 1u << (k0 + u);
+                        }
+                    }
                 }
 #pragma unroll
                 for (int u = 0; u < RB; ++u) {
@@ -725,12 +764,20 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
                     if (i < nc) {
                         const int j = jb + i;
                         const int b = bp[k0 + u];
-                        st_rec(&Rc[j], pol_rst, b, r[u][0], r[u][1], r[u][2], r[u][3], r[u][4], r[u][5], r[u][6]);
+                        st_rec(&Rc[(size_t)j * RS], pol_rst, b, r[u][0], r[u][1], r[u][2], r[u][3], r[u][4], r[u][5], r[u][6]);
                         // row of the ancestor L-2 steps back (new record = (b, r[0..6]))
                         int anc = j;
                         if (L == 3) anc = b;
                         else if (L > 3) anc = pick8(r[u], L - 4);
                         bp[k0 + u] = anc;
+                        if constexpr (HESS) {
+                            double al[4];
+                            sv_alpha_terms(s_k, xn[k0 + u], cur[u], yi, ylagH, al);
+                            const double c0 = al[0] + pa0[u].x, c1 = al[1] + pa0[u].y;
+                            const double c2 = al[2] + pa1[u].x, c3 = al[3] + pa1[u].y;
+                            st_keep_f64x4(&Rc[(size_t)j * RS + 1], pol_rst, c0, c1, c2, c3);
+                            st_stream_f64x4(&Pc[(size_t)j * RS + 1], pol_stream, c0, c1, c2, c3);
+                        }
                     }
                 }
             }
@@ -748,58 +795,32 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
         PROF_MARK(5);   // wait 1
         if (s_sc.abort_now) break;
         if constexpr (HESS) {
-            // alpha recursion (:361-390): cumulative alpha of the child = its own term + its parent's.  Q7: the
-            // "current" state is read through the flat layout: particles[t - 1 + ancestor] = sorted value `sl` of
-            // time tq (a table of the first SQ sorted values of every generation), or the unsorted new value `sl`
-            // (complete since barrier 1), or 0.  Q8: obs[t - LAG] wraps.
-            const double yi = a.obs[t], ylagH = obs_wrap(a.obs, t - L, NOBS);
-            const double4* CAp = a.CA + (size_t)((t - 1) % a.RPH) * N;
-            double4* CAt = a.CA + (size_t)(t % a.RPH) * N;
-            const PEntry* Pnow = a.P + (size_t)(t % RP) * N;
-            const int SQ = a.SQ;
-#pragma unroll
-            for (int k0 = 0; k0 < KPT; k0 += 4) {
-                double2 pa0[4], pa1[4];
-                double cur[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int i = (k0 + u) * GT + tid;
-                    pa0[u] = pa1[u] = make_double2(0.0, 0.0);
-                    cur[u] = 0.0;
-                    if (i < nc) {
-                        const int j = jb + i;
-                        const int b = min(max(pb[k0 + u], 0), N - 1);
-                        pa0[u] = __ldcg((const double2*)&CAp[b]);
-                        pa1[u] = __ldcg((const double2*)&CAp[b] + 1);
-                        const int ppos = __ldcg(&a.H[j]);
-                        const long long qq = (long long)t - 1 + ppos;
-                        const int tq = (int)(qq % NOBS), sl = (int)(qq / NOBS);
-                        if (tq < t) cur[u] = (sl < SQ) ? __ldcg(&a.xlow[(size_t)tq * SQ + sl]) : 0.0;
-                        else if (tq == t) cur[u] = (sl <= j && sl < N) ? __ldcg(&Pnow[sl].x) : 0.0;
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int i = (k0 + u) * GT + tid;
-                    if (i < nc) {
-                        const double x = xn[k0 + u], curr = cur[u];
-                        double sq = x - s_k.mu - s_k.phi * (curr - s_k.mu);
-                        const double ec = exp(-0.5 * curr);
-                        sq -= s_k.sr * ec * ylagH;
-                        const double a0 = s_k.q * sq * s_k.one_m_phi;
-                        const double a1 = s_k.q * sq * (curr - s_k.mu) * s_k.one_m_phi2;
-                        double a2 = sq;
-                        a2 += s_k.sr * ec * yi;
-                        a2 *= s_k.q * sq;
-                        a2 -= 1.0;
-                        double a3 = s_k.rho - s_k.q * s_k.rho * sq * sq;
-                        a3 += s_k.inv_sv * sq * ec * yi;
-                        double2* dst = (double2*)&CAt[jb + i];
-                        __stcg(dst, make_double2(a0 + pa0[u].x, a1 + pa0[u].y));
-                        __stcg(dst + 1, make_double2(a2 + pa1[u].x, a3 + pa1[u].y));
-                    }
+            // Q7 reads that fall into this generation (ancestor position = 1 mod NOBS: one child in NOBS): the unsorted
+            // new value `sl` (complete since barrier 1) if sl <= j, else 0; the parent row is looked up again
+            if (__any_sync(kFullMask, defer != 0u)) {
+                const double yi = a.obs[t], ylagH = obs_wrap(a.obs, t - L, NOBS);
+                const REntry* Rp = a.R + (size_t)((t - 1) & 1) * N * RS;
+                REntry* Rc = a.R + (size_t)(t & 1) * N * RS;
+                REntry* Pc = (REntry*)(a.P + (size_t)(t % RP) * N * RS);
+#pragma unroll 1
+                for (int kk = 0; kk < KPT; ++kk) {
+                    if (!((defer >> kk) & 1u)) continue;
+                    const int j = jb + kk * GT + tid;
+                    const int ppos = min(max(__ldcg(&a.H[j]), 0), N - 1);
+                    const int b = min(max(__ldcg(&a.perm[ppos]), 0), N - 1);
+                    const int sl = (int)(((unsigned)(t - 1) + (unsigned)ppos) / (unsigned)NOBS);
+                    const double curr = (sl <= j && sl < N) ? __ldcg(&a.P[((size_t)(t % RP) * N + sl) * RS].x) : 0.0;
+                    const double2 p0 = __ldcg((const double2*)&Rp[(size_t)b * RS + 1]);
+                    const double2 p1 = __ldcg((const double2*)&Rp[(size_t)b * RS + 1] + 1);
+                    double al[4];
+                    sv_alpha_terms(s_k, xn[kk], curr, yi, ylagH, al);
+                    const double c0 = al[0] + p0.x, c1 = al[1] + p0.y, c2 = al[2] + p1.x, c3 = al[3] + p1.y;
+                    __stcg((double2*)&Rc[(size_t)j * RS + 1], make_double2(c0, c1));
+                    __stcg((double2*)&Rc[(size_t)j * RS + 1] + 1, make_double2(c2, c3));
+                    st_stream_f64x4(&Pc[(size_t)j * RS + 1], pol_stream, c0, c1, c2, c3);
                 }
             }
+            PROF_MARK(14);   // deferred alpha terms (Hessian branch)
         }
 
         // --------------------------------------------------------------------------------------
@@ -1087,7 +1108,7 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
                     }
                     st_hint_b32(&a.perm[pstart + q], pol_keep, j);
                     if constexpr (HESS) {
-                        if (pstart + q < a.SQ) a.xlow[(size_t)t * a.SQ + pstart + q] = x;
+                        if (pstart + q < a.SQ) a.xlow[(size_t)(pstart + q) * NOBS + t] = x;
                     }
                     s_sh[q] = sh;
                     if (pstart + q == 0) a.xminv[t] = x;   // Q10/Q11: traj[t] = X_t[0]
@@ -1168,41 +1189,37 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
         if (t >= L && !(a.dbg & 4)) {
             // fixed-lag score terms (:445-470): weight x monomials of the payload of the ancestor
             // LAG-2 generations back (one random sector each), fixed summation order
-            const PEntry* Pg = a.P + (size_t)((t - (L - 2)) % RP) * N;
+            const PEntry* Pg = a.P + (size_t)((t - (L - 2)) % RP) * N * RS;
             double sc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-            // Hessian branch (:472-534): the cumulative alpha of the same ancestor (one more random sector) and
-            // the 20 hessian1 / hessian2 terms, weighted with the unnormalised weight (divided by S afterwards)
-            constexpr int SB = HESS ? 2 : 4;   // gathers in flight per thread
-            const double4* CAg = HESS ? a.CA + (size_t)((t - (L - 2)) % a.RPH) * N : nullptr;
-            double hacc[HESS ? 20 : 1];
+            // Hessian branch (:472-534): hessian1 is a polynomial in (curr - mu, sq, ey) with constant coefficients, so
+            // four more weighted monomials (ey, curr^2, curr ey, ey^2 -> hacc[0..3]) next to the five of the gradient
+            // give its ten entries afterwards (grid_hess_finish_kernel); hessian2 needs the cumulative alpha of the
+            // same ancestor (the second sector of its payload entry) and is accumulated entry by entry in a second
+            // pass (hacc[10..19]; the payloads come from L2 there).  Weights are the unnormalised ones (divided by S
+            // afterwards).  The isfinite guards of :521-534 are kept for hessian2; a non-finite particle value
+            // abandons the evaluation (phase A1), so hessian1 needs none.
+            double hm[HESS ? 4 : 1];
             if constexpr (HESS) {
 #pragma unroll
-                for (int i = 0; i < 20; ++i) hacc[i] = 0.0;
+                for (int i = 0; i < 4; ++i) hm[i] = 0.0;
             }
 #pragma unroll
-            for (int k0 = 0; k0 < KPT; k0 += SB) {
-                double pc[SB], psq[SB], pey[SB];
-                double2 al0[HESS ? SB : 1], al1[HESS ? SB : 1];
+            for (int k0 = 0; k0 < KPT; k0 += 4) {
+                double pc[4], psq[4], pey[4];
 #pragma unroll
-                for (int u = 0; u < SB; ++u) {
+                for (int u = 0; u < 4; ++u) {
                     const int q = (k0 + u) * GT + tid;
                     pc[u] = psq[u] = pey[u] = 0.0;
-                    if constexpr (HESS) al0[u] = al1[u] = make_double2(0.0, 0.0);
                     if (q < n) {
-                        const int row = min(max(s_ab[q], 0), N - 1);
-                        const PEntry* pp = &Pg[row];
+                        const PEntry* pp = &Pg[(size_t)min(max(s_ab[q], 0), N - 1) * RS];
                         double d3;
                         asm volatile("ld.global.cg.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
                                      : "=d"(pc[u]), "=d"(psq[u]), "=d"(pey[u]), "=d"(d3)
-                                     : "l"(pp), "l"(pol_pld));
-                        if constexpr (HESS) {
-                            al0[u] = __ldcg((const double2*)&CAg[row]);
-                            al1[u] = __ldcg((const double2*)&CAg[row] + 1);
-                        }
+                                     : "l"(pp), "l"(HESS ? pol_keep : pol_pld));
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < SB; ++u) {
+                for (int u = 0; u < 4; ++u) {
                     const int q = (k0 + u) * GT + tid;
                     if (q < n) {
                         const double wd = s_sh[q];
@@ -1213,44 +1230,100 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
                         sc[3] = fma(ws, psq[u], sc[3]);
                         sc[4] = fma(ws, pey[u], sc[4]);
                         if constexpr (HESS) {
-                            // g of :454-465 from (curr, sq, ey)
-                            const double sq = psq[u], ey = pey[u];
-                            double g[4];
-                            g[0] = s_k.q * sq * s_k.one_m_phi;
-                            g[1] = s_k.q * sq * (pc[u] - s_k.mu) * s_k.one_m_phi2;
-                            double g2 = sq;
-                            g2 += s_k.sr * ey;
-                            g2 *= s_k.q * sq;
-                            g2 -= 1.0;
-                            g[2] = g2;
-                            double g3 = s_k.rho - s_k.q * s_k.rho * sq * sq;
-                            g3 += s_k.inv_sv * sq * ey;
-                            g[3] = g3;
-                            const double al[4] = {al0[u].x, al0[u].y, al1[u].x, al1[u].y};
-                            sv_hessian_terms_ey(s_k, pc[u], ey, sq, g, al, wd, hacc);
+                            const double we = wd * pey[u], wc = wd * pc[u];
+                            hm[0] += we;
+                            hm[1] = fma(wc, pc[u], hm[1]);
+                            hm[2] = fma(wc, pey[u], hm[2]);
+                            hm[3] = fma(we, pey[u], hm[3]);
                         }
                     }
                 }
             }
-            if constexpr (HESS) {
-#pragma unroll
-                for (int i = 0; i < 20; ++i) hacc[i] = warp_sum(hacc[i]);
-            }
 #pragma unroll
             for (int i = 0; i < 5; ++i) sc[i] = warp_sum(sc[i]);
             __syncthreads();
+            if constexpr (HESS) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) hm[i] = warp_sum(hm[i]);
+            }
             if (lane == 0) {
 #pragma unroll
                 for (int i = 0; i < 5; ++i) s_red[32 * i + warp] = sc[i];
                 if constexpr (HESS) {
 #pragma unroll
-                    for (int i = 0; i < 20; ++i) s_redH[32 * i + warp] = hacc[i];
+                    for (int i = 0; i < 4; ++i) s_redH[32 * i + warp] = hm[i];
+                }
+            }
+            if constexpr (HESS) {
+                constexpr int SB = PMMH_GRID_HESS_SB;   // 64-byte entries in flight per thread
+                double h2[10];
+#pragma unroll
+                for (int i = 0; i < 10; ++i) h2[i] = 0.0;
+#pragma unroll
+                for (int k0 = 0; k0 < KPT; k0 += SB) {
+                    double pc[SB], psq[SB], pey[SB];
+                    double2 al0[SB], al1[SB];
+#pragma unroll
+                    for (int u = 0; u < SB; ++u) {
+                        const int q = (k0 + u) * GT + tid;
+                        pc[u] = psq[u] = pey[u] = 0.0;
+                        al0[u] = al1[u] = make_double2(0.0, 0.0);
+                        if (q < n) {
+                            const PEntry* pp = &Pg[(size_t)min(max(s_ab[q], 0), N - 1) * RS];
+                            double d3;
+                            asm volatile("ld.global.cg.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
+                                         : "=d"(pc[u]), "=d"(psq[u]), "=d"(pey[u]), "=d"(d3)
+                                         : "l"(pp), "l"(pol_pld));
+                            asm volatile("ld.global.cg.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
+                                         : "=d"(al0[u].x), "=d"(al0[u].y), "=d"(al1[u].x), "=d"(al1[u].y)
+                                         : "l"(pp + 1), "l"(pol_pld));
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < SB; ++u) {
+                        const int q = (k0 + u) * GT + tid;
+                        if (q < n) {
+                            const double wd = s_sh[q];
+                            const double sq = psq[u], ey = pey[u];
+                            // g of :454-465 from (curr, sq, ey)
+                            const double g0 = s_k.q * sq * s_k.one_m_phi;
+                            const double g1 = s_k.q * sq * (pc[u] - s_k.mu) * s_k.one_m_phi2;
+                            double g2 = sq;
+                            g2 += s_k.sr * ey;
+                            g2 *= s_k.q * sq;
+                            g2 -= 1.0;
+                            double g3 = s_k.rho - s_k.q * s_k.rho * sq * sq;
+                            g3 += s_k.inv_sv * sq * ey;
+                            const double a0 = al0[u].x, a1 = al0[u].y, a2 = al1[u].x, a3 = al1[u].y;
+                            double h;   // :505-519 (the '*' typos of :513,514,517 kept)
+#define HESS2_ADD(slot, expr)                           \
+    h = (expr);                                         \
+    if (isfinite(h)) h2[slot - 10] += h * wd;
+                            HESS2_ADD(10, g0 * g0 + 2.0 * a0 * g0)
+                            HESS2_ADD(11, g0 * g1 + a0 * g1 + a1 * g0)
+                            HESS2_ADD(12, g0 * g2 + a0 * g2 + a2 * g0)
+                            HESS2_ADD(13, g0 * g3 + a0 * g3 + a3 * g0)
+                            HESS2_ADD(14, g1 * g1 + 2.0 * a1 * g1)
+                            HESS2_ADD(15, g1 * g2 + a1 * g2 * a2 * g1)
+                            HESS2_ADD(16, g1 * g3 + a1 * g3 * a3 * g1)
+                            HESS2_ADD(17, g2 * g2 + 2.0 * a2 * g2)
+                            HESS2_ADD(18, g2 * g3 + a2 * g3 * a3 * g2)
+                            HESS2_ADD(19, g3 * g3 + 2.0 * a3 * g3)
+#undef HESS2_ADD
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 10; ++i) h2[i] = warp_sum(h2[i]);
+                if (lane == 0) {
+#pragma unroll
+                    for (int i = 0; i < 10; ++i) s_redH[32 * (10 + i) + warp] = h2[i];
                 }
             }
             __syncthreads();
             if constexpr (HESS) {
                 for (int k = warp; k < 20; k += NW) {   // a warp sums component k over the warps (fixed order)
-                    const double v = warp_sum((lane < NW) ? s_redH[32 * k + lane] : 0.0);
+                    const double v = (k < 4 || k >= 10) ? warp_sum((lane < NW) ? s_redH[32 * k + lane] : 0.0) : 0.0;
                     if (lane == 0) a.psumH[((size_t)t * G + c) * 20 + k] = v;
                 }
             }
@@ -1319,7 +1392,8 @@ __global__ void __launch_bounds__(256) grid_tail_kernel(GridArgs a, const double
     const double ST = sums[(size_t)T * 8], Si = sums[(size_t)i * 8];
     const double* shT = a.shring + (size_t)(T % L) * N;
     const double* shi = a.shring + (size_t)(i % L) * N;
-    const REntry* Rt = a.R + (size_t)(T & 1) * N;
+    const int RS = a.RS;
+    const REntry* Rt = a.R + (size_t)(T & 1) * N * RS;
     double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     double hacc[HESS ? 20 : 1];
     if constexpr (HESS) {
@@ -1338,8 +1412,8 @@ __global__ void __launch_bounds__(256) grid_tail_kernel(GridArgs a, const double
         } else {
             // entry of the ancestor idx-1 steps back holds (next = its value, curr = its parent's value)
             const int m = idx - 1;
-            const int row = (m == 0) ? b : min(max(Rt[b].a[m - 1], 0), N - 1);
-            const PEntry pe = a.P[(size_t)((T - m) % RP) * N + row];
+            const int row = (m == 0) ? b : min(max(Rt[(size_t)b * RS].a[m - 1], 0), N - 1);
+            const PEntry pe = a.P[((size_t)((T - m) % RP) * N + row) * RS];
             curr = pe.c;
             const double pe_n = pe.x;
             acc[0] += wT * curr;
@@ -1351,9 +1425,9 @@ __global__ void __launch_bounds__(256) grid_tail_kernel(GridArgs a, const double
             for (int q = 0; q < 4; ++q) acc[1 + q] += g[q] * wi;
             if constexpr (HESS) {
                 const int m2 = L - 2;
-                const int row2 = (m2 == 0) ? b : min(max(Rt[b].a[m2 - 1], 0), N - 1);
-                const double4 a4 = a.CA[(size_t)((T - m2) % a.RPH) * N + row2];
-                const double al[4] = {a4.x, a4.y, a4.z, a4.w};
+                const int row2 = (m2 == 0) ? b : min(max(Rt[(size_t)b * RS].a[m2 - 1], 0), N - 1);
+                const double* a4 = (const double*)&a.P[((size_t)((T - m2) % RP) * N + row2) * RS + 1];
+                const double al[4] = {a4[0], a4[1], a4[2], a4[3]};
                 sv_hessian_terms_e(k, curr, ec, exp(-curr), sq, ylagH, g, al, wi, hacc);
             }
         }
@@ -1383,15 +1457,52 @@ __global__ void __launch_bounds__(640) grid_reduceH_kernel(const double* __restr
 __global__ void __launch_bounds__(32) grid_hess_finish_kernel(const GridCtrl* __restrict__ ctrl,
                                                               const double* __restrict__ sums,
                                                               const double* __restrict__ sumsH,
-                                                              const double* __restrict__ partH, int nblk, int nobs,
+                                                              const double* __restrict__ partH,
+                                                              const double* __restrict__ params, int nblk, int nobs,
                                                               int lag, double* __restrict__ hess1,
                                                               double* __restrict__ hess2) {
     __shared__ double tri[20];
     const int k = threadIdx.x;
     if (ctrl->status != 0) return;   // abandoned: the general kernel writes the outputs
     if (k < 20) {
+        SvConst c;
+        sv_const_init(c, params);
         double h = 0.0;
-        for (int t = lag; t < nobs; ++t) h += sumsH[(size_t)t * 20 + k] / sums[(size_t)t * 8];
+        for (int t = lag; t < nobs; ++t) {
+            const double* sm = sums + (size_t)t * 8;
+            const double* sh = sumsH + (size_t)t * 20;
+            const double S = sm[0];
+            double v;
+            if (k >= 10) {
+                v = sh[k];
+            } else {
+                // weighted monomials in cm = curr - mu, sq, ey (sums[t][2..6] = c, sq, sq c, sq^2, sq ey; sumsH[t][0..3] =
+                // ey, c^2, c ey, ey^2)
+                const double A = c.one_m_phi2, B = c.one_m_phi;
+                const double Mc = sm[2] - c.mu * S, Ms = sm[3], Me = sh[0];
+                const double Mcc = sh[1] - 2.0 * c.mu * sm[2] + c.mu * c.mu * S;
+                const double Mcs = sm[4] - c.mu * sm[3], Mce = sh[2] - c.mu * sh[0];
+                const double Mss = sm[5], Mse = sm[6], Mee = sh[3];
+                switch (k) {
+                    case 0: v = -c.q * (B * B) * S; break;                                              // (0,0)
+                    case 1: v = -c.q * A * (B * Mc + Ms); break;                                        // (0,1)
+                    case 2: v = -2.0 * B * Ms - c.q * B * c.sr * Mse; break;                            // (0,2)
+                    case 3: v = 2.0 * c.q * c.rho * B * Ms - c.inv_sv2 * B * c.sigmav * Me; break;      // (0,3)
+                    case 4: v = -c.q * A * (2.0 * c.phi * Mcs + A * Mcc); break;                        // (1,1)
+                    case 5: v = -c.q * A * (2.0 * Mcs + c.sr * Mce); break;                             // (1,2)
+                    case 6: v = c.q * A * (2.0 * c.rho * Mcs - c.sigmav * c.rho_term * Mce); break;     // (1,3)
+                    case 7: v = -2.0 * c.q * Mss - c.q * c.sr * Mse - c.q * (c.sr * c.sr) * Mee; break; // (2,2)
+                    case 8:                                                                              // (2,3)
+                        v = 2.0 * c.q * c.rho * Mss + (2.0 * (c.rho * c.rho) * c.q * c.sigmav + c.inv_sv) * Mse - c.rho * Mee;
+                        break;
+                    default:                                                                             // (3,3), "sigmav*(-2)" typo kept
+                        v = c.rho_term * S - 2.0 * c.q * (c.rho * c.rho) * Mss + 2.0 * c.sigmav * Mss +
+                            2.0 * c.inv_sv * c.rho * Mse - c.rho_term * Mee;
+                        break;
+                }
+            }
+            h += v / S;
+        }
         for (int irel = 0; irel < lag - 1; ++irel)
             for (int q = 0; q < nblk; ++q) h += partH[((size_t)irel * nblk + q) * 20 + k];
         tri[k] = h;
@@ -1475,7 +1586,7 @@ __global__ void grid_finish_kernel(const GridCtrl* __restrict__ ctrl, const doub
 
 struct GridLayout {
     size_t ctrl, ghist, tilecnt, tinfo, H, XE, perm, R, P, psum, shiftv, xminv, shring, parentpos, sums,
-        tailpart, tail, info, CA, xlow, psumH, sumsH, tailpartH, total;
+        tailpart, tail, info, xlow, psumH, sumsH, tailpartH, total;
     int RP, nblk, SQ;
 };
 
@@ -1495,8 +1606,9 @@ GridLayout grid_layout(int nobs, int n, int lag, int G, int hist, int hess) {
     L.H = o;         o += al256(N * 4);
     L.XE = o;        o += al256(N * 16);
     L.perm = o;      o += al256(N * 4);
-    L.R = o;         o += al256(2 * N * 32);
-    L.P = o;         o += al256((size_t)L.RP * N * 32);
+    const size_t RS = hess ? 2 : 1;   // Hessian branch: 64-byte entries (record | alpha, payload | alpha)
+    L.R = o;         o += al256(2 * N * 32 * RS);
+    L.P = o;         o += al256((size_t)L.RP * N * 32 * RS);
     L.psum = o;      o += al256((size_t)nobs * G * 8 * 8);
     L.shiftv = o;    o += al256((size_t)nobs * 8);
     L.xminv = o;     o += al256((size_t)nobs * 8);
@@ -1506,10 +1618,9 @@ GridLayout grid_layout(int nobs, int n, int lag, int G, int hist, int hess) {
     L.tailpart = o;  o += al256((size_t)lag * L.nblk * 8 * 8);
     L.tail = o;      o += al256((size_t)lag * 8 * 8);
     L.info = o;      o += al256(8 * 8);
-    // Hessian branch: cumulative alpha ring (32 B per particle and generation), the first SQ sorted values of every
-    // generation (Q7: particles[i - 1 + ancestor] read through the flat layout), per-tile / per-step sums
+    // Hessian branch: the first SQ sorted values of every generation (Q7: particles[i - 1 + ancestor] read through
+    // the flat layout), per-tile / per-step sums
     L.SQ = hess ? (nobs + n - 2) / nobs + 1 : 1;
-    L.CA = o;        o += al256(hess ? (size_t)L.RP * N * 32 : 0);
     L.xlow = o;      o += al256(hess ? (size_t)nobs * L.SQ * 8 : 0);
     L.psumH = o;     o += al256(hess ? (size_t)nobs * G * 20 * 8 : 0);
     L.sumsH = o;     o += al256(hess ? (size_t)nobs * 20 * 8 : 0);
@@ -1596,11 +1707,10 @@ int sv_grid_run(const double* d_obs, const double* d_params, const double* d_rvr
     a.xminv = (double*)(ws + L.xminv);
     a.shring = (double*)(ws + L.shring);
     a.parentpos = (int*)(ws + L.parentpos);
-    a.CA = (double4*)(ws + L.CA);
     a.xlow = (double*)(ws + L.xlow);
     a.psumH = (double*)(ws + L.psumH);
     a.SQ = L.SQ;
-    a.RPH = L.RP;
+    a.RS = hess ? 2 : 1;
     a.Xhist = d_xh;
     a.Ahist = d_ah;
     a.prof = d_prof;
@@ -1653,7 +1763,7 @@ int sv_grid_run(const double* d_obs, const double* d_params, const double* d_rvr
         double* tailpartH = (double*)(ws + L.tailpartH);
         grid_reduceH_kernel<<<nobs, 640, 0, st>>>(a.psumH, G, lag, sumsH);
         grid_tail_kernel<true><<<dim3(L.nblk, lag), 256, 0, st>>>(a, sums, tailpart, tailpartH, L.nblk);
-        grid_hess_finish_kernel<<<1, 32, 0, st>>>(a.ctrl, sums, sumsH, tailpartH, L.nblk, nobs, lag, d_hess1, d_hess2);
+        grid_hess_finish_kernel<<<1, 32, 0, st>>>(a.ctrl, sums, sumsH, tailpartH, d_params, L.nblk, nobs, lag, d_hess1, d_hess2);
     } else {
         grid_tail_kernel<false><<<dim3(L.nblk, lag), 256, 0, st>>>(a, sums, tailpart, nullptr, L.nblk);
     }

@@ -258,6 +258,25 @@ __device__ __forceinline__ void sv_hessian_terms_ey(const SvConst& c, double cur
     }
 }
 
+// alpha recursion, own term of a child (:361-390): x = the new state, curr = the "current" state as the reference
+// reads it (Q7), yi = obs[i], yl = obs[i - LAG] (Q8)
+__device__ __forceinline__ void sv_alpha_terms(const SvConst& c, double x, double curr, double yi, double yl,
+                                               double al[4]) {
+    double sq = x - c.mu - c.phi * (curr - c.mu);
+    const double ec = exp(-0.5 * curr);
+    sq -= c.sr * ec * yl;
+    al[0] = c.q * sq * c.one_m_phi;
+    al[1] = c.q * sq * (curr - c.mu) * c.one_m_phi2;
+    double a2 = sq;
+    a2 += c.sr * ec * yi;
+    a2 *= c.q * sq;
+    a2 -= 1.0;
+    al[2] = a2;
+    double a3 = c.rho - c.q * c.rho * sq * sq;
+    a3 += c.inv_sv * sq * ec * yi;
+    al[3] = a3;
+}
+
 __device__ __forceinline__ double obs_wrap(const double* obs, int k, int nobs) {
     return obs[k < 0 ? k + nobs : k];   // Cython memoryview wraparound (Q8)
 }

@@ -17,6 +17,7 @@ from pmmh_qn_b200 import kernels as K, _lib
 logn = int(sys.argv[1])
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
 ctas = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+HESS = bool(os.environ.get("PMMH_PROBE_HESS"))   # the Hessian branch
 dev = torch.device("cuda:0")
 n, nobs = 1 << logn, T + 1
 obs = torch.from_numpy(gi.sv_obs(nobs)).to(dev)
@@ -27,13 +28,13 @@ u = torch.randn((nobs, n), dtype=torch.float64, device=dev, generator=g)
 rvr = torch.rand((nobs,), dtype=torch.float64, device=dev, generator=g)
 K.set_sv_algorithm(6)
 ws = K.Workspace()
-out = K.flps_sv_corr(obs, params, rvr, u, lag=10, workspace=ws, ctas_per_problem=ctas)
+out = K.flps_sv_corr(obs, params, rvr, u, lag=10, workspace=ws, ctas_per_problem=ctas, compute_hessian=HESS)
 torch.cuda.synchronize()
 buf = torch.zeros((160, 16), dtype=torch.int64, device=dev)
 _lib.load().pmmh_sv_debug_profile(ctypes.c_void_p(buf.data_ptr()))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
-out = K.flps_sv_corr(obs, params, rvr, u, lag=10, workspace=ws, ctas_per_problem=ctas)
+out = K.flps_sv_corr(obs, params, rvr, u, lag=10, workspace=ws, ctas_per_problem=ctas, compute_hessian=HESS)
 e1.record()
 torch.cuda.synchronize()
 _lib.load().pmmh_sv_debug_profile(None)
@@ -42,7 +43,7 @@ d = out["diag"][0].cpu().numpy()
 c = buf.cpu().numpy().astype(np.float64)
 c = c[c.sum(axis=1) > 0]
 names = ["C:ranges+fill", "zero hist", "wait 4", "A1:children+hist", "A1:records", "wait 1", "A2:scan+scatter",
-         "zero+prefetch", "wait 2", "B:bin sort", "B:rank+wts+score", "B:scan+publish", "wait 3", "score terms"]
+         "zero+prefetch", "wait 2", "B:bin sort", "B:rank+wts+score", "B:scan+publish", "wait 3", "score terms", "alpha (Hessian)"]
 clk = c.sum(axis=1).mean() / (ms * 1e-3) / 1e6   # MHz seen by clock64
 print(json.dumps({"N": n, "T": T, "ms": ms, "us_per_step": ms * 1e3 / T, "particle_steps_per_s": n * T / ms * 1e3,
                   "kernel": int(d[6]), "status": int(d[2]), "info": int(d[7]), "near_ties": int(d[0]),
