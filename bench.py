@@ -638,6 +638,33 @@ def run_ours(args, rank, world, local_rank):
     finally:
         K.set_sv_algorithm(0)
 
+    # ---- the same workload with the Hessian branch (compute_hessian = 1, what the QN sampler's
+    # 'hessian_estimate: kalman' style settings call), automatic kernel selection: the grid kernel's second
+    # instantiation.  Algorithmic bytes per particle-step: the 96 B of the gradient path + 64 B (cumulative alpha
+    # written next to the record and read back by the children and by the descendants lag - 2 steps later)
+    with_hessian = None
+    try:
+        wsh = K.Workspace()
+        oh = K.flps_sv_corr(obs, params, rvr, u, lag=LAG, compute_hessian=True, workspace=wsh)   # warm-up
+        torch.cuda.synchronize()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record()
+        for _ in range(2):
+            oh = K.flps_sv_corr(obs, params, rvr, u, lag=LAG, compute_hessian=True, workspace=wsh)
+        h1.record()
+        torch.cuda.synchronize()
+        msh = h0.elapsed_time(h1) / 2
+        with_hessian = {"kernel": KERNEL_NAMES.get(int(oh["diag"][0, 6]), "?"), "ms_per_step": msh,
+                        "value": n * T_STEPS / (msh * 1e-3), "unit": UNIT + " (this rank)",
+                        "status": int(oh["diag"][0, 2]),
+                        "rel_diff_log_like": abs(float(oh["log_like"][0]) - ll) / abs(ll),
+                        "hess1_trace": float(oh["hess1"][0].diagonal().sum()),
+                        "roofline": {"bound": "hbm", "achieved": 160.0 * n * T_STEPS / (msh * 1e-3) / 1e9,
+                                     "unit": "GB/s", "bytes_per_particle_step": 160}}
+        del wsh, oh
+    except Exception as e:   # reported, never silently replaced
+        with_hessian = {"error": str(e)[:200]}
+
     # ---- launches of one step, counted (CUPTI activity trace of one extra, untimed step)
     launches_per_step, launch_top = count_launches(step)
 
@@ -793,6 +820,10 @@ def run_ours(args, rank, world, local_rank):
                 line[key] = blk
         if alt is not None:
             line["alt_kernel_same_workload"] = alt
+        if with_hessian is not None:
+            if "roofline" in with_hessian:
+                with_hessian["roofline"].update(peak=peak, frac=with_hessian["roofline"]["achieved"] / peak)
+            line["same_workload_with_hessian"] = with_hessian
         if split_line is not None:
             line["config5_split_pf"] = split_line
         if world == 1 and not args.no_cpu_baseline:
