@@ -334,6 +334,34 @@ __device__ __forceinline__ int block_excl_max_int(int v, int init, int* s_w, int
     return max(woff, ex);
 }
 
+// Hessian branch: the alpha terms whose Q7 read falls into the generation being built (listed by the records pass),
+// one thread per entry
+__device__ __forceinline__ void deferred_alpha_pass(const GridArgs& a, const SvConst& k, const int2* list, int nd, int t,
+                                                    int jb, int tid, int nthreads, unsigned long long pol_rld,
+                                                    unsigned long long pol_rst, unsigned long long pol_stream) {
+    const int N = a.N, NOBS = a.NOBS, RS = a.RS;
+    const double yi = a.obs[t], ylagH = obs_wrap(a.obs, t - a.LAG, NOBS);
+    const REntry* Rp = a.R + (size_t)((t - 1) & 1) * N * RS;
+    REntry* Rc = a.R + (size_t)(t & 1) * N * RS;
+    PEntry* Pt = a.P + (size_t)(t % a.RP) * N * RS;
+    for (int d = tid; d < nd; d += nthreads) {
+        const int2 e = list[d];
+        const int j = jb + e.x;
+        const int b = min(max(e.y, 0), N - 1);
+        const int ppos = min(max(__ldcg(&a.H[j]), 0), N - 1);
+        const int sl = (int)(((unsigned)(t - 1) + (unsigned)ppos) / (unsigned)NOBS);
+        const double x = __ldcg(&Pt[(size_t)j * RS].x);
+        const double curr = (sl <= j && sl < N) ? __ldcg(&Pt[(size_t)sl * RS].x) : 0.0;
+        double p0, p1, p2, p3;
+        ld_f64x4(&Rp[(size_t)b * RS + 1], pol_rld, p0, p1, p2, p3);
+        double al[4];
+        sv_alpha_terms(k, x, curr, yi, ylagH, al);
+        const double c0 = al[0] + p0, c1 = al[1] + p1, c2 = al[2] + p2, c3 = al[3] + p3;
+        st_keep_f64x4(&Rc[(size_t)j * RS + 1], pol_rst, c0, c1, c2, c3);
+        st_stream_f64x4((REntry*)&Pt[(size_t)j * RS] + 1, pol_stream, c0, c1, c2, c3);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
@@ -363,7 +391,8 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
     double* s_sh = (double*)(smem + 131072);           // [kCap] unnormalised weights, sorted order
     int* s_sub = (int*)(smem + 196608);                // [kNSB] sub-bin counters, then first positions
     int* s_ub = s_jb;                                  // [kCap] child range ends (phase C)
-    // phase A view
+    // phase A view (Hessian branch: list of deferred alpha terms = (child, parent row) pairs in the s_jb / s_ab region)
+    int2* s_deflist = (int2*)(smem + 65536);         // [kCap]
     int* s_fhist = (int*)smem;                         // [kNF] histogram of this CTA's children
     unsigned short* s_tileof = (unsigned short*)(smem + 32768);   // [kNF] tile of a histogram bin
 
@@ -375,6 +404,7 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
     __shared__ double s_redH[HESS ? 20 * 32 : 1];   // Hessian branch: warp sums of the 20 hessian1 / hessian2 terms
     __shared__ int s_wi[32];
     __shared__ long long s_prof[kProf];
+    __shared__ int s_ndef;   // Hessian branch: length of the list of deferred alpha terms
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = blockIdx.x, G = a.G, N = a.N, NOBS = a.NOBS, L = a.LAG, Wc = a.Wc, RP = a.RP;
@@ -708,6 +738,7 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
             if (bad) GRID_FLAG(2);
             if (orphan) GRID_FLAG(4);
         }
+        if (HESS && tid == 0) s_ndef = 0;
         __syncthreads();
         {
             int* gh = a.ghist + ((size_t)par * kNCopy + (c % kNCopy)) * kNF;
@@ -720,7 +751,6 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
         }
         PROF_MARK(3);   // A1 children+hist
         GRID_ARRIVE();   // ---- barrier 1: global histogram complete
-        unsigned defer = 0;   // Hessian branch: children whose Q7 read needs generation t complete (bit kk)
         if (!(a.dbg & 1)) {
             // genealogy records (only feed outputs): child = (parent row, parent's ancestors 1..7)
             const REntry* Rp = a.R + (size_t)((t - 1) & 1) * N * RS;
@@ -754,7 +784,7 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
                             const unsigned qq = (unsigned)(t - 1) + (unsigned)__ldcg(&a.H[jb + i]);
                             const unsigned sl = qq / (unsigned)NOBS, tq = qq - sl * (unsigned)NOBS;
                             if ((int)tq < t) cur[u] = ((int)sl < a.SQ) ? __ldcg(&a.xlow[(size_t)sl * NOBS + tq]) : 0.0;
-                            else if ((int)tq == t) defer |= 1u << (k0 + u);
+                            else if ((int)tq == t) s_deflist[atomicAdd(&s_ndef, 1)] = make_int2(i, bp[k0 + u]);
                         }
                     }
                 }
@@ -794,33 +824,15 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
         GRID_WAIT();
         PROF_MARK(5);   // wait 1
         if (s_sc.abort_now) break;
+        // Hessian branch, Q7 reads that fall into this generation (ancestor position = 1 mod NOBS: one child in NOBS):
+        // the unsorted new value `sl` (complete since barrier 1) if sl <= j, else 0.  The records pass listed these
+        // children; one thread per entry redoes the term after the arrive of barrier 2 (outputs only: read by the
+        // children of the next step and by the score terms LAG-2 steps later; LAG = 2: before the arrive)
         if constexpr (HESS) {
-            // Q7 reads that fall into this generation (ancestor position = 1 mod NOBS: one child in NOBS): the unsorted
-            // new value `sl` (complete since barrier 1) if sl <= j, else 0; the parent row is looked up again
-            if (__any_sync(kFullMask, defer != 0u)) {
-                const double yi = a.obs[t], ylagH = obs_wrap(a.obs, t - L, NOBS);
-                const REntry* Rp = a.R + (size_t)((t - 1) & 1) * N * RS;
-                REntry* Rc = a.R + (size_t)(t & 1) * N * RS;
-                REntry* Pc = (REntry*)(a.P + (size_t)(t % RP) * N * RS);
-#pragma unroll 1
-                for (int kk = 0; kk < KPT; ++kk) {
-                    if (!((defer >> kk) & 1u)) continue;
-                    const int j = jb + kk * GT + tid;
-                    const int ppos = min(max(__ldcg(&a.H[j]), 0), N - 1);
-                    const int b = min(max(__ldcg(&a.perm[ppos]), 0), N - 1);
-                    const int sl = (int)(((unsigned)(t - 1) + (unsigned)ppos) / (unsigned)NOBS);
-                    const double curr = (sl <= j && sl < N) ? __ldcg(&a.P[((size_t)(t % RP) * N + sl) * RS].x) : 0.0;
-                    const double2 p0 = __ldcg((const double2*)&Rp[(size_t)b * RS + 1]);
-                    const double2 p1 = __ldcg((const double2*)&Rp[(size_t)b * RS + 1] + 1);
-                    double al[4];
-                    sv_alpha_terms(s_k, xn[kk], curr, yi, ylagH, al);
-                    const double c0 = al[0] + p0.x, c1 = al[1] + p0.y, c2 = al[2] + p1.x, c3 = al[3] + p1.y;
-                    __stcg((double2*)&Rc[(size_t)j * RS + 1], make_double2(c0, c1));
-                    __stcg((double2*)&Rc[(size_t)j * RS + 1] + 1, make_double2(c2, c3));
-                    st_stream_f64x4(&Pc[(size_t)j * RS + 1], pol_stream, c0, c1, c2, c3);
-                }
+            if (L == 2) {
+                __syncthreads();
+                deferred_alpha_pass(a, s_k, s_deflist, min(s_ndef, kCap), t, jb, tid, GT, pol_rld, pol_rst, pol_stream);
             }
-            PROF_MARK(14);   // deferred alpha terms (Hessian branch)
         }
 
         // --------------------------------------------------------------------------------------
@@ -942,6 +954,10 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
         }
         PROF_MARK(6);   // A2 scan+scatter
         GRID_ARRIVE();   // ---- barrier 2: mailboxes complete
+        if constexpr (HESS) {
+            if (L != 2) deferred_alpha_pass(a, s_k, s_deflist, min(s_ndef, kCap), t, jb, tid, GT, pol_rld, pol_rst, pol_stream);
+            PROF_MARK(14);   // deferred alpha terms (Hessian branch)
+        }
         for (int b = tid; b < kNSB; b += GT) s_sub[b] = 0;
         if (warp == 0 && nc > 0) {
             // the generation the fixed-lag terms of this step gather from, and the next step's slice of u -> L2
