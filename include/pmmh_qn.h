@@ -291,6 +291,13 @@ int pmmh_svsplit_plan(void* d_ws, size_t ws_bytes, long long cap_particles, long
 int pmmh_svsplit_pack(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
                       const int* d_perm, const double* d_rec, double* d_send, double* d_send_keys,
                       void* stream);
+/* the same with the children that stay on this rank written straight into this rank's receive buffers
+ * (d_self_rec = the d_rec_new pmmh_svsplit_sort will read, d_self_keys = its d_keys, NULL without
+ * d_send_keys) at their arrival slots [sum of the receive counts of the ranks in front, ...): the exchange
+ * that follows moves only what crosses ranks; all other send / receive offsets are unchanged */
+int pmmh_svsplit_pack_direct(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
+                             const int* d_perm, const double* d_rec, double* d_send, double* d_send_keys,
+                             double* d_self_rec, double* d_self_keys, void* stream);
 /* argsort of the arrivals (:392-424): d_xs / d_perm of the new generation.  The values come from
  * d_keys [n_arrivals] if given, else from column 0 of d_rec_new; keys_are_children = 1 (world == 1
  * only): arrival e is child e, its value is read from the dense child array in the workspace */

@@ -67,6 +67,7 @@ SIGNATURES = {
                                       c_ull, c_ull, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "pmmh_svsplit_plan": (c_int, [c_vp, c_size, c_ll, c_ll, c_int, c_vp, c_vp, c_vp]),
     "pmmh_svsplit_pack": (c_int, [c_vp, c_size, c_ll, c_ll, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "pmmh_svsplit_pack_direct": (c_int, [c_vp, c_size, c_ll, c_ll, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "pmmh_svsplit_sort": (c_int, [c_vp, c_size, c_ll, c_ll, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),
     "pmmh_svsplit_normalise": (c_int, [c_vp, c_int, c_vp, c_vp, c_vp]),
     "pmmh_svsplit_tail": (c_int, [c_vp, c_size, c_ll, c_ll, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp,

@@ -759,10 +759,18 @@ __global__ void __launch_bounds__(1024) split_plan_kernel(SplitState* __restrict
 __global__ void __launch_bounds__(256) split_pack_kernel(
     SplitState* __restrict__ st, const double* __restrict__ xc, const int* __restrict__ pa,
     const unsigned short* __restrict__ cb, const int* __restrict__ dest, const int* __restrict__ perm,
-    const double* __restrict__ rec, double* __restrict__ send, double* __restrict__ send_keys) {
+    const double* __restrict__ rec, double* __restrict__ send, double* __restrict__ send_keys,
+    double* __restrict__ self_rec, double* __restrict__ self_keys) {
     __shared__ int s_cnt[kMaxWorld], s_base[kMaxWorld];
     const int tid = threadIdx.x, lane = tid & 31;
     const int nc = st->nc, G = st->world, LR = st->LR;
+    // self_rec / self_keys (optional): the receive buffers of THIS rank.  Children that stay on this rank are
+    // written straight to their arrival slots (behind the arrivals from the ranks in front), so the exchange
+    // moves only what crosses ranks.  Slots of such children are encoded as -2 - arrival slot.
+    long long self_off = 0;
+    if (self_rec)
+        for (int r = 0; r < st->rank; ++r) self_off += st->recv_cnt[r];
+    const int me = self_rec ? st->rank : -1;
     for (long long base = (long long)blockIdx.x * 256; base < nc; base += (long long)gridDim.x * 256) {
         const long long k = base + tid;
         const bool valid = k < nc;
@@ -780,13 +788,19 @@ __global__ void __launch_bounds__(256) split_pack_kernel(
             __syncthreads();
             if (tid < G && s_cnt[tid] > 0) s_base[tid] = atomicAdd(&st->cursor[tid], s_cnt[tid]);
             __syncthreads();
-            if (valid) slot = st->send_off[d] + s_base[d] + r;
+            if (valid) slot = (d == me) ? -2 - (self_off + s_base[d] + r) : st->send_off[d] + s_base[d] + r;
             __syncthreads();
         }
         const double xv = valid ? xc[k] : 0.0;
-        if (send_keys && valid) send_keys[slot] = xv;   // values alone, for the receiver's sort
+        if (send_keys && valid) {   // values alone, for the receiver's sort
+            if (slot >= 0) send_keys[slot] = xv;
+            else if (self_keys) self_keys[-2 - slot] = xv;
+        }
         if (LR == 1) {
-            if (valid) send[slot] = xv;
+            if (valid) {
+                if (slot >= 0) send[slot] = xv;
+                else self_rec[-2 - slot] = xv;
+            }
             continue;
         }
         // the warp copies its 32 records together: consecutive lanes move consecutive doubles of
@@ -798,6 +812,7 @@ __global__ void __launch_bounds__(256) split_pack_kernel(
             const long long rc = __shfl_sync(kFullMask, row, cc);
             const double xvc = __shfl_sync(kFullMask, xv, cc);
             if (sc >= 0) send[(size_t)sc * LR + m] = (m == 0) ? xvc : rec[(size_t)rc * LR + m - 1];
+            else if (sc <= -2) self_rec[(size_t)(-2 - sc) * LR + m] = (m == 0) ? xvc : rec[(size_t)rc * LR + m - 1];
         }
     }
 }
@@ -1660,7 +1675,28 @@ int pmmh_svsplit_pack(void* d_ws, size_t ws_bytes, long long cap_particles, long
     split_pack_kernel<<<148 * 8, 256, 0, st>>>(state, (const double*)(ws + L.xc), (const int*)(ws + L.pa),
                                                (const unsigned short*)(ws + L.cb),
                                                (const int*)(ws + L.dest), d_perm, d_rec, d_send,
-                                               d_send_keys);
+                                               d_send_keys, nullptr, nullptr);
+    SPLIT_CUDA(cudaGetLastError());
+    return PMMH_OK;
+}
+
+// pmmh_svsplit_pack with the children that stay on this rank written straight into this rank's receive buffers
+// (d_self_rec = the d_rec_new the sort will read, d_self_keys = its d_keys or NULL) at their arrival slots; the
+// exchange that follows skips the self part (send / receive offsets of the other ranks are unchanged)
+int pmmh_svsplit_pack_direct(void* d_ws, size_t ws_bytes, long long cap_particles, long long cap_children,
+                             const int* d_perm, const double* d_rec, double* d_send, double* d_send_keys,
+                             double* d_self_rec, double* d_self_keys, void* stream) {
+    Layout L = Layout();
+    if (int rc = check_ws(d_ws, ws_bytes, cap_particles, cap_children, &L)) return rc;
+    if (!d_self_rec) return pmmh::set_error(PMMH_ERR_INVALID, "pmmh_svsplit_pack_direct: d_self_rec is required");
+    if (d_send_keys && !d_self_keys) return pmmh::set_error(PMMH_ERR_INVALID, "pmmh_svsplit_pack_direct: d_self_keys is required with d_send_keys");
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)d_ws;
+    SplitState* state = (SplitState*)(ws + L.state);
+    split_pack_kernel<<<148 * 8, 256, 0, st>>>(state, (const double*)(ws + L.xc), (const int*)(ws + L.pa),
+                                               (const unsigned short*)(ws + L.cb),
+                                               (const int*)(ws + L.dest), d_perm, d_rec, d_send,
+                                               d_send_keys, d_self_rec, d_self_keys);
     SPLIT_CUDA(cudaGetLastError());
     return PMMH_OK;
 }

@@ -167,6 +167,15 @@ class _Rank(object):
         _lib.check(self.lib.pmmh_svsplit_plan(*self._c(), self.world, _p(self.hist),
                                               ctypes.c_void_p(self.h_counts.data_ptr()), self._stream()),
                    "pmmh_svsplit_plan")
+        if self.world > 1:
+            # children that stay on this rank go straight to their arrival slots in the receive buffers: the
+            # exchange moves only what crosses ranks (the self part was a device copy of up to 80 B per particle)
+            _lib.check(self.lib.pmmh_svsplit_pack_direct(*self._c(), _p(self.perm), _p(self.rec), _p(self.send),
+                                                         None if self.send_keys is None else _p(self.send_keys),
+                                                         _p(self.rec_next),
+                                                         None if self.recv_keys is None else _p(self.recv_keys),
+                                                         self._stream()), "pmmh_svsplit_pack_direct")
+            return
         _lib.check(self.lib.pmmh_svsplit_pack(*self._c(), _p(self.perm), _p(self.rec), _p(self.send),
                                               None if self.send_keys is None else _p(self.send_keys),
                                               self._stream()), "pmmh_svsplit_pack")
@@ -203,7 +212,8 @@ class LocalComm(object):
             for r, s in enumerate(sends):
                 o[r].copy_(s)
 
-    def all_to_all(self, sends, send_counts, recvs, recv_counts):
+    def all_to_all(self, sends, send_counts, recvs, recv_counts, skip_self=False):
+        """skip_self: the part a rank sends to itself is already in place (pmmh_svsplit_pack_direct)."""
         G = self.world
         soff = [np.concatenate([[0], np.cumsum(c)]) for c in send_counts]
         roff = [np.concatenate([[0], np.cumsum(c)]) for c in recv_counts]
@@ -211,11 +221,11 @@ class LocalComm(object):
             for d in range(G):
                 n = send_counts[s][d]
                 assert n == recv_counts[d][s]
-                if n:
+                if n and not (skip_self and s == d):
                     recvs[d][roff[d][s]:roff[d][s] + n].copy_(sends[s][soff[s][d]:soff[s][d] + n])
 
-    def all_to_all_async(self, sends, send_counts, recvs, recv_counts):
-        self.all_to_all(sends, send_counts, recvs, recv_counts)
+    def all_to_all_async(self, sends, send_counts, recvs, recv_counts, skip_self=False):
+        self.all_to_all(sends, send_counts, recvs, recv_counts, skip_self)
         return None
 
     def all_reduce_sum(self, tensors):
@@ -241,14 +251,34 @@ class DistComm(object):
     def all_gather(self, sends, outs):
         self.dist.all_gather_into_tensor(outs[0].view(-1), sends[0].view(-1), group=self.group)
 
-    def all_to_all(self, sends, send_counts, recvs, recv_counts):
+    def _views(self, buf, counts, skip):
+        """One view of ``buf`` per peer at the cumulative offsets of ``counts``; an empty one for ``skip``."""
+        out, off = [], 0
+        for r, n in enumerate(counts):
+            n = int(n)
+            out.append(buf[off:off] if r == skip else buf[off:off + n])
+            off += n
+        return out
+
+    def all_to_all(self, sends, send_counts, recvs, recv_counts, skip_self=False):
+        if skip_self:
+            # the self part is already in place (pmmh_svsplit_pack_direct): grouped send / recv per peer over views at
+            # the unchanged offsets, nothing for this rank itself
+            me = self.local_ranks[0]
+            self.dist.all_to_all(self._views(recvs[0], recv_counts[0], me), self._views(sends[0], send_counts[0], me),
+                                 group=self.group)
+            return
         nrecv, nsend = int(sum(recv_counts[0])), int(sum(send_counts[0]))
         self.dist.all_to_all_single(recvs[0][:nrecv], sends[0][:nsend], list(recv_counts[0]),
                                     list(send_counts[0]), group=self.group)
 
-    def all_to_all_async(self, sends, send_counts, recvs, recv_counts):
+    def all_to_all_async(self, sends, send_counts, recvs, recv_counts, skip_self=False):
         """Enqueued behind the current stream's work; later kernels on the current stream overlap
         it until ``handle.wait()`` (which makes the current stream wait, not the host)."""
+        if skip_self:
+            me = self.local_ranks[0]
+            return self.dist.all_to_all(self._views(recvs[0], recv_counts[0], me),
+                                        self._views(sends[0], send_counts[0], me), group=self.group, async_op=True)
         nrecv, nsend = int(sum(recv_counts[0])), int(sum(send_counts[0]))
         return self.dist.all_to_all_single(recvs[0][:nrecv], sends[0][:nsend], list(recv_counts[0]),
                                            list(send_counts[0]), group=self.group, async_op=True)
@@ -318,12 +348,12 @@ def run_split_smoother(comm, obs, params, n_total, lag, rvr_d, u_d=None, philox=
             # values first (8 B per particle), then the records asynchronously: the sort needs only
             # the values and runs while the records are in flight
             comm.all_to_all([rk.send_keys for rk in ranks], [c[0] for c in cnt],
-                            [rk.recv_keys for rk in ranks], [c[1] for c in cnt])
+                            [rk.recv_keys for rk in ranks], [c[1] for c in cnt], skip_self=True)
             pending = comm.all_to_all_async([rk.send for rk in ranks], [c[0] for c in cnt],
-                                            [rk.rec_next for rk in ranks], [c[1] for c in cnt])
+                                            [rk.rec_next for rk in ranks], [c[1] for c in cnt], skip_self=True)
         else:
             comm.all_to_all([rk.send for rk in ranks], [c[0] for c in cnt],
-                            [rk.rec_next for rk in ranks], [c[1] for c in cnt])
+                            [rk.rec_next for rk in ranks], [c[1] for c in cnt], skip_self=True)
             pending = None
         for rk, c in zip(ranks, cnt):
             rk.sort(c[2], c[4])

@@ -24,7 +24,7 @@ def test_header_declares_the_expected_entry_points():
                  "pmmh_flps_sv_corr_host", "pmmh_bpf_sv_corr_host",
                  "pmmh_importance_discrete_host", "pmmh_stratified_host",
                  "pmmh_svsplit_init", "pmmh_svsplit_weights", "pmmh_svsplit_children", "pmmh_svsplit_plan",
-                 "pmmh_svsplit_pack", "pmmh_svsplit_sort", "pmmh_svsplit_tail", "pmmh_svsplit_finish",
+                 "pmmh_svsplit_pack", "pmmh_svsplit_pack_direct", "pmmh_svsplit_sort", "pmmh_svsplit_tail", "pmmh_svsplit_finish",
                  "pmmh_flps_sv_corr_philox", "pmmh_flps_sv_corr_streamed"):
         assert must in syms
 
