@@ -260,13 +260,28 @@ class DistComm(object):
             off += n
         return out
 
+    def _exchange_views(self, send, send_counts, recv, recv_counts, async_op=False):
+        """Everything but the self part: NCCL = one grouped send / recv per peer (all_to_all over views);
+        other backends (gloo, CPU tests) = point-to-point pairs."""
+        me = self.local_ranks[0]
+        outs, ins = self._views(recv, recv_counts, me), self._views(send, send_counts, me)
+        if self.dist.get_backend(self.group) == "nccl":
+            return self.dist.all_to_all(outs, ins, group=self.group, async_op=async_op)
+        ops = []
+        for r in range(self.world):
+            if r != me and ins[r].numel():
+                ops.append(self.dist.P2POp(self.dist.isend, ins[r].contiguous(), r, self.group))
+            if r != me and outs[r].numel():
+                ops.append(self.dist.P2POp(self.dist.irecv, outs[r], r, self.group))
+        for w in (self.dist.batch_isend_irecv(ops) if ops else []):
+            w.wait()
+        return None
+
     def all_to_all(self, sends, send_counts, recvs, recv_counts, skip_self=False):
         if skip_self:
             # the self part is already in place (pmmh_svsplit_pack_direct): grouped send / recv per peer over views at
             # the unchanged offsets, nothing for this rank itself
-            me = self.local_ranks[0]
-            self.dist.all_to_all(self._views(recvs[0], recv_counts[0], me), self._views(sends[0], send_counts[0], me),
-                                 group=self.group)
+            self._exchange_views(sends[0], send_counts[0], recvs[0], recv_counts[0])
             return
         nrecv, nsend = int(sum(recv_counts[0])), int(sum(send_counts[0]))
         self.dist.all_to_all_single(recvs[0][:nrecv], sends[0][:nsend], list(recv_counts[0]),
@@ -276,9 +291,7 @@ class DistComm(object):
         """Enqueued behind the current stream's work; later kernels on the current stream overlap
         it until ``handle.wait()`` (which makes the current stream wait, not the host)."""
         if skip_self:
-            me = self.local_ranks[0]
-            return self.dist.all_to_all(self._views(recvs[0], recv_counts[0], me),
-                                        self._views(sends[0], send_counts[0], me), group=self.group, async_op=True)
+            return self._exchange_views(sends[0], send_counts[0], recvs[0], recv_counts[0], async_op=True)
         nrecv, nsend = int(sum(recv_counts[0])), int(sum(send_counts[0]))
         return self.dist.all_to_all_single(recvs[0][:nrecv], sends[0][:nsend], list(recv_counts[0]),
                                            list(send_counts[0]), group=self.group, async_op=True)

@@ -68,6 +68,18 @@ def _worker(rank, world, port, ret):
     sc, rc = S.interval_exchange_counts(n_src, n_dst, rank)
     comm.all_to_all([mine], [sc], [got], [rc])
     ok3 = np.array_equal(got[:n_dst[rank]].numpy(), full[d0:d0 + n_dst[rank]])
+    # the per-step exchange after pmmh_svsplit_pack_direct: the self part is already in place and must stay
+    # untouched, the other parts land at the unchanged offsets (rows of LR doubles)
+    LR = 3
+    sc2, rc2 = ([2, 3], [2, 4]) if rank == 0 else ([4, 1], [3, 1])
+    send2 = torch.arange(5 * LR, dtype=torch.float64).reshape(5, LR) + 100.0 * (rank + 1)
+    recv2 = torch.full((8, LR), -1.0, dtype=torch.float64)
+    comm.all_to_all([send2], [sc2], [recv2], [rc2], skip_self=True)
+    if rank == 0:    # rows 0..1 = self (untouched), rows 2..5 = rank 1's rows 0..3
+        want2 = np.vstack([np.full((2, LR), -1.0), np.arange(4 * LR).reshape(4, LR) + 200.0, np.full((2, LR), -1.0)])
+    else:            # rows 0..2 = rank 0's rows 2..4, row 3 = self (untouched)
+        want2 = np.vstack([np.arange(2 * LR, 5 * LR).reshape(3, LR) + 100.0, np.full((5, LR), -1.0)])
+    ok3 = ok3 and np.array_equal(recv2.numpy(), want2)
     # and the small all-gather / all-reduce the time loop uses
     g_out = torch.zeros((world, 4), dtype=torch.float64)
     comm.all_gather([torch.full((4,), float(rank + 1), dtype=torch.float64)], [g_out])
