@@ -77,7 +77,7 @@ constexpr int kMaxTiles = 160;     // >= SM count
 constexpr int kCntStride = 32;     // ints between two slot counters (one 128-byte line each)
 constexpr double kZ = 6.5;         // histogram range: predicted mean +- 6.5 predicted sd
 constexpr int kDynSmem = 208 * 1024;
-constexpr int kProf = 16;
+constexpr int kProf = 32;
 
 struct __align__(16) MailEntry {   // aliases one (x, exp(-x/2)) pair of the sorted generation
     double x;
@@ -613,6 +613,7 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
             mom2 = warp_sum(l2);
         }
         __syncthreads();
+        PROF_MARK(16);   // C: totals -> offsets (warp 0)
         {
             const double invS = s_sc.invS, offk = s_sc.offk;
             const int Lc = ((n + GT - 1) / GT) | 1, q0 = tid * Lc;
@@ -644,6 +645,7 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
                 }
             }
             // parallel scans are monotone only up to an ulp: a running maximum over all parents
+            PROF_MARK(17);   // C: cumulative weights + child counts
             // (and over the tiles in front) keeps the child ranges disjoint
             int prev = block_excl_max_int<GT>(rmax, s_sc.carry, s_wi, lane, warp);
 #pragma unroll
@@ -656,6 +658,7 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
             }
         }
         __syncthreads();
+        PROF_MARK(18);   // C: running maximum
         {
             // ancestor of every child: parent q owns the children [ub(q-1), ub(q)); consecutive
             // lanes hold consecutive parents, so the stores of a warp fall into a few lines
@@ -778,6 +781,7 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
             if (bad) GRID_FLAG(2);
             if (orphan) GRID_FLAG(4);
         }
+        PROF_MARK(19);   // A1: gathers + propagation + histogram
         if (HESS && tid == 0) s_ndef = 0;
         __syncthreads();
         {
@@ -932,6 +936,7 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
             }
         }
         __syncthreads();
+        PROF_MARK(20);   // A2: histogram scan + tile map
         int kr[KPT];
         {
             const double mhat = s_sc.mhat, inv_shat = s_sc.inv_shat;
@@ -948,6 +953,7 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
             }
         }
         __syncthreads();
+        PROF_MARK(21);   // A2: slot counting
         if (tid < G) {
             // slots of this CTA's run in every mailbox
             const int cnt = s_tcnt[tid];
@@ -957,6 +963,7 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
             s_tcnt[tid] = 0;
         }
         __syncthreads();
+        PROF_MARK(22);   // A2: global reservation
         {
             MailEntry* mail = (MailEntry*)a.XE;
 #pragma unroll
@@ -1049,6 +1056,7 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
                 }
             }
             __syncthreads();
+            PROF_MARK(23);   // B: mailbox load + sub-bin count
             {
                 // exclusive scan of the sub-bin counters in place (SPT consecutive bins per thread)
                 int cnt[SPT];
@@ -1080,6 +1088,7 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
                     *(int4*)(s_sub + SPT * tid + i) = make_int4(cnt[i], cnt[i + 1], cnt[i + 2], cnt[i + 3]);
             }
             __syncthreads();
+            PROF_MARK(24);   // B: sub-bin scan
 #pragma unroll
             for (int kk = 0; kk < KPT; ++kk) {
                 const int e = kk * GT + tid;
@@ -1128,6 +1137,7 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
                 }
             }
             __syncthreads();
+            PROF_MARK(25);   // B: exact ranks
 #pragma unroll
             for (int kk = 0; kk < KPT; ++kk) {
                 const int q = kk * GT + tid;
@@ -1138,6 +1148,7 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
                 }
             }
             __syncthreads();
+            PROF_MARK(26);   // B: reorder
         }
         {
             // weights (:427-437): lw = -0.9189 - x/2 - y^2 exp(-x) / 2, sh = exp(lw - shift);
