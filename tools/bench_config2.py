@@ -18,4 +18,12 @@ for alg in (6, 2):
             r = probe_sv.run(n, hess=False, reps=3)
         except Exception as e:
             print('{"alg": %d, "n": %d, "error": "%s"}' % (alg, n, str(e)[:80]))
+# the Hessian branch around its automatic threshold (2^16): grid kernel forced (6) against the general kernel (1)
+for alg in (6, 1):
+    K.set_sv_algorithm(alg)
+    for n in (1 << 14, 1 << 15, 1 << 16, 1 << 17):
+        try:
+            r = probe_sv.run(n, hess=True, reps=2)
+        except Exception as e:
+            print('{"alg": %d, "n": %d, "hess": 1, "error": "%s"}' % (alg, n, str(e)[:80]))
 K.set_sv_algorithm(0)
