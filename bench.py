@@ -545,7 +545,8 @@ def run_split_pf(args, rank, world, dev, dist):
             "near_ties_rank0": int(out["diag"][0]), "status": int(out["diag"][2]),
             "max_particles_per_rank": int(out["counts"].max()),
             "exchange": "none (one rank, record variant: faster than path storage from N = 2^23 on)" if world == 1 else
-                        "per step: all_gather 32 B + all_gather 16 KB + all_to_all of 80-byte records (NCCL)"}
+                        "per step: all_gather 32 B + all_gather 16 KB + all_to_all of the 80-byte records that cross ranks (NCCL; the ones "
+                        "that stay are packed straight into the receive buffer)"}
 
 
 def run_ours(args, rank, world, local_rank):
