@@ -806,8 +806,10 @@ def run_ours(args, rank, world, local_rank):
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                     "api": "ParticleMethodsCUDA.smoother(model, rvs={'rvs': pinned ndarray})",
                     "note": "host rvs -> pmmh_flps_sv_corr_streamed: the copy engine feeds the running grid kernel "
-                            "in particle-major chunks of 256 time steps (2 KB rows, no layout kernel), the kernel "
-                            "polls one flag per time step; bound by the host link; results read back to the host"},
+                            "in particle-major pieces of up to 256 time steps (2 KB rows, no layout kernel; pieces of ~0.3 x "
+                            "the remaining steps towards the end so that the kernel ends a few ms after the last copy); the "
+                            "kernel polls one flag per time step and re-lays every 32-byte sector (4 steps) of its particles "
+                            "time-major once; bound by the host link (~52 GB/s); results read back to the host"},
             "gpu_launches": (launches_per_step * args.steps) if launches_per_step is not None else None,
             "gpu_launches_per_step": launches_per_step, "gpu_launches_top": launch_top,
             "gpu_launches_source": "CUPTI activity trace (torch.profiler) of one extra untimed step x steps",

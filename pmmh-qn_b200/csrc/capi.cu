@@ -436,7 +436,17 @@ int grid_u_chunk() {
     if (!v) {
         const char* e = getenv("PMMH_GRID_U_CHUNK");
         v = e ? atoi(e) : 256;
-        if (v < 16 || v > 4096) v = 256;
+        if (v < 16 || v > 4096 || (v & 3)) v = 256;   // a multiple of 4 (32-byte sectors of the staged rows)
+    }
+    return v;
+}
+// smallest copy of the tapered schedule of the last chunk slot, in time steps (0 = no taper)
+int grid_u_taper_min() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PMMH_GRID_U_TAPER");
+        v = e ? atoi(e) : 48;
+        if (v < 0 || v > 4096) v = 48;
     }
     return v;
 }
@@ -550,21 +560,46 @@ int pmmh_flps_sv_corr_streamed(const double* h_rvs, const double* d_obs, const d
         cudaStream_t stg = (cudaStream_t)stream;
         char* stageg = (char*)d_stage;
         int* d_flagg = (int*)(stageg + gdata);
+        // development: PMMH_STREAM_TIMING=1 prints when the copies and the kernel of this call ended (blocks the host)
+        static const bool timing = getenv("PMMH_STREAM_TIMING") != nullptr;
+        cudaEvent_t tv[3] = {nullptr, nullptr, nullptr};
+        if (timing)
+            for (int i = 0; i < 3; ++i) PMMH_CUDA(cudaEventCreate(&tv[i]));
         PMMH_CUDA(cudaEventRecord(sg.ev_start, stg));
         PMMH_CUDA(cudaStreamWaitEvent(sg.copy_stream, sg.ev_start, 0));
+        if (timing) PMMH_CUDA(cudaEventRecord(tv[0], sg.copy_stream));
         PMMH_CUDA(cudaMemsetAsync(d_flagg, 0, sizeof(int), sg.copy_stream));
         PMMH_CUDA(cudaEventRecord(sg.ev_reset, sg.copy_stream));
-        const int chunksg = (n_obs + ch - 1) / ch;
-        for (int c = 0; c < chunksg; ++c) {
-            const int t0 = c * ch;
-            const int wsteps = (n_obs - t0 < ch) ? (n_obs - t0) : ch;
+        // Copy schedule.  The kernel needs ~0.11 ms per time step, the host link ~0.157 ms (2 KB rows: 53.5 GB/s; 1 KB:
+        // 51.7; 512 B: 48.4; and ~8 ns per row whatever its width, i.e. 8.4 ms for any piece of fewer than ~52 steps at
+        // N = 2^20).  The kernel can only start a piece when all of it has landed, so after the last copy it still has
+        // to work off what it was behind: a piece of p steps that starts with `rem` steps to go delays the end unless
+        // 0.157 p <= (0.157 - 0.11) rem + 0.11 p_last, i.e. p <= 0.3 rem + 0.7 p_last.  Hence: whole slots (widest rows) while
+        // that holds, then pieces of ~0.3 x what remains, the last one ~52 steps.  Measured at T = 1000, N = 2^20
+        // (PMMH_STREAM_TIMING=1): one copy per slot 157.7 ms of copies + 26.3 ms of kernel after the last one; this
+        // schedule: see DESIGN 3.  PMMH_GRID_U_TAPER=0: one copy per slot.  The staging layout does not change.
+        const int taper_min = grid_u_taper_min();
+        int t0 = 0;
+        while (t0 < n_obs) {
+            const int c = t0 / ch, in = t0 - c * ch;
+            const int rem = n_obs - t0;
+            int wsteps = (rem < ch - in) ? rem : ch - in;            // what is left of this slot
+            if (taper_min > 0 && rem >= 2 * taper_min) {
+                int w = (3 * rem) / 10 + (7 * taper_min) / 10;
+                if (w < taper_min) w = taper_min;
+                if (w < wsteps) wsteps = w;
+            }
+            if (t0 + wsteps < n_obs) wsteps = (wsteps + 3) & ~3;   // pieces end on 32-byte sectors of the staged rows (ch % 4 == 0)
+            if (wsteps > ch - in) wsteps = ch - in;
             const double* src = h_rvs + (size_t)n_obs + (size_t)t0;   // rvp[i + j * n_obs], cython.py:89-91
-            char* dst = stageg + (size_t)c * (size_t)n_particles * ch * sizeof(double);
+            char* dst = stageg + ((size_t)c * (size_t)n_particles * ch + (size_t)in) * sizeof(double);
             PMMH_CUDA(cudaMemcpy2DAsync(dst, (size_t)ch * sizeof(double), src, (size_t)n_obs * sizeof(double),
                                         (size_t)wsteps * sizeof(double), (size_t)n_particles, cudaMemcpyHostToDevice,
                                         sg.copy_stream));
             PMMH_CUDA(cudaMemcpyAsync(d_flagg, &tab[t0 + wsteps], sizeof(int), cudaMemcpyHostToDevice, sg.copy_stream));
+            t0 += wsteps;
         }
+        if (timing) PMMH_CUDA(cudaEventRecord(tv[1], sg.copy_stream));
         PMMH_CUDA(cudaEventRecord(sg.ev_done, sg.copy_stream));
         PMMH_CUDA(cudaStreamWaitEvent(stg, sg.ev_reset, 0));   // the kernel must not start before the flag is reset
         int rcg = pmmh::sv_grid_run(d_obs, d_params, d_rvr, (const double*)d_stage, n_obs, n_particles, lag, GGs, d_filt,
@@ -575,6 +610,16 @@ int pmmh_flps_sv_corr_streamed(const double* h_rvs, const double* d_obs, const d
         PMMH_CUDA(cudaMemsetAsync(d_hess2, 0, 16 * sizeof(double), stg));
         // an evaluation that is abandoned early leaves copies behind: the caller's stream ends after them
         PMMH_CUDA(cudaStreamWaitEvent(stg, sg.ev_done, 0));
+        if (timing) {
+            PMMH_CUDA(cudaEventRecord(tv[2], stg));
+            PMMH_CUDA(cudaEventSynchronize(tv[2]));
+            float copies_ms = 0.f, all_ms = 0.f;
+            cudaEventElapsedTime(&copies_ms, tv[0], tv[1]);
+            cudaEventElapsedTime(&all_ms, tv[0], tv[2]);
+            fprintf(stderr, "[pmmh stream timing] copies %.2f ms (%.1f GB/s), kernel ends %.2f ms after the last copy\n",
+                    copies_ms, (double)n_obs * n_particles * 8.0 / (copies_ms * 1e6), all_ms - copies_ms);
+            for (int i = 0; i < 3; ++i) cudaEventDestroy(tv[i]);
+        }
         return PMMH_OK;
     }
     // Host-resident u runs on the exchange kernel where it takes the size (measured at N = 2^20:

@@ -110,6 +110,7 @@ struct GridArgs {
     long long u_cstride, u_tstride, u_jstride;
     int u_cs;
     const int* u_flag;   // host-streamed u: number of time rows that have landed (written by the copy engine)
+    double* ustash;      // [4][N] host-streamed u: the four time steps of one 32-byte sector per particle, time-major
     GridCtrl* ctrl;
     int* ghist;        // [2][kNCopy][kNF]
     int* tilecnt;      // [2][kMaxTiles * kCntStride]
@@ -704,8 +705,10 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
         for (int b = tid; b < kNF; b += GT) s_fhist[b] = 0;
         PROF_MARK(1);   // zero hist
         if (a.u_flag && tid == 0) {
-            // host-streamed u: row t has to have landed (the flag is written by the copy engine)
-            while (ld_acquire_sys_s32(a.u_flag) <= t) {
+            // host-streamed u: row t has to have landed (the flag is written by the copy engine); at the first of
+            // the four steps that share a 32-byte sector, all four (see the stash below)
+            const int need = (((t % a.u_cs) & 3) == 0 || t == 1) ? min(t | 3, NOBS - 1) : t;
+            while (ld_acquire_sys_s32(a.u_flag) <= need) {
             }
         }
         GRID_WAIT();
@@ -729,7 +732,35 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
             const double mhat = s_sc.mhat, inv_shat = s_sc.inv_shat;
             const double mu = s_k.mu, phi = s_k.phi, sr = s_k.sr, sd = s_k.sd;
             const double* Ut = a.U + (size_t)(t / a.u_cs) * a.u_cstride + (size_t)(t % a.u_cs) * a.u_tstride;
-            const long long ujs = a.u_jstride;
+            long long ujs = a.u_jstride;
+            if (a.u_flag) {
+                // host-streamed u lies particle-major (rows of u_cs steps): a strided 8-byte read per particle and step
+                // fetches a 64-byte DRAM burst for 8 bytes and costs the LSU one sector per lane (measured: 142 instead
+                // of 94 us per step).  Every fourth step each thread reads the whole 32-byte sector of its particles once
+                // and lays the four steps down time-major in a small stash (coalesced stores); all steps then read the
+                // stash coalesced.  A thread reads back only what it wrote itself: no synchronisation.
+                const int tin = t % a.u_cs;
+                if ((tin & 3) == 0 || t == 1) {   // (the time loop starts at t = 1: that step fills the first sector)
+                    const double* Ug = Ut - (tin & 3);
+#pragma unroll
+                    for (int kk = 0; kk < KPT; ++kk) {
+                        const int i = kk * GT + tid;
+                        if (i < nc) {
+                            double v0, v1, v2, v3;
+                            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
+                                         : "=d"(v0), "=d"(v1), "=d"(v2), "=d"(v3)
+                                         : "l"(Ug + (size_t)(jb + i) * ujs), "l"(pol_stream));
+                            double* sp = a.ustash + jb + i;
+                            __stcg(sp, v0);
+                            __stcg(sp + N, v1);
+                            __stcg(sp + 2 * (size_t)N, v2);
+                            __stcg(sp + 3 * (size_t)N, v3);
+                        }
+                    }
+                }
+                Ut = a.ustash + (size_t)(tin & 3) * N;
+                ujs = 1;
+            }
             PEntry* Pt = a.P + (size_t)(t % RP) * N * RS;
             bool bad = false, orphan = false;
 #pragma unroll
@@ -754,7 +785,8 @@ __global__ void __launch_bounds__(GT, 1) sv_grid_kernel(const GridArgs a) {
                             xe[u].y = __longlong_as_double(((long long)xr.w << 32) | (long long)(unsigned)xr.z);
                         }
                         bp[k0 + u] = ld_hint_b32(&a.perm[p], pol_xld);
-                        uu[u] = ld_stream_hint_f64(Ut + (size_t)(jb + i) * ujs, pol_stream);
+                        // (the stash is rewritten every four steps: coherent load, not the read-only path)
+                        uu[u] = a.u_flag ? __ldcg(Ut + (size_t)(jb + i) * ujs) : ld_stream_hint_f64(Ut + (size_t)(jb + i) * ujs, pol_stream);
                         if (a.hist) a.parentpos[jb + i] = p;
                     }
                 }
@@ -1657,7 +1689,7 @@ __global__ void grid_finish_kernel(const GridCtrl* __restrict__ ctrl, const doub
 
 struct GridLayout {
     size_t ctrl, ghist, tilecnt, tinfo, H, XE, perm, R, P, psum, shiftv, xminv, shring, parentpos, sums,
-        tailpart, tail, info, xlow, psumH, sumsH, tailpartH, total;
+        tailpart, tail, info, ustash, xlow, psumH, sumsH, tailpartH, total;
     int RP, nblk, SQ;
 };
 
@@ -1689,6 +1721,7 @@ GridLayout grid_layout(int nobs, int n, int lag, int G, int hist, int hess) {
     L.tailpart = o;  o += al256((size_t)lag * L.nblk * 8 * 8);
     L.tail = o;      o += al256((size_t)lag * 8 * 8);
     L.info = o;      o += al256(8 * 8);
+    L.ustash = o;    o += al256(4 * N * 8);   // host-streamed u: four time steps, time-major
     // Hessian branch: the first SQ sorted values of every generation (Q7: particles[i - 1 + ancestor] read through
     // the flat layout), per-tile / per-step sums
     L.SQ = hess ? (nobs + n - 2) / nobs + 1 : 1;
@@ -1757,6 +1790,7 @@ int sv_grid_run(const double* d_obs, const double* d_params, const double* d_rvr
         a.u_tstride = 1;
         a.u_jstride = u_chunk_steps;
         a.u_flag = d_u_flag;
+        a.ustash = (double*)(ws + L.ustash);
     } else {
         a.u_cs = 1 << 30;
         a.u_cstride = 0;
