@@ -130,7 +130,8 @@ int pmmh_flps_sv_corr(const double* d_obs, long long obs_stride, const double* d
  * layout kernel) while the persistent kernel is already running; the kernel waits for a chunk only
  * when it reaches it, and the caller's stream ends after the last copy.  d_rvr = Phi of the first
  * n_obs flat entries (computed by the caller as in cython.py:90).  Kernel by size: the grid kernel
- * where a tile fits one SM (2^16 <= N <= ~1.06 M, chunks of 256 time steps), else the exchange
+ * where a tile fits one SM (2^14 <= N <= ~1.06 M; slots of 256 time steps filled by copies that get
+ * shorter towards the end of the series, so that the kernel ends a few ms after the last copy), else the exchange
  * kernel where it is eligible (chunks of 64), else the streaming kernels, whose host-driven step
  * loop waits for a chunk's event when it enters it (pmmh_sv_streamed_eligible tells whether a size
  * is taken at all).  There is no fallback inside: if d_diag[PMMH_DIAG_STATUS] == 1 afterwards,
