@@ -1,6 +1,7 @@
 // capi.cu -- extern "C" boundary of libpmmh_qn_b200.so (declared in include/pmmh_qn.h).
 // Plain pointers and sizes in, status codes out; no torch types, no CPU fallback.
 #include <cuda_runtime.h>
+#include <stdint.h>
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
@@ -545,6 +546,7 @@ int pmmh_flps_sv_corr_streamed(const double* h_rvs, const double* d_obs, const d
         if (workspace_bytes < gws) return fail(PMMH_ERR_WORKSPACE, "workspace too small (pmmh_sv_streamed_workspace_bytes)");
         const size_t gdata = streamed_grid_data_bytes(n_obs, n_particles);
         if (stage_bytes < gdata + 256) return fail(PMMH_ERR_WORKSPACE, "staging buffer too small");
+        if (((uintptr_t)d_stage & 31) != 0) return fail(PMMH_ERR_INVALID, "d_stage must be 32-byte aligned (the kernel reads 32-byte sectors of the staged rows)");
         int devg = 0;
         PMMH_CUDA(cudaGetDevice(&devg));
         if (devg < 0 || devg >= 64) return fail(PMMH_ERR_NO_DEVICE, "device ordinal out of range");
