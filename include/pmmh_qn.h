@@ -141,6 +141,9 @@ int pmmh_flps_sv_corr(const double* d_obs, long long obs_stride, const double* d
  * copy stream and its events are per (thread, device) state. */
 int pmmh_sv_streamed_workspace_bytes(int n_obs, int n_particles, int lag, int ctas_per_problem, size_t* bytes);
 int pmmh_sv_stage_bytes(int n_obs, int n_particles, size_t* bytes);
+/* the copy schedule of the host-streamed grid path for a series of n_obs steps (no device needed): the number of
+ * pieces (negative: bad arguments); the first max_pieces lengths, in time steps, are written to pieces */
+int pmmh_sv_stream_schedule(int n_obs, int* pieces, int max_pieces);
 int pmmh_sv_streamed_eligible(int n_obs, int n_particles, int lag, int ctas_per_problem);
 int pmmh_flps_sv_corr_streamed(const double* h_rvs, const double* d_obs, const double* d_params,
                                const double* d_rvr, int n_obs, int n_particles, int lag, void* d_stage,

@@ -451,6 +451,23 @@ int grid_u_taper_min() {
     }
     return v;
 }
+// next piece of the copy schedule of the host-streamed grid path (see pmmh_flps_sv_corr_streamed): time steps
+// [t0, t0 + return value); never crosses a slot of `ch` steps, ends on a multiple of 4 steps unless it ends the series
+int grid_u_next_piece(int t0, int n_obs, int ch, int taper_min) {
+    const int c = t0 / ch, in = t0 - c * ch;
+    const int rem = n_obs - t0;
+    int wsteps = (rem < ch - in) ? rem : ch - in;            // what is left of this slot
+    if (taper_min > 0 && rem >= 2 * taper_min) {
+        int w = (3 * rem) / 10 + (7 * taper_min) / 10;
+        if (w < taper_min) w = taper_min;
+        if (w < wsteps) wsteps = w;
+    }
+    if (t0 + wsteps < n_obs) wsteps = (wsteps + 3) & ~3;   // pieces end on 32-byte sectors of the staged rows (ch % 4 == 0)
+    const int whole = (rem < ch - in) ? rem : ch - in;
+    // no sliver at the end of a slot (what is left over at the end of the series may be half as short: it is the last piece)
+    if (wsteps > whole || (taper_min > 0 && whole - wsteps < (whole == rem ? taper_min / 2 : taper_min))) wsteps = whole;
+    return wsteps;
+}
 size_t streamed_grid_data_bytes(int n_obs, int n) {
     const int ch = grid_u_chunk();
     return (size_t)((n_obs + ch - 1) / ch) * (size_t)n * ch * sizeof(double);
@@ -483,6 +500,19 @@ bool streamed_grid_ok(int n_obs, int n, int lag, int ctas, int* G_out) {
     return true;
 }
 }  // namespace
+
+int pmmh_sv_stream_schedule(int n_obs, int* pieces, int max_pieces) {
+    if (n_obs < 1 || (max_pieces > 0 && !pieces)) return -1;
+    const int ch = grid_u_chunk(), taper = grid_u_taper_min();
+    int t0 = 0, k = 0;
+    while (t0 < n_obs) {
+        const int w = grid_u_next_piece(t0, n_obs, ch, taper);
+        if (k < max_pieces) pieces[k] = w;
+        ++k;
+        t0 += w;
+    }
+    return k;
+}
 
 int pmmh_sv_stage_bytes(int n_obs, int n_particles, size_t* bytes) {
     if (!bytes || n_obs < 2 || n_particles < 1) return fail(PMMH_ERR_INVALID, "pmmh_sv_stage_bytes: bad arguments");
@@ -580,19 +610,10 @@ int pmmh_flps_sv_corr_streamed(const double* h_rvs, const double* d_obs, const d
         // that holds, then pieces of ~0.3 x what remains, the last one ~52 steps.  Measured at T = 1000, N = 2^20
         // (PMMH_STREAM_TIMING=1): one copy per slot 157.7 ms of copies + 26.3 ms of kernel after the last one; this
         // schedule: see DESIGN 3.  PMMH_GRID_U_TAPER=0: one copy per slot.  The staging layout does not change.
-        const int taper_min = grid_u_taper_min();
         int t0 = 0;
         while (t0 < n_obs) {
             const int c = t0 / ch, in = t0 - c * ch;
-            const int rem = n_obs - t0;
-            int wsteps = (rem < ch - in) ? rem : ch - in;            // what is left of this slot
-            if (taper_min > 0 && rem >= 2 * taper_min) {
-                int w = (3 * rem) / 10 + (7 * taper_min) / 10;
-                if (w < taper_min) w = taper_min;
-                if (w < wsteps) wsteps = w;
-            }
-            if (t0 + wsteps < n_obs) wsteps = (wsteps + 3) & ~3;   // pieces end on 32-byte sectors of the staged rows (ch % 4 == 0)
-            if (wsteps > ch - in) wsteps = ch - in;
+            const int wsteps = grid_u_next_piece(t0, n_obs, ch, grid_u_taper_min());
             const double* src = h_rvs + (size_t)n_obs + (size_t)t0;   // rvp[i + j * n_obs], cython.py:89-91
             char* dst = stageg + ((size_t)c * (size_t)n_particles * ch + (size_t)in) * sizeof(double);
             PMMH_CUDA(cudaMemcpy2DAsync(dst, (size_t)ch * sizeof(double), src, (size_t)n_obs * sizeof(double),

@@ -87,3 +87,27 @@ def test_split_default_capacities():
     for world in (2, 4, 8):
         cap, capc = default_capacities(1 << 24, world)
         assert (1 << 24) // world < cap <= (1 << 24) and capc == (1 << 24)
+
+
+def test_stream_copy_schedule_invariants():
+    """Copy schedule of the host-streamed grid path (pmmh_sv_stream_schedule, no device needed): the pieces cover the
+    series exactly, none crosses a slot of 256 time steps, every piece but the last ends on a multiple of 4 steps (the
+    kernel reads 32-byte sectors of the staged rows), whole slots first and shorter pieces towards the end."""
+    import ctypes
+    from pmmh_qn_b200 import _lib
+    lib = _lib.load()
+    for n_obs in list(range(1, 40)) + [71, 101, 255, 256, 257, 300, 511, 512, 513, 1000, 1001, 1002, 1003, 2000, 5000]:
+        buf = (ctypes.c_int * 256)()
+        k = lib.pmmh_sv_stream_schedule(n_obs, buf, 256)
+        assert 1 <= k <= 256
+        pieces = list(buf[:k])
+        assert sum(pieces) == n_obs and min(pieces) >= 1
+        t0 = 0
+        for i, w in enumerate(pieces):
+            assert t0 // 256 == (t0 + w - 1) // 256, (n_obs, pieces)      # inside one slot
+            assert (t0 + w) % 4 == 0 or i == k - 1, (n_obs, pieces)       # sector aligned
+            t0 += w
+    buf = (ctypes.c_int * 16)()
+    assert lib.pmmh_sv_stream_schedule(1001, buf, 16) == 7
+    assert list(buf[:7]) == [256, 256, 180, 76, 104, 72, 57]
+    assert lib.pmmh_sv_stream_schedule(0, buf, 16) < 0
