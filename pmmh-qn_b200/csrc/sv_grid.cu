@@ -42,7 +42,12 @@
 //     tables instead of records, bulk L2 prefetch of the lagged generation, L2 prefetch of the record / payload
 //     sectors a phase ahead, 16-byte payloads with an exp in the score terms, pointer-jumping tables by all
 //     threads (DRAM traffic 189 -> 138 MB per step, but the three dependent 4-byte gathers still miss L2:
-//     27 us against 14 us for the records, 118 us per step).  This version: 100 us.
+//     27 us against 14 us for the records, 118 us per step).  With the hints: 100 us; with the fence-free barrier
+//     (release / acquire on the counter, abandon flag in its bit 31): 94 - 96 us.
+//   * second instantiation HESS = true: the Hessian branch (:361-390, :472-534, :564-626), cumulative alpha in the second
+//     sector of 64-byte record / payload entries; 162 us per step.
+//   * host-resident u: particle-major slots filled by the copy engine, one 32-byte sector (4 steps) per particle re-laid
+//     time-major every fourth step.
 //
 // Deviations from the reference's operation order: parallel sums / scans, log(exp(x/2)) = x/2 and
 // 1/exp(x/2)^2 = exp(-x/2)^2 in the log-weight, cumulative weights multiplied by 1/S; any
